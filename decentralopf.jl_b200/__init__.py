@@ -1,0 +1,10 @@
+"""decentralopf.jl_b200 - B200-native ADMM iteration for DecentralOPF.jl's hot path.
+
+The directory name carries a dot, so it is loaded by path: `from __graft_entry__ import
+load_package; dopf = load_package()` (registers the package as `dopf_b200`).
+"""
+from .structures import (Convergence, Generator, Line, Node, Result, ResultGenerator,  # noqa: F401
+                         ResultStorage, Storage)
+from .problem import Problem  # noqa: F401
+from .ptdf import calculate_ptdf, ptdf_from_arrays  # noqa: F401
+from . import cases  # noqa: F401
