@@ -1,0 +1,466 @@
+// Per-agent math of the B200 ADMM iteration, shared by every kernel (host+device inline).
+//
+// What is solved (derivation in DESIGN.md section 3; reference objective:
+// /root/reference/src/optimization/subproblems.jl:63-83,162-183 + penalty_terms.jl:1-53):
+// after eliminating the per-agent slack copies U,K the agent at node n sees, per timestep t,
+//     phi'(delta) = g0 + s1*delta + corr(delta)
+// where (g0,s1) is the linearisation with the slack-clip pattern of delta = 0 ("anchor") and
+// corr() collects the hinges whose clip state differs from the anchor at delta.
+//   generator: root of  mc + phi'(delta) + prox*delta  on the box      (1-D, monotone)
+//   storage:   min sum_t mc(D+C) + prox/2((D-Db)^2+(C-Cb)^2) + phi_t(delta_t)
+//              s.t. 0<=D,C<=p, 0<=E_t=cumsum(C-D)<=emax; solved through the multiplier path
+//              eta_t of the level constraints ("funnel"/planning-horizon algorithm).
+#ifndef DOPF_MATH_H
+#define DOPF_MATH_H
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define DOPF_HD __host__ __device__ __forceinline__
+#else
+#define DOPF_HD inline
+#endif
+
+namespace dopf {
+
+// ---------------------------------------------------------------------------------------------
+// Hinges.  One hinge = one (line, side) whose per-agent slack clips at 0 when the agent moves:
+//   term(delta) = s*(delta-bp)  on the active side  dir*(delta-bp) > 0,  0 otherwise.
+// `anchored` = active at delta=0 (then its linear part is already inside g0,s1).
+// ---------------------------------------------------------------------------------------------
+struct Hinge {
+    double bp;   // breakpoint in delta
+    double sg;   // dir * s   (s = beta*p^2 > 0)
+};
+
+DOPF_HD void hinge_accum(const Hinge h, double delta, double &val, double &slope)
+{
+    const double dir = h.sg > 0.0 ? 1.0 : -1.0;
+    const double s = fabs(h.sg);
+    const bool anchored = dir * h.bp < 0.0;
+    const double e = dir * (delta - h.bp);
+    if (!anchored) {
+        if (e > 0.0) { val += s * (delta - h.bp); slope += s; }
+    } else {
+        if (e < 0.0) { val -= s * (delta - h.bp); slope -= s; }
+    }
+}
+
+// view of a hinge list (possibly empty)
+struct HingeList {
+    const Hinge *h;
+    int n;
+    DOPF_HD void eval(double delta, double &val, double &slope) const
+    {
+        val = 0.0; slope = 0.0;
+        for (int i = 0; i < n; ++i) hinge_accum(h[i], delta, val, slope);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Generator: root of f(delta) = c + a*delta + corr(delta) on [lo,hi], f increasing (a>0 and
+// every piece of corr keeps the total slope >= prox).  Exact for piecewise-linear f:
+// safeguarded Newton that ends as soon as a Newton step stays inside one linear piece.
+// ---------------------------------------------------------------------------------------------
+DOPF_HD double root_monotone_pl(double c, double a, const HingeList &hl, double lo, double hi)
+{
+    if (hl.n == 0) {
+        double d = -c / a;
+        return d < lo ? lo : (d > hi ? hi : d);
+    }
+    double v, s;
+    hl.eval(lo, v, s);
+    double flo = c + a * lo + v;
+    if (flo >= 0.0) return lo;
+    hl.eval(hi, v, s);
+    double fhi = c + a * hi + v;
+    if (fhi <= 0.0) return hi;
+    double x = -c / a;
+    if (!(x > lo && x < hi)) x = 0.5 * (lo + hi);
+    for (int it = 0; it < 200; ++it) {
+        hl.eval(x, v, s);
+        const double f = c + a * x + v;
+        if (f == 0.0) return x;
+        if (f < 0.0) { lo = x; flo = f; } else { hi = x; fhi = f; }
+        double xn = x - f / (a + s);
+        if (!(xn > lo && xn < hi)) xn = lo - flo * (hi - lo) / (fhi - flo);   // secant inside bracket
+        if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+        if (fabs(xn - x) <= 1e-15 * (1.0 + fabs(x))) return xn;
+        x = xn;
+    }
+    return x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Storage, one timestep, for a given level multiplier eta (Lagrangian term  eta*(C-D)).
+// Stationarity:  D = clip(Db - (mc+nu)/prox), C = clip(Cb - (mc-nu)/prox)   with
+//                nu = g0 - eta + s1*delta + corr(delta),  delta = (D-Db) - (C-Cb).
+// Psi(nu) = nu - (g0-eta) - s1*delta(nu) - corr(delta(nu)) is increasing with slope >= 1.
+// ---------------------------------------------------------------------------------------------
+struct StoStep {
+    double Db, Cb;   // previous discharge / charge
+    double g0, s1;   // anchor linearisation at this (node, t)
+};
+
+struct StoConst {
+    double mc, pmax, emax, prox;
+};
+
+DOPF_HD double clip01(double v, double hi) { return v < 0.0 ? 0.0 : (v > hi ? hi : v); }
+
+struct StoEval {
+    double D, C;     // solution at this eta
+    double dy;       // d(C-D)/d eta  (<= 0)
+};
+
+DOPF_HD void sto_dc_of_nu(const StoStep &st, const StoConst &k, double nu, double &D, double &C, int &nfree)
+{
+    const double du = st.Db - (k.mc + nu) / k.prox;
+    const double cu = st.Cb - (k.mc - nu) / k.prox;
+    D = clip01(du, k.pmax);
+    C = clip01(cu, k.pmax);
+    nfree = (du > 0.0 && du < k.pmax) + (cu > 0.0 && cu < k.pmax);
+}
+
+DOPF_HD StoEval sto_eval(const StoStep &st, const StoConst &k, const HingeList &hl, double eta)
+{
+    const double base = st.g0 - eta;
+    double D, C; int nf;
+    StoEval r;
+    if (hl.n == 0) {
+        // closed form: Psi is piecewise linear with the 4 clip breakpoints of D(nu), C(nu)
+        double b0 = k.prox * (st.Db - k.pmax) - k.mc;  // D leaves pmax
+        double b1 = k.prox * st.Db - k.mc;             // D reaches 0
+        double b2 = k.mc - k.prox * st.Cb;             // C leaves 0
+        double b3 = k.mc + k.prox * (k.pmax - st.Cb);  // C reaches pmax
+        // sort 4 (b0<=b1, b2<=b3 already)
+        double t;
+        if (b0 > b2) { t = b0; b0 = b2; b2 = t; }
+        if (b1 > b3) { t = b1; b1 = b3; b3 = t; }
+        if (b1 > b2) { t = b1; b1 = b2; b2 = t; }
+        const double bb[4] = { b0, b1, b2, b3 };
+        double pl = 0.0, pv = 0.0;  // previous breakpoint and Psi there
+        int found = -1;
+        double psi[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int i = 0; i < 4; ++i) {
+            sto_dc_of_nu(st, k, bb[i], D, C, nf);
+            psi[i] = bb[i] - base - st.s1 * ((D - st.Db) - (C - st.Cb));
+        }
+        double nu;
+        if (psi[0] >= 0.0) nu = bb[0] - psi[0];                 // slope 1 left of all breakpoints
+        else if (psi[3] <= 0.0) nu = bb[3] - psi[3];            // slope 1 right of all breakpoints
+        else {
+            found = psi[1] >= 0.0 ? 0 : (psi[2] >= 0.0 ? 1 : 2);
+            pl = bb[found]; pv = psi[found];
+            const double ql = bb[found + 1], qv = psi[found + 1];
+            nu = (qv == pv) ? pl : pl - pv * (ql - pl) / (qv - pv);
+        }
+        sto_dc_of_nu(st, k, nu, D, C, nf);
+        r.D = D; r.C = C;
+        r.dy = -(double)nf / (k.prox + st.s1 * nf);
+        return r;
+    }
+    // general case (hinges present): safeguarded Newton on Psi
+    const double big = k.mc + k.prox * k.pmax + 1.0;
+    double lo = -big + base - 1.0, hi = big + base + 1.0;  // |delta|<=2pmax; widened below if needed
+    {
+        double v, s;
+        hl.eval(2.0 * k.pmax, v, s);  hi += st.s1 * 2.0 * k.pmax + fabs(v);
+        hl.eval(-2.0 * k.pmax, v, s); lo -= st.s1 * 2.0 * k.pmax + fabs(v);
+    }
+    double nu = base, sl = 0.0;
+    double flo = -1.0, fhi = 1.0;
+    bool have_lo = false, have_hi = false;
+    for (int it = 0; it < 200; ++it) {
+        sto_dc_of_nu(st, k, nu, D, C, nf);
+        const double delta = (D - st.Db) - (C - st.Cb);
+        double v;
+        hl.eval(delta, v, sl);
+        const double psi = nu - base - st.s1 * delta - v;
+        if (psi == 0.0) break;
+        if (psi < 0.0) { lo = nu; flo = psi; have_lo = true; } else { hi = nu; fhi = psi; have_hi = true; }
+        const double slope = 1.0 + (st.s1 + sl) * nf / k.prox;
+        double nn = nu - psi / slope;
+        if (!(nn > lo && nn < hi)) {
+            nn = (have_lo && have_hi) ? lo - flo * (hi - lo) / (fhi - flo) : 0.5 * (lo + hi);
+            if (!(nn > lo && nn < hi)) nn = 0.5 * (lo + hi);
+        }
+        if (fabs(nn - nu) <= 1e-15 * (1.0 + fabs(nu))) { nu = nn; break; }
+        nu = nn;
+    }
+    sto_dc_of_nu(st, k, nu, D, C, nf);
+    {
+        double v;
+        hl.eval((D - st.Db) - (C - st.Cb), v, sl);
+    }
+    r.D = D; r.C = C;
+    r.dy = -(double)nf / (k.prox + (st.s1 + sl) * nf);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lane groups.  The storage solver is written once over a group of W lanes that own the
+// timesteps t = lane, lane+W, ...  W=32 is a warp on the device; W=1 is the sequential
+// restatement used by the host-side emulation in tests/.
+// ---------------------------------------------------------------------------------------------
+template <int W> struct Group;
+
+template <> struct Group<1> {
+    static DOPF_HD int lane() { return 0; }
+    static DOPF_HD double sum(double v) { return v; }
+    static DOPF_HD double scan_incl(double v) { return v; }
+    static DOPF_HD double bcast(double v, int) { return v; }
+    static DOPF_HD unsigned ballot(bool p) { return p ? 1u : 0u; }
+    static DOPF_HD void sync() {}
+};
+
+#if defined(__CUDACC__)
+template <> struct Group<32> {
+    static __device__ __forceinline__ int lane() { return threadIdx.x & 31; }
+    static __device__ __forceinline__ double sum(double v)
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    static __device__ __forceinline__ double scan_incl(double v)
+    {
+        const int l = threadIdx.x & 31;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double u = __shfl_up_sync(0xffffffffu, v, o);
+            if (l >= o) v += u;
+        }
+        return v;
+    }
+    static __device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+    static __device__ __forceinline__ unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+    static __device__ __forceinline__ void sync() { __syncwarp(); }
+};
+#endif
+
+DOPF_HD int first_bit(unsigned m)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs(m) - 1;
+#else
+    for (int i = 0; i < 32; ++i) if (m & (1u << i)) return i;
+    return -1;
+#endif
+}
+
+// Per-storage problem view.  `step[t]` lives in shared memory (device) or a plain array (host);
+// `hinges`/`hcnt` are null in the predict pass (anchor linearisation only).
+struct StoProblem {
+    int T;
+    StoConst k;
+    const StoStep *step;
+    const Hinge *hinges;   // [T][hcap] or null
+    const int *hcnt;       // [T] or null
+    int hcap;
+    DOPF_HD HingeList list(int t) const
+    {
+        HingeList l;
+        l.h = hinges ? hinges + (size_t)t * hcap : nullptr;
+        l.n = hinges ? hcnt[t] : 0;
+        return l;
+    }
+};
+
+struct StoStats { int evals; int solves; int segments; };
+
+template <int W>
+struct StoSolver {
+    typedef Group<W> G;
+    const StoProblem &p;
+    double tolE;
+    StoStats stats;
+
+    DOPF_HD StoSolver(const StoProblem &pp) : p(pp)
+    {
+        tolE = 1e-9 * (p.k.emax > 1.0 ? p.k.emax : 1.0);
+        stats.evals = stats.solves = stats.segments = 0;
+    }
+
+    // sum_{t in [t0,t1)} y_t(eta) and its derivative
+    DOPF_HD void seg_eval(double eta, int t0, int t1, double &s, double &ds)
+    {
+        double a = 0.0, b = 0.0;
+        for (int t = t0 + G::lane(); t < t1; t += W) {
+            StoEval e = sto_eval(p.step[t], p.k, p.list(t), eta);
+            a += e.C - e.D; b += e.dy;
+        }
+        s = G::sum(a); ds = G::sum(b);
+        stats.evals += t1 - t0;
+    }
+
+    // eta with sum_{[t0,t1)} y(eta) = target   (sum is non-increasing in eta)
+    DOPF_HD double seg_solve(double target, int t0, int t1, double eta)
+    {
+        stats.solves++;
+        double lo = -INFINITY, hi = INFINITY;   // sum(lo) > target > sum(hi)
+        double rlo = 0.0, rhi = 0.0;
+        double step = 1.0;
+        const double tolS = 1e-13 * (1.0 + fabs(target) + p.k.pmax);
+        for (int it = 0; it < 300; ++it) {
+            double s, ds;
+            seg_eval(eta, t0, t1, s, ds);
+            const double r = s - target;
+            if (fabs(r) <= tolS) return eta;
+            if (r > 0.0) { lo = eta; rlo = r; } else { hi = eta; rhi = r; }
+            double en;
+            if (ds < -1e-300) en = eta - r / ds;
+            else { en = r > 0.0 ? eta + step : eta - step; step *= 4.0; }
+            if (!(en > lo && en < hi)) {
+                if (isfinite(lo) && isfinite(hi)) {
+                    en = lo - rlo * (hi - lo) / (rhi - rlo);
+                    if (!(en > lo && en < hi)) en = 0.5 * (lo + hi);
+                } else {
+                    en = r > 0.0 ? eta + step : eta - step; step *= 4.0;
+                }
+            }
+            if (isfinite(lo) && isfinite(hi) && (hi - lo) <= 1e-15 * (1.0 + fabs(lo))) return en;
+            eta = en;
+        }
+        return eta;
+    }
+
+    // first t in [t0,t1) whose level leaves [0,emax] when eta is used from t0 on (level e0
+    // before t0).  returns t (or -1) and kind = +1 (above emax) / -1 (below 0).
+    DOPF_HD int scan(double eta, int t0, double e0, int t1, int &kind)
+    {
+        double carry = e0;
+        for (int base = t0; base < t1; base += W) {
+            const int t = base + G::lane();
+            double y = 0.0;
+            if (t < t1) {
+                StoEval e = sto_eval(p.step[t], p.k, p.list(t), eta);
+                y = e.C - e.D;
+            }
+            const double E = carry + G::scan_incl(y);
+            const bool up = (t < t1) && (E > p.k.emax + tolE);
+            const bool dn = (t < t1) && (E < -tolE);
+            const unsigned m = G::ballot(up || dn);
+            if (m) {
+                const int f = first_bit(m);
+                const double Ef = G::bcast(E, f);
+                kind = Ef > p.k.emax ? 1 : -1;
+                stats.evals += (base - t0) + W;
+                return base + f;
+            }
+            carry = G::bcast(E, W - 1);
+        }
+        stats.evals += t1 - t0;
+        kind = 0;
+        return -1;
+    }
+
+    // Planning-horizon ("funnel") solve; writes the multiplier path eta_out[t].
+    DOPF_HD void solve(double *eta_out)
+    {
+        const int T = p.T;
+        int t0 = 0;
+        double e0 = 0.0;
+        while (t0 < T) {
+            stats.segments++;
+            double eta = 0.0;       // free end: no level constraint binds after the horizon
+            int dir = 0;            // +1: eta was raised (upper level bound met at tauA), -1: lowered
+            int tauA = -1;
+            int end = T;
+            double e_next = 0.0;
+            for (int guard = 0; guard < 4 * T + 8; ++guard) {
+                int kind;
+                const int tv = scan(eta, t0, e0, T, kind);
+                if (tv < 0) {
+                    if (dir != 0) { end = tauA + 1; e_next = dir > 0 ? p.k.emax : 0.0; }
+                    break;
+                }
+                if (dir != 0 && kind != dir) {  // opposite bound hit later: close at the anchor
+                    end = tauA + 1; e_next = dir > 0 ? p.k.emax : 0.0;
+                    break;
+                }
+                const double eta2 = seg_solve((kind > 0 ? p.k.emax : 0.0) - e0, t0, tv + 1, eta);
+                int kind2;
+                int tw = scan(eta2, t0, e0, tv, kind2);
+                if (tw < 0) { eta = eta2; dir = kind; tauA = tv; continue; }
+                // conflict between the bound at tv and the opposite bound before it
+                double etac = eta2;
+                int tauB = tw, kB = kind2;
+                for (int g2 = 0; g2 < T + 4 && tw >= 0; ++g2) {
+                    etac = seg_solve((kind2 > 0 ? p.k.emax : 0.0) - e0, t0, tw + 1, etac);
+                    tauB = tw; kB = kind2;
+                    tw = scan(etac, t0, e0, tv, kind2);
+                }
+                eta = etac; end = tauB + 1; e_next = kB > 0 ? p.k.emax : 0.0;
+                break;
+            }
+            for (int t = t0 + G::lane(); t < end; t += W) eta_out[t] = eta;
+            G::sync();
+            t0 = end; e0 = e_next;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Shared per-(line,t) quantities (row preparation) - see DESIGN.md section 3.
+// ---------------------------------------------------------------------------------------------
+struct Coef {
+    double gamma, w2, kk, kappa, beta, g2w;   // w2=2w, kk=2w+gamma, kappa=2w*gamma/kk, beta=4w^2/kk, g2w=gamma/(2w)
+    double prox, mask_tol, eps;
+    DOPF_HD static Coef make(double gamma, double w, double prox, double mask_tol, double eps)
+    {
+        Coef c;
+        c.gamma = gamma; c.w2 = 2.0 * w; c.kk = c.w2 + gamma;
+        c.kappa = c.w2 * gamma / c.kk; c.beta = c.w2 * c.w2 / c.kk; c.g2w = gamma / c.w2;
+        c.prox = prox; c.mask_tol = mask_tol; c.eps = eps;
+        return c;
+    }
+};
+
+struct RowPrep { double bplus, bminus, M, Wt; };
+
+DOPF_HD RowPrep row_prep(const Coef &c, double fmax, double F, double U, double K, double mu, double rho)
+{
+    RowPrep r;
+    r.bplus = (fmax - F) + c.g2w * U;
+    r.bminus = (fmax + F) + c.g2w * K;
+    const bool mp = r.bplus < 0.0, mm = r.bminus < 0.0;
+    r.M = mu - rho + c.kappa * (U - K + 2.0 * F) + c.beta * ((mm ? r.bminus : 0.0) - (mp ? r.bplus : 0.0));
+    r.Wt = c.beta * ((mp ? 1.0 : 0.0) + (mm ? 1.0 : 0.0));
+    return r;
+}
+
+// hinge of (line l, side) seen from a node with PTDF entry p; returns false if p == 0
+DOPF_HD bool make_hinge(const Coef &c, double p, double b, int side /*0: upper(U), 1: lower(K)*/, Hinge &h)
+{
+    if (p == 0.0) return false;
+    const double s = c.beta * p * p;
+    if (side == 0) { h.bp = b / p; h.sg = (p > 0.0 ? s : -s); }
+    else { h.bp = -b / p; h.sg = (p > 0.0 ? -s : s); }
+    return true;
+}
+
+// exact positive-part sums for the average slacks: avgU = (2w/(kk*A)) * sum_i (bplus - p*delta_i)_+ ,
+// avgK = (2w/(kk*A)) * sum_i (bminus + p*delta_i)_+
+DOPF_HD double pospart(double v) { return v > 0.0 ? v : 0.0; }
+
+// monotone map double -> uint64 for atomicMax on non-negative doubles
+DOPF_HD unsigned long long nonneg_bits(double v)
+{
+    union { double d; unsigned long long u; } x;
+    x.d = v < 0.0 ? 0.0 : v;
+    return x.u;
+}
+DOPF_HD double bits_nonneg(unsigned long long u)
+{
+    union { double d; unsigned long long u; } x;
+    x.u = u;
+    return x.d;
+}
+
+}  // namespace dopf
+#endif
