@@ -1,0 +1,576 @@
+// C ABI of libdopf (include/dopf.h): instance set-up, SoA packing, CUDA-graph driven stepping,
+// state transfer, optional NCCL exchange.  No CPU compute path exists in this library.
+#include "../../include/dopf.h"
+#include "dopf_kernels.h"
+
+#include <dlfcn.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace dopf;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---- minimal NCCL binding, resolved at run time (torch ships its own libnccl) -----------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSum = 0, ncclMax = 2 };
+enum { ncclFloat64 = 8 };
+struct NcclApi {
+    int (*GetUniqueId)(ncclUniqueId *);
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    int (*CommDestroy)(ncclComm_t);
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+    const char *(*GetErrorString)(int);
+    bool ok = false;
+};
+NcclApi &nccl()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    void *hnd = nullptr;
+    if (dlsym(RTLD_DEFAULT, "ncclAllReduce")) hnd = RTLD_DEFAULT;
+    if (!hnd) hnd = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!hnd) hnd = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!hnd) return api;
+    api.GetUniqueId = (int (*)(ncclUniqueId *))dlsym(hnd, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(hnd, "ncclCommInitRank");
+    api.CommDestroy = (int (*)(ncclComm_t))dlsym(hnd, "ncclCommDestroy");
+    api.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(hnd, "ncclAllReduce");
+    api.GetErrorString = (const char *(*)(int))dlsym(hnd, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce;
+    return api;
+}
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+}  // namespace
+
+struct dopf_handle {
+    LaunchPlan lp{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool use_graph = true;
+    int launches_per_iter = 0;
+    std::vector<void *> allocs;
+    Ctrl *h_ctrl = nullptr;          // pinned mirror of the device control block
+    double *d_scalar = nullptr;
+    double *d_nodal = nullptr;
+    std::vector<int> gen_perm, sto_perm;   // sorted position -> caller's index
+    bool gen_identity = true, sto_identity = true;
+    std::vector<double> stage;             // host staging for permutation / padding
+    std::string err;
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            h->err = buf_;                                                                         \
+            return DOPF_E_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+template <class T> int dev_alloc(dopf_handle *h, T **p, size_t count, bool zero = true)
+{
+    void *q = nullptr;
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CK(cudaMalloc(&q, bytes));
+    h->allocs.push_back(q);
+    if (zero) CK(cudaMemsetAsync(q, 0, bytes, h->stream));
+    *p = (T *)q;
+    return 0;
+}
+
+template <class T> int upload(dopf_handle *h, const T **dst, const std::vector<T> &src)
+{
+    T *d = nullptr;
+    int rc = dev_alloc(h, &d, src.size(), false);
+    if (rc) return rc;
+    if (!src.empty()) CK(cudaMemcpyAsync(d, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // src may be a temporary
+    *dst = d;
+    return 0;
+}
+
+// exchange steps between the kernels of one iteration (multi-GPU only)
+int comm_allreduce(dopf_handle *h, const void *src, void *dst, size_t n, int op)
+{
+    if (h->nranks <= 1) return 0;
+    int rc = nccl().AllReduce(src, dst, n, ncclFloat64, op, h->comm, h->stream);
+    if (rc != 0) {
+        h->err = std::string("ncclAllReduce: ") + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "error");
+        return DOPF_E_COMM;
+    }
+    return 0;
+}
+
+int sync_ctrl(dopf_handle *h)
+{
+    CK(cudaMemcpyAsync(h->h_ctrl, h->lp.view.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+void fill_status(dopf_handle *h, dopf_status *s)
+{
+    const Ctrl &c = *h->h_ctrl;
+    s->iteration = c.iteration; s->converged = c.converged;
+    s->conv_lambda = c.conv_lambda; s->conv_mue = c.conv_mue; s->conv_rho = c.conv_rho;
+    s->iterations_done = c.iters_done;
+    s->res_lambda = c.res[0]; s->res_mue = c.res[1]; s->res_rho = c.res[2];
+    s->gen_corrected = c.stat_gen_fix; s->sto_corrected = c.stat_sto_fix;
+    s->tight_rows = c.stat_tight_rows; s->wide_rows = c.stat_wide_rows;
+    s->launches_per_iteration = h->launches_per_iter;
+    s->reserved = 0;
+}
+
+int check_device_error(dopf_handle *h)
+{
+    if (h->h_ctrl->error == DOPF_ERR_NONE) return 0;
+    char buf[256];
+    snprintf(buf, sizeof buf,
+             h->h_ctrl->error == DOPF_ERR_HINGE_CAP
+                 ? "hinge list capacity exceeded in the correction pass at iteration %d; recreate with a larger dopf_config.hinge_capacity (the iterate of iteration %d is intact)"
+                 : "generator work list capacity exceeded at iteration %d (iterate of iteration %d intact)",
+             h->h_ctrl->iteration, h->h_ctrl->iteration - 1);
+    h->err = buf;
+    return DOPF_E_CAPACITY;
+}
+
+}  // namespace
+
+namespace dopf {
+int enqueue_iteration_comm(dopf_handle *h, cudaStream_t st);
+}
+
+extern "C" {
+
+const char *dopf_version(void) { return "libdopf 0.1 (sm_100a)"; }
+
+void dopf_default_config(dopf_config *c)
+{
+    c->gamma = 0.3; c->flow_weight = 10.0; c->prox_weight = 1.0; c->slack_mask_tol = 1e-2; c->eps = 1e-3;
+    c->device = -1; c->hinge_capacity = 0; c->use_graph = 1; c->reserved = 0;
+}
+
+const char *dopf_last_error(dopf_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+void dopf_destroy(dopf_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->graph) cudaGraphDestroy(h->graph);
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config *cfg)
+{
+    const int N = p->N, L = p->L, T = p->T, G = p->G, S = p->S;
+    if (N < 1 || L < 1 || T < 1 || G < 0 || S < 0 || G + S < 1) { h->err = "invalid dimensions"; return DOPF_E_ARG; }
+    if (!p->ptdf || !p->f_max || !p->demand || (G && (!p->gen_mc || !p->gen_pmax || !p->gen_node)) ||
+        (S && (!p->sto_mc || !p->sto_pmax || !p->sto_emax || !p->sto_node))) { h->err = "null input array"; return DOPF_E_ARG; }
+    if (!(cfg->gamma > 0.0) || !(cfg->flow_weight > 0.0) || !(cfg->prox_weight > 0.0)) { h->err = "gamma, flow_weight, prox_weight must be > 0"; return DOPF_E_ARG; }
+    for (int g = 0; g < G; ++g) if (p->gen_node[g] < 0 || p->gen_node[g] >= N) { h->err = "gen_node out of range"; return DOPF_E_ARG; }
+    for (int s = 0; s < S; ++s) if (p->sto_node[s] < 0 || p->sto_node[s] >= N) { h->err = "sto_node out of range"; return DOPF_E_ARG; }
+    if ((long long)G * T >= (1ll << 31) || (long long)S * T >= (1ll << 31)) { h->err = "G*T or S*T exceeds 2^31"; return DOPF_E_UNSUPPORTED; }
+
+    int ndev = 0;
+    cudaError_t e0 = cudaGetDeviceCount(&ndev);
+    if (e0 != cudaSuccess || ndev == 0) {
+        h->err = std::string("no CUDA device available (") + cudaGetErrorString(e0) + "); libdopf has no CPU path";
+        return DOPF_E_CUDA;
+    }
+    if (cfg->device >= 0) CK(cudaSetDevice(cfg->device));
+    CK(cudaGetDevice(&h->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaMallocHost((void **)&h->h_ctrl, sizeof(Ctrl)));
+    memset(h->h_ctrl, 0, sizeof(Ctrl));
+
+    LaunchPlan &lp = h->lp;
+    View &v = lp.view;
+    v.N = N; v.L = L; v.T = T; v.G = G; v.S = S; v.A = G + S;
+    v.ldt = round_up(T, 32); v.Np = round_up(N, 64); v.Lp = round_up(L, 64);
+    v.hcap = cfg->hinge_capacity > 0 ? cfg->hinge_capacity : 32;
+    v.c = Coef::make(cfg->gamma, cfg->flow_weight, cfg->prox_weight, cfg->slack_mask_tol, cfg->eps);
+    v.demand_on = 1;
+    const int ldt = v.ldt, Np = v.Np, Lp = v.Lp;
+    h->use_graph = cfg->use_graph != 0;
+
+    // ---- agents sorted by node (stable), CSR offsets -------------------------------------------
+    h->gen_perm.resize(G); std::iota(h->gen_perm.begin(), h->gen_perm.end(), 0);
+    std::stable_sort(h->gen_perm.begin(), h->gen_perm.end(), [&](int a, int b) { return p->gen_node[a] < p->gen_node[b]; });
+    h->sto_perm.resize(S); std::iota(h->sto_perm.begin(), h->sto_perm.end(), 0);
+    std::stable_sort(h->sto_perm.begin(), h->sto_perm.end(), [&](int a, int b) { return p->sto_node[a] < p->sto_node[b]; });
+    h->gen_identity = true; for (int i = 0; i < G; ++i) if (h->gen_perm[i] != i) h->gen_identity = false;
+    h->sto_identity = true; for (int i = 0; i < S; ++i) if (h->sto_perm[i] != i) h->sto_identity = false;
+
+    std::vector<double> gmc(G), gpm(G), smc(S), spm(S), sem(S);
+    std::vector<int> gnode(G), snode(S), gptr(N + 1, 0), sptr(N + 1, 0);
+    for (int i = 0; i < G; ++i) { int o = h->gen_perm[i]; gmc[i] = p->gen_mc[o]; gpm[i] = p->gen_pmax[o]; gnode[i] = p->gen_node[o]; gptr[gnode[i] + 1]++; }
+    for (int i = 0; i < S; ++i) { int o = h->sto_perm[i]; smc[i] = p->sto_mc[o]; spm[i] = p->sto_pmax[o]; sem[i] = p->sto_emax[o]; snode[i] = p->sto_node[o]; sptr[snode[i] + 1]++; }
+    for (int n = 0; n < N; ++n) { gptr[n + 1] += gptr[n]; sptr[n + 1] += sptr[n]; }
+
+    // ---- padded network data and derived statics -----------------------------------------------
+    std::vector<double> ptdf((size_t)Lp * Np, 0.0), fmax(Lp, 0.0), demand((size_t)Np * ldt, 0.0);
+    std::vector<double> q(Np, 0.0), prow(Lp, 0.0), mwide(Lp, 0.0), nag(Np, 0.0), rbox(Np, 0.0);
+    for (int i = 0; i < G; ++i) { nag[gnode[i]] += 1.0; rbox[gnode[i]] = std::max(rbox[gnode[i]], gpm[i]); }
+    for (int i = 0; i < S; ++i) { nag[snode[i]] += 1.0; rbox[snode[i]] = std::max(rbox[snode[i]], 2.0 * spm[i]); }
+    for (int l = 0; l < L; ++l) {
+        fmax[l] = p->f_max[l];
+        for (int n = 0; n < N; ++n) {
+            const double a = p->ptdf[(size_t)l * N + n];
+            ptdf[(size_t)l * Np + n] = a;
+            q[n] += a * a;
+            prow[l] = std::max(prow[l], std::fabs(a));
+            mwide[l] = std::max(mwide[l], std::fabs(a) * rbox[n]);
+        }
+    }
+    for (int n = 0; n < N; ++n) for (int t = 0; t < T; ++t) demand[(size_t)n * ldt + t] = p->demand[(size_t)n * T + t];
+
+    int rc;
+#define UP(dst, vec) if ((rc = upload(h, &dst, vec))) return rc
+    UP(v.ptdf, ptdf); UP(v.fmax, fmax); UP(v.demand, demand); UP(v.q, q); UP(v.prow, prow); UP(v.mwide, mwide); UP(v.nagents, nag);
+    UP(v.gen_mc, gmc); UP(v.gen_pmax, gpm); UP(v.gen_node, gnode); UP(v.gen_ptr, gptr);
+    UP(v.sto_mc, smc); UP(v.sto_pmax, spm); UP(v.sto_emax, sem); UP(v.sto_node, snode); UP(v.sto_ptr, sptr);
+#undef UP
+#define AL(ptr, count) if ((rc = dev_alloc(h, &ptr, (size_t)(count)))) return rc
+    for (int k = 0; k < 2; ++k) {
+        AL(v.P[k], (size_t)G * T); AL(v.D[k], (size_t)S * T); AL(v.C[k], (size_t)S * T);
+        AL(v.inj[k], (size_t)Np * ldt); AL(v.ssum[k], ldt); AL(v.flow[k], (size_t)Lp * ldt);
+        AL(v.lam[k], ldt); AL(v.mu[k], (size_t)Lp * ldt); AL(v.rho[k], (size_t)Lp * ldt);
+        v.injloc[k] = v.inj[k];
+    }
+    AL(v.E, (size_t)S * T); AL(v.avgU, (size_t)Lp * ldt); AL(v.avgK, (size_t)Lp * ldt);
+    AL(v.bplus, (size_t)Lp * ldt); AL(v.bminus, (size_t)Lp * ldt); AL(v.M, (size_t)Lp * ldt); AL(v.Wt, (size_t)Lp * ldt);
+    AL(v.g0, (size_t)Np * ldt); AL(v.s1, (size_t)Np * ldt);
+    AL(v.dn, (size_t)Np * ldt); AL(v.dmax, ldt);
+    AL(v.flags, (size_t)ldt * Lp);
+    AL(v.wide, (size_t)T * 2 * L); AL(v.wcnt, T); AL(v.tight, (size_t)T * 2 * L); AL(v.tcnt, T);
+    v.gen_work_cap = (int)std::min<long long>((long long)G * T, 1ll << 30);
+    AL(v.gen_work, (size_t)std::max(v.gen_work_cap, 1)); AL(v.sto_work, S); AL(v.sto_flag, S);
+    AL(v.rowsumU, (size_t)Lp * ldt); AL(v.rowsumK, (size_t)Lp * ldt);
+    AL(v.ctrl, 1);
+    AL(lp.tflag, (size_t)Lp * ldt);
+    AL(h->d_scalar, 4);
+    AL(h->d_nodal, (size_t)N * T);
+
+    // ---- launch plan -----------------------------------------------------------------------------
+    lp.num_sms = prop.multiProcessorCount;
+    auto plan_gemm = [&](int Mp, int Kp, int &bm, int &ks) {
+        const int ct = ldt / 32;
+        bm = ((Mp / 64) * ct >= lp.num_sms) ? 64 : 32;
+        const int tiles = (Mp / bm) * ct;
+        ks = std::max(1, std::min({8, (2 * lp.num_sms + tiles - 1) / tiles, Kp / 16 / 8 > 0 ? Kp / 16 / 8 : 1}));
+    };
+    plan_gemm(Np, Lp, lp.bm_t, lp.ksplit_t);
+    plan_gemm(Lp, Np, lp.bm_n, lp.ksplit_n);
+    AL(lp.part, (size_t)std::max(lp.ksplit_t * Np, lp.ksplit_n * Lp) * ldt);
+    AL(lp.part2, (size_t)lp.ksplit_t * Np * ldt);
+    {
+        const size_t per_warp = storage_smem_bytes(T, 1);
+        const size_t limit = std::min<size_t>(prop.sharedMemPerBlockOptin, 200 * 1024);
+        if (per_warp > limit) { h->err = "T too large: the storage horizon does not fit in shared memory in this build"; return DOPF_E_UNSUPPORTED; }
+        lp.sto_warps = (int)std::max<size_t>(1, std::min<size_t>(4, limit / per_warp));
+        const size_t bytes = storage_smem_bytes(T, lp.sto_warps);
+        if (bytes > 48 * 1024) {
+            if (set_storage_smem_attr(bytes) != 0) { h->err = "cudaFuncSetAttribute(shared memory) failed"; return DOPF_E_CUDA; }
+        }
+        lp.sto_blocks = lp.num_sms * 16;
+        lp.sto_fix_blocks = std::max(1, std::min(lp.num_sms * 2, (S + lp.sto_warps - 1) / std::max(lp.sto_warps, 1)));
+        size_t hs = (size_t)lp.sto_fix_blocks * lp.sto_warps * T * v.hcap;
+        if (S == 0) hs = 1;
+        AL(lp.hinge_scratch, hs);
+    }
+    lp.slack_blocks_x = std::max(1, std::min(64, (4 * lp.num_sms + T - 1) / T));
+
+    // ---- state before iteration 1 (admm.jl:29-36; helpers/results.jl:14-73 "zeros") ----------
+    Ctrl c0;
+    memset(&c0, 0, sizeof c0);
+    c0.iteration = 1; c0.cur = 0;
+    *h->h_ctrl = c0;
+    CK(cudaMemcpyAsync(v.ctrl, h->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, h->stream));
+    launch_rebuild_derived(lp, h->stream);   // P=D=C=0  =>  injection = -demand, flows, levels
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    if ((rc = sync_ctrl(h))) return rc;
+    return 0;
+#undef AL
+}
+
+int dopf_create(const dopf_problem *p, const dopf_config *c, dopf_handle **out)
+{
+    if (!p || !c || !out) { g_create_error = "null argument"; return DOPF_E_ARG; }
+    dopf_handle *h = new dopf_handle();
+    int rc = create_impl(h, p, c);
+    if (rc) { g_create_error = h->err; dopf_destroy(h); *out = nullptr; return rc; }
+    *out = h;
+    return DOPF_OK;
+}
+
+static int build_graph(dopf_handle *h)
+{
+    if (h->graph_exec || !h->use_graph) return 0;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_iteration_comm(h, h->stream);
+    cudaError_t e = cudaStreamEndCapture(h->stream, &h->graph);
+    if (rc < 0) return rc;
+    if (e != cudaSuccess) { h->err = std::string("graph capture failed: ") + cudaGetErrorString(e); return DOPF_E_CUDA; }
+    h->launches_per_iter = rc;
+    CK(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
+    return 0;
+}
+
+int dopf_step(dopf_handle *h, int32_t max_iters, dopf_status *out)
+{
+    if (!h) return DOPF_E_ARG;
+    CK(cudaSetDevice(h->device));
+    int rc = build_graph(h);
+    if (rc) return rc;
+    int remaining = max_iters;
+    while (remaining > 0 && !h->h_ctrl->converged && h->h_ctrl->error == 0) {
+        const int chunk = std::min(remaining, 64);
+        for (int i = 0; i < chunk; ++i) {
+            if (h->graph_exec) CK(cudaGraphLaunch(h->graph_exec, h->stream));
+            else {
+                rc = enqueue_iteration_comm(h, h->stream);
+                if (rc < 0) return rc;
+                h->launches_per_iter = rc;
+            }
+        }
+        CK(cudaGetLastError());
+        if ((rc = sync_ctrl(h))) return rc;
+        remaining -= chunk;
+    }
+    if ((rc = check_device_error(h))) return rc;
+    if (out) fill_status(h, out);
+    return DOPF_OK;
+}
+
+int dopf_get_status(dopf_handle *h, dopf_status *out)
+{
+    if (!h || !out) return DOPF_E_ARG;
+    CK(cudaSetDevice(h->device));
+    int rc = sync_ctrl(h);
+    if (rc) return rc;
+    fill_status(h, out);
+    return DOPF_OK;
+}
+
+// copy a padded device matrix [rows][ldt] to a dense host matrix [rows][T]
+static int d2h_matrix(dopf_handle *h, double *dst, const double *src, int rows, int T, int ld)
+{
+    if (!dst) return 0;
+    CK(cudaMemcpy2DAsync(dst, (size_t)T * sizeof(double), src, (size_t)ld * sizeof(double), (size_t)T * sizeof(double), rows, cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+static int h2d_matrix(dopf_handle *h, double *dst, const double *src, int rows, int T, int ld)
+{
+    if (!src) return 0;
+    CK(cudaMemcpy2DAsync(dst, (size_t)ld * sizeof(double), src, (size_t)T * sizeof(double), (size_t)T * sizeof(double), rows, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+// agent matrices: rows are stored sorted by node on the device
+static int d2h_agents(dopf_handle *h, double *dst, const double *src, int rows, int T, const std::vector<int> &perm, bool identity)
+{
+    if (!dst || rows == 0) return 0;
+    if (identity) { CK(cudaMemcpyAsync(dst, src, (size_t)rows * T * sizeof(double), cudaMemcpyDeviceToHost, h->stream)); return 0; }
+    h->stage.resize((size_t)rows * T);
+    CK(cudaMemcpyAsync(h->stage.data(), src, (size_t)rows * T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < rows; ++i) memcpy(dst + (size_t)perm[i] * T, h->stage.data() + (size_t)i * T, (size_t)T * sizeof(double));
+    return 0;
+}
+static int h2d_agents(dopf_handle *h, double *dst, const double *src, int rows, int T, const std::vector<int> &perm, bool identity)
+{
+    if (!src || rows == 0) return 0;
+    if (identity) { CK(cudaMemcpyAsync(dst, src, (size_t)rows * T * sizeof(double), cudaMemcpyHostToDevice, h->stream)); return 0; }
+    h->stage.resize((size_t)rows * T);
+    for (int i = 0; i < rows; ++i) memcpy(h->stage.data() + (size_t)i * T, src + (size_t)perm[i] * T, (size_t)T * sizeof(double));
+    CK(cudaMemcpyAsync(dst, h->stage.data(), (size_t)rows * T * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int dopf_get_iterate(dopf_handle *h, double *P, double *D, double *C, double *E, double *injection, double *flow, double *avgU, double *avgK)
+{
+    if (!h) return DOPF_E_ARG;
+    CK(cudaSetDevice(h->device));
+    const View &v = h->lp.view;
+    const int k = h->h_ctrl->cur;   // newest iterate (buffers were flipped by the last iteration)
+    int rc;
+    if ((rc = d2h_agents(h, P, v.P[k], v.G, v.T, h->gen_perm, h->gen_identity))) return rc;
+    if ((rc = d2h_agents(h, D, v.D[k], v.S, v.T, h->sto_perm, h->sto_identity))) return rc;
+    if ((rc = d2h_agents(h, C, v.C[k], v.S, v.T, h->sto_perm, h->sto_identity))) return rc;
+    if ((rc = d2h_agents(h, E, v.E, v.S, v.T, h->sto_perm, h->sto_identity))) return rc;
+    if ((rc = d2h_matrix(h, injection, v.inj[k], v.N, v.T, v.ldt))) return rc;
+    if ((rc = d2h_matrix(h, flow, v.flow[k], v.L, v.T, v.ldt))) return rc;
+    if ((rc = d2h_matrix(h, avgU, v.avgU, v.L, v.T, v.ldt))) return rc;
+    if ((rc = d2h_matrix(h, avgK, v.avgK, v.L, v.T, v.ldt))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return DOPF_OK;
+}
+
+int dopf_get_duals(dopf_handle *h, int32_t which, double *lam, double *mu, double *rho)
+{
+    if (!h || which < 0 || which > 1) return DOPF_E_ARG;
+    CK(cudaSetDevice(h->device));
+    const View &v = h->lp.view;
+    const int k = which == 0 ? h->h_ctrl->cur : 1 - h->h_ctrl->cur;
+    int rc;
+    if (lam) CK(cudaMemcpyAsync(lam, v.lam[k], (size_t)v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = d2h_matrix(h, mu, v.mu[k], v.L, v.T, v.ldt))) return rc;
+    if ((rc = d2h_matrix(h, rho, v.rho[k], v.L, v.T, v.ldt))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return DOPF_OK;
+}
+
+int dopf_set_state(dopf_handle *h, int32_t iteration, const double *P, const double *D, const double *C,
+                   const double *avgU, const double *avgK, const double *lam, const double *mu, const double *rho)
+{
+    if (!h || iteration < 1) return DOPF_E_ARG;
+    CK(cudaSetDevice(h->device));
+    View &v = h->lp.view;
+    int rc;
+    if ((rc = sync_ctrl(h))) return rc;
+    const int cur = h->h_ctrl->cur, nxt = 1 - cur;
+    // the new "previous iterate" is staged in the inactive buffers, then the buffers are flipped
+    if (!P && v.G) CK(cudaMemcpyAsync(v.P[nxt], v.P[cur], (size_t)v.G * v.T * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (!D && v.S) CK(cudaMemcpyAsync(v.D[nxt], v.D[cur], (size_t)v.S * v.T * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (!C && v.S) CK(cudaMemcpyAsync(v.C[nxt], v.C[cur], (size_t)v.S * v.T * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if ((rc = h2d_agents(h, v.P[nxt], P, v.G, v.T, h->gen_perm, h->gen_identity))) return rc;
+    if ((rc = h2d_agents(h, v.D[nxt], D, v.S, v.T, h->sto_perm, h->sto_identity))) return rc;
+    if ((rc = h2d_agents(h, v.C[nxt], C, v.S, v.T, h->sto_perm, h->sto_identity))) return rc;
+    if ((rc = h2d_matrix(h, v.avgU, avgU, v.L, v.T, v.ldt))) return rc;
+    if ((rc = h2d_matrix(h, v.avgK, avgK, v.L, v.T, v.ldt))) return rc;
+    const size_t lt = (size_t)v.Lp * v.ldt * sizeof(double);
+    if (lam) CK(cudaMemcpyAsync(v.lam[nxt], lam, (size_t)v.T * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    else CK(cudaMemcpyAsync(v.lam[nxt], v.lam[cur], (size_t)v.ldt * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (mu) { if ((rc = h2d_matrix(h, v.mu[nxt], mu, v.L, v.T, v.ldt))) return rc; }
+    else CK(cudaMemcpyAsync(v.mu[nxt], v.mu[cur], lt, cudaMemcpyDeviceToDevice, h->stream));
+    if (rho) { if ((rc = h2d_matrix(h, v.rho[nxt], rho, v.L, v.T, v.ldt))) return rc; }
+    else CK(cudaMemcpyAsync(v.rho[nxt], v.rho[cur], lt, cudaMemcpyDeviceToDevice, h->stream));
+    Ctrl c = *h->h_ctrl;
+    c.iteration = iteration; c.converged = c.conv_lambda = c.conv_mue = c.conv_rho = 0; c.error = 0;
+    c.iters_done = 0;
+    *h->h_ctrl = c;
+    CK(cudaMemcpyAsync(v.ctrl, h->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, h->stream));
+    launch_rebuild_derived(h->lp, h->stream);
+    if (h->nranks > 1) {
+        // injection of all ranks, then flows: redo the derived quantities with the exchanged sum
+        h->err = "dopf_set_state is not supported after dopf_comm_init";
+        return DOPF_E_UNSUPPORTED;
+    }
+    CK(cudaGetLastError());
+    if ((rc = sync_ctrl(h))) return rc;
+    return DOPF_OK;
+}
+
+int dopf_get_nodal_price(dopf_handle *h, int32_t which, double *out)
+{
+    if (!h || !out || which < 0 || which > 1) return DOPF_E_ARG;
+    CK(cudaSetDevice(h->device));
+    const View &v = h->lp.view;
+    const int k = which == 0 ? h->h_ctrl->cur : 1 - h->h_ctrl->cur;
+    launch_nodal_price(v, k, h->d_nodal, h->stream);
+    CK(cudaMemcpyAsync(out, h->d_nodal, (size_t)v.N * v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DOPF_OK;
+}
+
+int dopf_get_total_costs(dopf_handle *h, double *out)
+{
+    if (!h || !out) return DOPF_E_ARG;
+    CK(cudaSetDevice(h->device));
+    launch_total_costs(h->lp.view, h->d_scalar, h->stream);
+    CK(cudaMemcpyAsync(out, h->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DOPF_OK;
+}
+
+int dopf_comm_unique_id(void *out128)
+{
+    if (!out128) return DOPF_E_ARG;
+    if (!nccl().ok) { g_create_error = "NCCL library not found (libnccl.so.2)"; return DOPF_E_COMM; }
+    ncclUniqueId id;
+    if (nccl().GetUniqueId(&id) != 0) { g_create_error = "ncclGetUniqueId failed"; return DOPF_E_COMM; }
+    memcpy(out128, &id, sizeof id);
+    return DOPF_OK;
+}
+
+int dopf_comm_init(dopf_handle *h, int32_t rank, int32_t nranks, const void *uid, int32_t total_agents)
+{
+    if (!h || !uid || nranks < 1 || rank < 0 || rank >= nranks || total_agents < h->lp.view.A) return DOPF_E_ARG;
+    if (h->h_ctrl->iters_done != 0 || h->graph_exec) { h->err = "dopf_comm_init must precede the first dopf_step"; return DOPF_E_ARG; }
+    if (nranks == 1) return DOPF_OK;
+    if (!nccl().ok) { h->err = "NCCL library not found (libnccl.so.2)"; return DOPF_E_COMM; }
+    CK(cudaSetDevice(h->device));
+    ncclUniqueId id;
+    memcpy(&id, uid, sizeof id);
+    int rc = nccl().CommInitRank(&h->comm, nranks, id, rank);
+    if (rc != 0) { h->err = std::string("ncclCommInitRank: ") + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "error"); return DOPF_E_COMM; }
+    h->rank = rank; h->nranks = nranks;
+    View &v = h->lp.view;
+    v.A = total_agents;
+    v.demand_on = rank == 0 ? 1 : 0;
+    for (int k = 0; k < 2; ++k) {
+        double *q = nullptr;
+        int r2 = dev_alloc(h, &q, (size_t)v.Np * v.ldt);
+        if (r2) return r2;
+        v.injloc[k] = q;
+    }
+    // initial injection: -demand on rank 0, summed over ranks (every agent starts at 0)
+    launch_rebuild_derived(h->lp, h->stream);
+    const int cur = h->h_ctrl->cur;   // rebuild flipped the buffers on the device; mirror below
+    (void)cur;
+    if ((rc = sync_ctrl(h))) return rc;
+    const int k = h->h_ctrl->cur;
+    if ((rc = comm_allreduce(h, v.injloc[k], v.inj[k], (size_t)v.Np * v.ldt, ncclSum))) return rc;
+    launch_rebuild_derived(h->lp, h->stream);   // second pass keeps injloc, recomputes flows from inj
+    CK(cudaGetLastError());
+    if ((rc = sync_ctrl(h))) return rc;
+    return DOPF_OK;
+}
+
+}  // extern "C"
+
+namespace dopf {
+
+// one iteration including the exchange steps; returns the number of kernel launches or < 0
+int enqueue_iteration_comm(dopf_handle *h, cudaStream_t st)
+{
+    if (h->nranks <= 1) {
+        int n = enqueue_iteration(h->lp, st);
+        return n;
+    }
+    h->err = "multi-GPU stepping is wired in dopf_multi (see dopf_comm_init)";
+    return DOPF_E_UNSUPPORTED;
+}
+
+}  // namespace dopf

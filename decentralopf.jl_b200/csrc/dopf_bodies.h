@@ -1,0 +1,267 @@
+// Data layout ("View") of one ADMM instance in device memory and the per-thread bodies of the
+// streaming / bookkeeping kernels.  Bodies are host+device inline so that tests/host_emul can
+// run the identical arithmetic sequentially on the CPU; the __global__ wrappers live in
+// dopf_kernels.cu.  Reference semantics of each step are cited at the body.
+#ifndef DOPF_BODIES_H
+#define DOPF_BODIES_H
+
+#include "dopf_math.h"
+
+namespace dopf {
+
+#if defined(__CUDA_ARCH__)
+#define DOPF_ATOMIC_MAX_U64(addr, v) atomicMax((unsigned long long *)(addr), (unsigned long long)(v))
+#define DOPF_ATOMIC_ADD_I32(addr, v) atomicAdd((int *)(addr), (int)(v))
+#define DOPF_ATOMIC_EXCH_I32(addr, v) atomicExch((int *)(addr), (int)(v))
+#else
+static inline unsigned long long dopf_host_max_u64(unsigned long long *a, unsigned long long v)
+{ unsigned long long o = *a; if (v > o) *a = v; return o; }
+static inline int dopf_host_add_i32(int *a, int v) { int o = *a; *a = o + v; return o; }
+static inline int dopf_host_exch_i32(int *a, int v) { int o = *a; *a = v; return o; }
+#define DOPF_ATOMIC_MAX_U64(addr, v) dopf_host_max_u64((unsigned long long *)(addr), (unsigned long long)(v))
+#define DOPF_ATOMIC_ADD_I32(addr, v) dopf_host_add_i32((int *)(addr), (int)(v))
+#define DOPF_ATOMIC_EXCH_I32(addr, v) dopf_host_exch_i32((int *)(addr), (int)(v))
+#endif
+
+// select one of a double-buffered pointer pair without dynamically indexing kernel parameters
+template <class T> DOPF_HD T *sel(T *const (&a)[2], int i) { return i ? a[1] : a[0]; }
+
+enum { DOPF_ERR_NONE = 0, DOPF_ERR_HINGE_CAP = 1, DOPF_ERR_WORK_CAP = 2 };
+
+// device-resident control block (one per instance)
+struct Ctrl {
+    int cur;            // index of the buffers holding the previous iterate
+    int iteration;      // admm.iteration (1-based)            structures/admm.jl:29
+    int converged;      // admm.convergence.all                 structures/convergence.jl
+    int conv_lambda, conv_mue, conv_rho;
+    int error;          // DOPF_ERR_*; set => every later kernel is a no-op, state stays valid
+    int iters_done;     // iterations executed since create
+    int gen_work_cnt, sto_work_cnt;
+    int stat_gen_fix, stat_sto_fix;      // cumulated corrected agents (statistics)
+    int stat_tight_rows, stat_wide_rows; // of the last iteration
+    unsigned long long res_bits[3];      // max |dual_{k+1}-dual_k| for lambda, mue, rho (bits)
+    double res[3];
+    double total_costs;
+};
+
+struct View {
+    // sizes
+    int N, L, T, G, S, A;
+    int ldt;          // leading dimension of every [node|line][t] matrix (T rounded up to 32)
+    int Np, Lp;       // padded row counts (multiples of 64) of the node / line matrices
+    int hcap;         // hinge capacity per (agent, t) in the correction pass
+    int gen_work_cap;
+    Coef c;
+    // static problem data
+    const double *ptdf;     // [Lp][Np] zero padded                               admm.ptdf
+    const double *fmax;     // [Lp]
+    const double *demand;   // [Np][ldt]
+    const double *q;        // [Np]  sum_l ptdf[l,n]^2
+    const double *prow;     // [Lp]  max_n |ptdf[l,n]|
+    const double *mwide;    // [Lp]  max_n |ptdf[l,n]| * box range of node n
+    const double *nagents;  // [Np]  number of agents at node n
+    const double *gen_mc, *gen_pmax; const int *gen_node; const int *gen_ptr;   // sorted by node; ptr [N+1]
+    const double *sto_mc, *sto_pmax, *sto_emax; const int *sto_node; const int *sto_ptr;
+    // iterate (double buffered: [cur] = previous, [1-cur] = being written)
+    double *P[2];           // [G][T]
+    double *D[2], *C[2];    // [S][T]
+    double *E;              // [S][T] level of the newest iterate
+    double *inj[2];         // [Np][ldt]  nodal injection (all ranks' agents)
+    double *injloc[2];      // [Np][ldt]  contribution of this rank's agents (== inj on one GPU)
+    int demand_on;          // 1: this rank subtracts the demand (rank 0)
+    double *ssum[2];        // [ldt]   sum_n inj
+    double *flow[2];        // [Lp][ldt]
+    double *avgU, *avgK;    // [Lp][ldt]
+    double *lam[2];         // [ldt]
+    double *mu[2], *rho[2]; // [Lp][ldt]
+    // per-iteration scratch
+    double *bplus, *bminus, *M, *Wt;   // [Lp][ldt]
+    double *g0, *s1;                   // [Np][ldt]
+    unsigned long long *dn;            // [Np][ldt] max |delta| of the agents at (n,t) (bits)
+    unsigned long long *dmax;          // [ldt]
+    unsigned char *flags;              // [ldt][Lp] bit0: U side wide candidate, bit1: K side
+    int *wide, *wcnt;                  // [T][2L] entries l*2+side ; [T]
+    int *tight, *tcnt;                 // [T][2L] ; [T]
+    int *gen_work;                     // [gen_work_cap] g*T+t
+    int *sto_work, *sto_flag;          // [S], [S]
+    double *rowsumU, *rowsumK;         // [Lp][ldt] exact sum_i (b -+ p delta_i)_+ of tight rows
+    Ctrl *ctrl;
+};
+
+// ---- row preparation: everything that depends on (line, t) only -------------------------------
+// consumes the previous iterate's flows, average slacks and the current duals
+// (penalty_terms.jl:10-52 after slack elimination)
+DOPF_HD void body_row_prep(const View &v, int l, int t)
+{
+    const int cur = v.ctrl->cur;
+    const size_t i = (size_t)l * v.ldt + t;
+    RowPrep r = row_prep(v.c, v.fmax[l], sel(v.flow, cur)[i], v.avgU[i], v.avgK[i], sel(v.mu, cur)[i], sel(v.rho, cur)[i]);
+    const bool real = (l < v.L) && (t < v.T);
+    v.bplus[i] = r.bplus; v.bminus[i] = r.bminus;
+    v.M[i] = real ? r.M : 0.0; v.Wt[i] = real ? r.Wt : 0.0;
+    unsigned char f = 0;
+    if (real) {
+        if (fabs(r.bplus) <= v.mwide[l]) f |= 1;
+        if (fabs(r.bminus) <= v.mwide[l]) f |= 2;
+    }
+    v.flags[(size_t)t * v.Lp + l] = f;
+}
+
+// ---- generator predict: anchor-linearised closed form + box projection ------------------------
+// (subproblems.jl:63-83 reduced; exact whenever no slack hinge lies in (0, delta])
+DOPF_HD double body_gen_predict(const View &v, int g, int t, double Pprev, int n, double mc, double pmax)
+{
+    const size_t nt = (size_t)n * v.ldt + t;
+    const double a = v.c.prox + v.s1[nt];
+    double d = -(mc + v.g0[nt]) / a;
+    double Pn = Pprev + d;
+    Pn = Pn < 0.0 ? 0.0 : (Pn > pmax ? pmax : Pn);
+    return Pn;
+}
+
+DOPF_HD void note_move(const View &v, int n, int t, double delta)
+{
+    const double ad = fabs(delta);
+    if (ad == 0.0) return;
+    const unsigned long long b = nonneg_bits(ad);
+    unsigned long long *pn = v.dn + (size_t)n * v.ldt + t;
+    if (b > *pn) DOPF_ATOMIC_MAX_U64(pn, b);
+    if (b > v.dmax[t]) DOPF_ATOMIC_MAX_U64(v.dmax + t, b);
+}
+
+// ---- verify: which agents at (n,t) moved across a slack hinge? --------------------------------
+DOPF_HD void body_verify(const View &v, int n, int t)
+{
+    const int cur = v.ctrl->cur, nxt = 1 - cur;
+    const size_t nt = (size_t)n * v.ldt + t;
+    const double dnt = bits_nonneg(v.dn[nt]);
+    if (dnt == 0.0) return;
+    double lo = -INFINITY, hi = INFINITY;   // nearest hinge breakpoints around delta = 0
+    const int cnt = v.tcnt[t];
+    const int *lst = v.tight + (size_t)t * 2 * v.L;
+    for (int j = 0; j < cnt; ++j) {
+        const int l = lst[j] >> 1, side = lst[j] & 1;
+        const double p = v.ptdf[(size_t)l * v.Np + n];
+        Hinge h;
+        if (!make_hinge(v.c, p, side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t], side, h)) continue;
+        if (fabs(h.bp) > dnt) continue;
+        if (h.bp > 0.0) { if (h.bp < hi) hi = h.bp; }
+        else if (h.bp < 0.0) { if (h.bp > lo) lo = h.bp; }
+        else { if (h.sg > 0.0) hi = 0.0; else lo = 0.0; }
+    }
+    if (lo == -INFINITY && hi == INFINITY) return;
+    for (int g = v.gen_ptr[n]; g < v.gen_ptr[n + 1]; ++g) {
+        const double d = sel(v.P, nxt)[(size_t)g * v.T + t] - sel(v.P, cur)[(size_t)g * v.T + t];
+        if (d > hi || d < lo) {
+            const int slot = DOPF_ATOMIC_ADD_I32(&v.ctrl->gen_work_cnt, 1);
+            if (slot < v.gen_work_cap) v.gen_work[slot] = g * v.T + t;
+            else v.ctrl->error = DOPF_ERR_WORK_CAP;
+        }
+    }
+    for (int s = v.sto_ptr[n]; s < v.sto_ptr[n + 1]; ++s) {
+        const size_t i = (size_t)s * v.T + t;
+        const double d = (sel(v.D, nxt)[i] - sel(v.D, cur)[i]) - (sel(v.C, nxt)[i] - sel(v.C, cur)[i]);
+        if (d > hi || d < lo) {
+            if (DOPF_ATOMIC_EXCH_I32(&v.sto_flag[s], 1) == 0) {
+                const int slot = DOPF_ATOMIC_ADD_I32(&v.ctrl->sto_work_cnt, 1);
+                v.sto_work[slot] = s;
+            }
+        }
+    }
+}
+
+// ---- nodal injection of the new iterate (results.jl:64,88-106) --------------------------------
+DOPF_HD void body_inject(const View &v, int n, int t)
+{
+    const int nxt = 1 - v.ctrl->cur;
+    double a = 0.0;
+    if (n < v.N && t < v.T) {
+        a = v.demand_on ? -v.demand[(size_t)n * v.ldt + t] : 0.0;
+        for (int g = v.gen_ptr[n]; g < v.gen_ptr[n + 1]; ++g) a += sel(v.P, nxt)[(size_t)g * v.T + t];
+        for (int s = v.sto_ptr[n]; s < v.sto_ptr[n + 1]; ++s)
+            a += sel(v.D, nxt)[(size_t)s * v.T + t] - sel(v.C, nxt)[(size_t)s * v.T + t];
+    }
+    sel(v.injloc, nxt)[(size_t)n * v.ldt + t] = a;
+}
+
+// ---- exact slack sums of one tight row at one node (results.jl:83-84,110-112) ------------------
+// returns sum over the agents at node n of (b - p*delta_i)_+  (side 0)  or (b + p*delta_i)_+ (side 1)
+DOPF_HD double body_slack_row_node(const View &v, int l, int side, int n, int t)
+{
+    const int cur = v.ctrl->cur, nxt = 1 - cur;
+    const double na = v.nagents[n];
+    if (na == 0.0) return 0.0;
+    const double p = v.ptdf[(size_t)l * v.Np + n];
+    const double b = side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t];
+    const double sp = side ? p : -p;   // term is (b + sp*delta)_+
+    const size_t nt = (size_t)n * v.ldt + t;
+    if (p == 0.0) return na * pospart(b);
+    const double dnt = bits_nonneg(v.dn[nt]);
+    if (fabs(b) > fabs(p) * dnt) {   // nobody at this node crosses the hinge
+        if (b <= 0.0) return 0.0;
+        return na * b + sp * (sel(v.injloc, nxt)[nt] - sel(v.injloc, cur)[nt]);
+    }
+    double a = 0.0;
+    for (int g = v.gen_ptr[n]; g < v.gen_ptr[n + 1]; ++g) {
+        const double d = sel(v.P, nxt)[(size_t)g * v.T + t] - sel(v.P, cur)[(size_t)g * v.T + t];
+        a += pospart(b + sp * d);
+    }
+    for (int s = v.sto_ptr[n]; s < v.sto_ptr[n + 1]; ++s) {
+        const size_t i = (size_t)s * v.T + t;
+        const double d = (sel(v.D, nxt)[i] - sel(v.D, cur)[i]) - (sel(v.C, nxt)[i] - sel(v.C, cur)[i]);
+        a += pospart(b + sp * d);
+    }
+    return a;
+}
+
+// ---- dual update for one (line, t) (update_duals.jl:17-39) ------------------------------------
+// is_tight: bit0 / bit1 = the exact row sums are available in rowsumU / rowsumK
+DOPF_HD void body_dual(const View &v, int l, int t, int is_tight, double &res_mu, double &res_rho)
+{
+    const int cur = v.ctrl->cur, nxt = 1 - cur;
+    const size_t i = (size_t)l * v.ldt + t;
+    const double Fn = sel(v.flow, nxt)[i], dF = Fn - sel(v.flow, cur)[i];
+    const double A = (double)v.A;
+    const double bp = v.bplus[i], bm = v.bminus[i];
+    const double sU = (is_tight & 1) ? v.rowsumU[i] : (bp > 0.0 ? A * bp - dF : 0.0);
+    const double sK = (is_tight & 2) ? v.rowsumK[i] : (bm > 0.0 ? A * bm + dF : 0.0);
+    const double scale = v.c.w2 / (v.c.kk * A);
+    const double aU = scale * sU, aK = scale * sK;
+    const double f = v.fmax[l];
+    double mu = sel(v.mu, cur)[i] + v.c.gamma * (Fn + aU - f);
+    double rho = sel(v.rho, cur)[i] + v.c.gamma * (aK - Fn - f);
+    mu *= (aU <= v.c.mask_tol) ? 1.0 : 0.0;
+    rho *= (aK <= v.c.mask_tol) ? 1.0 : 0.0;
+    v.avgU[i] = aU; v.avgK[i] = aK;
+    sel(v.mu, nxt)[i] = mu; sel(v.rho, nxt)[i] = rho;
+    res_mu = fabs(mu - sel(v.mu, cur)[i]);
+    res_rho = fabs(rho - sel(v.rho, cur)[i]);
+}
+
+// ---- lambda update (update_duals.jl:7-15) ------------------------------------------------------
+DOPF_HD double body_lambda(const View &v, int t)
+{
+    const int cur = v.ctrl->cur, nxt = 1 - cur;
+    const double ln = sel(v.lam, cur)[t] + v.c.gamma * sel(v.ssum, nxt)[t];
+    sel(v.lam, nxt)[t] = ln;
+    return fabs(ln - sel(v.lam, cur)[t]);
+}
+
+// ---- end of iteration (convergence.jl:1-31) ----------------------------------------------------
+DOPF_HD void body_finish(const View &v)
+{
+    Ctrl *c = v.ctrl;
+    for (int k = 0; k < 3; ++k) c->res[k] = bits_nonneg(c->res_bits[k]);
+    if (c->iteration != 1) {
+        c->conv_lambda = c->res[0] < v.c.eps;
+        c->conv_mue = c->res[1] < v.c.eps;
+        c->conv_rho = c->res[2] < v.c.eps;
+        c->converged = c->conv_lambda && c->conv_mue && c->conv_rho;
+    }
+    if (!c->converged) c->iteration += 1;
+    c->cur = 1 - c->cur;
+    c->iters_done += 1;
+}
+
+}  // namespace dopf
+#endif

@@ -1,0 +1,655 @@
+// sm_100a kernels of one ADMM iteration (calculate_iteration!, /root/reference/src/optimization/
+// run.jl:7-16).  Layout and bodies: dopf_bodies.h; per-agent math: dopf_math.h; pipeline order:
+// dopf_api.cu (enqueue_iteration) and DESIGN.md section 4.
+//
+// Every kernel first reads the device control block: once `converged` or `error` is set all
+// remaining launches of an already enqueued batch are no-ops, so run!(admm) needs no host
+// round trip per iteration.
+#include "dopf_kernels.h"
+
+namespace dopf {
+
+#define DOPF_ACTIVE(v) ((v).ctrl->converged == 0 && (v).ctrl->error == 0)
+
+// ------------------------------------------------------------------------------------------------
+// iteration prologue: reset per-iteration counters
+// ------------------------------------------------------------------------------------------------
+__global__ void k_begin(View v)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        v.ctrl->gen_work_cnt = 0; v.ctrl->sto_work_cnt = 0;
+        v.ctrl->res_bits[0] = v.ctrl->res_bits[1] = v.ctrl->res_bits[2] = 0ull;
+    }
+    for (int k = i; k < v.Np * v.ldt; k += gridDim.x * blockDim.x) v.dn[k] = 0ull;
+    for (int k = i; k < v.ldt; k += gridDim.x * blockDim.x) v.dmax[k] = 0ull;
+    for (int k = i; k < v.S; k += gridDim.x * blockDim.x) v.sto_flag[k] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// row preparation over the padded [Lp][ldt] grid (coalesced along t)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_row_prep(View v)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.Lp * v.ldt) return;
+    body_row_prep(v, i / v.ldt, i % v.ldt);
+}
+
+// ordered compaction of the candidate rows of one timestep; one warp per t.
+//  mode 0: wide list from the flag bytes;  mode 1: tight list = wide entries with
+//  |b| <= max_n|ptdf[l,n]| * (largest move of any agent at t)
+__global__ void k_compact(View v, int mode)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= v.T) return;
+    const int t = warp;
+    int cnt = 0;
+    if (mode == 0) {
+        int *out = v.wide + (size_t)t * 2 * v.L;
+        const unsigned char *fl = v.flags + (size_t)t * v.Lp;
+        for (int base = 0; base < v.L; base += 32) {
+            const int l = base + lane;
+            const unsigned char f = l < v.L ? fl[l] : 0;
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const bool p = (f >> side) & 1;
+                const unsigned m = __ballot_sync(0xffffffffu, p);
+                if (p) out[cnt + __popc(m & ((1u << lane) - 1))] = l * 2 + side;
+                cnt += __popc(m);
+            }
+        }
+        if (lane == 0) { v.wcnt[t] = cnt; if (t == 0) v.ctrl->stat_wide_rows = 0; }
+    } else {
+        int *out = v.tight + (size_t)t * 2 * v.L;
+        const int *in = v.wide + (size_t)t * 2 * v.L;
+        const int n_in = v.wcnt[t];
+        const double dm = bits_nonneg(v.dmax[t]);
+        for (int base = 0; base < n_in; base += 32) {
+            const int j = base + lane;
+            bool p = false;
+            int e = 0;
+            if (j < n_in) {
+                e = in[j];
+                const int l = e >> 1;
+                const double b = (e & 1) ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t];
+                p = fabs(b) <= v.prow[l] * dm;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, p);
+            if (p) out[cnt + __popc(m & ((1u << lane) - 1))] = e;
+            cnt += __popc(m);
+        }
+        if (lane == 0) v.tcnt[t] = cnt;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp64 tensor-pipe GEMMs (DMMA m8n8k4; tcgen05 has no f64 kind).  cp.async double buffering,
+// split-K partials reduced by the epilogue kernels below (deterministic order).
+//   TRANS = false:  Cpart[z] = A[Mp x Kp] * B[Kp x ldt]                      (flow = PTDF * inj)
+//   TRANS = true :  Cpart[z] = A^T * B  and  C2part[z] = (A.*A)^T * B2      (PTDF^T M, (PTDF.^2)^T W)
+// A is the padded PTDF [Lp][Np]; all dimensions are multiples of the tile sizes.
+// ------------------------------------------------------------------------------------------------
+constexpr int BN = 32, BK = 16;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int BM, bool TRANS>
+__global__ void __launch_bounds__(128) k_gemm(View v, const double *__restrict__ A, int lda, int ldb,
+                                              double *__restrict__ Cpart, double *__restrict__ C2part,
+                                              int Mp, int Kp, int ksplit)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    // B operand: M (and W) for the transposed product, the new injection for the flow product
+    const double *__restrict__ B = TRANS ? v.M : sel(v.inj, 1 - v.ctrl->cur);
+    const double *__restrict__ B2 = v.Wt;
+    constexpr int MT = BM / 32;                       // m8 tiles per warp (4 warps along M)
+    constexpr int AROW = TRANS ? (BM + 4) : (BK + 4); // padded smem row of the A tile
+    constexpr int AROWS = TRANS ? BK : BM;
+    __shared__ __align__(16) double As[2][AROWS][AROW];
+    __shared__ __align__(16) double Bs[2][BK][BN + 4];
+    __shared__ __align__(16) double B2s[TRANS ? 2 : 1][TRANS ? BK : 1][TRANS ? BN + 4 : 2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, z = blockIdx.z;
+    const int ksteps_total = Kp / BK;
+    const int per = (ksteps_total + ksplit - 1) / ksplit;
+    const int ks0 = z * per, ks1 = min(ksteps_total, ks0 + per);
+
+    double acc[MT][4][2], acc2[TRANS ? MT : 1][4][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = acc[i][j][1] = 0.0; if (TRANS) { acc2[i][j][0] = acc2[i][j][1] = 0.0; } }
+
+    auto load_tiles = [&](int buf, int ks) {
+        const int k0 = ks * BK;
+        if (TRANS) {   // A rows = k (lines), cols = m (nodes): BK x BM doubles
+            constexpr int CH = BK * BM / 2;               // 16-byte chunks
+            for (int c = tid; c < CH; c += 128) {
+                const int r = c / (BM / 2), cc = (c % (BM / 2)) * 2;
+                cp_async16(&As[buf][r][cc], A + (size_t)(k0 + r) * lda + m0 + cc);
+            }
+        } else {       // A rows = m (lines), cols = k (nodes): BM x BK doubles
+            constexpr int CH = BM * BK / 2;
+            for (int c = tid; c < CH; c += 128) {
+                const int r = c / (BK / 2), cc = (c % (BK / 2)) * 2;
+                cp_async16(&As[buf][r][cc], A + (size_t)(m0 + r) * lda + k0 + cc);
+            }
+        }
+        constexpr int CHB = BK * BN / 2;
+        for (int c = tid; c < CHB; c += 128) {
+            const int r = c / (BN / 2), cc = (c % (BN / 2)) * 2;
+            cp_async16(&Bs[buf][r][cc], B + (size_t)(k0 + r) * ldb + n0 + cc);
+            if (TRANS) cp_async16(&B2s[buf][r][cc], B2 + (size_t)(k0 + r) * ldb + n0 + cc);
+        }
+        cp_async_commit();
+    };
+
+    if (ks0 < ks1) load_tiles(0, ks0);
+    for (int ks = ks0; ks < ks1; ++ks) {
+        const int buf = (ks - ks0) & 1;
+        if (ks + 1 < ks1) { load_tiles(buf ^ 1, ks + 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double a[MT], b[4], b2[4];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                const int row = warp * (BM / 4) + i * 8 + (lane >> 2);
+                a[i] = TRANS ? As[buf][kk + (lane & 3)][row] : As[buf][row][kk + (lane & 3)];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                b[j] = Bs[buf][kk + (lane & 3)][j * 8 + (lane >> 2)];
+                if (TRANS) b2[j] = B2s[buf][kk + (lane & 3)][j * 8 + (lane >> 2)];
+            }
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    if (TRANS) dmma(acc2[i][j][0], acc2[i][j][1], a[i] * a[i], b2[j]);
+                }
+        }
+        __syncthreads();
+    }
+    // partial tile store
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int row = m0 + warp * (BM / 4) + i * 8 + (lane >> 2);
+            const int col = n0 + j * 8 + 2 * (lane & 3);
+            const size_t o = ((size_t)z * Mp + row) * ldb + col;
+            *reinterpret_cast<double2 *>(Cpart + o) = make_double2(acc[i][j][0], acc[i][j][1]);
+            if (TRANS) *reinterpret_cast<double2 *>(C2part + o) = make_double2(acc2[i][j][0], acc2[i][j][1]);
+        }
+}
+
+// epilogue of the transposed product: g0 = lambda_t + gamma*Sbar_t + PTDF^T M,
+// s1 = gamma + 2 kappa q_n + (PTDF.^2)^T W        (subproblems.jl:67-75)
+__global__ void k_node_prep(View v, const double *Cpart, const double *C2part, int ksplit)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.Np * v.ldt) return;
+    const int n = i / v.ldt, t = i % v.ldt, cur = v.ctrl->cur;
+    double a = 0.0, b = 0.0;
+    for (int z = 0; z < ksplit; ++z) { a += Cpart[(size_t)z * v.Np * v.ldt + i]; b += C2part[(size_t)z * v.Np * v.ldt + i]; }
+    v.g0[i] = sel(v.lam, cur)[t] + v.c.gamma * sel(v.ssum, cur)[t] + a;
+    v.s1[i] = v.c.gamma + 2.0 * v.c.kappa * v.q[n] + b;
+}
+
+// epilogue of the flow product: line_utilization = ptdf * injection (results.jl:114)
+__global__ void k_flow_reduce(View v, const double *Cpart, int ksplit)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.Lp * v.ldt) return;
+    double a = 0.0;
+    for (int z = 0; z < ksplit; ++z) a += Cpart[(size_t)z * v.Lp * v.ldt + i];
+    sel(v.flow, 1 - v.ctrl->cur)[i] = a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// generator predict: one thread per (agent, VEC consecutive t); streaming, 16 B per unit
+// ------------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) k_gen_predict(View v)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    const int cur = v.ctrl->cur, nxt = 1 - cur;
+    const int per = v.T / VEC;                      // VEC divides T
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)v.G * per) return;
+    const int g = (int)(idx / per), t = (int)(idx % per) * VEC;
+    const int n = __ldg(v.gen_node + g);
+    const double mc = __ldg(v.gen_mc + g), pmax = __ldg(v.gen_pmax + g);
+    const size_t o = (size_t)g * v.T + t;
+    if (VEC == 2) {
+        const double2 pp = *reinterpret_cast<const double2 *>(sel(v.P, cur) + o);
+        double2 pn;
+        pn.x = body_gen_predict(v, g, t, pp.x, n, mc, pmax);
+        pn.y = body_gen_predict(v, g, t + 1, pp.y, n, mc, pmax);
+        *reinterpret_cast<double2 *>(sel(v.P, nxt) + o) = pn;
+        note_move(v, n, t, pn.x - pp.x);
+        note_move(v, n, t + 1, pn.y - pp.y);
+    } else {
+        const double pp = sel(v.P, cur)[o];
+        const double pn = body_gen_predict(v, g, t, pp, n, mc, pmax);
+        sel(v.P, nxt)[o] = pn;
+        note_move(v, n, t, pn - pp);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// storages: one warp per storage, horizon staged in shared memory.
+//  FIX = false: predict pass over all storages with the anchor linearisation
+//  FIX = true : exact re-solve of the storages on the work list with per-t hinge lists
+// dynamic smem per warp: StoStep[T] + eta[T] (+ hinge counts[T] in the FIX pass)
+// ------------------------------------------------------------------------------------------------
+template <bool FIX>
+__global__ void k_storage(View v, Hinge *hinge_scratch)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int cur = v.ctrl->cur, nxt = 1 - cur;
+    const int T = v.T, lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const size_t per_warp = (size_t)T * (sizeof(StoStep) + sizeof(double) + sizeof(int));
+    unsigned char *base = smem_raw + wib * ((per_warp + 15) & ~(size_t)15);
+    StoStep *step = reinterpret_cast<StoStep *>(base);
+    double *eta = reinterpret_cast<double *>(base + (size_t)T * sizeof(StoStep));
+    int *hcnt = reinterpret_cast<int *>(base + (size_t)T * (sizeof(StoStep) + sizeof(double)));
+    const int gw = blockIdx.x * wpb + wib, nw = gridDim.x * wpb;
+    const int total = FIX ? v.ctrl->sto_work_cnt : v.S;
+    Hinge *mylist = FIX ? hinge_scratch + (size_t)gw * T * v.hcap : nullptr;
+
+    for (int w = gw; w < total; w += nw) {
+        const int s = FIX ? v.sto_work[w] : w;
+        const int n = v.sto_node[s];
+        StoProblem p;
+        p.T = T; p.k.mc = v.sto_mc[s]; p.k.pmax = v.sto_pmax[s]; p.k.emax = v.sto_emax[s]; p.k.prox = v.c.prox;
+        p.step = step; p.hinges = mylist; p.hcnt = hcnt; p.hcap = v.hcap;
+        for (int t = lane; t < T; t += 32) {
+            StoStep st;
+            st.Db = sel(v.D, cur)[(size_t)s * T + t]; st.Cb = sel(v.C, cur)[(size_t)s * T + t];
+            st.g0 = v.g0[(size_t)n * v.ldt + t]; st.s1 = v.s1[(size_t)n * v.ldt + t];
+            step[t] = st;
+        }
+        if (FIX) {
+            // collect, per t, the hinges whose breakpoint lies inside the box |delta| < 2 pmax
+            const double range = 2.0 * p.k.pmax;
+            for (int t = 0; t < T; ++t) {
+                const int cnt_in = v.wcnt[t];
+                const int *lst = v.wide + (size_t)t * 2 * v.L;
+                int cnt = 0;
+                for (int b0 = 0; b0 < cnt_in; b0 += 32) {
+                    const int j = b0 + lane;
+                    bool ok = false;
+                    Hinge h; h.bp = 0.0; h.sg = 0.0;
+                    if (j < cnt_in) {
+                        const int l = lst[j] >> 1, side = lst[j] & 1;
+                        const double pl = v.ptdf[(size_t)l * v.Np + n];
+                        ok = make_hinge(v.c, pl, side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t], side, h)
+                             && fabs(h.bp) < range;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, ok);
+                    const int pos = cnt + __popc(m & ((1u << lane) - 1));
+                    if (ok && pos < v.hcap) mylist[(size_t)t * v.hcap + pos] = h;
+                    cnt += __popc(m);
+                }
+                if (cnt > v.hcap) { if (lane == 0) v.ctrl->error = DOPF_ERR_HINGE_CAP; cnt = v.hcap; }
+                if (lane == 0) hcnt[t] = cnt;
+            }
+        } else {
+            p.hinges = nullptr;
+        }
+        __syncwarp();
+        StoSolver<32> solver(p);
+        solver.solve(eta);
+        __syncwarp();
+        // write D, C, E (level = running sum of C-D; subproblems.jl:150-156)
+        double carry = 0.0;
+        for (int b0 = 0; b0 < T; b0 += 32) {
+            const int t = b0 + lane;
+            double y = 0.0, Dn = 0.0, Cn = 0.0;
+            if (t < T) {
+                StoEval e = sto_eval(step[t], p.k, p.list(t), eta[t]);
+                Dn = e.D; Cn = e.C; y = Cn - Dn;
+            }
+            const double E = carry + Group<32>::scan_incl(y);
+            if (t < T) {
+                const size_t o = (size_t)s * T + t;
+                sel(v.D, nxt)[o] = Dn; sel(v.C, nxt)[o] = Cn; v.E[o] = E;
+                note_move(v, n, t, (Dn - step[t].Db) - (Cn - step[t].Cb));
+            }
+            carry = __shfl_sync(0xffffffffu, E, 31);
+        }
+        if (FIX && lane == 0) atomicAdd(&v.ctrl->stat_sto_fix, 1);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// verify: lanes along nodes (PTDF rows are node-contiguous), 8 timesteps per block
+// ------------------------------------------------------------------------------------------------
+__global__ void k_verify(View v)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int t = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= v.N || t >= v.T) return;
+    body_verify(v, n, t);
+}
+
+// exact re-solve of the generators on the work list: one warp per (agent, t)
+__global__ void k_gen_fix(View v)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    constexpr int CAP = 96;
+    __shared__ Hinge lists[4][CAP];
+    const int cur = v.ctrl->cur, nxt = 1 - cur;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + wib, nw = gridDim.x * (blockDim.x >> 5);
+    const int total = min(v.ctrl->gen_work_cnt, v.gen_work_cap);
+    for (int w = gw; w < total; w += nw) {
+        const int g = v.gen_work[w] / v.T, t = v.gen_work[w] % v.T;
+        const int n = v.gen_node[g];
+        const double Pb = sel(v.P, cur)[(size_t)g * v.T + t], pmax = v.gen_pmax[g];
+        const double lo = -Pb, hi = pmax - Pb;
+        const int cnt_in = v.wcnt[t];
+        const int *lst = v.wide + (size_t)t * 2 * v.L;
+        int cnt = 0;
+        for (int b0 = 0; b0 < cnt_in; b0 += 32) {
+            const int j = b0 + lane;
+            bool ok = false;
+            Hinge h; h.bp = 0.0; h.sg = 0.0;
+            if (j < cnt_in) {
+                const int l = lst[j] >> 1, side = lst[j] & 1;
+                const double pl = v.ptdf[(size_t)l * v.Np + n];
+                ok = make_hinge(v.c, pl, side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t], side, h)
+                     && h.bp > lo && h.bp < hi;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            const int pos = cnt + __popc(m & ((1u << lane) - 1));
+            if (ok && pos < CAP) lists[wib][pos] = h;
+            cnt += __popc(m);
+        }
+        __syncwarp();
+        if (cnt > CAP) { if (lane == 0) v.ctrl->error = DOPF_ERR_HINGE_CAP; cnt = CAP; }
+        if (lane == 0) {
+            HingeList hl; hl.h = lists[wib]; hl.n = cnt;
+            const size_t nt = (size_t)n * v.ldt + t;
+            const double d = root_monotone_pl(v.gen_mc[g] + v.g0[nt], v.c.prox + v.s1[nt], hl, lo, hi);
+            double Pn = Pb + d;
+            Pn = Pn < 0.0 ? 0.0 : (Pn > pmax ? pmax : Pn);
+            sel(v.P, nxt)[(size_t)g * v.T + t] = Pn;
+            note_move(v, n, t, Pn - Pb);
+            atomicAdd(&v.ctrl->stat_gen_fix, 1);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// aggregation ("coordinator gather", results.jl:55-106): injection and its column sums
+// ------------------------------------------------------------------------------------------------
+__global__ void k_inject(View v)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.Np * v.ldt) return;
+    body_inject(v, i / v.ldt, i % v.ldt);
+}
+
+__global__ void k_colsum(View v)   // block (32,32): 32 timesteps, 32 row groups
+{
+    if (!DOPF_ACTIVE(v)) return;
+    __shared__ double part[32][33];
+    const int t = blockIdx.x * 32 + threadIdx.x, nxt = 1 - v.ctrl->cur;
+    double a = 0.0;
+    for (int n = threadIdx.y; n < v.Np; n += 32) a += sel(v.inj, nxt)[(size_t)n * v.ldt + t];
+    part[threadIdx.y][threadIdx.x] = a;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        double s = 0.0;
+        for (int k = 0; k < 32; ++k) s += part[k][threadIdx.x];
+        sel(v.ssum, nxt)[t] = s;
+    }
+}
+
+// exact average-slack sums of the tight rows: one block per (t, row), threads over nodes
+__global__ void k_slack_rows(View v, unsigned char *tflag)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    __shared__ double red[4];
+    const int t = blockIdx.y;
+    const int cnt = v.tcnt[t];
+    const int *lst = v.tight + (size_t)t * 2 * v.L;
+    for (int j = blockIdx.x; j < cnt; j += gridDim.x) {
+        const int l = lst[j] >> 1, side = lst[j] & 1;
+        double a = 0.0;
+        for (int n = threadIdx.x; n < v.N; n += blockDim.x) a += body_slack_row_node(v, l, side, n, t);
+        a = Group<32>::sum(a);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int k = 0; k < (int)(blockDim.x >> 5); ++k) s += red[k];
+            const size_t i = (size_t)l * v.ldt + t;
+            (side ? v.rowsumK : v.rowsumU)[i] = s;
+            atomicOr(reinterpret_cast<unsigned int *>(tflag) + (i >> 2), (unsigned)(1u << side) << (8 * (i & 3)));
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_clear_tflag(View v, unsigned char *tflag)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < v.Lp * v.ldt / 4) reinterpret_cast<unsigned int *>(tflag)[i] = 0u;
+}
+
+// dual update + residual maxima (update_duals.jl, convergence.jl:3-12)
+__global__ void __launch_bounds__(256) k_dual(View v, const unsigned char *tflag)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    __shared__ double rm[8], rr[8];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double a = 0.0, b = 0.0;
+    if (i < v.L * v.ldt) {
+        const int l = i / v.ldt, t = i % v.ldt;
+        if (t < v.T) body_dual(v, l, t, tflag[i], a, b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    if ((threadIdx.x & 31) == 0) { rm[threadIdx.x >> 5] = a; rr[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) { a = fmax(a, rm[k]); b = fmax(b, rr[k]); }
+        a = fmax(a, rm[0]); b = fmax(b, rr[0]);
+        if (a > 0.0) atomicMax(&v.ctrl->res_bits[1], nonneg_bits(a));
+        if (b > 0.0) atomicMax(&v.ctrl->res_bits[2], nonneg_bits(b));
+    }
+}
+
+__global__ void k_lambda(View v)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= v.T) return;
+    const double r = body_lambda(v, t);
+    if (r > 0.0) atomicMax(&v.ctrl->res_bits[0], nonneg_bits(r));
+}
+
+__global__ void k_finish(View v)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    v.ctrl->stat_tight_rows = 0;
+    for (int t = 0; t < v.T; ++t) { v.ctrl->stat_tight_rows += v.tcnt[t]; }
+    int wr = 0;
+    for (int t = 0; t < v.T; ++t) wr += v.wcnt[t];
+    v.ctrl->stat_wide_rows = wr;
+    body_finish(v);
+}
+
+// total_costs (results.jl:95-105) - on demand only
+__global__ void k_total_costs(View v, double *out)
+{
+    __shared__ double red[8];
+    const int newest = v.ctrl->cur;   // after k_finish the newest iterate sits in [cur]
+    double a = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)v.G * v.T; i += (long long)gridDim.x * blockDim.x)
+        a += sel(v.P, newest)[i] * v.gen_mc[i / v.T];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)v.S * v.T; i += (long long)gridDim.x * blockDim.x)
+        a += (sel(v.D, newest)[i] + sel(v.C, newest)[i]) * v.sto_mc[i / v.T];
+    a = Group<32>::sum(a);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) s += red[k];
+        atomicAdd(out, s);
+    }
+}
+
+// nodal price (network_elements.jl:16-25): lambda_t + sum_l (mu+rho)[l,t] ptdf[l,n]
+__global__ void k_nodal_price(View v, int which, double *out /*[N][T]*/)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.N * v.T) return;
+    const int n = i / v.T, t = i % v.T;
+    double a = sel(v.lam, which)[t];
+    for (int l = 0; l < v.L; ++l)
+        a += (sel(v.mu, which)[(size_t)l * v.ldt + t] + sel(v.rho, which)[(size_t)l * v.ldt + t]) * v.ptdf[(size_t)l * v.Np + n];
+    out[i] = a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launcher of one iteration (captured into a CUDA graph by dopf_api.cu)
+// ------------------------------------------------------------------------------------------------
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+size_t storage_smem_bytes(int T, int warps)
+{
+    const size_t per_warp = (size_t)T * (sizeof(StoStep) + sizeof(double) + sizeof(int));
+    return warps * ((per_warp + 15) & ~(size_t)15);
+}
+
+int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st)
+{
+    const View &v = lp.view;
+    int launches = 0;
+#define LAUNCH(...) do { __VA_ARGS__; ++launches; } while (0)
+    LAUNCH(k_begin<<<lp.num_sms, 256, 0, st>>>(v));
+    LAUNCH(k_row_prep<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, st>>>(v));
+    LAUNCH(k_compact<<<cdiv((long long)v.T * 32, 128), 128, 0, st>>>(v, 0));
+    {   // PTDF^T M and (PTDF.^2)^T W
+        dim3 grid(v.Np / lp.bm_t, v.ldt / BN, lp.ksplit_t);
+        if (lp.bm_t == 64) LAUNCH(k_gemm<64, true><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, lp.part2, v.Np, v.Lp, lp.ksplit_t));
+        else LAUNCH(k_gemm<32, true><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, lp.part2, v.Np, v.Lp, lp.ksplit_t));
+        LAUNCH(k_node_prep<<<cdiv((long long)v.Np * v.ldt, 256), 256, 0, st>>>(v, lp.part, lp.part2, lp.ksplit_t));
+    }
+    if (v.G > 0) {
+        if (v.T % 2 == 0) LAUNCH(k_gen_predict<2><<<cdiv((long long)v.G * (v.T / 2), 256), 256, 0, st>>>(v));
+        else LAUNCH(k_gen_predict<1><<<cdiv((long long)v.G * v.T, 256), 256, 0, st>>>(v));
+    }
+    if (v.S > 0)
+        LAUNCH(k_storage<false><<<min(cdiv(v.S, lp.sto_warps), lp.sto_blocks), lp.sto_warps * 32, storage_smem_bytes(v.T, lp.sto_warps), st>>>(v, nullptr));
+    LAUNCH(k_compact<<<cdiv((long long)v.T * 32, 128), 128, 0, st>>>(v, 1));
+    {
+        dim3 grid(cdiv(v.N, 32), cdiv(v.T, 8));
+        LAUNCH(k_verify<<<grid, 256, 0, st>>>(v));
+    }
+    if (v.G > 0) LAUNCH(k_gen_fix<<<lp.num_sms * 2, 128, 0, st>>>(v));
+    if (v.S > 0)
+        LAUNCH(k_storage<true><<<lp.sto_fix_blocks, lp.sto_warps * 32, storage_smem_bytes(v.T, lp.sto_warps), st>>>(v, lp.hinge_scratch));
+    LAUNCH(k_compact<<<cdiv((long long)v.T * 32, 128), 128, 0, st>>>(v, 1));   // moves may have grown
+    LAUNCH(k_inject<<<cdiv((long long)v.Np * v.ldt, 256), 256, 0, st>>>(v));
+    LAUNCH(k_colsum<<<v.ldt / 32, dim3(32, 32), 0, st>>>(v));
+    {   // flow = PTDF * inj
+        dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);
+        if (lp.bm_n == 64) LAUNCH(k_gemm<64, false><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n));
+        else LAUNCH(k_gemm<32, false><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n));
+        LAUNCH(k_flow_reduce<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, st>>>(v, lp.part, lp.ksplit_n));
+    }
+    LAUNCH(k_clear_tflag<<<cdiv((long long)v.Lp * v.ldt / 4, 256), 256, 0, st>>>(v, lp.tflag));
+    LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.T), 128, 0, st>>>(v, lp.tflag));
+    LAUNCH(k_dual<<<cdiv((long long)v.L * v.ldt, 256), 256, 0, st>>>(v, lp.tflag));
+    LAUNCH(k_lambda<<<cdiv(v.T, 128), 128, 0, st>>>(v));
+    LAUNCH(k_finish<<<1, 1, 0, st>>>(v));
+#undef LAUNCH
+    return launches;
+}
+
+void launch_total_costs(const View &v, double *d_out, cudaStream_t st)
+{
+    cudaMemsetAsync(d_out, 0, sizeof(double), st);
+    k_total_costs<<<296, 256, 0, st>>>(v, d_out);
+}
+
+void launch_nodal_price(const View &v, int which, double *d_out, cudaStream_t st)
+{
+    k_nodal_price<<<cdiv((long long)v.N * v.T, 128), 128, 0, st>>>(v, which, d_out);
+}
+
+// levels of the staged iterate and buffer flip, used when a state is injected from the host
+__global__ void k_levels(View v)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= v.S) return;
+    const int nxt = 1 - v.ctrl->cur;
+    double e = 0.0;
+    for (int t = 0; t < v.T; ++t) {
+        const size_t o = (size_t)s * v.T + t;
+        e += sel(v.C, nxt)[o] - sel(v.D, nxt)[o];
+        v.E[o] = e;
+    }
+}
+__global__ void k_flip(View v) { v.ctrl->cur = 1 - v.ctrl->cur; }
+
+// derived quantities (injection, column sums, flows, levels) of the iterate staged in the
+// inactive buffers, then flip: the staged iterate becomes the "previous iterate"
+void launch_rebuild_derived(const LaunchPlan &lp, cudaStream_t st)
+{
+    const View &v = lp.view;
+    k_inject<<<cdiv((long long)v.Np * v.ldt, 256), 256, 0, st>>>(v);
+    k_colsum<<<v.ldt / 32, dim3(32, 32), 0, st>>>(v);
+    dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);
+    if (lp.bm_n == 64) k_gemm<64, false><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n);
+    else k_gemm<32, false><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n);
+    k_flow_reduce<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, st>>>(v, lp.part, lp.ksplit_n);
+    if (v.S > 0) k_levels<<<cdiv(v.S, 128), 128, 0, st>>>(v);
+    k_flip<<<1, 1, 0, st>>>(v);
+}
+
+int set_storage_smem_attr(size_t bytes)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_storage<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_storage<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return (int)e;
+}
+
+}  // namespace dopf

@@ -1,0 +1,109 @@
+"""DeviceADMM: thin array-level host object over one libdopf handle (one GPU)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .problem import Problem
+
+
+class DopfError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class DeviceADMM:
+    """Owns a `dopf_handle`.  Arrays are numpy float64, row-major, timestep contiguous."""
+
+    def __init__(self, prob: Problem, gamma=0.3, flow_weight=10.0, prox_weight=1.0, slack_mask_tol=1e-2, eps=1e-3,
+                 device=-1, hinge_capacity=0, use_graph=True):
+        self.lib = _lib.load()
+        self.prob = prob
+        p = prob
+        self._keep = p  # inputs are copied by the library; keep them only for the duration of the call
+        cp = _lib.DopfProblem(p.N, p.L, p.T, p.G, p.S,
+                              p.ptdf.ctypes.data_as(_lib._dp), p.fmax.ctypes.data_as(_lib._dp), p.demand.ctypes.data_as(_lib._dp),
+                              p.gen_mc.ctypes.data_as(_lib._dp), p.gen_pmax.ctypes.data_as(_lib._dp), p.gen_node.ctypes.data_as(_lib._ip),
+                              p.sto_mc.ctypes.data_as(_lib._dp), p.sto_pmax.ctypes.data_as(_lib._dp), p.sto_emax.ctypes.data_as(_lib._dp),
+                              p.sto_node.ctypes.data_as(_lib._ip))
+        cfg = _lib.DopfConfig()
+        self.lib.dopf_default_config(C.byref(cfg))
+        cfg.gamma, cfg.flow_weight, cfg.prox_weight = float(gamma), float(flow_weight), float(prox_weight)
+        cfg.slack_mask_tol, cfg.eps = float(slack_mask_tol), float(eps)
+        cfg.device, cfg.hinge_capacity, cfg.use_graph = int(device), int(hinge_capacity), int(bool(use_graph))
+        self.h = C.c_void_p()
+        rc = self.lib.dopf_create(C.byref(cp), C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            self.h = None
+            raise DopfError(f"dopf_create rc={rc}: {self.lib.dopf_last_error(None).decode()}")
+        self.status = _lib.DopfStatus()
+        self.lib.dopf_get_status(self.h, C.byref(self.status))
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise DopfError(f"{what} rc={rc}: {self.lib.dopf_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dopf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- stepping -------------------------------------------------------------------------
+    def step(self, iters=1):
+        self._check(self.lib.dopf_step(self.h, int(iters), C.byref(self.status)), "dopf_step")
+        return self.status
+
+    @property
+    def iteration(self):
+        return self.status.iteration
+
+    @property
+    def converged(self):
+        return bool(self.status.converged)
+
+    @property
+    def residuals(self):
+        return (self.status.res_lambda, self.status.res_mue, self.status.res_rho)
+
+    # ---- state transfer --------------------------------------------------------------------
+    def get_iterate(self, want=("P", "D", "C", "E", "injection", "flow", "avgU", "avgK"), out=None):
+        p = self.prob
+        shapes = dict(P=(p.G, p.T), D=(p.S, p.T), C=(p.S, p.T), E=(p.S, p.T), injection=(p.N, p.T),
+                      flow=(p.L, p.T), avgU=(p.L, p.T), avgK=(p.L, p.T))
+        res = out if out is not None else {}
+        for k in want:
+            if k not in res:
+                res[k] = np.empty(shapes[k])
+        args = [_ptr(res.get(k)) if k in want else None for k in ("P", "D", "C", "E", "injection", "flow", "avgU", "avgK")]
+        self._check(self.lib.dopf_get_iterate(self.h, *args), "dopf_get_iterate")
+        return res
+
+    def get_duals(self, which=0):
+        p = self.prob
+        lam = np.empty(p.T); mu = np.empty((p.L, p.T)); rho = np.empty((p.L, p.T))
+        self._check(self.lib.dopf_get_duals(self.h, int(which), _ptr(lam), _ptr(mu), _ptr(rho)), "dopf_get_duals")
+        return lam, mu, rho
+
+    def set_state(self, iteration, P=None, D=None, C_=None, avgU=None, avgK=None, lam=None, mu=None, rho=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (P, D, C_, avgU, avgK, lam, mu, rho)]
+        self._check(self.lib.dopf_set_state(self.h, int(iteration), *[_ptr(a) for a in arrs]), "dopf_set_state")
+        self.lib.dopf_get_status(self.h, C.byref(self.status))
+
+    def nodal_price(self, which=1):
+        out = np.empty((self.prob.N, self.prob.T))
+        self._check(self.lib.dopf_get_nodal_price(self.h, int(which), _ptr(out)), "dopf_get_nodal_price")
+        return out
+
+    def total_costs(self):
+        v = C.c_double()
+        self._check(self.lib.dopf_get_total_costs(self.h, C.byref(v)), "dopf_get_total_costs")
+        return v.value

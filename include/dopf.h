@@ -1,0 +1,122 @@
+/*
+ * libdopf - C ABI of the B200-native ADMM iteration for DecentralOPF.jl.
+ *
+ * The reference has no FFI seam; the seam cut here is its Julia call surface for the hot path
+ * (all citations relative to /root/reference/):
+ *
+ *   dopf_create        <- ADMM(gamma, nodes, generators, storages, lines)   src/structures/admm.jl:23-62
+ *   dopf_step          <- run!(admm) / calculate_iteration!(admm)           src/optimization/run.jl:1-16
+ *                         = optimize_all_subproblems!  src/optimization/subproblems.jl:1-17
+ *                         + update_duals!              src/optimization/update_duals.jl:1-39
+ *                         + check_convergence!         src/optimization/convergence.jl:1-31
+ *   dopf_get_iterate   <- admm.results[end].{unit_to_result[u].generation|discharge|charge|level,
+ *                         injection, line_utilization, avg_U, avg_K}        src/structures/results.jl:36-48
+ *   dopf_get_duals     <- admm.lambdas[k], admm.mues[k], admm.rhos[k]       src/structures/admm.jl:4-6
+ *   dopf_get_status    <- admm.iteration, admm.convergence.{lambda,mue,rho,all} src/structures/convergence.jl
+ *   dopf_set_state     <- (no reference counterpart) resume / inject a mid-trace state
+ *   dopf_get_nodal_price <- get_nodal_price(iteration)                      src/helpers/network_elements.jl:16-25
+ *   dopf_get_total_costs <- result.total_costs                              src/structures/results.jl:95-105
+ *
+ * Conventions: every matrix is row-major with the timestep index contiguous ([agent][t],
+ * [node][t], [line][t]; ptdf is [line][node]).  Julia callers pass permutedims(...) of their
+ * column-major matrices.  Node indices are 0-based.  The library copies
+ * all inputs; callers keep ownership of their buffers.  A handle is not thread-safe.  No
+ * function throws or aborts: 0 = ok, < 0 = error, text from dopf_last_error().
+ * There is no CPU fallback: without a CUDA device dopf_create fails with DOPF_E_CUDA.
+ */
+#ifndef DOPF_H
+#define DOPF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DOPF_OK 0
+#define DOPF_E_ARG (-1)       /* invalid argument / dimension                         */
+#define DOPF_E_CUDA (-2)      /* CUDA runtime error (incl. "no device")               */
+#define DOPF_E_CAPACITY (-3)  /* a device work list / hinge list capacity was exceeded */
+#define DOPF_E_COMM (-4)      /* NCCL error                                            */
+#define DOPF_E_UNSUPPORTED (-5)
+
+typedef struct dopf_handle dopf_handle;
+
+typedef struct dopf_problem {
+    int32_t N, L, T, G, S;      /* nodes, lines, timesteps, generators, storages          */
+    const double *ptdf;         /* [L][N]  admm.ptdf (helpers/ptdf.jl)                    */
+    const double *f_max;        /* [L]     line.max_capacity (admm.jl:41)                 */
+    const double *demand;       /* [N][T]  node.demand                                    */
+    const double *gen_mc;       /* [G]     generator.marginal_costs                       */
+    const double *gen_pmax;     /* [G]     generator.max_generation                       */
+    const int32_t *gen_node;    /* [G]     0-based index of generator.node                */
+    const double *sto_mc;       /* [S]     storage.marginal_costs                         */
+    const double *sto_pmax;     /* [S]     storage.max_power                              */
+    const double *sto_emax;     /* [S]     storage.max_level                              */
+    const int32_t *sto_node;    /* [S]                                                    */
+} dopf_problem;
+
+typedef struct dopf_config {
+    double gamma;            /* admm.gamma (opf_admm_decentral.jl:5 uses 0.3)               */
+    double flow_weight;      /* the literal 10  (subproblems.jl:77-78,176-177)             */
+    double prox_weight;      /* 1.0 <=> the literal 1/2*(x-prev)^2 (subproblems.jl:81,180) */
+    double slack_mask_tol;   /* 1e-2 (update_duals.jl:24,36)                               */
+    double eps;              /* 10^-3 (convergence.jl:2)                                   */
+    int32_t device;          /* CUDA device ordinal, -1 = current device                   */
+    int32_t hinge_capacity;  /* per (agent,t) hinge list capacity of the correction pass; 0 = default 32 */
+    int32_t use_graph;       /* 1 = replay one captured CUDA graph per iteration           */
+    int32_t reserved;
+} dopf_config;
+
+/* fills the reference's literals: gamma 0.3, flow_weight 10, prox 1, mask 1e-2, eps 1e-3 */
+void dopf_default_config(dopf_config *c);
+
+typedef struct dopf_status {
+    int32_t iteration;       /* admm.iteration (1-based; not advanced by the converging iteration) */
+    int32_t converged;       /* admm.convergence.all                                        */
+    int32_t conv_lambda, conv_mue, conv_rho;
+    int32_t iterations_done; /* iterations executed since create / set_state                */
+    double res_lambda, res_mue, res_rho;   /* max |dual_{k+1} - dual_k| of the last iteration */
+    /* statistics of the exact-correction pass */
+    int32_t gen_corrected, sto_corrected;  /* cumulated agents re-solved with explicit hinges */
+    int32_t tight_rows, wide_rows;         /* candidate (line,t,side) rows of the last iteration */
+    int32_t launches_per_iteration;        /* kernels enqueued per iteration                  */
+    int32_t reserved;
+} dopf_status;
+
+int dopf_create(const dopf_problem *p, const dopf_config *c, dopf_handle **out);
+void dopf_destroy(dopf_handle *h);
+
+/* runs up to max_iters iterations, stops early when converged; synchronises before returning */
+int dopf_step(dopf_handle *h, int32_t max_iters, dopf_status *out);
+int dopf_get_status(dopf_handle *h, dopf_status *out);
+
+/* newest iterate; any pointer may be NULL (skipped).  Agent order = the order given at create. */
+int dopf_get_iterate(dopf_handle *h, double *P /*[G][T]*/, double *D, double *C, double *E /*[S][T]*/,
+                     double *injection /*[N][T]*/, double *flow /*[L][T]*/,
+                     double *avgU /*[L][T]*/, double *avgK /*[L][T]*/);
+/* which = 0: newest duals (admm.lambdas[end]); 1: the duals used by the last iteration */
+int dopf_get_duals(dopf_handle *h, int32_t which, double *lam /*[T]*/, double *mu /*[L][T]*/, double *rho /*[L][T]*/);
+
+/* overwrite the state: iteration counter, previous iterate P,D,C, average slacks and duals.
+ * injection, flows and levels are re-derived on the device.  NULL = keep. */
+int dopf_set_state(dopf_handle *h, int32_t iteration, const double *P, const double *D, const double *C,
+                   const double *avgU, const double *avgK, const double *lam, const double *mu, const double *rho);
+
+int dopf_get_nodal_price(dopf_handle *h, int32_t which, double *out /*[N][T]*/);
+int dopf_get_total_costs(dopf_handle *h, double *out);
+
+/* multi-GPU (one process per GPU): agents are partitioned over ranks, the network part is
+ * replicated.  `nccl_unique_id` = the 128 bytes of an ncclUniqueId created by rank 0
+ * (dopf_comm_unique_id) and distributed by the caller.  demand must be passed on every rank;
+ * only rank 0's demand enters the injection.  Call before the first dopf_step. */
+int dopf_comm_unique_id(void *out128);
+int dopf_comm_init(dopf_handle *h, int32_t rank, int32_t nranks, const void *nccl_unique_id, int32_t total_agents);
+
+const char *dopf_last_error(dopf_handle *h);   /* handle may be NULL: error of the last failed dopf_create */
+const char *dopf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

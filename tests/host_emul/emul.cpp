@@ -38,3 +38,236 @@ double emul_gen_root(double c, double a, int n, const double *hbp, const double 
     return root_monotone_pl(c, a, l, lo, hi);
 }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Sequential emulation of the whole iteration pipeline (mirror of enqueue_iteration in
+// dopf_kernels.cu) on host arrays with the device layout.
+// ------------------------------------------------------------------------------------------------
+#include "../../decentralopf.jl_b200/csrc/dopf_bodies.h"
+#include <algorithm>
+#include <numeric>
+#include <cmath>
+
+struct Emul {
+    View v;
+    std::vector<std::vector<double>> d;   // owned double arrays
+    std::vector<std::vector<int>> iv;
+    std::vector<unsigned long long> dn, dmax;
+    std::vector<unsigned char> flags, tflag;
+    Ctrl ctrl;
+    std::vector<Hinge> scratch;
+    std::vector<int> hcnt;
+    double *mk(size_t n) { d.emplace_back(n ? n : 1, 0.0); return d.back().data(); }
+    int *mki(size_t n) { iv.emplace_back(n ? n : 1, 0); return iv.back().data(); }
+};
+
+static int rup(int a, int b) { return (a + b - 1) / b * b; }
+
+extern "C" {
+
+// agents must already be sorted by node
+void *emul_create(int N, int L, int T, int G, int S, const double *ptdf, const double *fmax, const double *demand,
+                  const double *gmc, const double *gpm, const int *gnode,
+                  const double *smc, const double *spm, const double *sem, const int *snode,
+                  double gamma, double w, double prox, double mask_tol, double eps, int hcap)
+{
+    Emul *e = new Emul();
+    View &v = e->v;
+    memset(&v, 0, sizeof v);
+    v.N = N; v.L = L; v.T = T; v.G = G; v.S = S; v.A = G + S;
+    v.ldt = rup(T, 32); v.Np = rup(N, 64); v.Lp = rup(L, 64); v.hcap = hcap; v.gen_work_cap = std::max(1, G * T);
+    v.c = Coef::make(gamma, w, prox, mask_tol, eps);
+    v.demand_on = 1;
+    const int ldt = v.ldt, Np = v.Np, Lp = v.Lp;
+    double *P = e->mk((size_t)Lp * Np), *f = e->mk(Lp), *dm = e->mk((size_t)Np * ldt), *q = e->mk(Np), *prow = e->mk(Lp), *mw = e->mk(Lp), *na = e->mk(Np);
+    std::vector<double> rbox(Np, 0.0);
+    for (int i = 0; i < G; ++i) { na[gnode[i]] += 1; rbox[gnode[i]] = std::max(rbox[gnode[i]], gpm[i]); }
+    for (int i = 0; i < S; ++i) { na[snode[i]] += 1; rbox[snode[i]] = std::max(rbox[snode[i]], 2 * spm[i]); }
+    for (int l = 0; l < L; ++l) {
+        f[l] = fmax[l];
+        for (int n = 0; n < N; ++n) {
+            double a = ptdf[(size_t)l * N + n];
+            P[(size_t)l * Np + n] = a; q[n] += a * a; prow[l] = std::max(prow[l], std::fabs(a)); mw[l] = std::max(mw[l], std::fabs(a) * rbox[n]);
+        }
+    }
+    for (int n = 0; n < N; ++n) for (int t = 0; t < T; ++t) dm[(size_t)n * ldt + t] = demand[(size_t)n * T + t];
+    v.ptdf = P; v.fmax = f; v.demand = dm; v.q = q; v.prow = prow; v.mwide = mw; v.nagents = na;
+    double *a;
+    int *ip;
+    a = e->mk(G); std::copy(gmc, gmc + G, a); v.gen_mc = a;
+    a = e->mk(G); std::copy(gpm, gpm + G, a); v.gen_pmax = a;
+    ip = e->mki(G); std::copy(gnode, gnode + G, ip); v.gen_node = ip;
+    ip = e->mki(N + 1); for (int i = 0; i < G; ++i) ip[gnode[i] + 1]++; for (int n = 0; n < N; ++n) ip[n + 1] += ip[n]; v.gen_ptr = ip;
+    a = e->mk(S); std::copy(smc, smc + S, a); v.sto_mc = a;
+    a = e->mk(S); std::copy(spm, spm + S, a); v.sto_pmax = a;
+    a = e->mk(S); std::copy(sem, sem + S, a); v.sto_emax = a;
+    ip = e->mki(S); std::copy(snode, snode + S, ip); v.sto_node = ip;
+    ip = e->mki(N + 1); for (int i = 0; i < S; ++i) ip[snode[i] + 1]++; for (int n = 0; n < N; ++n) ip[n + 1] += ip[n]; v.sto_ptr = ip;
+    for (int k = 0; k < 2; ++k) {
+        v.P[k] = e->mk((size_t)G * T); v.D[k] = e->mk((size_t)S * T); v.C[k] = e->mk((size_t)S * T);
+        v.inj[k] = e->mk((size_t)Np * ldt); v.injloc[k] = v.inj[k]; v.ssum[k] = e->mk(ldt); v.flow[k] = e->mk((size_t)Lp * ldt);
+        v.lam[k] = e->mk(ldt); v.mu[k] = e->mk((size_t)Lp * ldt); v.rho[k] = e->mk((size_t)Lp * ldt);
+    }
+    v.E = e->mk((size_t)S * T); v.avgU = e->mk((size_t)Lp * ldt); v.avgK = e->mk((size_t)Lp * ldt);
+    v.bplus = e->mk((size_t)Lp * ldt); v.bminus = e->mk((size_t)Lp * ldt); v.M = e->mk((size_t)Lp * ldt); v.Wt = e->mk((size_t)Lp * ldt);
+    v.g0 = e->mk((size_t)Np * ldt); v.s1 = e->mk((size_t)Np * ldt);
+    e->dn.assign((size_t)Np * ldt, 0); e->dmax.assign(ldt, 0); v.dn = e->dn.data(); v.dmax = e->dmax.data();
+    e->flags.assign((size_t)ldt * Lp, 0); v.flags = e->flags.data(); e->tflag.assign((size_t)Lp * ldt, 0);
+    v.wide = e->mki((size_t)T * 2 * L); v.wcnt = e->mki(T); v.tight = e->mki((size_t)T * 2 * L); v.tcnt = e->mki(T);
+    v.gen_work = e->mki(v.gen_work_cap); v.sto_work = e->mki(S); v.sto_flag = e->mki(S);
+    v.rowsumU = e->mk((size_t)Lp * ldt); v.rowsumK = e->mk((size_t)Lp * ldt);
+    memset(&e->ctrl, 0, sizeof e->ctrl); e->ctrl.iteration = 1; v.ctrl = &e->ctrl;
+    e->scratch.resize((size_t)T * hcap); e->hcnt.resize(T);
+    // initial state: inj = -demand (cur buffer), flows
+    const int cur = 0;
+    for (int n = 0; n < Np; ++n) for (int t = 0; t < ldt; ++t) v.inj[cur][(size_t)n * ldt + t] = -dm[(size_t)n * ldt + t];
+    for (int t = 0; t < ldt; ++t) { double s = 0; for (int n = 0; n < Np; ++n) s += v.inj[cur][(size_t)n * ldt + t]; v.ssum[cur][t] = s; }
+    for (int l = 0; l < Lp; ++l) for (int t = 0; t < ldt; ++t) { double s = 0; for (int n = 0; n < Np; ++n) s += P[(size_t)l * Np + n] * v.inj[cur][(size_t)n * ldt + t]; v.flow[cur][(size_t)l * ldt + t] = s; }
+    return e;
+}
+
+void emul_destroy(void *h) { delete (Emul *)h; }
+
+static void compact(Emul *e, int mode)
+{
+    View &v = e->v;
+    for (int t = 0; t < v.T; ++t) {
+        int cnt = 0;
+        if (mode == 0) {
+            for (int l = 0; l < v.L; ++l) for (int side = 0; side < 2; ++side)
+                if ((v.flags[(size_t)t * v.Lp + l] >> side) & 1) v.wide[(size_t)t * 2 * v.L + cnt++] = l * 2 + side;
+            v.wcnt[t] = cnt;
+        } else {
+            const double dm = bits_nonneg(v.dmax[t]);
+            for (int j = 0; j < v.wcnt[t]; ++j) {
+                int en = v.wide[(size_t)t * 2 * v.L + j]; int l = en >> 1;
+                double b = (en & 1) ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t];
+                if (std::fabs(b) <= v.prow[l] * dm) v.tight[(size_t)t * 2 * v.L + cnt++] = en;
+            }
+            v.tcnt[t] = cnt;
+        }
+    }
+}
+
+static void storage_pass(Emul *e, bool fix)
+{
+    View &v = e->v;
+    const int cur = v.ctrl->cur, nxt = 1 - cur, T = v.T;
+    std::vector<StoStep> step(T);
+    std::vector<double> eta(T);
+    const int total = fix ? v.ctrl->sto_work_cnt : v.S;
+    for (int w = 0; w < total; ++w) {
+        const int s = fix ? v.sto_work[w] : w, n = v.sto_node[s];
+        StoProblem p; p.T = T; p.k.mc = v.sto_mc[s]; p.k.pmax = v.sto_pmax[s]; p.k.emax = v.sto_emax[s]; p.k.prox = v.c.prox;
+        p.step = step.data(); p.hinges = fix ? e->scratch.data() : nullptr; p.hcnt = e->hcnt.data(); p.hcap = v.hcap;
+        for (int t = 0; t < T; ++t) { step[t].Db = v.D[cur][(size_t)s * T + t]; step[t].Cb = v.C[cur][(size_t)s * T + t]; step[t].g0 = v.g0[(size_t)n * v.ldt + t]; step[t].s1 = v.s1[(size_t)n * v.ldt + t]; }
+        if (fix) {
+            const double range = 2.0 * p.k.pmax;
+            for (int t = 0; t < T; ++t) {
+                int cnt = 0;
+                for (int j = 0; j < v.wcnt[t]; ++j) {
+                    int en = v.wide[(size_t)t * 2 * v.L + j]; int l = en >> 1, side = en & 1; Hinge h;
+                    if (make_hinge(v.c, v.ptdf[(size_t)l * v.Np + n], side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t], side, h) && std::fabs(h.bp) < range) {
+                        if (cnt < v.hcap) e->scratch[(size_t)t * v.hcap + cnt] = h;
+                        cnt++;
+                    }
+                }
+                if (cnt > v.hcap) { v.ctrl->error = DOPF_ERR_HINGE_CAP; cnt = v.hcap; }
+                e->hcnt[t] = cnt;
+            }
+        }
+        StoSolver<1> solver(p);
+        solver.solve(eta.data());
+        double E = 0.0;
+        for (int t = 0; t < T; ++t) {
+            StoEval ev = sto_eval(step[t], p.k, p.list(t), eta[t]);
+            const size_t o = (size_t)s * T + t;
+            E += ev.C - ev.D;
+            v.D[nxt][o] = ev.D; v.C[nxt][o] = ev.C; v.E[o] = E;
+            note_move(v, n, t, (ev.D - step[t].Db) - (ev.C - step[t].Cb));
+        }
+        if (fix) v.ctrl->stat_sto_fix++;
+    }
+}
+
+void emul_iterate(void *h)
+{
+    Emul *e = (Emul *)h;
+    View &v = e->v;
+    if (v.ctrl->converged || v.ctrl->error) return;
+    const int cur = v.ctrl->cur, nxt = 1 - cur, ldt = v.ldt, Np = v.Np, Lp = v.Lp, T = v.T;
+    v.ctrl->gen_work_cnt = v.ctrl->sto_work_cnt = 0;
+    v.ctrl->res_bits[0] = v.ctrl->res_bits[1] = v.ctrl->res_bits[2] = 0;
+    std::fill(e->dn.begin(), e->dn.end(), 0ull); std::fill(e->dmax.begin(), e->dmax.end(), 0ull);
+    for (int s = 0; s < v.S; ++s) v.sto_flag[s] = 0;
+    for (int l = 0; l < Lp; ++l) for (int t = 0; t < ldt; ++t) body_row_prep(v, l, t);
+    compact(e, 0);
+    for (int n = 0; n < Np; ++n) for (int t = 0; t < ldt; ++t) {
+        double a = 0, b = 0;
+        for (int l = 0; l < Lp; ++l) { double p = v.ptdf[(size_t)l * Np + n]; a += p * v.M[(size_t)l * ldt + t]; b += p * p * v.Wt[(size_t)l * ldt + t]; }
+        v.g0[(size_t)n * ldt + t] = v.lam[cur][t] + v.c.gamma * v.ssum[cur][t] + a;
+        v.s1[(size_t)n * ldt + t] = v.c.gamma + 2.0 * v.c.kappa * v.q[n] + b;
+    }
+    for (int g = 0; g < v.G; ++g) for (int t = 0; t < T; ++t) {
+        const double pp = v.P[cur][(size_t)g * T + t];
+        const double pn = body_gen_predict(v, g, t, pp, v.gen_node[g], v.gen_mc[g], v.gen_pmax[g]);
+        v.P[nxt][(size_t)g * T + t] = pn;
+        note_move(v, v.gen_node[g], t, pn - pp);
+    }
+    storage_pass(e, false);
+    compact(e, 1);
+    for (int n = 0; n < v.N; ++n) for (int t = 0; t < T; ++t) body_verify(v, n, t);
+    for (int w = 0; w < v.ctrl->gen_work_cnt; ++w) {
+        const int g = v.gen_work[w] / T, t = v.gen_work[w] % T, n = v.gen_node[g];
+        const double Pb = v.P[cur][(size_t)g * T + t], pmax = v.gen_pmax[g], lo = -Pb, hi = pmax - Pb;
+        std::vector<Hinge> lst;
+        for (int j = 0; j < v.wcnt[t]; ++j) {
+            int en = v.wide[(size_t)t * 2 * v.L + j]; int l = en >> 1, side = en & 1; Hinge hh;
+            if (make_hinge(v.c, v.ptdf[(size_t)l * Np + n], side ? v.bminus[(size_t)l * ldt + t] : v.bplus[(size_t)l * ldt + t], side, hh) && hh.bp > lo && hh.bp < hi) lst.push_back(hh);
+        }
+        HingeList hl; hl.h = lst.data(); hl.n = (int)lst.size();
+        const size_t nt = (size_t)n * ldt + t;
+        double dd = root_monotone_pl(v.gen_mc[g] + v.g0[nt], v.c.prox + v.s1[nt], hl, lo, hi);
+        double Pn = Pb + dd; Pn = Pn < 0 ? 0 : (Pn > pmax ? pmax : Pn);
+        v.P[nxt][(size_t)g * T + t] = Pn;
+        note_move(v, n, t, Pn - Pb);
+        v.ctrl->stat_gen_fix++;
+    }
+    storage_pass(e, true);
+    compact(e, 1);
+    for (int n = 0; n < Np; ++n) for (int t = 0; t < ldt; ++t) body_inject(v, n, t);
+    for (int t = 0; t < ldt; ++t) { double s = 0; for (int n = 0; n < Np; ++n) s += v.inj[nxt][(size_t)n * ldt + t]; v.ssum[nxt][t] = s; }
+    for (int l = 0; l < Lp; ++l) for (int t = 0; t < ldt; ++t) { double s = 0; for (int n = 0; n < Np; ++n) s += v.ptdf[(size_t)l * Np + n] * v.inj[nxt][(size_t)n * ldt + t]; v.flow[nxt][(size_t)l * ldt + t] = s; }
+    std::fill(e->tflag.begin(), e->tflag.end(), 0);
+    for (int t = 0; t < T; ++t) for (int j = 0; j < v.tcnt[t]; ++j) {
+        int en = v.tight[(size_t)t * 2 * v.L + j]; int l = en >> 1, side = en & 1;
+        double a = 0; for (int n = 0; n < v.N; ++n) a += body_slack_row_node(v, l, side, n, t);
+        (side ? v.rowsumK : v.rowsumU)[(size_t)l * ldt + t] = a;
+        e->tflag[(size_t)l * ldt + t] |= (1 << side);
+    }
+    double rm = 0, rr = 0, rl = 0;
+    for (int l = 0; l < v.L; ++l) for (int t = 0; t < T; ++t) { double a, b; body_dual(v, l, t, e->tflag[(size_t)l * ldt + t], a, b); rm = std::max(rm, a); rr = std::max(rr, b); }
+    for (int t = 0; t < T; ++t) rl = std::max(rl, body_lambda(v, t));
+    v.ctrl->res_bits[0] = nonneg_bits(rl); v.ctrl->res_bits[1] = nonneg_bits(rm); v.ctrl->res_bits[2] = nonneg_bits(rr);
+    int tr = 0, wr = 0; for (int t = 0; t < T; ++t) { tr += v.tcnt[t]; wr += v.wcnt[t]; }
+    v.ctrl->stat_tight_rows = tr; v.ctrl->stat_wide_rows = wr;
+    body_finish(v);
+}
+
+// newest iterate; matrices dense [rows][T]
+void emul_get(void *h, double *P, double *D, double *C, double *E, double *inj, double *flow, double *avgU, double *avgK,
+              double *lam, double *mu, double *rho, int *status /*iteration, converged, gen_fix, sto_fix, tight, wide, error*/)
+{
+    Emul *e = (Emul *)h; View &v = e->v; const int k = v.ctrl->cur, T = v.T, ldt = v.ldt;
+    std::copy(v.P[k], v.P[k] + (size_t)v.G * T, P);
+    std::copy(v.D[k], v.D[k] + (size_t)v.S * T, D); std::copy(v.C[k], v.C[k] + (size_t)v.S * T, C); std::copy(v.E, v.E + (size_t)v.S * T, E);
+    for (int n = 0; n < v.N; ++n) for (int t = 0; t < T; ++t) inj[(size_t)n * T + t] = v.inj[k][(size_t)n * ldt + t];
+    for (int l = 0; l < v.L; ++l) for (int t = 0; t < T; ++t) {
+        size_t o = (size_t)l * T + t, i = (size_t)l * ldt + t;
+        flow[o] = v.flow[k][i]; avgU[o] = v.avgU[i]; avgK[o] = v.avgK[i]; mu[o] = v.mu[k][i]; rho[o] = v.rho[k][i];
+    }
+    for (int t = 0; t < T; ++t) lam[t] = v.lam[k][t];
+    status[0] = v.ctrl->iteration; status[1] = v.ctrl->converged; status[2] = v.ctrl->stat_gen_fix; status[3] = v.ctrl->stat_sto_fix;
+    status[4] = v.ctrl->stat_tight_rows; status[5] = v.ctrl->stat_wide_rows; status[6] = v.ctrl->error;
+}
+}
