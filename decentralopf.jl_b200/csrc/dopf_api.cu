@@ -256,6 +256,11 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
 
     int rc;
 #define UP(dst, vec) if ((rc = upload(h, &dst, vec))) return rc
+    {
+        std::vector<double> ptdfT((size_t)Np * Lp, 0.0);
+        for (int l = 0; l < L; ++l) for (int n = 0; n < N; ++n) ptdfT[(size_t)n * Lp + l] = ptdf[(size_t)l * Np + n];
+        UP(v.ptdfT, ptdfT);
+    }
     UP(v.ptdf, ptdf); UP(v.fmax, fmax); UP(v.demand, demand); UP(v.q, q); UP(v.prow, prow); UP(v.mwide, mwide); UP(v.nagents, nag);
     UP(v.gen_mc, gmc); UP(v.gen_pmax, gpm); UP(v.gen_node, gnode); UP(v.gen_ptr, gptr);
     UP(v.sto_mc, smc); UP(v.sto_pmax, spm); UP(v.sto_emax, sem); UP(v.sto_node, snode); UP(v.sto_ptr, sptr);
@@ -267,7 +272,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
         AL(v.lam[k], ldt); AL(v.mu[k], (size_t)Lp * ldt); AL(v.rho[k], (size_t)Lp * ldt);
         v.injloc[k] = v.inj[k];
     }
-    AL(v.E, (size_t)S * T); AL(v.avgU, (size_t)Lp * ldt); AL(v.avgK, (size_t)Lp * ldt);
+    AL(v.E, (size_t)S * T); AL(v.eta, (size_t)S * T); AL(v.cold_work, S); AL(v.wide_b, (size_t)T * 2 * L); AL(v.avgU, (size_t)Lp * ldt); AL(v.avgK, (size_t)Lp * ldt);
     AL(v.bplus, (size_t)Lp * ldt); AL(v.bminus, (size_t)Lp * ldt); AL(v.M, (size_t)Lp * ldt); AL(v.Wt, (size_t)Lp * ldt);
     AL(v.g0, (size_t)Np * ldt); AL(v.s1, (size_t)Np * ldt);
     AL(v.dn, (size_t)Np * ldt); AL(v.dmax, ldt);
@@ -294,19 +299,10 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     AL(lp.part, (size_t)std::max(lp.ksplit_t * Np, lp.ksplit_n * Lp) * ldt);
     AL(lp.part2, (size_t)lp.ksplit_t * Np * ldt);
     {
-        const size_t per_warp = storage_smem_bytes(T, 1);
-        const size_t limit = std::min<size_t>(prop.sharedMemPerBlockOptin, 200 * 1024);
-        if (per_warp > limit) { h->err = "T too large: the storage horizon does not fit in shared memory in this build"; return DOPF_E_UNSUPPORTED; }
-        lp.sto_warps = (int)std::max<size_t>(1, std::min<size_t>(4, limit / per_warp));
-        const size_t bytes = storage_smem_bytes(T, lp.sto_warps);
-        if (bytes > 48 * 1024) {
-            if (set_storage_smem_attr(bytes) != 0) { h->err = "cudaFuncSetAttribute(shared memory) failed"; return DOPF_E_CUDA; }
-        }
-        lp.sto_blocks = lp.num_sms * 16;
-        lp.sto_fix_blocks = std::max(1, std::min(lp.num_sms * 2, (S + lp.sto_warps - 1) / std::max(lp.sto_warps, 1)));
-        size_t hs = (size_t)lp.sto_fix_blocks * lp.sto_warps * T * v.hcap;
-        if (S == 0) hs = 1;
-        AL(lp.hinge_scratch, hs);
+        lp.sto_fix_blocks = std::max(1, std::min(lp.num_sms * 4, (S + 3) / 4));
+        const size_t warps = (size_t)lp.sto_fix_blocks * 4;
+        AL(lp.hinge_scratch, S ? warps * T * v.hcap : 1);
+        AL(lp.hcnt_scratch, S ? warps * T : 1);
     }
     lp.slack_blocks_x = std::max(1, std::min(64, (4 * lp.num_sms + T - 1) / T));
 

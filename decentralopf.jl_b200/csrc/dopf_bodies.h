@@ -36,7 +36,8 @@ struct Ctrl {
     int conv_lambda, conv_mue, conv_rho;
     int error;          // DOPF_ERR_*; set => every later kernel is a no-op, state stays valid
     int iters_done;     // iterations executed since create
-    int gen_work_cnt, sto_work_cnt;
+    int gen_work_cnt, sto_work_cnt, cold_work_cnt;
+    int stat_sto_cold;                   // storages solved by the cold funnel in the last iteration
     int stat_gen_fix, stat_sto_fix;      // cumulated corrected agents (statistics)
     int stat_tight_rows, stat_wide_rows; // of the last iteration
     unsigned long long res_bits[3];      // max |dual_{k+1}-dual_k| for lambda, mue, rho (bits)
@@ -66,6 +67,7 @@ struct View {
     double *P[2];           // [G][T]
     double *D[2], *C[2];    // [S][T]
     double *E;              // [S][T] level of the newest iterate
+    double *eta;            // [S][T] level-multiplier path of the last storage solve (warm start)
     double *inj[2];         // [Np][ldt]  nodal injection (all ranks' agents)
     double *injloc[2];      // [Np][ldt]  contribution of this rank's agents (== inj on one GPU)
     int demand_on;          // 1: this rank subtracts the demand (rank 0)
@@ -81,6 +83,9 @@ struct View {
     unsigned long long *dmax;          // [ldt]
     unsigned char *flags;              // [ldt][Lp] bit0: U side wide candidate, bit1: K side
     int *wide, *wcnt;                  // [T][2L] entries l*2+side ; [T]
+    double *wide_b;                    // [T][2L] b of the wide entries (coalesced companion)
+    const double *ptdfT;               // [Np][Lp] transposed PTDF (node-major) for per-agent hinge collection
+    int *cold_work;                    // [S] storages whose warm start did not verify
     int *tight, *tcnt;                 // [T][2L] ; [T]
     int *gen_work;                     // [gen_work_cap] g*T+t
     int *sto_work, *sto_flag;          // [S], [S]
@@ -127,6 +132,76 @@ DOPF_HD void note_move(const View &v, int n, int t, double delta)
     unsigned long long *pn = v.dn + (size_t)n * v.ldt + t;
     if (b > *pn) DOPF_ATOMIC_MAX_U64(pn, b);
     if (b > v.dmax[t]) DOPF_ATOMIC_MAX_U64(v.dmax + t, b);
+}
+
+// ---- storages: accessors over the device layout ------------------------------------------------
+struct GlobalSteps {     // previous iterate and anchor linearisation of one storage, read in place
+    const double *Db, *Cb, *g0, *s1;
+    const Hinge *hinges; const int *hcnt; int hcap;
+    DOPF_HD StoStep step(int t) const { StoStep st; st.Db = Db[t]; st.Cb = Cb[t]; st.g0 = g0[t]; st.s1 = s1[t]; return st; }
+    DOPF_HD HingeList list(int t) const
+    {
+        HingeList l;
+        l.h = hinges ? hinges + (size_t)t * hcap : nullptr;
+        l.n = hinges ? hcnt[t] : 0;
+        return l;
+    }
+};
+
+struct StoEmit {         // writes D, C, E, eta of the new iterate and records the move
+    const View &v; const GlobalSteps &sp; StoConst k; int s, n; double E;
+    DOPF_HD StoEmit(const View &vv, const GlobalSteps &ss, const StoConst &kk, int s_, int n_) : v(vv), sp(ss), k(kk), s(s_), n(n_), E(0.0) {}
+    DOPF_HD void operator()(int t, double eta)
+    {
+        if (t == 0) E = 0.0;
+        const int nxt = 1 - v.ctrl->cur;
+        const StoStep st = sp.step(t);
+        const StoEval e = sto_eval(st, k, sp.list(t), eta);
+        E += e.C - e.D;
+        const size_t o = (size_t)s * v.T + t;
+        sel(v.D, nxt)[o] = e.D; sel(v.C, nxt)[o] = e.C; v.E[o] = E; v.eta[o] = eta;
+    }
+};
+
+DOPF_HD void sto_setup(const View &v, int s, StoConst &k, GlobalSteps &sp)
+{
+    const int cur = v.ctrl->cur, n = v.sto_node[s];
+    k.mc = v.sto_mc[s]; k.pmax = v.sto_pmax[s]; k.emax = v.sto_emax[s]; k.prox = v.c.prox; k.iprox = 1.0 / v.c.prox;
+    sp.Db = sel(v.D, cur) + (size_t)s * v.T; sp.Cb = sel(v.C, cur) + (size_t)s * v.T;
+    sp.g0 = v.g0 + (size_t)n * v.ldt; sp.s1 = v.s1 + (size_t)n * v.ldt;
+    sp.hinges = nullptr; sp.hcnt = nullptr; sp.hcap = 0;
+}
+
+// record the moves of a finished storage (after its final emit pass)
+DOPF_HD void sto_note_moves(const View &v, int s)
+{
+    const int cur = v.ctrl->cur, nxt = 1 - cur, n = v.sto_node[s];
+    for (int t = 0; t < v.T; ++t) {
+        const size_t o = (size_t)s * v.T + t;
+        note_move(v, n, t, (sel(v.D, nxt)[o] - sel(v.D, cur)[o]) - (sel(v.C, nxt)[o] - sel(v.C, cur)[o]));
+    }
+}
+
+// warm attempt for storage s; on failure the storage is queued for the cold funnel
+DOPF_HD void body_sto_warm(const View &v, int s)
+{
+    StoConst k; GlobalSteps sp;
+    sto_setup(v, s, k, sp);
+    StoEmit emit(v, sp, k, s, v.sto_node[s]);
+    const double *ep = v.eta + (size_t)s * v.T;
+    auto prev = [ep](int t) { return ep[t]; };
+    if (sto_warm_try(sp, k, v.T, prev, emit)) sto_note_moves(v, s);
+    else v.cold_work[DOPF_ATOMIC_ADD_I32(&v.ctrl->cold_work_cnt, 1)] = s;
+}
+
+DOPF_HD void body_sto_cold(const View &v, int s, const Hinge *hinges, const int *hcnt)
+{
+    StoConst k; GlobalSteps sp;
+    sto_setup(v, s, k, sp);
+    sp.hinges = hinges; sp.hcnt = hcnt; sp.hcap = v.hcap;
+    StoEmit emit(v, sp, k, s, v.sto_node[s]);
+    sto_funnel_seq(sp, k, v.T, emit);
+    sto_note_moves(v, s);
 }
 
 // ---- verify: which agents at (n,t) moved across a slack hinge? --------------------------------

@@ -19,7 +19,7 @@ __global__ void k_begin(View v)
     if (!DOPF_ACTIVE(v)) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
-        v.ctrl->gen_work_cnt = 0; v.ctrl->sto_work_cnt = 0;
+        v.ctrl->gen_work_cnt = 0; v.ctrl->sto_work_cnt = 0; v.ctrl->cold_work_cnt = 0;
         v.ctrl->res_bits[0] = v.ctrl->res_bits[1] = v.ctrl->res_bits[2] = 0ull;
     }
     for (int k = i; k < v.Np * v.ldt; k += gridDim.x * blockDim.x) v.dn[k] = 0ull;
@@ -58,7 +58,11 @@ __global__ void k_compact(View v, int mode)
             for (int side = 0; side < 2; ++side) {
                 const bool p = (f >> side) & 1;
                 const unsigned m = __ballot_sync(0xffffffffu, p);
-                if (p) out[cnt + __popc(m & ((1u << lane) - 1))] = l * 2 + side;
+                if (p) {
+                    const int pos = cnt + __popc(m & ((1u << lane) - 1));
+                    out[pos] = l * 2 + side;
+                    v.wide_b[(size_t)t * 2 * v.L + pos] = side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t];
+                }
                 cnt += __popc(m);
             }
         }
@@ -260,89 +264,83 @@ __global__ void __launch_bounds__(256) k_gen_predict(View v)
 }
 
 // ------------------------------------------------------------------------------------------------
-// storages: one warp per storage, horizon staged in shared memory.
-//  FIX = false: predict pass over all storages with the anchor linearisation
-//  FIX = true : exact re-solve of the storages on the work list with per-t hinge lists
-// dynamic smem per warp: StoStep[T] + eta[T] (+ hinge counts[T] in the FIX pass)
+// storages (subproblems.jl:107-207 reduced).  Segments between level-bound hits are only a few
+// timesteps long, so the horizon offers little parallelism while the agents offer plenty:
+//   k_sto_warm : one thread per storage, re-solve with last iteration's active set + KKT check
+//   k_sto_cold : one thread per storage that failed the check: sequential planning-horizon solve
+//   k_sto_fix  : one warp per storage that moved across a slack hinge: cooperative collection of
+//                its hinges (coalesced over the wide row list), exact re-solve by lane 0
 // ------------------------------------------------------------------------------------------------
-template <bool FIX>
-__global__ void k_storage(View v, Hinge *hinge_scratch)
+__global__ void __launch_bounds__(128) k_sto_warm(View v)
 {
     if (!DOPF_ACTIVE(v)) return;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int cur = v.ctrl->cur, nxt = 1 - cur;
-    const int T = v.T, lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const size_t per_warp = (size_t)T * (sizeof(StoStep) + sizeof(double) + sizeof(int));
-    unsigned char *base = smem_raw + wib * ((per_warp + 15) & ~(size_t)15);
-    StoStep *step = reinterpret_cast<StoStep *>(base);
-    double *eta = reinterpret_cast<double *>(base + (size_t)T * sizeof(StoStep));
-    int *hcnt = reinterpret_cast<int *>(base + (size_t)T * (sizeof(StoStep) + sizeof(double)));
-    const int gw = blockIdx.x * wpb + wib, nw = gridDim.x * wpb;
-    const int total = FIX ? v.ctrl->sto_work_cnt : v.S;
-    Hinge *mylist = FIX ? hinge_scratch + (size_t)gw * T * v.hcap : nullptr;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= v.S) return;
+    body_sto_warm(v, s);
+}
 
+__global__ void __launch_bounds__(64) k_sto_cold(View v)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    const int total = v.ctrl->cold_work_cnt;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x)
+        body_sto_cold(v, v.cold_work[w], nullptr, nullptr);
+    if (blockIdx.x == 0 && threadIdx.x == 0) v.ctrl->stat_sto_cold = total;
+}
+
+// hinges of node n at time t with breakpoint inside (lo,hi), collected by one warp from the wide
+// row list; returns the (uncapped) count, stores at most cap entries
+__device__ __forceinline__ int collect_hinges(const View &v, int n, int t, double lo, double hi, Hinge *out, int cap)
+{
+    const int lane = threadIdx.x & 31;
+    const int cnt_in = v.wcnt[t];
+    const int *lst = v.wide + (size_t)t * 2 * v.L;
+    const double *lb = v.wide_b + (size_t)t * 2 * v.L;
+    const double *prow = v.ptdfT + (size_t)n * v.Lp;
+    int cnt = 0;
+    for (int b0 = 0; b0 < cnt_in; b0 += 64) {
+        Hinge h[2]; bool ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int j = b0 + u * 32 + lane;
+            ok[u] = false; h[u].bp = 0.0; h[u].sg = 0.0;
+            if (j < cnt_in) {
+                const int e = lst[j];
+                ok[u] = make_hinge(v.c, prow[e >> 1], lb[j], e & 1, h[u]) && h[u].bp > lo && h[u].bp < hi;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const unsigned m = __ballot_sync(0xffffffffu, ok[u]);
+            const int pos = cnt + __popc(m & ((1u << lane) - 1));
+            if (ok[u] && pos < cap) out[pos] = h[u];
+            cnt += __popc(m);
+        }
+    }
+    return cnt;
+}
+
+__global__ void __launch_bounds__(128) k_sto_fix(View v, Hinge *hinge_scratch, int *hcnt_scratch)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int total = v.ctrl->sto_work_cnt;
+    Hinge *mylist = hinge_scratch + (size_t)gw * v.T * v.hcap;
+    int *mycnt = hcnt_scratch + (size_t)gw * v.T;
     for (int w = gw; w < total; w += nw) {
-        const int s = FIX ? v.sto_work[w] : w;
-        const int n = v.sto_node[s];
-        StoProblem p;
-        p.T = T; p.k.mc = v.sto_mc[s]; p.k.pmax = v.sto_pmax[s]; p.k.emax = v.sto_emax[s]; p.k.prox = v.c.prox;
-        p.step = step; p.hinges = mylist; p.hcnt = hcnt; p.hcap = v.hcap;
-        for (int t = lane; t < T; t += 32) {
-            StoStep st;
-            st.Db = sel(v.D, cur)[(size_t)s * T + t]; st.Cb = sel(v.C, cur)[(size_t)s * T + t];
-            st.g0 = v.g0[(size_t)n * v.ldt + t]; st.s1 = v.s1[(size_t)n * v.ldt + t];
-            step[t] = st;
-        }
-        if (FIX) {
-            // collect, per t, the hinges whose breakpoint lies inside the box |delta| < 2 pmax
-            const double range = 2.0 * p.k.pmax;
-            for (int t = 0; t < T; ++t) {
-                const int cnt_in = v.wcnt[t];
-                const int *lst = v.wide + (size_t)t * 2 * v.L;
-                int cnt = 0;
-                for (int b0 = 0; b0 < cnt_in; b0 += 32) {
-                    const int j = b0 + lane;
-                    bool ok = false;
-                    Hinge h; h.bp = 0.0; h.sg = 0.0;
-                    if (j < cnt_in) {
-                        const int l = lst[j] >> 1, side = lst[j] & 1;
-                        const double pl = v.ptdf[(size_t)l * v.Np + n];
-                        ok = make_hinge(v.c, pl, side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t], side, h)
-                             && fabs(h.bp) < range;
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, ok);
-                    const int pos = cnt + __popc(m & ((1u << lane) - 1));
-                    if (ok && pos < v.hcap) mylist[(size_t)t * v.hcap + pos] = h;
-                    cnt += __popc(m);
-                }
-                if (cnt > v.hcap) { if (lane == 0) v.ctrl->error = DOPF_ERR_HINGE_CAP; cnt = v.hcap; }
-                if (lane == 0) hcnt[t] = cnt;
-            }
-        } else {
-            p.hinges = nullptr;
+        const int s = v.sto_work[w], n = v.sto_node[s];
+        const double range = 2.0 * v.sto_pmax[s];
+        for (int t = 0; t < v.T; ++t) {
+            int cnt = collect_hinges(v, n, t, -range, range, mylist + (size_t)t * v.hcap, v.hcap);
+            if (cnt > v.hcap) { if (lane == 0) v.ctrl->error = DOPF_ERR_HINGE_CAP; cnt = v.hcap; }
+            if (lane == 0) mycnt[t] = cnt;
         }
         __syncwarp();
-        StoSolver<32> solver(p);
-        solver.solve(eta);
-        __syncwarp();
-        // write D, C, E (level = running sum of C-D; subproblems.jl:150-156)
-        double carry = 0.0;
-        for (int b0 = 0; b0 < T; b0 += 32) {
-            const int t = b0 + lane;
-            double y = 0.0, Dn = 0.0, Cn = 0.0;
-            if (t < T) {
-                StoEval e = sto_eval(step[t], p.k, p.list(t), eta[t]);
-                Dn = e.D; Cn = e.C; y = Cn - Dn;
-            }
-            const double E = carry + Group<32>::scan_incl(y);
-            if (t < T) {
-                const size_t o = (size_t)s * T + t;
-                sel(v.D, nxt)[o] = Dn; sel(v.C, nxt)[o] = Cn; v.E[o] = E;
-                note_move(v, n, t, (Dn - step[t].Db) - (Cn - step[t].Cb));
-            }
-            carry = __shfl_sync(0xffffffffu, E, 31);
+        if (lane == 0) {
+            body_sto_cold(v, s, mylist, mycnt);
+            atomicAdd(&v.ctrl->stat_sto_fix, 1);
         }
-        if (FIX && lane == 0) atomicAdd(&v.ctrl->stat_sto_fix, 1);
         __syncwarp();
     }
 }
@@ -374,24 +372,7 @@ __global__ void k_gen_fix(View v)
         const int n = v.gen_node[g];
         const double Pb = sel(v.P, cur)[(size_t)g * v.T + t], pmax = v.gen_pmax[g];
         const double lo = -Pb, hi = pmax - Pb;
-        const int cnt_in = v.wcnt[t];
-        const int *lst = v.wide + (size_t)t * 2 * v.L;
-        int cnt = 0;
-        for (int b0 = 0; b0 < cnt_in; b0 += 32) {
-            const int j = b0 + lane;
-            bool ok = false;
-            Hinge h; h.bp = 0.0; h.sg = 0.0;
-            if (j < cnt_in) {
-                const int l = lst[j] >> 1, side = lst[j] & 1;
-                const double pl = v.ptdf[(size_t)l * v.Np + n];
-                ok = make_hinge(v.c, pl, side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t], side, h)
-                     && h.bp > lo && h.bp < hi;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            const int pos = cnt + __popc(m & ((1u << lane) - 1));
-            if (ok && pos < CAP) lists[wib][pos] = h;
-            cnt += __popc(m);
-        }
+        int cnt = collect_hinges(v, n, t, lo, hi, lists[wib], CAP);
         __syncwarp();
         if (cnt > CAP) { if (lane == 0) v.ctrl->error = DOPF_ERR_HINGE_CAP; cnt = CAP; }
         if (lane == 0) {
@@ -551,12 +532,6 @@ __global__ void k_nodal_price(View v, int which, double *out /*[N][T]*/)
 // ------------------------------------------------------------------------------------------------
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-size_t storage_smem_bytes(int T, int warps)
-{
-    const size_t per_warp = (size_t)T * (sizeof(StoStep) + sizeof(double) + sizeof(int));
-    return warps * ((per_warp + 15) & ~(size_t)15);
-}
-
 int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st)
 {
     const View &v = lp.view;
@@ -575,16 +550,17 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st)
         if (v.T % 2 == 0) LAUNCH(k_gen_predict<2><<<cdiv((long long)v.G * (v.T / 2), 256), 256, 0, st>>>(v));
         else LAUNCH(k_gen_predict<1><<<cdiv((long long)v.G * v.T, 256), 256, 0, st>>>(v));
     }
-    if (v.S > 0)
-        LAUNCH(k_storage<false><<<min(cdiv(v.S, lp.sto_warps), lp.sto_blocks), lp.sto_warps * 32, storage_smem_bytes(v.T, lp.sto_warps), st>>>(v, nullptr));
+    if (v.S > 0) {
+        LAUNCH(k_sto_warm<<<cdiv(v.S, 128), 128, 0, st>>>(v));
+        LAUNCH(k_sto_cold<<<min(cdiv(v.S, 64), lp.num_sms * 8), 64, 0, st>>>(v));
+    }
     LAUNCH(k_compact<<<cdiv((long long)v.T * 32, 128), 128, 0, st>>>(v, 1));
     {
         dim3 grid(cdiv(v.N, 32), cdiv(v.T, 8));
         LAUNCH(k_verify<<<grid, 256, 0, st>>>(v));
     }
     if (v.G > 0) LAUNCH(k_gen_fix<<<lp.num_sms * 2, 128, 0, st>>>(v));
-    if (v.S > 0)
-        LAUNCH(k_storage<true><<<lp.sto_fix_blocks, lp.sto_warps * 32, storage_smem_bytes(v.T, lp.sto_warps), st>>>(v, lp.hinge_scratch));
+    if (v.S > 0) LAUNCH(k_sto_fix<<<lp.sto_fix_blocks, 128, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch));
     LAUNCH(k_compact<<<cdiv((long long)v.T * 32, 128), 128, 0, st>>>(v, 1));   // moves may have grown
     LAUNCH(k_inject<<<cdiv((long long)v.Np * v.ldt, 256), 256, 0, st>>>(v));
     LAUNCH(k_colsum<<<v.ldt / 32, dim3(32, 32), 0, st>>>(v));
@@ -644,12 +620,5 @@ void launch_rebuild_derived(const LaunchPlan &lp, cudaStream_t st)
     k_flip<<<1, 1, 0, st>>>(v);
 }
 
-int set_storage_smem_attr(size_t bytes)
-{
-    cudaError_t e = cudaFuncSetAttribute(k_storage<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k_storage<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    return (int)e;
-}
 
 }  // namespace dopf

@@ -105,6 +105,7 @@ struct StoStep {
 
 struct StoConst {
     double mc, pmax, emax, prox;
+    double iprox;   // 1/prox
 };
 
 DOPF_HD double clip01(double v, double hi) { return v < 0.0 ? 0.0 : (v > hi ? hi : v); }
@@ -116,8 +117,8 @@ struct StoEval {
 
 DOPF_HD void sto_dc_of_nu(const StoStep &st, const StoConst &k, double nu, double &D, double &C, int &nfree)
 {
-    const double du = st.Db - (k.mc + nu) / k.prox;
-    const double cu = st.Cb - (k.mc - nu) / k.prox;
+    const double du = st.Db - (k.mc + nu) * k.iprox;
+    const double cu = st.Cb - (k.mc - nu) * k.iprox;
     D = clip01(du, k.pmax);
     C = clip01(cu, k.pmax);
     nfree = (du > 0.0 && du < k.pmax) + (cu > 0.0 && cu < k.pmax);
@@ -202,6 +203,27 @@ DOPF_HD StoEval sto_eval(const StoStep &st, const StoConst &k, const HingeList &
     return r;
 }
 
+// eta-breakpoints of one step without hinges: eta(nu_b) = g0 + s1*delta(nu_b) - nu_b at the four
+// clip breakpoints nu_b of D(nu), C(nu).  Returns the nearest one strictly beyond `eta` in the
+// direction `up` (or +-1e300 if none).
+DOPF_HD double sto_next_break(const StoStep &st, const StoConst &k, double eta, bool up)
+{
+    const double nb[4] = { k.prox * (st.Db - k.pmax) - k.mc, k.prox * st.Db - k.mc,
+                           k.mc - k.prox * st.Cb, k.mc + k.prox * (k.pmax - st.Cb) };
+    double best = up ? 1e300 : -1e300;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 4; ++i) {
+        double D, C; int nf;
+        sto_dc_of_nu(st, k, nb[i], D, C, nf);
+        const double e = st.g0 + st.s1 * ((D - st.Db) - (C - st.Cb)) - nb[i];
+        if (up) { if (e > eta && e < best) best = e; }
+        else { if (e < eta && e > best) best = e; }
+    }
+    return best;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Lane groups.  The storage solver is written once over a group of W lanes that own the
 // timesteps t = lane, lane+W, ...  W=32 is a warp on the device; W=1 is the sequential
@@ -271,7 +293,7 @@ struct StoProblem {
     }
 };
 
-struct StoStats { int evals; int solves; int segments; };
+struct StoStats { int evals; int solves; int segments; int passes; };
 
 template <int W>
 struct StoSolver {
@@ -283,7 +305,7 @@ struct StoSolver {
     DOPF_HD StoSolver(const StoProblem &pp) : p(pp)
     {
         tolE = 1e-9 * (p.k.emax > 1.0 ? p.k.emax : 1.0);
-        stats.evals = stats.solves = stats.segments = 0;
+        stats.evals = stats.solves = stats.segments = stats.passes = 0;
     }
 
     // sum_{t in [t0,t1)} y_t(eta) and its derivative
@@ -295,7 +317,7 @@ struct StoSolver {
             a += e.C - e.D; b += e.dy;
         }
         s = G::sum(a); ds = G::sum(b);
-        stats.evals += t1 - t0;
+        stats.evals += t1 - t0; stats.passes++;
     }
 
     // eta with sum_{[t0,t1)} y(eta) = target   (sum is non-increasing in eta)
@@ -404,6 +426,166 @@ struct StoSolver {
         }
     }
 };
+
+// ---------------------------------------------------------------------------------------------
+// Sequential planning-horizon solve (one thread per storage).  Walks t once, keeping the
+// interval [lo,hi] of level multipliers eta for which the levels of the current segment stay
+// inside [0,emax]; lo/hi are tightened by exact 1-D solves when a bound is met and the segment
+// is closed at the binding time when the interval becomes empty (Modigliani-Hohn).
+// `emit(t, eta)` is called once per timestep in increasing t with its final multiplier.
+// `Steps` provides step(t) -> StoStep and list(t) -> HingeList.
+// ---------------------------------------------------------------------------------------------
+template <class Steps, class Emit>
+DOPF_HD void sto_funnel_seq(const Steps &sp, const StoConst &k, int T, Emit &emit, StoStats *stats = nullptr)
+{
+    const double tolE = 1e-9 * (k.emax > 1.0 ? k.emax : 1.0);
+    const double BIG = 1e300;
+    int nev = 0;
+    auto yof = [&](int t, double eta, double &dy) -> double {
+        if (eta >= BIG) { dy = 0.0; return -k.pmax; }
+        if (eta <= -BIG) { dy = 0.0; return k.pmax; }
+        StoEval e = sto_eval(sp.step(t), k, sp.list(t), eta);
+        dy = e.dy; ++nev;
+        return e.C - e.D;
+    };
+    // eta in [a,b] (a<b; sum(a) >= target >= sum(b)) with sum_{t0..t1} y(eta) = target
+    auto solve = [&](int t0, int t1, double target, double a, double b) -> double {
+        double ra = 0.0, rb = 0.0;
+        bool fa = false, fb = false;
+        double eta = (a > -BIG) ? a : ((b < BIG) ? b : 0.0);
+        if (a > -BIG && b < BIG) eta = 0.5 * (a + b);
+        double step = 1.0;
+        const double tolS = 1e-13 * (1.0 + fabs(target) + k.pmax);
+        if (stats) stats->solves++;
+        for (int it = 0; it < 300; ++it) {
+            double s = 0.0, ds = 0.0, dy;
+            if (stats) stats->passes++;
+            for (int t = t0; t <= t1; ++t) { s += yof(t, eta, dy); ds += dy; }
+            const double r = s - target;
+            if (fabs(r) <= tolS) return eta;
+            if (r > 0.0) { a = eta; ra = r; fa = true; } else { b = eta; rb = r; fb = true; }
+            double en;
+            if (ds < -1e-300) en = eta - r / ds;
+            else {
+                // flat: every step of the segment is saturated at eta -> go to the nearest clip
+                // breakpoint in the required direction (exact for hinge-free steps)
+                const bool up = r > 0.0;
+                double best = up ? BIG : -BIG;
+                bool ok = true;
+                for (int t = t0; t <= t1 && ok; ++t) {
+                    if (sp.list(t).n != 0) { ok = false; break; }
+                    const double e2 = sto_next_break(sp.step(t), k, eta, up);
+                    if (up ? e2 < best : e2 > best) best = e2;
+                }
+                if (ok && fabs(best) < BIG) en = best + (up ? 1.0 : -1.0) * 1e-11 * (1.0 + fabs(best));
+                else { en = up ? eta + step : eta - step; step *= 4.0; }
+            }
+            if (!(en > a && en < b)) {
+                if (fa && fb) { en = a - ra * (b - a) / (rb - ra); if (!(en > a && en < b)) en = 0.5 * (a + b); }
+                else if (a > -BIG && b < BIG) en = 0.5 * (a + b);
+                else { en = r > 0.0 ? eta + step : eta - step; step *= 4.0; }
+            }
+            if (a > -BIG && b < BIG && (b - a) <= 1e-15 * (1.0 + fabs(a))) return en;
+            eta = en;
+        }
+        return eta;
+    };
+
+    int t0 = 0;
+    double e0 = 0.0;
+    while (t0 < T) {
+        double lo = -BIG, hi = BIG;     // feasible multiplier interval of the segment starting at t0
+        int tlo = -1, thi = -1;         // times at which lo / hi were fixed (level = emax / 0 there)
+        double Elo = e0, Ehi = e0;      // levels along the lo / hi paths
+        int end = -1; double eta = 0.0, e_next = 0.0;
+        for (int t = t0; t < T && end < 0; ++t) {
+            double dy;
+            Elo += yof(t, lo, dy);
+            Ehi += yof(t, hi, dy);
+            if (Elo > k.emax + tolE) {
+                if (Ehi > k.emax + tolE) { end = thi; eta = hi; e_next = 0.0; break; }   // empty: lower anchor binds
+                lo = solve(t0, t, k.emax - e0, lo, hi); tlo = t; Elo = k.emax;
+            }
+            if (Ehi < -tolE) {
+                if (Elo < -tolE) { end = tlo; eta = lo; e_next = k.emax; break; }        // empty: upper anchor binds
+                hi = solve(t0, t, 0.0 - e0, lo, hi); thi = t; Ehi = 0.0;
+            }
+        }
+        if (end < 0) {                  // horizon reached: multiplier closest to 0 (free end)
+            if (lo > 0.0) { end = tlo; eta = lo; e_next = k.emax; }
+            else if (hi < 0.0) { end = thi; eta = hi; e_next = 0.0; }
+            else { end = T - 1; eta = 0.0; }
+        }
+        for (int t = t0; t <= end; ++t) emit(t, eta);
+        t0 = end + 1; e0 = e_next;
+        if (stats) stats->segments++;
+    }
+    if (stats) stats->evals += nev;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warm start: re-use the active set of the previous ADMM iteration.  `eta_prev(t)` is the
+// multiplier path of the last solve; its runs of equal value are the segments, the sign of the
+// jump between two runs tells which level bound was active at the junction (eta drops after a
+// full storage, rises after an empty one).  Each run is re-solved with its end level fixed and
+// the KKT conditions (levels inside [0,emax], multiplier signs at the junctions and at the end
+// of the horizon) are verified.  Returns true and has emitted the exact solution if they hold;
+// otherwise the caller falls back to the cold funnel (which re-emits every t).
+// ---------------------------------------------------------------------------------------------
+template <class Steps, class Prev, class Emit>
+DOPF_HD bool sto_warm_try(const Steps &sp, const StoConst &k, int T, const Prev &eta_prev, Emit &emit, StoStats *stats = nullptr)
+{
+    const double tolE = 1e-9 * (k.emax > 1.0 ? k.emax : 1.0);
+    int nev = 0;
+    int a = 0;
+    double e0 = 0.0, eta_last = 0.0;
+    int kind_last = 0;           // bound that closed the previous run: +1 emax, -1 zero
+    while (a < T) {
+        const double ep = eta_prev(a);
+        int b = a;
+        while (b + 1 < T && eta_prev(b + 1) == ep) ++b;
+        int kind;                // bound at the end of this run (0 = free end of horizon)
+        if (b + 1 < T) kind = eta_prev(b + 1) < ep ? 1 : -1;
+        else kind = ep > 0.0 ? 1 : (ep < 0.0 ? -1 : 0);
+        const double target = (kind > 0 ? k.emax : 0.0) - e0;
+        double eta = ep, lo = -1e300, hi = 1e300, Emin = 0.0, Emax = 0.0;
+        bool done = false;
+        const double tolS = 1e-13 * (1.0 + fabs(target) + k.pmax);
+        for (int it = 0; it < 12 && !done; ++it) {
+            double sum = 0.0, ds = 0.0;
+            Emin = 1e300; Emax = -1e300;
+            for (int t = a; t <= b; ++t) {
+                StoEval e = sto_eval(sp.step(t), k, sp.list(t), eta);
+                ++nev;
+                sum += e.C - e.D; ds += e.dy;
+                const double E = e0 + sum;
+                Emin = E < Emin ? E : Emin; Emax = E > Emax ? E : Emax;
+            }
+            if (kind == 0) { done = true; break; }          // free end: eta stays 0
+            const double r = sum - target;
+            if (fabs(r) <= tolS) { done = true; break; }
+            if (r > 0.0) lo = eta; else hi = eta;
+            if (!(ds < -1e-300)) return false;               // flat: leave it to the cold solve
+            double en = eta - r / ds;
+            if (!(en > lo && en < hi)) return false;
+            eta = en;
+        }
+        if (!done) return false;
+        if (Emin < -tolE || Emax > k.emax + tolE) return false;
+        // multiplier sign at the junction with the previous run
+        if (kind_last > 0 && eta > eta_last) return false;
+        if (kind_last < 0 && eta < eta_last) return false;
+        if (kind == 0 && eta != 0.0) return false;
+        if (b + 1 == T && ((kind > 0 && eta < 0.0) || (kind < 0 && eta > 0.0))) return false;
+        for (int t = a; t <= b; ++t) emit(t, eta);
+        e0 = kind > 0 ? k.emax : (kind < 0 ? 0.0 : e0);
+        eta_last = eta; kind_last = kind;
+        a = b + 1;
+        if (stats) stats->segments++;
+    }
+    if (stats) stats->evals += nev;
+    return true;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Shared per-(line,t) quantities (row preparation) - see DESIGN.md section 3.

@@ -19,7 +19,7 @@ void emul_storage_solve(int T, double mc, double pmax, double emax, double prox,
     std::vector<Hinge> h((size_t)T * (hcap > 0 ? hcap : 1));
     for (int i = 0; i < T * hcap; ++i) { h[i].bp = hbp[i]; h[i].sg = hsg[i]; }
     StoProblem p;
-    p.T = T; p.k.mc = mc; p.k.pmax = pmax; p.k.emax = emax; p.k.prox = prox;
+    p.T = T; p.k.mc = mc; p.k.pmax = pmax; p.k.emax = emax; p.k.prox = prox; p.k.iprox = 1.0 / prox;
     p.step = st.data(); p.hinges = hcap > 0 ? h.data() : nullptr; p.hcnt = hcnt; p.hcap = hcap;
     StoSolver<1> s(p);
     s.solve(eta);
@@ -27,7 +27,53 @@ void emul_storage_solve(int T, double mc, double pmax, double emax, double prox,
         StoEval e = sto_eval(p.step[t], p.k, p.list(t), eta[t]);
         D[t] = e.D; C[t] = e.C;
     }
-    stats[0] = s.stats.evals; stats[1] = s.stats.solves; stats[2] = s.stats.segments;
+    stats[0] = s.stats.evals; stats[1] = s.stats.solves; stats[2] = s.stats.segments; stats[3] = s.stats.passes;
+}
+
+struct SeqSteps {
+    const StoProblem *p;
+    StoStep step(int t) const { return p->step[t]; }
+    HingeList list(int t) const { return p->list(t); }
+};
+void emul_storage_solve_seq(int T, double mc, double pmax, double emax, double prox,
+                        const double *Db, const double *Cb, const double *g0, const double *s1,
+                        int hcap, const int *hcnt, const double *hbp, const double *hsg,
+                        double *D, double *C, double *eta, int *stats)
+{
+    std::vector<StoStep> st(T);
+    for (int t = 0; t < T; ++t) { st[t].Db = Db[t]; st[t].Cb = Cb[t]; st[t].g0 = g0[t]; st[t].s1 = s1[t]; }
+    std::vector<Hinge> h((size_t)T * (hcap > 0 ? hcap : 1));
+    for (int i = 0; i < T * hcap; ++i) { h[i].bp = hbp[i]; h[i].sg = hsg[i]; }
+    StoProblem p;
+    p.T = T; p.k.mc = mc; p.k.pmax = pmax; p.k.emax = emax; p.k.prox = prox; p.k.iprox = 1.0 / prox;
+    p.step = st.data(); p.hinges = hcap > 0 ? h.data() : nullptr; p.hcnt = hcnt; p.hcap = hcap;
+    SeqSteps sp{&p};
+    StoStats ss{0, 0, 0, 0};
+    auto emit = [&](int t, double e) { eta[t] = e; StoEval ev = sto_eval(p.step[t], p.k, p.list(t), e); D[t] = ev.D; C[t] = ev.C; };
+    sto_funnel_seq(sp, p.k, T, emit, &ss);
+    stats[0] = ss.evals; stats[1] = ss.solves; stats[2] = ss.segments; stats[3] = ss.passes;
+}
+
+// warm-started solve: eta_io holds the previous multiplier path on entry, the new one on exit.
+// returns 1 if the warm path verified, 0 if the cold funnel had to be used.
+int emul_storage_solve_warm(int T, double mc, double pmax, double emax, double prox,
+                        const double *Db, const double *Cb, const double *g0, const double *s1,
+                        double *D, double *C, double *eta_io, int *stats)
+{
+    std::vector<StoStep> st(T);
+    for (int t = 0; t < T; ++t) { st[t].Db = Db[t]; st[t].Cb = Cb[t]; st[t].g0 = g0[t]; st[t].s1 = s1[t]; }
+    StoProblem p;
+    p.T = T; p.k.mc = mc; p.k.pmax = pmax; p.k.emax = emax; p.k.prox = prox; p.k.iprox = 1.0 / prox;
+    p.step = st.data(); p.hinges = nullptr; p.hcnt = nullptr; p.hcap = 0;
+    SeqSteps sp{&p};
+    StoStats ss{0, 0, 0, 0};
+    std::vector<double> prev(eta_io, eta_io + T);
+    auto emit = [&](int t, double e) { eta_io[t] = e; StoEval ev = sto_eval(p.step[t], p.k, p.list(t), e); D[t] = ev.D; C[t] = ev.C; };
+    auto pv = [&](int t) { return prev[t]; };
+    int warm = sto_warm_try(sp, p.k, T, pv, emit, &ss) ? 1 : 0;
+    if (!warm) sto_funnel_seq(sp, p.k, T, emit, &ss);
+    stats[0] = ss.evals; stats[1] = ss.solves; stats[2] = ss.segments; stats[3] = ss.passes;
+    return warm;
 }
 
 double emul_gen_root(double c, double a, int n, const double *hbp, const double *hsg, double lo, double hi)
@@ -108,7 +154,9 @@ void *emul_create(int N, int L, int T, int G, int S, const double *ptdf, const d
         v.inj[k] = e->mk((size_t)Np * ldt); v.injloc[k] = v.inj[k]; v.ssum[k] = e->mk(ldt); v.flow[k] = e->mk((size_t)Lp * ldt);
         v.lam[k] = e->mk(ldt); v.mu[k] = e->mk((size_t)Lp * ldt); v.rho[k] = e->mk((size_t)Lp * ldt);
     }
-    v.E = e->mk((size_t)S * T); v.avgU = e->mk((size_t)Lp * ldt); v.avgK = e->mk((size_t)Lp * ldt);
+    v.E = e->mk((size_t)S * T); v.eta = e->mk((size_t)S * T); v.cold_work = e->mki(S); v.wide_b = e->mk((size_t)T * 2 * L);
+    { double *pt = e->mk((size_t)Np * Lp); for (int l = 0; l < L; ++l) for (int n = 0; n < N; ++n) pt[(size_t)n * Lp + l] = P[(size_t)l * Np + n]; v.ptdfT = pt; }
+    v.avgU = e->mk((size_t)Lp * ldt); v.avgK = e->mk((size_t)Lp * ldt);
     v.bplus = e->mk((size_t)Lp * ldt); v.bminus = e->mk((size_t)Lp * ldt); v.M = e->mk((size_t)Lp * ldt); v.Wt = e->mk((size_t)Lp * ldt);
     v.g0 = e->mk((size_t)Np * ldt); v.s1 = e->mk((size_t)Np * ldt);
     e->dn.assign((size_t)Np * ldt, 0); e->dmax.assign(ldt, 0); v.dn = e->dn.data(); v.dmax = e->dmax.data();
@@ -135,7 +183,10 @@ static void compact(Emul *e, int mode)
         int cnt = 0;
         if (mode == 0) {
             for (int l = 0; l < v.L; ++l) for (int side = 0; side < 2; ++side)
-                if ((v.flags[(size_t)t * v.Lp + l] >> side) & 1) v.wide[(size_t)t * 2 * v.L + cnt++] = l * 2 + side;
+                if ((v.flags[(size_t)t * v.Lp + l] >> side) & 1) {
+                    v.wide_b[(size_t)t * 2 * v.L + cnt] = side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t];
+                    v.wide[(size_t)t * 2 * v.L + cnt++] = l * 2 + side;
+                }
             v.wcnt[t] = cnt;
         } else {
             const double dm = bits_nonneg(v.dmax[t]);
@@ -152,41 +203,31 @@ static void compact(Emul *e, int mode)
 static void storage_pass(Emul *e, bool fix)
 {
     View &v = e->v;
-    const int cur = v.ctrl->cur, nxt = 1 - cur, T = v.T;
-    std::vector<StoStep> step(T);
-    std::vector<double> eta(T);
-    const int total = fix ? v.ctrl->sto_work_cnt : v.S;
-    for (int w = 0; w < total; ++w) {
-        const int s = fix ? v.sto_work[w] : w, n = v.sto_node[s];
-        StoProblem p; p.T = T; p.k.mc = v.sto_mc[s]; p.k.pmax = v.sto_pmax[s]; p.k.emax = v.sto_emax[s]; p.k.prox = v.c.prox;
-        p.step = step.data(); p.hinges = fix ? e->scratch.data() : nullptr; p.hcnt = e->hcnt.data(); p.hcap = v.hcap;
-        for (int t = 0; t < T; ++t) { step[t].Db = v.D[cur][(size_t)s * T + t]; step[t].Cb = v.C[cur][(size_t)s * T + t]; step[t].g0 = v.g0[(size_t)n * v.ldt + t]; step[t].s1 = v.s1[(size_t)n * v.ldt + t]; }
-        if (fix) {
-            const double range = 2.0 * p.k.pmax;
-            for (int t = 0; t < T; ++t) {
-                int cnt = 0;
-                for (int j = 0; j < v.wcnt[t]; ++j) {
-                    int en = v.wide[(size_t)t * 2 * v.L + j]; int l = en >> 1, side = en & 1; Hinge h;
-                    if (make_hinge(v.c, v.ptdf[(size_t)l * v.Np + n], side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t], side, h) && std::fabs(h.bp) < range) {
-                        if (cnt < v.hcap) e->scratch[(size_t)t * v.hcap + cnt] = h;
-                        cnt++;
-                    }
-                }
-                if (cnt > v.hcap) { v.ctrl->error = DOPF_ERR_HINGE_CAP; cnt = v.hcap; }
-                e->hcnt[t] = cnt;
-            }
-        }
-        StoSolver<1> solver(p);
-        solver.solve(eta.data());
-        double E = 0.0;
+    const int T = v.T;
+    if (!fix) {
+        v.ctrl->cold_work_cnt = 0;
+        for (int s = 0; s < v.S; ++s) body_sto_warm(v, s);
+        for (int w = 0; w < v.ctrl->cold_work_cnt; ++w) body_sto_cold(v, v.cold_work[w], nullptr, nullptr);
+        v.ctrl->stat_sto_cold = v.ctrl->cold_work_cnt;
+        return;
+    }
+    for (int w = 0; w < v.ctrl->sto_work_cnt; ++w) {
+        const int s = v.sto_work[w], n = v.sto_node[s];
+        const double range = 2.0 * v.sto_pmax[s];
         for (int t = 0; t < T; ++t) {
-            StoEval ev = sto_eval(step[t], p.k, p.list(t), eta[t]);
-            const size_t o = (size_t)s * T + t;
-            E += ev.C - ev.D;
-            v.D[nxt][o] = ev.D; v.C[nxt][o] = ev.C; v.E[o] = E;
-            note_move(v, n, t, (ev.D - step[t].Db) - (ev.C - step[t].Cb));
+            int cnt = 0;
+            for (int j = 0; j < v.wcnt[t]; ++j) {
+                int en = v.wide[(size_t)t * 2 * v.L + j]; Hinge h;
+                if (make_hinge(v.c, v.ptdfT[(size_t)n * v.Lp + (en >> 1)], v.wide_b[(size_t)t * 2 * v.L + j], en & 1, h) && h.bp > -range && h.bp < range) {
+                    if (cnt < v.hcap) e->scratch[(size_t)t * v.hcap + cnt] = h;
+                    cnt++;
+                }
+            }
+            if (cnt > v.hcap) { v.ctrl->error = DOPF_ERR_HINGE_CAP; cnt = v.hcap; }
+            e->hcnt[t] = cnt;
         }
-        if (fix) v.ctrl->stat_sto_fix++;
+        body_sto_cold(v, s, e->scratch.data(), e->hcnt.data());
+        v.ctrl->stat_sto_fix++;
     }
 }
 
@@ -256,7 +297,7 @@ void emul_iterate(void *h)
 
 // newest iterate; matrices dense [rows][T]
 void emul_get(void *h, double *P, double *D, double *C, double *E, double *inj, double *flow, double *avgU, double *avgK,
-              double *lam, double *mu, double *rho, int *status /*iteration, converged, gen_fix, sto_fix, tight, wide, error*/)
+              double *lam, double *mu, double *rho, int *status /*iteration, converged, gen_fix, sto_fix, tight, wide, error, sto_cold*/)
 {
     Emul *e = (Emul *)h; View &v = e->v; const int k = v.ctrl->cur, T = v.T, ldt = v.ldt;
     std::copy(v.P[k], v.P[k] + (size_t)v.G * T, P);
@@ -268,6 +309,6 @@ void emul_get(void *h, double *P, double *D, double *C, double *E, double *inj, 
     }
     for (int t = 0; t < T; ++t) lam[t] = v.lam[k][t];
     status[0] = v.ctrl->iteration; status[1] = v.ctrl->converged; status[2] = v.ctrl->stat_gen_fix; status[3] = v.ctrl->stat_sto_fix;
-    status[4] = v.ctrl->stat_tight_rows; status[5] = v.ctrl->stat_wide_rows; status[6] = v.ctrl->error;
+    status[4] = v.ctrl->stat_tight_rows; status[5] = v.ctrl->stat_wide_rows; status[6] = v.ctrl->error; status[7] = v.ctrl->stat_sto_cold;
 }
 }

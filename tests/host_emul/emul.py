@@ -48,7 +48,7 @@ class EmulADMM:
         self.P = np.zeros((p.G, p.T)); self.D = np.zeros((p.S, p.T)); self.C = np.zeros((p.S, p.T)); self.E = np.zeros((p.S, p.T))
         self.inj = np.zeros((p.N, p.T)); self.flow = np.zeros((p.L, p.T)); self.avgU = np.zeros((p.L, p.T)); self.avgK = np.zeros((p.L, p.T))
         self.lam = np.zeros(p.T); self.mu = np.zeros((p.L, p.T)); self.rho = np.zeros((p.L, p.T))
-        self.status = np.zeros(7, dtype=np.int32)
+        self.status = np.zeros(8, dtype=np.int32)
 
     def iterate(self):
         lib().emul_iterate(self.h)
