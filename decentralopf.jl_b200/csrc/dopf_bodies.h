@@ -188,9 +188,10 @@ DOPF_HD void body_sto_warm(const View &v, int s)
     StoConst k; GlobalSteps sp;
     sto_setup(v, s, k, sp);
     StoEmit emit(v, sp, k, s, v.sto_node[s]);
-    const double *ep = v.eta + (size_t)s * v.T;
+    const double *ep = v.eta + (size_t)s * v.T, *Ep = v.E + (size_t)s * v.T;
     auto prev = [ep](int t) { return ep[t]; };
-    if (sto_warm_try(sp, k, v.T, prev, emit)) sto_note_moves(v, s);
+    auto prevE = [Ep](int t) { return Ep[t]; };
+    if (sto_warm_try(sp, k, v.T, prev, prevE, emit)) sto_note_moves(v, s);
     else v.cold_work[DOPF_ATOMIC_ADD_I32(&v.ctrl->cold_work_cnt, 1)] = s;
 }
 
@@ -200,7 +201,15 @@ DOPF_HD void body_sto_cold(const View &v, int s, const Hinge *hinges, const int 
     sto_setup(v, s, k, sp);
     sp.hinges = hinges; sp.hcnt = hcnt; sp.hcap = v.hcap;
     StoEmit emit(v, sp, k, s, v.sto_node[s]);
-    sto_funnel_seq(sp, k, v.T, emit);
+    bool done = false;
+    if (hinges) {
+        // correction pass: the multiplier path of the predict pass (just written) is the warm start
+        const double *ep = v.eta + (size_t)s * v.T, *Ep = v.E + (size_t)s * v.T;
+        auto prev = [ep](int t) { return ep[t]; };
+        auto prevE = [Ep](int t) { return Ep[t]; };
+        done = sto_warm_try(sp, k, v.T, prev, prevE, emit);
+    }
+    if (!done) sto_funnel_seq(sp, k, v.T, emit);
     sto_note_moves(v, s);
 }
 

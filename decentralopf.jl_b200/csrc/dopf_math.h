@@ -15,6 +15,9 @@
 
 #include <math.h>
 #include <stdint.h>
+#if !defined(__CUDACC__) && defined(DOPF_DEBUG_WARM)
+#include <cstdio>
+#endif
 
 #if defined(__CUDACC__)
 #define DOPF_HD __host__ __device__ __forceinline__
@@ -129,20 +132,18 @@ DOPF_HD StoEval sto_eval(const StoStep &st, const StoConst &k, const HingeList &
     const double base = st.g0 - eta;
     double D, C; int nf;
     StoEval r;
-    if (hl.n == 0) {
-        // closed form: Psi is piecewise linear with the 4 clip breakpoints of D(nu), C(nu)
+    double nu;
+    {
+        // closed form without hinges: Psi is piecewise linear with the 4 clip breakpoints of D(nu), C(nu)
         double b0 = k.prox * (st.Db - k.pmax) - k.mc;  // D leaves pmax
         double b1 = k.prox * st.Db - k.mc;             // D reaches 0
         double b2 = k.mc - k.prox * st.Cb;             // C leaves 0
         double b3 = k.mc + k.prox * (k.pmax - st.Cb);  // C reaches pmax
-        // sort 4 (b0<=b1, b2<=b3 already)
-        double t;
+        double t;                                      // sort (b0<=b1, b2<=b3 already)
         if (b0 > b2) { t = b0; b0 = b2; b2 = t; }
         if (b1 > b3) { t = b1; b1 = b3; b3 = t; }
         if (b1 > b2) { t = b1; b1 = b2; b2 = t; }
         const double bb[4] = { b0, b1, b2, b3 };
-        double pl = 0.0, pv = 0.0;  // previous breakpoint and Psi there
-        int found = -1;
         double psi[4];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -151,52 +152,49 @@ DOPF_HD StoEval sto_eval(const StoStep &st, const StoConst &k, const HingeList &
             sto_dc_of_nu(st, k, bb[i], D, C, nf);
             psi[i] = bb[i] - base - st.s1 * ((D - st.Db) - (C - st.Cb));
         }
-        double nu;
         if (psi[0] >= 0.0) nu = bb[0] - psi[0];                 // slope 1 left of all breakpoints
         else if (psi[3] <= 0.0) nu = bb[3] - psi[3];            // slope 1 right of all breakpoints
         else {
-            found = psi[1] >= 0.0 ? 0 : (psi[2] >= 0.0 ? 1 : 2);
-            pl = bb[found]; pv = psi[found];
-            const double ql = bb[found + 1], qv = psi[found + 1];
+            const int f = psi[1] >= 0.0 ? 0 : (psi[2] >= 0.0 ? 1 : 2);
+            const double pl = bb[f], pv = psi[f], ql = bb[f + 1], qv = psi[f + 1];
             nu = (qv == pv) ? pl : pl - pv * (ql - pl) / (qv - pv);
         }
         sto_dc_of_nu(st, k, nu, D, C, nf);
-        r.D = D; r.C = C;
-        r.dy = -(double)nf / (k.prox + st.s1 * nf);
-        return r;
     }
-    // general case (hinges present): safeguarded Newton on Psi
-    const double big = k.mc + k.prox * k.pmax + 1.0;
-    double lo = -big + base - 1.0, hi = big + base + 1.0;  // |delta|<=2pmax; widened below if needed
-    {
-        double v, s;
-        hl.eval(2.0 * k.pmax, v, s);  hi += st.s1 * 2.0 * k.pmax + fabs(v);
-        hl.eval(-2.0 * k.pmax, v, s); lo -= st.s1 * 2.0 * k.pmax + fabs(v);
-    }
-    double nu = base, sl = 0.0;
-    double flo = -1.0, fhi = 1.0;
-    bool have_lo = false, have_hi = false;
-    for (int it = 0; it < 200; ++it) {
-        sto_dc_of_nu(st, k, nu, D, C, nf);
-        const double delta = (D - st.Db) - (C - st.Cb);
-        double v;
-        hl.eval(delta, v, sl);
-        const double psi = nu - base - st.s1 * delta - v;
-        if (psi == 0.0) break;
-        if (psi < 0.0) { lo = nu; flo = psi; have_lo = true; } else { hi = nu; fhi = psi; have_hi = true; }
-        const double slope = 1.0 + (st.s1 + sl) * nf / k.prox;
-        double nn = nu - psi / slope;
-        if (!(nn > lo && nn < hi)) {
-            nn = (have_lo && have_hi) ? lo - flo * (hi - lo) / (fhi - flo) : 0.5 * (lo + hi);
-            if (!(nn > lo && nn < hi)) nn = 0.5 * (lo + hi);
-        }
-        if (fabs(nn - nu) <= 1e-15 * (1.0 + fabs(nu))) { nu = nn; break; }
-        nu = nn;
-    }
-    sto_dc_of_nu(st, k, nu, D, C, nf);
-    {
+    double sl = 0.0;
+    if (hl.n != 0) {
         double v;
         hl.eval((D - st.Db) - (C - st.Cb), v, sl);
+        if (v != 0.0 || sl != 0.0) {
+            // a hinge differs from its anchor state at this delta: safeguarded Newton on Psi with hinges
+            const double big = k.mc + k.prox * k.pmax + 1.0;
+            double lo = -big + base - 1.0, hi = big + base + 1.0;
+            {
+                double v2, s2;
+                hl.eval(2.0 * k.pmax, v2, s2);  hi += st.s1 * 2.0 * k.pmax + fabs(v2);
+                hl.eval(-2.0 * k.pmax, v2, s2); lo -= st.s1 * 2.0 * k.pmax + fabs(v2);
+            }
+            double flo = -1.0, fhi = 1.0;
+            bool have_lo = false, have_hi = false;
+            for (int it = 0; it < 200; ++it) {
+                sto_dc_of_nu(st, k, nu, D, C, nf);
+                const double delta = (D - st.Db) - (C - st.Cb);
+                hl.eval(delta, v, sl);
+                const double psi = nu - base - st.s1 * delta - v;
+                if (psi == 0.0) break;
+                if (psi < 0.0) { lo = nu; flo = psi; have_lo = true; } else { hi = nu; fhi = psi; have_hi = true; }
+                const double slope = 1.0 + (st.s1 + sl) * nf * k.iprox;
+                double nn = nu - psi / slope;
+                if (!(nn > lo && nn < hi)) {
+                    nn = (have_lo && have_hi) ? lo - flo * (hi - lo) / (fhi - flo) : 0.5 * (lo + hi);
+                    if (!(nn > lo && nn < hi)) nn = 0.5 * (lo + hi);
+                }
+                if (fabs(nn - nu) <= 1e-15 * (1.0 + fabs(nu))) { nu = nn; break; }
+                nu = nn;
+            }
+            sto_dc_of_nu(st, k, nu, D, C, nf);
+            hl.eval((D - st.Db) - (C - st.Cb), v, sl);
+        }
     }
     r.D = D; r.C = C;
     r.dy = -(double)nf / (k.prox + (st.s1 + sl) * nf);
@@ -222,6 +220,41 @@ DOPF_HD double sto_next_break(const StoStep &st, const StoConst &k, double eta, 
         else { if (e < eta && e > best) best = e; }
     }
     return best;
+}
+
+// maximal eta-interval [ilo,ihi] containing eta on which y_t = C-D of a hinge-free step stays
+// at its value y_t(eta): the union of the clip pieces (in nu) without a free variable that contain
+// or touch nu(eta), mapped through the decreasing map eta(nu) = g0 + s1*delta(nu) - nu.
+DOPF_HD void sto_flat_interval(const StoStep &st, const StoConst &k, double eta, double D, double C, double &ilo, double &ihi)
+{
+    ilo = ihi = eta;
+    const double nu = st.g0 - eta + st.s1 * ((D - st.Db) - (C - st.Cb));
+    double b0 = k.prox * (st.Db - k.pmax) - k.mc, b1 = k.prox * st.Db - k.mc;
+    double b2 = k.mc - k.prox * st.Cb, b3 = k.mc + k.prox * (k.pmax - st.Cb);
+    double t;
+    if (b0 > b2) { t = b0; b0 = b2; b2 = t; }
+    if (b1 > b3) { t = b1; b1 = b3; b3 = t; }
+    if (b1 > b2) { t = b1; b1 = b2; b2 = t; }
+    const double bb[4] = { b0, b1, b2, b3 };
+    const double tol = 1e-10 * (1.0 + fabs(nu));
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 5; ++j) {
+        const bool linf = j == 0, rinf = j == 4;
+        const double plo = linf ? 0.0 : bb[j - 1], phi = rinf ? 0.0 : bb[j];
+        if (!linf && nu < plo - tol) continue;
+        if (!rinf && nu > phi + tol) continue;
+        if (!linf && !rinf && !(phi > plo)) continue;
+        const double mid = linf ? phi - 1.0 : (rinf ? plo + 1.0 : 0.5 * (plo + phi));
+        double Dm, Cm; int nf;
+        sto_dc_of_nu(st, k, mid, Dm, Cm, nf);
+        if (nf != 0) continue;
+        const double dl = (Dm - st.Db) - (Cm - st.Cb);     // delta is constant on a flat piece
+        const double eh = linf ? 1e300 : st.g0 + st.s1 * dl - plo;
+        const double el = rinf ? -1e300 : st.g0 + st.s1 * dl - phi;
+        ilo = el < ilo ? el : ilo; ihi = eh > ihi ? eh : ihi;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -524,36 +557,50 @@ DOPF_HD void sto_funnel_seq(const Steps &sp, const StoConst &k, int T, Emit &emi
 }
 
 // ---------------------------------------------------------------------------------------------
-// Warm start: re-use the active set of the previous ADMM iteration.  `eta_prev(t)` is the
-// multiplier path of the last solve; its runs of equal value are the segments, the sign of the
-// jump between two runs tells which level bound was active at the junction (eta drops after a
-// full storage, rises after an empty one).  Each run is re-solved with its end level fixed and
-// the KKT conditions (levels inside [0,emax], multiplier signs at the junctions and at the end
-// of the horizon) are verified.  Returns true and has emitted the exact solution if they hold;
-// otherwise the caller falls back to the cold funnel (which re-emits every t).
+// Warm start: re-use the active set of the previous solve.  The anchors are the timesteps whose
+// previous level `E_prev(t)` sat at a bound (0 or emax); between two anchors the multiplier is
+// constant.  Each run is re-solved with its end level fixed (Newton from the previous multiplier
+// `eta_prev`, safeguarded), then the KKT conditions are verified: levels inside [0,emax] and a
+// multiplier path with the right sign at every anchor (eta may only drop after a full storage,
+// only rise after an empty one, and must end at 0 / >=0 / <=0).  Because saturated steps make the
+// multiplier of a run non-unique, each run carries the interval of multipliers that reproduce its
+// solution and the sign conditions are checked on intervals.  Returns true and has emitted the
+// exact solution if everything holds; otherwise the caller runs the cold funnel.
 // ---------------------------------------------------------------------------------------------
-template <class Steps, class Prev, class Emit>
-DOPF_HD bool sto_warm_try(const Steps &sp, const StoConst &k, int T, const Prev &eta_prev, Emit &emit, StoStats *stats = nullptr)
+#if !defined(__CUDACC__) && defined(DOPF_DEBUG_WARM)
+static int g_warm_fail[8];
+#define WFAIL(i) (g_warm_fail[i]++, false)
+#else
+#define WFAIL(i) false
+#endif
+template <class Steps, class PrevEta, class PrevE, class Emit>
+DOPF_HD bool sto_warm_try(const Steps &sp, const StoConst &k, int T, const PrevEta &eta_prev, const PrevE &E_prev,
+                          Emit &emit, StoStats *stats = nullptr)
 {
     const double tolE = 1e-9 * (k.emax > 1.0 ? k.emax : 1.0);
+    const double tolA = 1e-7 * (k.emax > 1.0 ? k.emax : 1.0);   // "was at a bound" in the previous solve
+    const double BIG = 1e300;
     int nev = 0;
     int a = 0;
-    double e0 = 0.0, eta_last = 0.0;
-    int kind_last = 0;           // bound that closed the previous run: +1 emax, -1 zero
+    double e0 = 0.0;
+    double Flo = -BIG, Fhi = BIG;   // multipliers the previous run can take
+    int kind_last = 0;              // bound that closed the previous run: +1 emax, -1 zero
     while (a < T) {
-        const double ep = eta_prev(a);
-        int b = a;
-        while (b + 1 < T && eta_prev(b + 1) == ep) ++b;
-        int kind;                // bound at the end of this run (0 = free end of horizon)
-        if (b + 1 < T) kind = eta_prev(b + 1) < ep ? 1 : -1;
-        else kind = ep > 0.0 ? 1 : (ep < 0.0 ? -1 : 0);
+        int b = a, kind = 0;
+        for (;; ++b) {
+            const double Ep = E_prev(b);
+            if (Ep >= k.emax - tolA) { kind = 1; break; }
+            if (Ep <= tolA) { kind = -1; break; }
+            if (b == T - 1) break;
+        }
         const double target = (kind > 0 ? k.emax : 0.0) - e0;
-        double eta = ep, lo = -1e300, hi = 1e300, Emin = 0.0, Emax = 0.0;
-        bool done = false;
+        double eta = kind == 0 ? 0.0 : eta_prev(b);
+        double lo = -BIG, hi = BIG, rlo = 0.0, rhi = 0.0, Emin = 0.0, Emax = 0.0, ds = 0.0;
+        bool done = false, flo = false, fhi = false, nohinge = true;
         const double tolS = 1e-13 * (1.0 + fabs(target) + k.pmax);
-        for (int it = 0; it < 12 && !done; ++it) {
-            double sum = 0.0, ds = 0.0;
-            Emin = 1e300; Emax = -1e300;
+        for (int it = 0; it < 40 && !done; ++it) {
+            double sum = 0.0;
+            ds = 0.0; Emin = BIG; Emax = -BIG;
             for (int t = a; t <= b; ++t) {
                 StoEval e = sto_eval(sp.step(t), k, sp.list(t), eta);
                 ++nev;
@@ -564,22 +611,58 @@ DOPF_HD bool sto_warm_try(const Steps &sp, const StoConst &k, int T, const Prev 
             if (kind == 0) { done = true; break; }          // free end: eta stays 0
             const double r = sum - target;
             if (fabs(r) <= tolS) { done = true; break; }
-            if (r > 0.0) lo = eta; else hi = eta;
-            if (!(ds < -1e-300)) return false;               // flat: leave it to the cold solve
-            double en = eta - r / ds;
-            if (!(en > lo && en < hi)) return false;
+            if (r > 0.0) { lo = eta; rlo = r; flo = true; } else { hi = eta; rhi = r; fhi = true; }
+            double en;
+            if (ds < -1e-300) en = eta - r / ds;
+            else {
+                // flat: every step saturated at eta -> nearest clip breakpoint in the needed direction
+                const bool up = r > 0.0;
+                double best = up ? BIG : -BIG;
+                for (int t = a; t <= b; ++t) {
+                    if (sp.list(t).n != 0) return WFAIL(0);
+                    const double e2 = sto_next_break(sp.step(t), k, eta, up);
+                    if (up ? e2 < best : e2 > best) best = e2;
+                }
+                if (!(fabs(best) < BIG)) return WFAIL(0);   // target unreachable: active set changed
+                en = best + (up ? 1.0 : -1.0) * 1e-11 * (1.0 + fabs(best));
+            }
+            if (!(en > lo && en < hi)) {
+                if (!(flo && fhi)) return WFAIL(1);
+                en = lo - rlo * (hi - lo) / (rhi - rlo);
+                if (!(en > lo && en < hi)) en = 0.5 * (lo + hi);
+                if ((hi - lo) <= 1e-15 * (1.0 + fabs(lo))) { eta = en; done = true; break; }
+            }
             eta = en;
         }
-        if (!done) return false;
-        if (Emin < -tolE || Emax > k.emax + tolE) return false;
-        // multiplier sign at the junction with the previous run
-        if (kind_last > 0 && eta > eta_last) return false;
-        if (kind_last < 0 && eta < eta_last) return false;
-        if (kind == 0 && eta != 0.0) return false;
-        if (b + 1 == T && ((kind > 0 && eta < 0.0) || (kind < 0 && eta > 0.0))) return false;
-        for (int t = a; t <= b; ++t) emit(t, eta);
-        e0 = kind > 0 ? k.emax : (kind < 0 ? 0.0 : e0);
-        eta_last = eta; kind_last = kind;
+        if (!done) return WFAIL(2);
+        if (Emin < -tolE || Emax > k.emax + tolE) return WFAIL(3);
+        // multipliers that give the same run solution: a point, or the flat stretch around eta
+        double Ilo = eta, Ihi = eta;
+        if (!(ds < -1e-300)) {
+            for (int t = a; t <= b && nohinge; ++t) nohinge = sp.list(t).n == 0;
+            if (nohinge) {
+                Ilo = -BIG; Ihi = BIG;
+                for (int t = a; t <= b; ++t) {
+                    const StoStep st = sp.step(t);
+                    const StoEval e = sto_eval(st, k, sp.list(t), eta);
+                    double l2, h2;
+                    sto_flat_interval(st, k, eta, e.D, e.C, l2, h2);
+                    Ihi = h2 < Ihi ? h2 : Ihi; Ilo = l2 > Ilo ? l2 : Ilo;
+                }
+            }
+        }
+        if (kind_last > 0) Ihi = Ihi < Fhi ? Ihi : Fhi;     // eta may not rise after a full storage
+        if (kind_last < 0) Ilo = Ilo > Flo ? Ilo : Flo;     // eta may not drop after an empty storage
+        if (b == T - 1) {                                   // end of horizon: eta_{T+1} = 0
+            if (kind > 0) Ilo = Ilo > 0.0 ? Ilo : 0.0;
+            if (kind < 0) Ihi = Ihi < 0.0 ? Ihi : 0.0;
+            if (kind == 0 && (Ilo > 0.0 || Ihi < 0.0)) return WFAIL(6);
+        }
+        if (Ilo > Ihi) return WFAIL(4);
+        const double eo = eta < Ilo ? Ilo : (eta > Ihi ? Ihi : eta);
+        for (int t = a; t <= b; ++t) emit(t, eo);
+        if (kind != 0) e0 = kind > 0 ? k.emax : 0.0;
+        Flo = Ilo; Fhi = Ihi; kind_last = kind;
         a = b + 1;
         if (stats) stats->segments++;
     }

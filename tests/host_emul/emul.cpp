@@ -58,7 +58,7 @@ void emul_storage_solve_seq(int T, double mc, double pmax, double emax, double p
 // returns 1 if the warm path verified, 0 if the cold funnel had to be used.
 int emul_storage_solve_warm(int T, double mc, double pmax, double emax, double prox,
                         const double *Db, const double *Cb, const double *g0, const double *s1,
-                        double *D, double *C, double *eta_io, int *stats)
+                        double *D, double *C, double *eta_io, const double *Eprev, int *stats)
 {
     std::vector<StoStep> st(T);
     for (int t = 0; t < T; ++t) { st[t].Db = Db[t]; st[t].Cb = Cb[t]; st[t].g0 = g0[t]; st[t].s1 = s1[t]; }
@@ -70,7 +70,8 @@ int emul_storage_solve_warm(int T, double mc, double pmax, double emax, double p
     std::vector<double> prev(eta_io, eta_io + T);
     auto emit = [&](int t, double e) { eta_io[t] = e; StoEval ev = sto_eval(p.step[t], p.k, p.list(t), e); D[t] = ev.D; C[t] = ev.C; };
     auto pv = [&](int t) { return prev[t]; };
-    int warm = sto_warm_try(sp, p.k, T, pv, emit, &ss) ? 1 : 0;
+    auto pe = [&](int t) { return Eprev[t]; };
+    int warm = sto_warm_try(sp, p.k, T, pv, pe, emit, &ss) ? 1 : 0;
     if (!warm) sto_funnel_seq(sp, p.k, T, emit, &ss);
     stats[0] = ss.evals; stats[1] = ss.solves; stats[2] = ss.segments; stats[3] = ss.passes;
     return warm;
@@ -175,6 +176,9 @@ void *emul_create(int N, int L, int T, int G, int S, const double *ptdf, const d
 }
 
 void emul_destroy(void *h) { delete (Emul *)h; }
+#ifdef DOPF_DEBUG_WARM
+void emul_warm_fail(int *out) { for (int i = 0; i < 8; ++i) { out[i] = g_warm_fail[i]; g_warm_fail[i] = 0; } }
+#endif
 
 static void compact(Emul *e, int mode)
 {
