@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""bench.py - ADMM iteration throughput of libdopf on B200 (one "step" = one ADMM iteration).
+
+    python bench.py --gpus N --steps K --warmup W [--workload target|cfg3|cfg2] [--impl reference]
+
+metric  : agent*timestep updates per second = (G+S)*T*iterations / time,
+          whole-job aggregate over all ranks; `iters_per_s` is reported beside it.
+workload: "target" = the north_star's synthetic 100k-agent x 96-period case (80k generators +
+          20k storages on the 2000-node / 3000-line grid of BASELINE configs[2]); inputs resident in
+          HBM; working set (~0.5 GB) exceeds the 126 MB L2, so no explicit L2 flush is needed.
+N > 1   : independent scenarios (BASELINE configs[3] style): every rank runs its own scenario of
+          the same shape, no data-path collective ("weak" scaling); time = max over ranks.
+--impl reference : the CPU oracle (oracle/, OpenMP on all host cores) on a bounded sample of the
+          same workload; the Julia/JuMP/Gurobi reference itself cannot be installed here (no Julia).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N, L, G, S, T)
+    "target": (2000, 3000, 80000, 20000, 96),
+    "cfg3": (2000, 3000, 20000, 5000, 96),
+    "cfg2": (118, 186, 1000, 200, 24),
+}
+SAMPLE_AGENTS = {"target": (200, 50), "cfg3": (200, 50), "cfg2": (1000, 200)}   # CPU-side bounded sample
+METRIC = "agent_timestep_updates_per_s"
+UNIT = "agent*timestep/s"
+
+
+def make_case(pkg, workload, seed, agents=None):
+    N, L, G, S, T = WORKLOADS[workload]
+    if agents is not None:
+        G, S = agents
+    d = pkg.cases.synthetic_arrays(N=N, L=L, G=G, S=S, T=T, seed=seed)
+    A = G + S
+    # gamma and flow weight scaled with 1/A keep the reference's Jacobi update stable at scale
+    # (DESIGN.md section 6); prox weight stays the reference's literal.
+    return pkg.Problem.from_arrays(d), dict(gamma=0.3 / A, flow_weight=1.0 / A, prox_weight=1.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_rate(pkg, workload, steps, warmup, budget_s=150.0):
+    """agent*timestep updates/s of the CPU oracle on a bounded sample of the workload: the sample's
+    agent count is scaled (from a one-iteration probe) so that warmup+steps fit `budget_s`."""
+    from oracle import oracle
+    g_s, s_s = SAMPLE_AGENTS[workload]
+    prob, cfg = make_case(pkg, workload, seed=0, agents=(max(g_s // 5, 8), max(s_s // 5, 2)))
+    ora = oracle.OracleADMM(prob, cfg["gamma"], flow_weight=cfg["flow_weight"], prox_weight=cfg["prox_weight"])
+    ora.iterate(0)
+    t0 = time.perf_counter(); ora.iterate(0); probe = time.perf_counter() - t0
+    scale = budget_s / max(steps + warmup, 1) / max(probe, 1e-6)      # affordable multiple of the probe size
+    frac = min(1.0, max(0.2, scale / 5.0))
+    prob, cfg = make_case(pkg, workload, seed=0, agents=(max(int(g_s * frac), 8), max(int(s_s * frac), 2)))
+    ora = oracle.OracleADMM(prob, cfg["gamma"], flow_weight=cfg["flow_weight"], prox_weight=cfg["prox_weight"])
+    for _ in range(warmup):
+        ora.iterate(0)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ora.iterate(0)
+    dt = time.perf_counter() - t0
+    A = prob.G + prob.S
+    sample = (f"{steps} iteration(s) of the oracle on {prob.G} generators + {prob.S} storages of the '{workload}' grid "
+              f"(N={prob.N}, L={prob.L}, T={prob.T}); exact per-agent solves, OpenMP")
+    return A * prob.T * steps / dt, dt / steps * 1e3, oracle.num_threads(), sample
+
+
+def run_reference(args):
+    import __graft_entry__ as g
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pkg = g.load_package()
+    value, ms, cores, sample = oracle_rate(pkg, args.workload, args.steps, args.warmup)
+    N, L, G, S, T = WORKLOADS[args.workload]
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "nodes": N, "lines": L, "generators": G, "storages": S, "timesteps": T,
+                       "note": "reference arm = CPU oracle port on a bounded sample (Julia/JuMP/Gurobi not installable offline)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_dopf(args):
+    import torch
+    import __graft_entry__ as g
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - libdopf has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = g.load_package()
+    from dopf_b200.device import DeviceADMM
+    N, L, G, S, T = WORKLOADS[args.workload]
+    A = G + S
+    prob, cfg = make_case(pkg, args.workload, seed=rank)   # one independent scenario per rank
+    dev = DeviceADMM(prob, device=local, hinge_capacity=64, **cfg)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    dev.step(args.warmup)
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.start()
+    st = dev.step(args.steps)                  # device time by CUDA events on the library's stream
+    barrier()
+    clk = clocks.stop() if clocks else None
+    ms_total = st.last_step_ms
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total = float(tmax.item())
+    value = world * A * T * args.steps / (ms_total * 1e-3)
+    steady = dict(gen_corrected_per_iter=None, sto_corrected_per_iter=None, sto_cold_last=st.sto_cold,
+                  tight_rows=st.tight_rows, wide_rows=st.wide_rows, residuals=[st.res_lambda, st.res_mue, st.res_rho])
+
+    # ---- per-kernel device times of one iteration (CUDA event pair per launch) -> roofline ----
+    prof = dev.profile_iteration()
+    kern = {}
+    for name, ms in prof:
+        kern[name] = kern.get(name, 0.0) + ms
+    dom = max(kern, key=kern.get)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # algorithmic bytes per launch
+    alg_bytes = {"k_gen_predict<2>": 16.0 * G * T, "k_gen_predict<1>": 16.0 * G * T,
+                 "k_sto_warm": 40.0 * S * T, "k_sto_cold": 40.0 * S * T, "k_sto_fix": 40.0 * S * T,
+                 "k_inject": 8.0 * (G + 2 * S) * T + 16.0 * N * T}
+    gemm_flops = {"k_gemm<32, true>": 4.0 * L * N * T, "k_gemm<64, true>": 4.0 * L * N * T,
+                  "k_gemm<32, false>": 2.0 * L * N * T, "k_gemm<64, false>": 2.0 * L * N * T}
+    if dom in gemm_flops:
+        ach = gemm_flops[dom] / (kern[dom] * 1e-3) / 1e12
+        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": 37.0, "unit": "TFLOP/s", "frac": ach / 37.0, "traffic": None,
+                "peak_source": "nominal B200 fp64 (DMMA) 37 TFLOP/s - no fp64 figure in MEASURED_PEAKS.json"}
+    else:
+        b = alg_bytes.get(dom, 40.0 * S * T)
+        ach = b / (kern[dom] * 1e-3) / 1e9
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": b}
+    roof["kernel_ms"] = kern[dom]
+    roof["kernel_share_of_iteration"] = kern[dom] / sum(kern.values())
+    gp = kern.get("k_gen_predict<2>", kern.get("k_gen_predict<1>"))
+    if gp:
+        roof["generator_stream"] = {"kernel_ms": gp, "achieved_GBps": 16.0 * G * T / (gp * 1e-3) / 1e9, "frac": 16.0 * G * T / (gp * 1e-3) / 1e9 / hbm}
+
+    # ---- end to end through the C ABI with host buffers (pinned): upload state, iterate, read back ----
+    e2e_steps = max(1, min(args.steps, 10))
+    pin = lambda shape: torch.empty(shape, dtype=torch.float64).pin_memory().numpy()
+    it = dev.get_iterate(("P", "D", "C", "E", "avgU", "avgK"))
+    lam, mu, rho = dev.get_duals(0)
+    hb = {k: pin(v.shape) for k, v in it.items()}
+    for k, v in it.items():
+        hb[k][...] = v
+    hl, hm, hr = pin(lam.shape), pin(mu.shape), pin(rho.shape)
+    hl[...] = lam; hm[...] = mu; hr[...] = rho
+    h2d = sum(hb[k].nbytes for k in ("P", "D", "C", "avgU", "avgK")) + hl.nbytes + hm.nbytes + hr.nbytes
+    d2h = sum(hb[k].nbytes for k in ("P", "D", "C", "E")) + hl.nbytes + hm.nbytes + hr.nbytes
+    import ctypes as C
+    iteration = dev.status.iteration
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        dev.set_state(iteration, P=hb["P"], D=hb["D"], C_=hb["C"], avgU=hb["avgU"], avgK=hb["avgK"], lam=hl, mu=hm, rho=hr)
+        dev.step(1)
+        dev.get_iterate(("P", "D", "C", "E"), out=hb)
+        dev.lib.dopf_get_duals(dev.h, 0, hl.ctypes.data_as(C.c_void_p), hm.ctypes.data_as(C.c_void_p), hr.ctypes.data_as(C.c_void_p))
+        iteration = dev.status.iteration
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tm = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    e2e_value = world * A * T * e2e_steps / float(tm.item())
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "nodes": N, "lines": L, "generators": G, "storages": S, "timesteps": T,
+                           "gamma": cfg["gamma"], "flow_weight": cfg["flow_weight"], "prox_weight": cfg["prox_weight"],
+                           "parallelism": f"{world} independent scenario(s), one per GPU, no collective",
+                           "l2": "working set larger than L2 (no flush)"},
+                "iters_per_s": world * args.steps / (ms_total * 1e-3),
+                "gpu_launches": st.launches_per_iteration * args.steps,
+                "clocks": clk, "roofline": roof,
+                "kernels_ms": {k: round(v, 4) for k, v in kern.items()},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "steps": e2e_steps, "what": "dopf_set_state(host) + dopf_step(1) + dopf_get_iterate/duals(host), pinned buffers"},
+                "steady_state": steady}
+        if world == 1 and not args.no_cpu_baseline:
+            v, ms, cores, sample = oracle_rate(pkg, args.workload, 3, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_iteration_of_sample": ms}
+        print(json.dumps(line))
+    dev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=30)
+    ap.add_argument("--impl", default="dopf", choices=["dopf", "reference"])
+    ap.add_argument("--workload", default="target", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_dopf(args)
+
+
+if __name__ == "__main__":
+    main()

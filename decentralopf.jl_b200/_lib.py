@@ -38,12 +38,12 @@ class DopfStatus(C.Structure):
                 ("res_lambda", C.c_double), ("res_mue", C.c_double), ("res_rho", C.c_double),
                 ("gen_corrected", C.c_int32), ("sto_corrected", C.c_int32),
                 ("tight_rows", C.c_int32), ("wide_rows", C.c_int32),
-                ("launches_per_iteration", C.c_int32), ("reserved", C.c_int32)]
+                ("launches_per_iteration", C.c_int32), ("sto_cold", C.c_int32), ("last_step_ms", C.c_double)]
 
 
 EXPORTS = ["dopf_version", "dopf_default_config", "dopf_create", "dopf_destroy", "dopf_step", "dopf_get_status",
            "dopf_get_iterate", "dopf_get_duals", "dopf_set_state", "dopf_get_nodal_price", "dopf_get_total_costs",
-           "dopf_comm_unique_id", "dopf_comm_init", "dopf_last_error"]
+           "dopf_comm_unique_id", "dopf_comm_init", "dopf_last_error", "dopf_profile_iteration"]
 
 
 def build(force=False, verbose=False):
@@ -86,6 +86,7 @@ def load():
     lib.dopf_set_state.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 8
     lib.dopf_get_nodal_price.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     lib.dopf_get_total_costs.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.dopf_profile_iteration.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]
     lib.dopf_comm_unique_id.argtypes = [C.c_void_p]
     lib.dopf_comm_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
     _lib = lib

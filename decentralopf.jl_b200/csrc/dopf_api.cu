@@ -71,6 +71,8 @@ struct dopf_handle {
     bool gen_identity = true, sto_identity = true;
     std::vector<double> stage;             // host staging for permutation / padding
     std::string err;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_step_ms = 0.0;
     // multi-GPU
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
@@ -140,7 +142,8 @@ void fill_status(dopf_handle *h, dopf_status *s)
     s->gen_corrected = c.stat_gen_fix; s->sto_corrected = c.stat_sto_fix;
     s->tight_rows = c.stat_tight_rows; s->wide_rows = c.stat_wide_rows;
     s->launches_per_iteration = h->launches_per_iter;
-    s->reserved = 0;
+    s->sto_cold = c.stat_sto_cold;
+    s->last_step_ms = h->last_step_ms;
 }
 
 int check_device_error(dopf_handle *h)
@@ -182,6 +185,8 @@ void dopf_destroy(dopf_handle *h)
     if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->graph) cudaGraphDestroy(h->graph);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
     for (void *p : h->allocs) cudaFree(p);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -211,6 +216,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     CK(cudaGetDeviceProperties(&prop, h->device));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaMallocHost((void **)&h->h_ctrl, sizeof(Ctrl)));
+    CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
     memset(h->h_ctrl, 0, sizeof(Ctrl));
 
     LaunchPlan &lp = h->lp;
@@ -350,8 +356,10 @@ int dopf_step(dopf_handle *h, int32_t max_iters, dopf_status *out)
     int rc = build_graph(h);
     if (rc) return rc;
     int remaining = max_iters;
+    h->last_step_ms = 0.0;
     while (remaining > 0 && !h->h_ctrl->converged && h->h_ctrl->error == 0) {
         const int chunk = std::min(remaining, 64);
+        CK(cudaEventRecord(h->ev0, h->stream));
         for (int i = 0; i < chunk; ++i) {
             if (h->graph_exec) CK(cudaGraphLaunch(h->graph_exec, h->stream));
             else {
@@ -360,13 +368,39 @@ int dopf_step(dopf_handle *h, int32_t max_iters, dopf_status *out)
                 h->launches_per_iter = rc;
             }
         }
+        CK(cudaEventRecord(h->ev1, h->stream));
         CK(cudaGetLastError());
         if ((rc = sync_ctrl(h))) return rc;
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->last_step_ms += ms;
         remaining -= chunk;
     }
     if ((rc = check_device_error(h))) return rc;
     if (out) fill_status(h, out);
     return DOPF_OK;
+}
+
+int dopf_profile_iteration(dopf_handle *h, int32_t cap, float *ms, const char **names, int32_t *count)
+{
+    if (!h || !ms || !names || !count || cap < 1) return DOPF_E_ARG;
+    if (h->nranks > 1) { h->err = "dopf_profile_iteration: single-GPU handles only"; return DOPF_E_UNSUPPORTED; }
+    CK(cudaSetDevice(h->device));
+    std::vector<cudaEvent_t> ev(2 * (size_t)cap);
+    for (auto &e : ev) CK(cudaEventCreate(&e));
+    std::vector<const char *> nm(cap, "");
+    int n = 0;
+    LaunchPlan lp = h->lp;
+    lp.prof_events = ev.data(); lp.prof_names = nm.data(); lp.prof_cap = cap; lp.prof_count = &n;
+    enqueue_iteration(lp, h->stream);
+    CK(cudaGetLastError());
+    int rc = sync_ctrl(h);
+    if (rc) return rc;
+    n = std::min(n, (int)cap);
+    for (int i = 0; i < n; ++i) { CK(cudaEventElapsedTime(&ms[i], ev[2 * i], ev[2 * i + 1])); names[i] = nm[i]; }
+    for (auto &e : ev) cudaEventDestroy(e);
+    *count = n;
+    return check_device_error(h);
 }
 
 int dopf_get_status(dopf_handle *h, dopf_status *out)

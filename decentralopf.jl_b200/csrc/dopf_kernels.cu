@@ -536,7 +536,14 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st)
 {
     const View &v = lp.view;
     int launches = 0;
-#define LAUNCH(...) do { __VA_ARGS__; ++launches; } while (0)
+#define LAUNCH(...)                                                                                \
+    do {                                                                                           \
+        const bool prof_ = lp.prof_events && launches < lp.prof_cap;                               \
+        if (prof_) cudaEventRecord(lp.prof_events[2 * launches], st);                              \
+        __VA_ARGS__;                                                                               \
+        if (prof_) { cudaEventRecord(lp.prof_events[2 * launches + 1], st); lp.prof_names[launches] = #__VA_ARGS__; } \
+        ++launches;                                                                                \
+    } while (0)
     LAUNCH(k_begin<<<lp.num_sms, 256, 0, st>>>(v));
     LAUNCH(k_row_prep<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, st>>>(v));
     LAUNCH(k_compact<<<cdiv((long long)v.T * 32, 128), 128, 0, st>>>(v, 0));
@@ -576,6 +583,7 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st)
     LAUNCH(k_lambda<<<cdiv(v.T, 128), 128, 0, st>>>(v));
     LAUNCH(k_finish<<<1, 1, 0, st>>>(v));
 #undef LAUNCH
+    if (lp.prof_count) *lp.prof_count = launches;
     return launches;
 }
 

@@ -17,6 +17,8 @@ struct LaunchPlan {
     unsigned char *tflag;     // [Lp][ldt] bit0/bit1: exact row sums present (U/K side)
     Hinge *hinge_scratch;     // [sto_fix_blocks*4][T][hcap]
     int *hcnt_scratch;        // [sto_fix_blocks*4][T]
+    // optional per-kernel profiling (dopf_profile_iteration): event pairs + names in launch order
+    cudaEvent_t *prof_events; const char **prof_names; int prof_cap; int *prof_count;
 };
 
 int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st);   // returns number of kernel launches

@@ -98,6 +98,18 @@ class DeviceADMM:
         self._check(self.lib.dopf_set_state(self.h, int(iteration), *[_ptr(a) for a in arrs]), "dopf_set_state")
         self.lib.dopf_get_status(self.h, C.byref(self.status))
 
+    def profile_iteration(self, cap=64):
+        """One iteration with a CUDA-event pair around every kernel -> [(kernel name, ms)]."""
+        import re
+        ms = (C.c_float * cap)(); names = (C.c_char_p * cap)(); n = C.c_int32()
+        self._check(self.lib.dopf_profile_iteration(self.h, cap, ms, names, C.byref(n)), "dopf_profile_iteration")
+        self.lib.dopf_get_status(self.h, C.byref(self.status))
+        out = []
+        for i in range(n.value):
+            m = re.match(r"\s*(k_\w+(?:<[^>]*>)?)", names[i].decode())
+            out.append((m.group(1) if m else names[i].decode()[:40], float(ms[i])))
+        return out
+
     def nodal_price(self, which=1):
         out = np.empty((self.prob.N, self.prob.T))
         self._check(self.lib.dopf_get_nodal_price(self.h, int(which), _ptr(out)), "dopf_get_nodal_price")

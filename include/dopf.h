@@ -81,7 +81,8 @@ typedef struct dopf_status {
     int32_t gen_corrected, sto_corrected;  /* cumulated agents re-solved with explicit hinges */
     int32_t tight_rows, wide_rows;         /* candidate (line,t,side) rows of the last iteration */
     int32_t launches_per_iteration;        /* kernels enqueued per iteration                  */
-    int32_t reserved;
+    int32_t sto_cold;                      /* storages that needed the cold solve in the last iteration */
+    double last_step_ms;                   /* device time of the last dopf_step (CUDA events on the library stream) */
 } dopf_status;
 
 int dopf_create(const dopf_problem *p, const dopf_config *c, dopf_handle **out);
@@ -102,6 +103,10 @@ int dopf_get_duals(dopf_handle *h, int32_t which, double *lam /*[T]*/, double *m
  * injection, flows and levels are re-derived on the device.  NULL = keep. */
 int dopf_set_state(dopf_handle *h, int32_t iteration, const double *P, const double *D, const double *C,
                    const double *avgU, const double *avgK, const double *lam, const double *mu, const double *rho);
+
+/* runs ONE iteration kernel by kernel with a CUDA event pair around each launch (no graph) and
+ * returns the device time of every kernel in launch order.  names[i] points to static strings. */
+int dopf_profile_iteration(dopf_handle *h, int32_t cap, float *ms, const char **names, int32_t *count);
 
 int dopf_get_nodal_price(dopf_handle *h, int32_t which, double *out /*[N][T]*/);
 int dopf_get_total_costs(dopf_handle *h, double *out);

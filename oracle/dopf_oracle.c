@@ -463,13 +463,19 @@ int oracle_iteration(const oracle_problem *p, oracle_state *s, int mode)
         for (int n = 0; n < N; ++n) a += s->inj[(size_t)n * T + t];
         c.Sbar[t] = a;
     }
-    for (int n = 0; n < N; ++n)
-        for (int t = 0; t < T; ++t) {
-            double a = s->lam[t];
-            for (int l = 0; l < L; ++l)
-                a += p->ptdf[(size_t)l * N + n] * (s->mu[l * T + t] - s->rho[l * T + t]);
-            c.pi[(size_t)n * T + t] = a;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int n = 0; n < N; ++n) {
+        double *row = c.pi + (size_t)n * T;
+        for (int t = 0; t < T; ++t) row[t] = s->lam[t];
+        for (int l = 0; l < L; ++l) {
+            const double a = p->ptdf[(size_t)l * N + n];
+            if (a == 0.0) continue;
+            const double *m = s->mu + (size_t)l * T, *r = s->rho + (size_t)l * T;
+            for (int t = 0; t < T; ++t) row[t] += a * (m[t] - r[t]);
         }
+    }
     for (int i = 0; i < L * T; ++i) {
         c.ap[i] = p->fmax[i / T] - s->flow[i];
         c.am[i] = p->fmax[i / T] + s->flow[i];

@@ -1,0 +1,75 @@
+"""The C ABI without a GPU: the library builds for sm_100a, loads, exports every symbol that
+include/dopf.h declares, mirrors the header's struct layouts, and refuses to run without a device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests.conftest import ROOT
+
+
+def _declared_functions():
+    hdr = open(os.path.join(ROOT, "include", "dopf.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(dopf_[a-z_]+)\s*\(", hdr)))
+
+
+def test_library_builds_and_exports_header_symbols(pkg):
+    from dopf_b200 import _lib
+    _lib.build()
+    lib = _lib.load()
+    names = _declared_functions()
+    assert set(names) == set(_lib.EXPORTS)
+    for n in names:
+        assert hasattr(lib, n), n
+    assert b"sm_100a" in lib.dopf_version()
+
+
+def test_struct_layouts_match_header(pkg):
+    from dopf_b200 import _lib
+    assert C.sizeof(_lib.DopfProblem) == 5 * 4 + 4 + 10 * 8            # 5 int32 + pad + 10 pointers
+    assert C.sizeof(_lib.DopfConfig) == 5 * 8 + 4 * 4
+    assert C.sizeof(_lib.DopfStatus) == 6 * 4 + 3 * 8 + 6 * 4 + 8
+    cfg = _lib.DopfConfig()
+    _lib.load().dopf_default_config(C.byref(cfg))
+    assert (cfg.gamma, cfg.flow_weight, cfg.prox_weight, cfg.slack_mask_tol, cfg.eps) == (0.3, 10.0, 1.0, 1e-2, 1e-3)
+
+
+def test_sass_contains_fp64_tensor_and_async_copy(pkg):
+    """the PTDF products run on the fp64 tensor pipe (DMMA) fed by cp.async (LDGSTS)"""
+    import shutil, subprocess
+    from dopf_b200 import _lib
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "DMMA" in sass and "LDGSTS" in sass
+
+
+def test_no_cpu_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from dopf_b200.device import DeviceADMM, DopfError
+    prob = pkg.Problem.from_structs(*pkg.cases.three_node())
+    with pytest.raises(DopfError, match="no CUDA device"):
+        DeviceADMM(prob)
+
+
+def test_invalid_arguments_are_reported(pkg):
+    from dopf_b200 import _lib
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.dopf_create(None, None, C.byref(h)) == -1
+    assert b"null" in lib.dopf_last_error(None)
+    assert lib.dopf_step(None, 1, None) == -1
+
+
+def test_product_package_does_not_import_oracle():
+    pkgdir = os.path.join(ROOT, "decentralopf.jl_b200")
+    for dirpath, _, files in os.walk(pkgdir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".jl")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower() or f == "__init__.py" and "oracle" not in src, (dirpath, f)
