@@ -8,3 +8,4 @@ from .structures import (Convergence, Generator, Line, Node, Result, ResultGener
 from .problem import Problem  # noqa: F401
 from .ptdf import calculate_ptdf, ptdf_from_arrays  # noqa: F401
 from . import cases  # noqa: F401
+from .admm import ADMM, calculate_iteration, get_nodal_price, run  # noqa: F401,E402

@@ -106,8 +106,8 @@ class DeviceADMM:
         self.lib.dopf_get_status(self.h, C.byref(self.status))
         out = []
         for i in range(n.value):
-            m = re.match(r"\s*(k_\w+(?:<[^>]*>)?)", names[i].decode())
-            out.append((m.group(1) if m else names[i].decode()[:40], float(ms[i])))
+            m = re.match(r"\s*(k_\w+)(<[^<>]*>)?\s*<<<", names[i].decode())
+            out.append(((m.group(1) + (m.group(2) or "")) if m else names[i].decode()[:40], float(ms[i])))
         return out
 
     def nodal_price(self, which=1):
