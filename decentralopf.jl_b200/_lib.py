@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libdopf.so")
 _SRCS = [os.path.join(_HERE, "csrc", f) for f in ("dopf_kernels.cu", "dopf_api.cu")]
-_HDRS = [os.path.join(_HERE, "csrc", f) for f in ("dopf_math.h", "dopf_bodies.h", "dopf_kernels.h")] + \
+_HDRS = [os.path.join(_HERE, "csrc", f) for f in ("dopf_math.h", "dopf_bodies.h", "dopf_kernels.h", "dopf_sto_warp.cuh")] + \
         [os.path.join(ROOT, "include", "dopf.h")]
 
 _dp = C.POINTER(C.c_double)

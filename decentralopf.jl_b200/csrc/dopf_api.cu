@@ -306,6 +306,12 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     AL(lp.part2, (size_t)lp.ksplit_t * Np * ldt);
     {
         lp.sto_fix_blocks = std::max(1, std::min(lp.num_sms * 4, (S + 3) / 4));
+        {
+            const int need = (T + 31) / 32;
+            const int opts[6] = {1, 2, 3, 4, 6, 8};
+            lp.sto_j = 0;
+            for (int o : opts) if (o >= need) { lp.sto_j = o; break; }
+        }
         const size_t warps = (size_t)lp.sto_fix_blocks * 4;
         AL(lp.hinge_scratch, S ? warps * T * v.hcap : 1);
         AL(lp.hcnt_scratch, S ? warps * T : 1);

@@ -6,6 +6,7 @@
 // remaining launches of an already enqueued batch are no-ops, so run!(admm) needs no host
 // round trip per iteration.
 #include "dopf_kernels.h"
+#include "dopf_sto_warp.cuh"
 
 namespace dopf {
 
@@ -279,6 +280,20 @@ __global__ void __launch_bounds__(128) k_sto_warm(View v)
     body_sto_warm(v, s);
 }
 
+// warp-parallel active-set solve (dopf_sto_warp.cuh); storages it cannot verify are queued for k_sto_cold
+template <int J>
+__global__ void __launch_bounds__(128) k_sto_warp(View v)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int s = gw; s < v.S; s += nw) {
+        const bool ok = sto_warp_solve<J, false>(v, s, nullptr, nullptr);
+        if (!ok && lane == 0) v.cold_work[atomicAdd(&v.ctrl->cold_work_cnt, 1)] = s;
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(64) k_sto_cold(View v)
 {
     if (!DOPF_ACTIVE(v)) return;
@@ -320,6 +335,7 @@ __device__ __forceinline__ int collect_hinges(const View &v, int n, int t, doubl
     return cnt;
 }
 
+template <int J>
 __global__ void __launch_bounds__(128) k_sto_fix(View v, Hinge *hinge_scratch, int *hcnt_scratch)
 {
     if (!DOPF_ACTIVE(v)) return;
@@ -337,8 +353,10 @@ __global__ void __launch_bounds__(128) k_sto_fix(View v, Hinge *hinge_scratch, i
             if (lane == 0) mycnt[t] = cnt;
         }
         __syncwarp();
+        bool ok = false;
+        if (J > 0) ok = sto_warp_solve<(J > 0 ? J : 1), true>(v, s, mylist, mycnt);
         if (lane == 0) {
-            body_sto_cold(v, s, mylist, mycnt);
+            if (!ok) body_sto_cold(v, s, mylist, mycnt);
             atomicAdd(&v.ctrl->stat_sto_fix, 1);
         }
         __syncwarp();
@@ -558,7 +576,16 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st)
         else LAUNCH(k_gen_predict<1><<<cdiv((long long)v.G * v.T, 256), 256, 0, st>>>(v));
     }
     if (v.S > 0) {
-        LAUNCH(k_sto_warm<<<cdiv(v.S, 128), 128, 0, st>>>(v));
+        const int wblocks = min(cdiv(v.S, 4), lp.num_sms * 16);
+        switch (lp.sto_j) {
+        case 1: LAUNCH(k_sto_warp<1><<<wblocks, 128, 0, st>>>(v)); break;
+        case 2: LAUNCH(k_sto_warp<2><<<wblocks, 128, 0, st>>>(v)); break;
+        case 3: LAUNCH(k_sto_warp<3><<<wblocks, 128, 0, st>>>(v)); break;
+        case 4: LAUNCH(k_sto_warp<4><<<wblocks, 128, 0, st>>>(v)); break;
+        case 6: LAUNCH(k_sto_warp<6><<<wblocks, 128, 0, st>>>(v)); break;
+        case 8: LAUNCH(k_sto_warp<8><<<wblocks, 128, 0, st>>>(v)); break;
+        default: LAUNCH(k_sto_warm<<<cdiv(v.S, 128), 128, 0, st>>>(v)); break;   // long horizons: sequential warm start
+        }
         LAUNCH(k_sto_cold<<<min(cdiv(v.S, 64), lp.num_sms * 8), 64, 0, st>>>(v));
     }
     LAUNCH(k_compact<<<cdiv((long long)v.T * 32, 128), 128, 0, st>>>(v, 1));
@@ -567,7 +594,17 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st)
         LAUNCH(k_verify<<<grid, 256, 0, st>>>(v));
     }
     if (v.G > 0) LAUNCH(k_gen_fix<<<lp.num_sms * 2, 128, 0, st>>>(v));
-    if (v.S > 0) LAUNCH(k_sto_fix<<<lp.sto_fix_blocks, 128, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch));
+    if (v.S > 0) {
+        switch (lp.sto_j) {
+        case 1: LAUNCH(k_sto_fix<1><<<lp.sto_fix_blocks, 128, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 2: LAUNCH(k_sto_fix<2><<<lp.sto_fix_blocks, 128, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 3: LAUNCH(k_sto_fix<3><<<lp.sto_fix_blocks, 128, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 4: LAUNCH(k_sto_fix<4><<<lp.sto_fix_blocks, 128, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 6: LAUNCH(k_sto_fix<6><<<lp.sto_fix_blocks, 128, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 8: LAUNCH(k_sto_fix<8><<<lp.sto_fix_blocks, 128, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        default: LAUNCH(k_sto_fix<0><<<lp.sto_fix_blocks, 128, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        }
+    }
     LAUNCH(k_compact<<<cdiv((long long)v.T * 32, 128), 128, 0, st>>>(v, 1));   // moves may have grown
     LAUNCH(k_inject<<<cdiv((long long)v.Np * v.ldt, 256), 256, 0, st>>>(v));
     LAUNCH(k_colsum<<<v.ldt / 32, dim3(32, 32), 0, st>>>(v));

@@ -12,6 +12,7 @@ struct LaunchPlan {
     int bm_t, ksplit_t;       // tile rows / split-K of the transposed product (PTDF^T M)
     int bm_n, ksplit_n;       // ... of the flow product (PTDF * inj)
     int sto_fix_blocks;       // grid of the storage correction pass (4 warps each; sizes the scratch)
+    int sto_j;                // timesteps per lane of the warp-parallel storage solve (0: horizon too long)
     int slack_blocks_x;
     double *part, *part2;     // split-K partial tiles
     unsigned char *tflag;     // [Lp][ldt] bit0/bit1: exact row sums present (U/K side)
