@@ -9,7 +9,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libdopf.so")
+LIB_PATH = os.environ.get("DOPF_LIB", os.path.join(_HERE, "libdopf.so"))
 _SRCS = [os.path.join(_HERE, "csrc", f) for f in ("dopf_kernels.cu", "dopf_api.cu")]
 _HDRS = [os.path.join(_HERE, "csrc", f) for f in ("dopf_math.h", "dopf_bodies.h", "dopf_kernels.h", "dopf_sto_warp.cuh")] + \
         [os.path.join(ROOT, "include", "dopf.h")]

@@ -289,6 +289,8 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     AL(v.rowsumU, (size_t)Lp * ldt); AL(v.rowsumK, (size_t)Lp * ldt);
     AL(v.ctrl, 1);
     AL(lp.tflag, (size_t)Lp * ldt);
+    AL(v.tslot, (size_t)2 * Lp * ldt);
+    AL(lp.slack_part, (size_t)slack_chunks(G, S) * ldt * slack_rows_cap());
     AL(h->d_scalar, 4);
     AL(h->d_nodal, (size_t)N * T);
 
@@ -305,14 +307,14 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     AL(lp.part, (size_t)std::max(lp.ksplit_t * Np, lp.ksplit_n * Lp) * ldt);
     AL(lp.part2, (size_t)lp.ksplit_t * Np * ldt);
     {
-        lp.sto_fix_blocks = std::max(1, std::min(lp.num_sms * 4, (S + 3) / 4));
+        lp.sto_fix_blocks = std::max(1, std::min(lp.num_sms * 2, S));
         {
             const int need = (T + 31) / 32;
             const int opts[6] = {1, 2, 3, 4, 6, 8};
             lp.sto_j = 0;
             for (int o : opts) if (o >= need) { lp.sto_j = o; break; }
         }
-        const size_t warps = (size_t)lp.sto_fix_blocks * 4;
+        const size_t warps = (size_t)lp.sto_fix_blocks;     // one scratch slot per block
         AL(lp.hinge_scratch, S ? warps * T * v.hcap : 1);
         AL(lp.hcnt_scratch, S ? warps * T : 1);
     }

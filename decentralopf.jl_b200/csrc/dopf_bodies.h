@@ -87,6 +87,7 @@ struct View {
     const double *ptdfT;               // [Np][Lp] transposed PTDF (node-major) for per-agent hinge collection
     int *cold_work;                    // [S] storages whose warm start did not verify
     int *tight, *tcnt;                 // [T][2L] ; [T]
+    int *tslot;                        // [2][Lp][ldt] position of (side,l,t) in the tight list of t (stale unless verified)
     int *gen_work;                     // [gen_work_cap] g*T+t
     int *sto_work, *sto_flag;          // [S], [S]
     double *rowsumU, *rowsumK;         // [Lp][ldt] exact sum_i (b -+ p delta_i)_+ of tight rows

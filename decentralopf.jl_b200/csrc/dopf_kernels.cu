@@ -39,55 +39,63 @@ __global__ void k_row_prep(View v)
     body_row_prep(v, i / v.ldt, i % v.ldt);
 }
 
-// ordered compaction of the candidate rows of one timestep; one warp per t.
+// ordered compaction of the candidate rows of one timestep; one block (8 warps) per t: every warp
+// counts its contiguous slice, the offsets come from a prefix over the 8 counts, then the slice is
+// written in order (deterministic list order).
 //  mode 0: wide list from the flag bytes;  mode 1: tight list = wide entries with
 //  |b| <= max_n|ptdf[l,n]| * (largest move of any agent at t)
-__global__ void k_compact(View v, int mode)
+__global__ void __launch_bounds__(256) k_compact(View v, int mode)
 {
     if (!DOPF_ACTIVE(v)) return;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= v.T) return;
-    const int t = warp;
-    int cnt = 0;
-    if (mode == 0) {
-        int *out = v.wide + (size_t)t * 2 * v.L;
-        const unsigned char *fl = v.flags + (size_t)t * v.Lp;
-        for (int base = 0; base < v.L; base += 32) {
-            const int l = base + lane;
-            const unsigned char f = l < v.L ? fl[l] : 0;
+    __shared__ int wcount[8];
+    const int t = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_in = mode == 0 ? v.L : v.wcnt[t];
+    const int per = ((n_in + 8 * 32 - 1) / (8 * 32)) * 32;       // slice length per warp (multiple of 32)
+    const int i0 = warp * per, i1 = min(i0 + per, n_in);
+    const unsigned char *fl = v.flags + (size_t)t * v.Lp;
+    const int *in = v.wide + (size_t)t * 2 * v.L;
+    const double dm = mode == 1 ? bits_nonneg(v.dmax[t]) : 0.0;
+    int *out = (mode == 0 ? v.wide : v.tight) + (size_t)t * 2 * v.L;
+    for (int pass = 0; pass < 2; ++pass) {
+        int cnt = 0;
+        if (pass == 1) { for (int w = 0; w < warp; ++w) cnt += wcount[w]; }
+        for (int base = i0; base < i1; base += 32) {
+            const int i = base + lane;
+            if (mode == 0) {
+                const unsigned char f = i < i1 ? fl[i] : 0;
 #pragma unroll
-            for (int side = 0; side < 2; ++side) {
-                const bool p = (f >> side) & 1;
+                for (int side = 0; side < 2; ++side) {
+                    const bool p = (f >> side) & 1;
+                    const unsigned m = __ballot_sync(0xffffffffu, p);
+                    if (pass == 1 && p) {
+                        const int pos = cnt + __popc(m & ((1u << lane) - 1));
+                        out[pos] = i * 2 + side;
+                        v.wide_b[(size_t)t * 2 * v.L + pos] = side ? v.bminus[(size_t)i * v.ldt + t] : v.bplus[(size_t)i * v.ldt + t];
+                    }
+                    cnt += __popc(m);
+                }
+            } else {
+                bool p = false;
+                int e = 0;
+                if (i < i1) {
+                    e = in[i];
+                    p = fabs(v.wide_b[(size_t)t * 2 * v.L + i]) <= v.prow[e >> 1] * dm;
+                }
                 const unsigned m = __ballot_sync(0xffffffffu, p);
-                if (p) {
+                if (pass == 1 && p) {
                     const int pos = cnt + __popc(m & ((1u << lane) - 1));
-                    out[pos] = l * 2 + side;
-                    v.wide_b[(size_t)t * 2 * v.L + pos] = side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t];
+                    out[pos] = e;
+                    v.tslot[((size_t)(e & 1) * v.Lp + (e >> 1)) * v.ldt + t] = pos;
                 }
                 cnt += __popc(m);
             }
         }
-        if (lane == 0) { v.wcnt[t] = cnt; if (t == 0) v.ctrl->stat_wide_rows = 0; }
-    } else {
-        int *out = v.tight + (size_t)t * 2 * v.L;
-        const int *in = v.wide + (size_t)t * 2 * v.L;
-        const int n_in = v.wcnt[t];
-        const double dm = bits_nonneg(v.dmax[t]);
-        for (int base = 0; base < n_in; base += 32) {
-            const int j = base + lane;
-            bool p = false;
-            int e = 0;
-            if (j < n_in) {
-                e = in[j];
-                const int l = e >> 1;
-                const double b = (e & 1) ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t];
-                p = fabs(b) <= v.prow[l] * dm;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, p);
-            if (p) out[cnt + __popc(m & ((1u << lane) - 1))] = e;
-            cnt += __popc(m);
+        if (pass == 0) {
+            if (lane == 0) wcount[warp] = cnt;
+            __syncthreads();
+        } else if (warp == 7 && lane == 0) {
+            (mode == 0 ? v.wcnt : v.tcnt)[t] = cnt;
         }
-        if (lane == 0) v.tcnt[t] = cnt;
     }
 }
 
@@ -281,8 +289,11 @@ __global__ void __launch_bounds__(128) k_sto_warm(View v)
 }
 
 // warp-parallel active-set solve (dopf_sto_warp.cuh); storages it cannot verify are queued for k_sto_cold
+#ifndef DOPF_STO_MINB
+#define DOPF_STO_MINB 4
+#endif
 template <int J>
-__global__ void __launch_bounds__(128) k_sto_warp(View v)
+__global__ void __launch_bounds__(128, DOPF_STO_MINB) k_sto_warp(View v)
 {
     if (!DOPF_ACTIVE(v)) return;
     const int lane = threadIdx.x & 31;
@@ -336,30 +347,35 @@ __device__ __forceinline__ int collect_hinges(const View &v, int n, int t, doubl
 }
 
 template <int J>
-__global__ void __launch_bounds__(128) k_sto_fix(View v, Hinge *hinge_scratch, int *hcnt_scratch)
+__global__ void __launch_bounds__(256) k_sto_fix(View v, Hinge *hinge_scratch, int *hcnt_scratch)
 {
     if (!DOPF_ACTIVE(v)) return;
-    const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    // one block per affected storage: the 8 warps collect the hinge lists of different timesteps,
+    // then warp 0 re-solves the storage exactly
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int total = v.ctrl->sto_work_cnt;
-    Hinge *mylist = hinge_scratch + (size_t)gw * v.T * v.hcap;
-    int *mycnt = hcnt_scratch + (size_t)gw * v.T;
-    for (int w = gw; w < total; w += nw) {
+    Hinge *mylist = hinge_scratch + (size_t)blockIdx.x * v.T * v.hcap;
+    int *mycnt = hcnt_scratch + (size_t)blockIdx.x * v.T;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int s = v.sto_work[w], n = v.sto_node[s];
-        const double range = 2.0 * v.sto_pmax[s];
-        for (int t = 0; t < v.T; ++t) {
-            int cnt = collect_hinges(v, n, t, -range, range, mylist + (size_t)t * v.hcap, v.hcap);
+        const double pm = v.sto_pmax[s];
+        for (int t = warp; t < v.T; t += nwarps) {
+            // delta = (D-Db)-(C-Cb) with 0<=D,C<=pmax  =>  delta in [-Db-(pmax-Cb), (pmax-Db)+Cb]
+            const double Db = sel(v.D, v.ctrl->cur)[(size_t)s * v.T + t], Cb = sel(v.C, v.ctrl->cur)[(size_t)s * v.T + t];
+            int cnt = collect_hinges(v, n, t, -Db - (pm - Cb), (pm - Db) + Cb, mylist + (size_t)t * v.hcap, v.hcap);
             if (cnt > v.hcap) { if (lane == 0) v.ctrl->error = DOPF_ERR_HINGE_CAP; cnt = v.hcap; }
             if (lane == 0) mycnt[t] = cnt;
         }
-        __syncwarp();
-        bool ok = false;
-        if (J > 0) ok = sto_warp_solve<(J > 0 ? J : 1), true>(v, s, mylist, mycnt);
-        if (lane == 0) {
-            if (!ok) body_sto_cold(v, s, mylist, mycnt);
-            atomicAdd(&v.ctrl->stat_sto_fix, 1);
+        __syncthreads();
+        if (warp == 0) {
+            bool ok = false;
+            if (J > 0) ok = sto_warp_solve<(J > 0 ? J : 1), true>(v, s, mylist, mycnt);
+            if (lane == 0) {
+                if (!ok) body_sto_cold(v, s, mylist, mycnt);
+                atomicAdd(&v.ctrl->stat_sto_fix, 1);
+            }
         }
-        __syncwarp();
+        __syncthreads();
     }
 }
 
@@ -434,26 +450,153 @@ __global__ void k_colsum(View v)   // block (32,32): 32 timesteps, 32 row groups
     }
 }
 
-// exact average-slack sums of the tight rows: one block per (t, row), threads over nodes
-__global__ void k_slack_rows(View v, unsigned char *tflag)
+// ------------------------------------------------------------------------------------------------
+// exact average-slack sums of the tight rows, agent-streaming form (results.jl:83-84,110-112):
+//   rowsum[l,t,side] = sum over ALL agents i of (b_lt -+ p_{l,n(i)} * delta_it)_+
+// Block = 32 timesteps x SLK_AGENTS agents; lane = timestep (coalesced along t), the 8 warps walk the
+// agents of the chunk.  Every lane accumulates the first SLK_ROWS tight rows of its own timestep;
+// per-chunk partials are written to slack_part[chunk][t][row] and reduced in fixed order by k_dual
+// (deterministic).  Rows beyond SLK_ROWS per timestep are handled by k_slack_rows below.
+// ------------------------------------------------------------------------------------------------
+constexpr int SLK_ROWS = 16, SLK_AGENTS = 512, SLK_WARPS = 4;
+
+__global__ void __launch_bounds__(SLK_WARPS * 32, 3) k_slack_stream(View v, double *part, int nchunk_gen)
 {
     if (!DOPF_ACTIVE(v)) return;
+    __shared__ double red[SLK_WARPS][SLK_ROWS][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.y * 32 + lane;
+    const int chunk = blockIdx.x;
+    const bool gens = chunk < nchunk_gen;
+    const int a0 = (gens ? chunk : chunk - nchunk_gen) * SLK_AGENTS;
+    const int a1 = min(a0 + SLK_AGENTS, gens ? v.G : v.S);
+    const int cur = v.ctrl->cur, nxt = 1 - cur;
+    const bool tv = t < v.T;
+    const int tt = tv ? t : 0;
+    const int cnt = tv ? min(v.tcnt[t], SLK_ROWS) : 0;
+    int rl[SLK_ROWS]; double rb[SLK_ROWS], acc[SLK_ROWS];
+    const int *lst = v.tight + (size_t)tt * 2 * v.L;
+#pragma unroll
+    for (int j = 0; j < SLK_ROWS; ++j) {
+        acc[j] = 0.0; rl[j] = 0; rb[j] = 0.0;
+        if (j < cnt) {
+            const int e = lst[j], l = e >> 1;
+            rl[j] = e;
+            rb[j] = (e & 1) ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t];
+        }
+    }
+    const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
+    if (maxcnt > 0) {
+        // every warp walks a contiguous agent range (consecutive agents share their node, so the PTDF
+        // entries of the lane's rows are re-gathered only when the node changes); 4 agents are loaded
+        // ahead of their use to keep several memory requests in flight
+        const int per = SLK_AGENTS / SLK_WARPS;
+        const int w0 = a0 + warp * per, w1 = min(w0 + per, a1);
+        const double *An = gens ? sel(v.P, nxt) : sel(v.D, nxt), *Ap = gens ? sel(v.P, cur) : sel(v.D, cur);
+        const double *Cn = sel(v.C, nxt), *Cp = sel(v.C, cur);
+        const int *nodes = gens ? v.gen_node : v.sto_node;
+        int ncur = -1;
+        double pj[SLK_ROWS];
+#pragma unroll
+        for (int j = 0; j < SLK_ROWS; ++j) pj[j] = 0.0;
+        for (int a = w0; a < w1; a += 4) {
+            double d[4]; int nn[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int aa = min(a + u, w1 - 1);
+                const size_t o = (size_t)aa * v.T + tt;
+                nn[u] = nodes[aa];
+                d[u] = An[o] - Ap[o];
+                if (!gens) d[u] -= Cn[o] - Cp[o];
+                if (a + u >= w1 || !tv) d[u] = 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (a + u >= w1) break;
+                if (nn[u] != ncur) {
+                    ncur = nn[u];
+                    const double *pcol = v.ptdfT + (size_t)ncur * v.Lp;
+#pragma unroll
+                    for (int j = 0; j < SLK_ROWS; ++j)
+                        if (j < cnt) { const double p = pcol[rl[j] >> 1]; pj[j] = (rl[j] & 1) ? p : -p; }
+                }
+                // rows beyond the lane's own count have rb = pj = 0 and add exactly 0: no per-lane predicate,
+                // only a warp-uniform cut at the largest count of the warp
+#pragma unroll
+                for (int j = 0; j < SLK_ROWS; ++j) {
+                    if (j >= maxcnt) break;
+                    acc[j] += fmax(fma(pj[j], d[u], rb[j]), 0.0);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < SLK_ROWS; ++j) red[warp][j][lane] = acc[j];
+    __syncthreads();
+    for (int j = warp; j < SLK_ROWS; j += SLK_WARPS) {   // fixed-order reduction over the warps
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < SLK_WARPS; ++w) sum += red[w][j][lane];
+        if (tv) part[((size_t)chunk * v.ldt + t) * SLK_ROWS + j] = sum;
+    }
+}
+
+// rows beyond SLK_ROWS per timestep (rare): one block per (t, row).  Threads classify the nodes;
+// nodes nobody crosses contribute in closed form, the (rare) crossed nodes are queued in shared
+// memory and summed by the warps with the lanes over the agents of the node.
+__global__ void __launch_bounds__(128) k_slack_rows(View v, unsigned char *tflag)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    constexpr int QCAP = 512;
     __shared__ double red[4];
-    const int t = blockIdx.y;
+    __shared__ int queue[QCAP];
+    __shared__ int qcnt;
+    const int t = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cur = v.ctrl->cur, nxt = 1 - cur;
     const int cnt = v.tcnt[t];
     const int *lst = v.tight + (size_t)t * 2 * v.L;
-    for (int j = blockIdx.x; j < cnt; j += gridDim.x) {
+    for (int j = SLK_ROWS + blockIdx.x; j < cnt; j += gridDim.x) {
         const int l = lst[j] >> 1, side = lst[j] & 1;
+        const double b = side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t];
+        if (threadIdx.x == 0) qcnt = 0;
+        __syncthreads();
         double a = 0.0;
-        for (int n = threadIdx.x; n < v.N; n += blockDim.x) a += body_slack_row_node(v, l, side, n, t);
+        for (int n = threadIdx.x; n < v.N; n += blockDim.x) {
+            const double na = v.nagents[n];
+            if (na == 0.0) continue;
+            const double p = v.ptdf[(size_t)l * v.Np + n];
+            const size_t nt = (size_t)n * v.ldt + t;
+            if (p == 0.0) { a += na * pospart(b); continue; }
+            if (fabs(b) > fabs(p) * bits_nonneg(v.dn[nt])) {      // nobody at this node crosses the hinge
+                if (b > 0.0) a += na * b + (side ? p : -p) * (sel(v.injloc, nxt)[nt] - sel(v.injloc, cur)[nt]);
+                continue;
+            }
+            const int q = atomicAdd(&qcnt, 1);
+            if (q < QCAP) queue[q] = n; else a += body_slack_row_node(v, l, side, n, t);   // overflow: serial path
+        }
+        __syncthreads();
+        const int nq = min(qcnt, QCAP);
+        for (int q = warp; q < nq; q += (blockDim.x >> 5)) {
+            const int n = queue[q];
+            const double sp = side ? v.ptdf[(size_t)l * v.Np + n] : -v.ptdf[(size_t)l * v.Np + n];
+            const int g0 = v.gen_ptr[n], g1 = v.gen_ptr[n + 1], s0 = v.sto_ptr[n], s1 = v.sto_ptr[n + 1];
+            for (int g = g0 + lane; g < g1; g += 32) {
+                const size_t o = (size_t)g * v.T + t;
+                a += pospart(b + sp * (sel(v.P, nxt)[o] - sel(v.P, cur)[o]));
+            }
+            for (int s = s0 + lane; s < s1; s += 32) {
+                const size_t o = (size_t)s * v.T + t;
+                a += pospart(b + sp * ((sel(v.D, nxt)[o] - sel(v.D, cur)[o]) - (sel(v.C, nxt)[o] - sel(v.C, cur)[o])));
+            }
+        }
         a = Group<32>::sum(a);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+        if (lane == 0) red[warp] = a;
         __syncthreads();
         if (threadIdx.x == 0) {
-            double s = 0.0;
-            for (int k = 0; k < (int)(blockDim.x >> 5); ++k) s += red[k];
+            double sum = 0.0;
+            for (int k2 = 0; k2 < (int)(blockDim.x >> 5); ++k2) sum += red[k2];
             const size_t i = (size_t)l * v.ldt + t;
-            (side ? v.rowsumK : v.rowsumU)[i] = s;
+            (side ? v.rowsumK : v.rowsumU)[i] = sum;
             atomicOr(reinterpret_cast<unsigned int *>(tflag) + (i >> 2), (unsigned)(1u << side) << (8 * (i & 3)));
         }
         __syncthreads();
@@ -468,7 +611,7 @@ __global__ void k_clear_tflag(View v, unsigned char *tflag)
 }
 
 // dual update + residual maxima (update_duals.jl, convergence.jl:3-12)
-__global__ void __launch_bounds__(256) k_dual(View v, const unsigned char *tflag)
+__global__ void __launch_bounds__(256) k_dual(View v, unsigned char *tflag, const double *part, int nchunks)
 {
     if (!DOPF_ACTIVE(v)) return;
     __shared__ double rm[8], rr[8];
@@ -476,7 +619,22 @@ __global__ void __launch_bounds__(256) k_dual(View v, const unsigned char *tflag
     double a = 0.0, b = 0.0;
     if (i < v.L * v.ldt) {
         const int l = i / v.ldt, t = i % v.ldt;
-        if (t < v.T) body_dual(v, l, t, tflag[i], a, b);
+        if (t < v.T) {
+            int flag = tflag[i];
+            // tight rows with a slot below SLK_ROWS: sum the per-chunk partials of k_slack_stream
+            const int tc = v.tcnt[t];
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const int slot = v.tslot[((size_t)side * v.Lp + l) * v.ldt + t];
+                if (slot >= 0 && slot < tc && slot < SLK_ROWS && v.tight[(size_t)t * 2 * v.L + slot] == l * 2 + side) {
+                    double sum = 0.0;
+                    for (int c = 0; c < nchunks; ++c) sum += part[((size_t)c * v.ldt + t) * SLK_ROWS + slot];
+                    (side ? v.rowsumK : v.rowsumU)[i] = sum;
+                    flag |= 1 << side;
+                }
+            }
+            body_dual(v, l, t, flag, a, b);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -550,6 +708,9 @@ __global__ void k_nodal_price(View v, int which, double *out /*[N][T]*/)
 // ------------------------------------------------------------------------------------------------
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+int slack_chunks(int G, int S) { return cdiv(G, SLK_AGENTS) + cdiv(S, SLK_AGENTS); }
+int slack_rows_cap() { return SLK_ROWS; }
+
 int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st)
 {
     const View &v = lp.view;
@@ -564,7 +725,7 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st)
     } while (0)
     LAUNCH(k_begin<<<lp.num_sms, 256, 0, st>>>(v));
     LAUNCH(k_row_prep<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, st>>>(v));
-    LAUNCH(k_compact<<<cdiv((long long)v.T * 32, 128), 128, 0, st>>>(v, 0));
+    LAUNCH(k_compact<<<v.T, 256, 0, st>>>(v, 0));
     {   // PTDF^T M and (PTDF.^2)^T W
         dim3 grid(v.Np / lp.bm_t, v.ldt / BN, lp.ksplit_t);
         if (lp.bm_t == 64) LAUNCH(k_gemm<64, true><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, lp.part2, v.Np, v.Lp, lp.ksplit_t));
@@ -588,7 +749,7 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st)
         }
         LAUNCH(k_sto_cold<<<min(cdiv(v.S, 64), lp.num_sms * 8), 64, 0, st>>>(v));
     }
-    LAUNCH(k_compact<<<cdiv((long long)v.T * 32, 128), 128, 0, st>>>(v, 1));
+    LAUNCH(k_compact<<<v.T, 256, 0, st>>>(v, 1));
     {
         dim3 grid(cdiv(v.N, 32), cdiv(v.T, 8));
         LAUNCH(k_verify<<<grid, 256, 0, st>>>(v));
@@ -596,16 +757,16 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st)
     if (v.G > 0) LAUNCH(k_gen_fix<<<lp.num_sms * 2, 128, 0, st>>>(v));
     if (v.S > 0) {
         switch (lp.sto_j) {
-        case 1: LAUNCH(k_sto_fix<1><<<lp.sto_fix_blocks, 128, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 2: LAUNCH(k_sto_fix<2><<<lp.sto_fix_blocks, 128, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 3: LAUNCH(k_sto_fix<3><<<lp.sto_fix_blocks, 128, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 4: LAUNCH(k_sto_fix<4><<<lp.sto_fix_blocks, 128, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 6: LAUNCH(k_sto_fix<6><<<lp.sto_fix_blocks, 128, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 8: LAUNCH(k_sto_fix<8><<<lp.sto_fix_blocks, 128, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        default: LAUNCH(k_sto_fix<0><<<lp.sto_fix_blocks, 128, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 1: LAUNCH(k_sto_fix<1><<<lp.sto_fix_blocks, 256, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 2: LAUNCH(k_sto_fix<2><<<lp.sto_fix_blocks, 256, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 3: LAUNCH(k_sto_fix<3><<<lp.sto_fix_blocks, 256, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 4: LAUNCH(k_sto_fix<4><<<lp.sto_fix_blocks, 256, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 6: LAUNCH(k_sto_fix<6><<<lp.sto_fix_blocks, 256, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 8: LAUNCH(k_sto_fix<8><<<lp.sto_fix_blocks, 256, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        default: LAUNCH(k_sto_fix<0><<<lp.sto_fix_blocks, 256, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
         }
     }
-    LAUNCH(k_compact<<<cdiv((long long)v.T * 32, 128), 128, 0, st>>>(v, 1));   // moves may have grown
+    LAUNCH(k_compact<<<v.T, 256, 0, st>>>(v, 1));   // moves may have grown
     LAUNCH(k_inject<<<cdiv((long long)v.Np * v.ldt, 256), 256, 0, st>>>(v));
     LAUNCH(k_colsum<<<v.ldt / 32, dim3(32, 32), 0, st>>>(v));
     {   // flow = PTDF * inj
@@ -615,8 +776,12 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st)
         LAUNCH(k_flow_reduce<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, st>>>(v, lp.part, lp.ksplit_n));
     }
     LAUNCH(k_clear_tflag<<<cdiv((long long)v.Lp * v.ldt / 4, 256), 256, 0, st>>>(v, lp.tflag));
-    LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.T), 128, 0, st>>>(v, lp.tflag));
-    LAUNCH(k_dual<<<cdiv((long long)v.L * v.ldt, 256), 256, 0, st>>>(v, lp.tflag));
+    {
+        const int ncg = cdiv(v.G, SLK_AGENTS), ncs = cdiv(v.S, SLK_AGENTS);
+        LAUNCH(k_slack_stream<<<dim3(ncg + ncs, v.ldt / 32), SLK_WARPS * 32, 0, st>>>(v, lp.slack_part, ncg));
+        LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.T), 128, 0, st>>>(v, lp.tflag));
+        LAUNCH(k_dual<<<cdiv((long long)v.L * v.ldt, 256), 256, 0, st>>>(v, lp.tflag, lp.slack_part, ncg + ncs));
+    }
     LAUNCH(k_lambda<<<cdiv(v.T, 128), 128, 0, st>>>(v));
     LAUNCH(k_finish<<<1, 1, 0, st>>>(v));
 #undef LAUNCH

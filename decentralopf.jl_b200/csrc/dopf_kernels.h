@@ -11,18 +11,21 @@ struct LaunchPlan {
     int num_sms;
     int bm_t, ksplit_t;       // tile rows / split-K of the transposed product (PTDF^T M)
     int bm_n, ksplit_n;       // ... of the flow product (PTDF * inj)
-    int sto_fix_blocks;       // grid of the storage correction pass (4 warps each; sizes the scratch)
+    int sto_fix_blocks;       // grid of the storage correction pass (one block = one affected storage; sizes the scratch)
     int sto_j;                // timesteps per lane of the warp-parallel storage solve (0: horizon too long)
     int slack_blocks_x;
     double *part, *part2;     // split-K partial tiles
     unsigned char *tflag;     // [Lp][ldt] bit0/bit1: exact row sums present (U/K side)
-    Hinge *hinge_scratch;     // [sto_fix_blocks*4][T][hcap]
-    int *hcnt_scratch;        // [sto_fix_blocks*4][T]
+    double *slack_part;       // [agent chunks][ldt][SLK_ROWS] partial slack sums of k_slack_stream
+    Hinge *hinge_scratch;     // [sto_fix_blocks][T][hcap]
+    int *hcnt_scratch;        // [sto_fix_blocks][T]
     // optional per-kernel profiling (dopf_profile_iteration): event pairs + names in launch order
     cudaEvent_t *prof_events; const char **prof_names; int prof_cap; int *prof_count;
 };
 
-int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st);   // returns number of kernel launches
+int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st);
+int slack_chunks(int G, int S);
+int slack_rows_cap();   // returns number of kernel launches
 void launch_total_costs(const View &v, double *d_out, cudaStream_t st);
 void launch_nodal_price(const View &v, int which, double *d_out, cudaStream_t st);
 void launch_rebuild_derived(const LaunchPlan &lp, cudaStream_t st);  // inj/ssum/flow/E of buffer [cur] from P,D,C

@@ -163,6 +163,7 @@ void *emul_create(int N, int L, int T, int G, int S, const double *ptdf, const d
     e->dn.assign((size_t)Np * ldt, 0); e->dmax.assign(ldt, 0); v.dn = e->dn.data(); v.dmax = e->dmax.data();
     e->flags.assign((size_t)ldt * Lp, 0); v.flags = e->flags.data(); e->tflag.assign((size_t)Lp * ldt, 0);
     v.wide = e->mki((size_t)T * 2 * L); v.wcnt = e->mki(T); v.tight = e->mki((size_t)T * 2 * L); v.tcnt = e->mki(T);
+    v.tslot = e->mki((size_t)2 * Lp * ldt);
     v.gen_work = e->mki(v.gen_work_cap); v.sto_work = e->mki(S); v.sto_flag = e->mki(S);
     v.rowsumU = e->mk((size_t)Lp * ldt); v.rowsumK = e->mk((size_t)Lp * ldt);
     memset(&e->ctrl, 0, sizeof e->ctrl); e->ctrl.iteration = 1; v.ctrl = &e->ctrl;
@@ -217,12 +218,14 @@ static void storage_pass(Emul *e, bool fix)
     }
     for (int w = 0; w < v.ctrl->sto_work_cnt; ++w) {
         const int s = v.sto_work[w], n = v.sto_node[s];
-        const double range = 2.0 * v.sto_pmax[s];
+        const double pm = v.sto_pmax[s];
         for (int t = 0; t < T; ++t) {
+            const double Db_ = sel(v.D, v.ctrl->cur)[(size_t)s * T + t], Cb_ = sel(v.C, v.ctrl->cur)[(size_t)s * T + t];
+            const double rlo_ = -Db_ - (pm - Cb_), rhi_ = (pm - Db_) + Cb_;
             int cnt = 0;
             for (int j = 0; j < v.wcnt[t]; ++j) {
                 int en = v.wide[(size_t)t * 2 * v.L + j]; Hinge h;
-                if (make_hinge(v.c, v.ptdfT[(size_t)n * v.Lp + (en >> 1)], v.wide_b[(size_t)t * 2 * v.L + j], en & 1, h) && h.bp > -range && h.bp < range) {
+                if (make_hinge(v.c, v.ptdfT[(size_t)n * v.Lp + (en >> 1)], v.wide_b[(size_t)t * 2 * v.L + j], en & 1, h) && h.bp > rlo_ && h.bp < rhi_) {
                     if (cnt < v.hcap) e->scratch[(size_t)t * v.hcap + cnt] = h;
                     cnt++;
                 }

@@ -151,12 +151,19 @@ def test_set_state_resumes_a_trajectory(pkg, DeviceADMM):
 
 
 def test_hinge_capacity_overflow_is_loud(pkg, DeviceADMM):
+    """a too small hinge list capacity must stop the run with an error, never silently truncate"""
     from dopf_b200.device import DopfError
-    d = pkg.cases.synthetic_arrays(N=12, L=18, G=30, S=8, T=6, seed=3)
-    prob = pkg.Problem.from_arrays(d)
-    dev = DeviceADMM(prob, gamma=0.02, flow_weight=10.0, device=0, hinge_capacity=1)
-    with pytest.raises(DopfError, match="hinge list capacity"):
-        dev.step(25)
+    raised = 0
+    for seed in range(8):
+        d = pkg.cases.synthetic_arrays(N=12, L=18, G=30, S=8, T=6, seed=seed, congest_frac=0.5)
+        prob = pkg.Problem.from_arrays(d)
+        dev = DeviceADMM(prob, gamma=0.02, flow_weight=10.0, device=0, hinge_capacity=1)
+        try:
+            dev.step(40)
+        except DopfError as e:
+            assert "hinge list capacity" in str(e)
+            raised += 1
+    assert raised > 0
 
 
 @pytest.mark.parametrize("dims", [(2000, 3000, 20000, 5000, 96)])
