@@ -76,6 +76,7 @@ struct dopf_handle {
     // multi-GPU
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
+    int host_cur = 0;   // host mirror of Ctrl::cur (multi-GPU exchanges)
 };
 
 namespace {
@@ -162,6 +163,7 @@ int check_device_error(dopf_handle *h)
 }  // namespace
 
 namespace dopf {
+static int exchange_cb(void *ctx, int what, cudaStream_t st);
 int enqueue_iteration_comm(dopf_handle *h, cudaStream_t st);
 }
 
@@ -286,7 +288,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     AL(v.wide, (size_t)T * 2 * L); AL(v.wcnt, T); AL(v.tight, (size_t)T * 2 * L); AL(v.tcnt, T);
     v.gen_work_cap = (int)std::min<long long>((long long)G * T, 1ll << 30);
     AL(v.gen_work, (size_t)std::max(v.gen_work_cap, 1)); AL(v.sto_work, S); AL(v.sto_flag, S);
-    AL(v.rowsumU, (size_t)Lp * ldt); AL(v.rowsumK, (size_t)Lp * ldt);
+    AL(v.rowsumU, (size_t)2 * Lp * ldt); v.rowsumK = v.rowsumU + (size_t)Lp * ldt;   // contiguous: one exchange
     AL(v.ctrl, 1);
     AL(lp.tflag, (size_t)Lp * ldt);
     AL(v.tslot, (size_t)2 * Lp * ldt);
@@ -365,6 +367,7 @@ int dopf_step(dopf_handle *h, int32_t max_iters, dopf_status *out)
     if (rc) return rc;
     int remaining = max_iters;
     h->last_step_ms = 0.0;
+    h->host_cur = h->h_ctrl->cur;
     while (remaining > 0 && !h->h_ctrl->converged && h->h_ctrl->error == 0) {
         const int chunk = std::min(remaining, 64);
         CK(cudaEventRecord(h->ev0, h->stream));
@@ -379,6 +382,7 @@ int dopf_step(dopf_handle *h, int32_t max_iters, dopf_status *out)
         CK(cudaEventRecord(h->ev1, h->stream));
         CK(cudaGetLastError());
         if ((rc = sync_ctrl(h))) return rc;
+        h->host_cur = h->h_ctrl->cur;
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         h->last_step_ms += ms;
@@ -519,12 +523,11 @@ int dopf_set_state(dopf_handle *h, int32_t iteration, const double *P, const dou
     c.iters_done = 0;
     *h->h_ctrl = c;
     CK(cudaMemcpyAsync(v.ctrl, h->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, h->stream));
-    launch_rebuild_derived(h->lp, h->stream);
     if (h->nranks > 1) {
-        // injection of all ranks, then flows: redo the derived quantities with the exchanged sum
         h->err = "dopf_set_state is not supported after dopf_comm_init";
         return DOPF_E_UNSUPPORTED;
     }
+    launch_rebuild_derived(h->lp, h->stream);
     CK(cudaGetLastError());
     if ((rc = sync_ctrl(h))) return rc;
     return DOPF_OK;
@@ -574,6 +577,7 @@ int dopf_comm_init(dopf_handle *h, int32_t rank, int32_t nranks, const void *uid
     int rc = nccl().CommInitRank(&h->comm, nranks, id, rank);
     if (rc != 0) { h->err = std::string("ncclCommInitRank: ") + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "error"); return DOPF_E_COMM; }
     h->rank = rank; h->nranks = nranks;
+    h->use_graph = false;          // exchanges are issued from the host between the kernels
     View &v = h->lp.view;
     v.A = total_agents;
     v.demand_on = rank == 0 ? 1 : 0;
@@ -583,16 +587,17 @@ int dopf_comm_init(dopf_handle *h, int32_t rank, int32_t nranks, const void *uid
         if (r2) return r2;
         v.injloc[k] = q;
     }
-    // initial injection: -demand on rank 0, summed over ranks (every agent starts at 0)
-    launch_rebuild_derived(h->lp, h->stream);
-    const int cur = h->h_ctrl->cur;   // rebuild flipped the buffers on the device; mirror below
-    (void)cur;
+    // state before iteration 1 with the exchanged injection (-demand from rank 0, agents at 0)
     if ((rc = sync_ctrl(h))) return rc;
-    const int k = h->h_ctrl->cur;
-    if ((rc = comm_allreduce(h, v.injloc[k], v.inj[k], (size_t)v.Np * v.ldt, ncclSum))) return rc;
-    launch_rebuild_derived(h->lp, h->stream);   // second pass keeps injloc, recomputes flows from inj
+    h->host_cur = h->h_ctrl->cur;
+    Exchange x{exchange_cb, h};
+    if ((rc = launch_rebuild_derived(h->lp, h->stream, &x)) < 0) return rc;
+    h->host_cur = 1 - h->host_cur;
+    // the local contribution of the *previous* iterate is needed by the slack sums: fill both buffers
+    CK(cudaMemcpyAsync(v.injloc[1 - h->host_cur], v.injloc[h->host_cur], (size_t)v.Np * v.ldt * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaGetLastError());
     if ((rc = sync_ctrl(h))) return rc;
+    if (h->h_ctrl->cur != h->host_cur) { h->err = "internal: buffer index mismatch after dopf_comm_init"; return DOPF_E_CUDA; }
     return DOPF_OK;
 }
 
@@ -600,15 +605,30 @@ int dopf_comm_init(dopf_handle *h, int32_t rank, int32_t nranks, const void *uid
 
 namespace dopf {
 
+static int exchange_cb(void *ctx, int what, cudaStream_t st)
+{
+    dopf_handle *h = (dopf_handle *)ctx;
+    (void)st;
+    View &v = h->lp.view;
+    const int nxt = 1 - h->host_cur;
+    switch (what) {
+    case DOPF_X_DMAX: return comm_allreduce(h, v.dmax, v.dmax, (size_t)v.ldt, ncclMax);            // bits of non-negative doubles
+    case DOPF_X_INJ: return comm_allreduce(h, v.injloc[nxt], v.inj[nxt], (size_t)v.Np * v.ldt, ncclSum);
+    case DOPF_X_ROWSUM: return comm_allreduce(h, v.rowsumU, v.rowsumU, (size_t)2 * v.Lp * v.ldt, ncclSum);
+    }
+    return 0;
+}
+
 // one iteration including the exchange steps; returns the number of kernel launches or < 0
 int enqueue_iteration_comm(dopf_handle *h, cudaStream_t st)
 {
-    if (h->nranks <= 1) {
-        int n = enqueue_iteration(h->lp, st);
-        return n;
-    }
-    h->err = "multi-GPU stepping is wired in dopf_multi (see dopf_comm_init)";
-    return DOPF_E_UNSUPPORTED;
+    if (h->nranks <= 1) return enqueue_iteration(h->lp, st);
+    // the exchanges address the double-buffered arrays from the host, so the host mirrors the buffer
+    // index; it advances by one per enqueued iteration (multi-GPU runs do not stop early on the device)
+    Exchange x{exchange_cb, h};
+    int n = enqueue_iteration(h->lp, st, &x);
+    h->host_cur = 1 - h->host_cur;
+    return n;
 }
 
 }  // namespace dopf

@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(SLK_WARPS * 32, 3) k_slack_stream(View v, doub
         const double *An = gens ? sel(v.P, nxt) : sel(v.D, nxt), *Ap = gens ? sel(v.P, cur) : sel(v.D, cur);
         const double *Cn = sel(v.C, nxt), *Cp = sel(v.C, cur);
         const int *nodes = gens ? v.gen_node : v.sto_node;
-        int ncur = -1;
+        int ncur = -1, nrest = 0;
         double pj[SLK_ROWS];
 #pragma unroll
         for (int j = 0; j < SLK_ROWS; ++j) pj[j] = 0.0;
@@ -513,6 +513,9 @@ __global__ void __launch_bounds__(SLK_WARPS * 32, 3) k_slack_stream(View v, doub
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (a + u >= w1) break;
+                // agents resting at a bound over the whole tile (delta = 0 for all 32 timesteps) add the
+                // constant (b)_+ to every row: count them instead of evaluating the rows
+                if (__all_sync(0xffffffffu, d[u] == 0.0)) { ++nrest; continue; }
                 if (nn[u] != ncur) {
                     ncur = nn[u];
                     const double *pcol = v.ptdfT + (size_t)ncur * v.Lp;
@@ -529,6 +532,8 @@ __global__ void __launch_bounds__(SLK_WARPS * 32, 3) k_slack_stream(View v, doub
                 }
             }
         }
+#pragma unroll
+        for (int j = 0; j < SLK_ROWS; ++j) acc[j] += (double)nrest * fmax(rb[j], 0.0);
     }
 #pragma unroll
     for (int j = 0; j < SLK_ROWS; ++j) red[warp][j][lane] = acc[j];
@@ -603,15 +608,37 @@ __global__ void __launch_bounds__(128) k_slack_rows(View v, unsigned char *tflag
     }
 }
 
+// fixed-order sum of the per-chunk partials of k_slack_stream into rowsumU / rowsumK: one warp per
+// (t, tight row slot), lanes over the chunks (shuffle tree => deterministic)
+__global__ void __launch_bounds__(128) k_slack_reduce(View v, unsigned char *tflag, const double *part, int nchunks)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.y;
+    const int cnt = min(v.tcnt[t], SLK_ROWS);
+    const int slot = blockIdx.x * 4 + warp;
+    if (slot >= cnt) return;
+    double sum = 0.0;
+    for (int c = lane; c < nchunks; c += 32) sum += part[((size_t)c * v.ldt + t) * SLK_ROWS + slot];
+    sum = Group<32>::sum(sum);
+    if (lane == 0) {
+        const int e = v.tight[(size_t)t * 2 * v.L + slot], l = e >> 1, side = e & 1;
+        const size_t i = (size_t)l * v.ldt + t;
+        (side ? v.rowsumK : v.rowsumU)[i] = sum;
+        atomicOr(reinterpret_cast<unsigned int *>(tflag) + (i >> 2), (unsigned)(1u << side) << (8 * (i & 3)));
+    }
+}
+
 __global__ void k_clear_tflag(View v, unsigned char *tflag)
 {
     if (!DOPF_ACTIVE(v)) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < v.Lp * v.ldt / 4) reinterpret_cast<unsigned int *>(tflag)[i] = 0u;
+    for (int k = i; k < v.Lp * v.ldt; k += gridDim.x * blockDim.x) { v.rowsumU[k] = 0.0; v.rowsumK[k] = 0.0; }
 }
 
 // dual update + residual maxima (update_duals.jl, convergence.jl:3-12)
-__global__ void __launch_bounds__(256) k_dual(View v, unsigned char *tflag, const double *part, int nchunks)
+__global__ void __launch_bounds__(256) k_dual(View v, const unsigned char *tflag)
 {
     if (!DOPF_ACTIVE(v)) return;
     __shared__ double rm[8], rr[8];
@@ -620,19 +647,7 @@ __global__ void __launch_bounds__(256) k_dual(View v, unsigned char *tflag, cons
     if (i < v.L * v.ldt) {
         const int l = i / v.ldt, t = i % v.ldt;
         if (t < v.T) {
-            int flag = tflag[i];
-            // tight rows with a slot below SLK_ROWS: sum the per-chunk partials of k_slack_stream
-            const int tc = v.tcnt[t];
-#pragma unroll
-            for (int side = 0; side < 2; ++side) {
-                const int slot = v.tslot[((size_t)side * v.Lp + l) * v.ldt + t];
-                if (slot >= 0 && slot < tc && slot < SLK_ROWS && v.tight[(size_t)t * 2 * v.L + slot] == l * 2 + side) {
-                    double sum = 0.0;
-                    for (int c = 0; c < nchunks; ++c) sum += part[((size_t)c * v.ldt + t) * SLK_ROWS + slot];
-                    (side ? v.rowsumK : v.rowsumU)[i] = sum;
-                    flag |= 1 << side;
-                }
-            }
+            const int flag = tflag[i];
             body_dual(v, l, t, flag, a, b);
         }
     }
@@ -711,8 +726,9 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 int slack_chunks(int G, int S) { return cdiv(G, SLK_AGENTS) + cdiv(S, SLK_AGENTS); }
 int slack_rows_cap() { return SLK_ROWS; }
 
-int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st)
+int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, const Exchange *x)
 {
+#define XCHG(what) do { if (x) { int rc_ = x->fn(x->ctx, what, st); if (rc_ < 0) return rc_; } } while (0)
     const View &v = lp.view;
     int launches = 0;
 #define LAUNCH(...)                                                                                \
@@ -766,8 +782,10 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st)
         default: LAUNCH(k_sto_fix<0><<<lp.sto_fix_blocks, 256, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
         }
     }
+    XCHG(DOPF_X_DMAX);   // all ranks must build the same tight lists
     LAUNCH(k_compact<<<v.T, 256, 0, st>>>(v, 1));   // moves may have grown
     LAUNCH(k_inject<<<cdiv((long long)v.Np * v.ldt, 256), 256, 0, st>>>(v));
+    XCHG(DOPF_X_INJ);    // nodal injection of all ranks' agents
     LAUNCH(k_colsum<<<v.ldt / 32, dim3(32, 32), 0, st>>>(v));
     {   // flow = PTDF * inj
         dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);
@@ -780,11 +798,14 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st)
         const int ncg = cdiv(v.G, SLK_AGENTS), ncs = cdiv(v.S, SLK_AGENTS);
         LAUNCH(k_slack_stream<<<dim3(ncg + ncs, v.ldt / 32), SLK_WARPS * 32, 0, st>>>(v, lp.slack_part, ncg));
         LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.T), 128, 0, st>>>(v, lp.tflag));
-        LAUNCH(k_dual<<<cdiv((long long)v.L * v.ldt, 256), 256, 0, st>>>(v, lp.tflag, lp.slack_part, ncg + ncs));
+        LAUNCH(k_slack_reduce<<<dim3(SLK_ROWS / 4, v.T), 128, 0, st>>>(v, lp.tflag, lp.slack_part, ncg + ncs));
+        XCHG(DOPF_X_ROWSUM); // exact slack sums over all ranks' agents
+        LAUNCH(k_dual<<<cdiv((long long)v.L * v.ldt, 256), 256, 0, st>>>(v, lp.tflag));
     }
     LAUNCH(k_lambda<<<cdiv(v.T, 128), 128, 0, st>>>(v));
     LAUNCH(k_finish<<<1, 1, 0, st>>>(v));
 #undef LAUNCH
+#undef XCHG
     if (lp.prof_count) *lp.prof_count = launches;
     return launches;
 }
@@ -817,10 +838,11 @@ __global__ void k_flip(View v) { v.ctrl->cur = 1 - v.ctrl->cur; }
 
 // derived quantities (injection, column sums, flows, levels) of the iterate staged in the
 // inactive buffers, then flip: the staged iterate becomes the "previous iterate"
-void launch_rebuild_derived(const LaunchPlan &lp, cudaStream_t st)
+int launch_rebuild_derived(const LaunchPlan &lp, cudaStream_t st, const Exchange *x)
 {
     const View &v = lp.view;
     k_inject<<<cdiv((long long)v.Np * v.ldt, 256), 256, 0, st>>>(v);
+    if (x) { int rc_ = x->fn(x->ctx, DOPF_X_INJ, st); if (rc_ < 0) return rc_; }
     k_colsum<<<v.ldt / 32, dim3(32, 32), 0, st>>>(v);
     dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);
     if (lp.bm_n == 64) k_gemm<64, false><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n);
@@ -828,6 +850,7 @@ void launch_rebuild_derived(const LaunchPlan &lp, cudaStream_t st)
     k_flow_reduce<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, st>>>(v, lp.part, lp.ksplit_n);
     if (v.S > 0) k_levels<<<cdiv(v.S, 128), 128, 0, st>>>(v);
     k_flip<<<1, 1, 0, st>>>(v);
+    return 0;
 }
 
 

@@ -1,0 +1,29 @@
+"""torchrun --nproc-per-node 2 scripts/multi_check.py : agent-partitioned run == single-GPU run."""
+import os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+import __graft_entry__ as g
+pkg = g.load_package()
+from dopf_b200.device import DeviceADMM
+from dopf_b200 import multi
+local = int(os.environ.get("LOCAL_RANK", "0")); torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+rank, world = dist.get_rank(), dist.get_world_size()
+for (N, L, G, S, T, iters) in [(40, 60, 200, 40, 24, 30), (118, 186, 1000, 200, 24, 25), (2000, 3000, 20000, 5000, 96, 12)]:
+    d = pkg.cases.synthetic_arrays(N=N, L=L, G=G, S=S, T=T, seed=1); prob = pkg.Problem.from_arrays(d); A = G + S
+    cfg = dict(gamma=0.3 / A, flow_weight=1.0 / A)
+    sub, gi, si = multi.shard_problem(prob, rank, world)
+    dev = DeviceADMM(sub, device=local, hinge_capacity=64, **cfg)
+    multi.connect(dev, A)
+    t0 = time.time(); st = dev.step(iters); dt = time.time() - t0
+    it = dev.get_iterate(); lam, mu, rho = dev.get_duals(0)
+    if rank == 0:
+        ref = DeviceADMM(prob, device=local, hinge_capacity=64, **cfg); ref.step(iters)
+        rit = ref.get_iterate(); rl, rm, rr = ref.get_duals(0)
+        err = dict(P=np.abs(it["P"] - rit["P"][gi]).max(), D=np.abs(it["D"] - rit["D"][si]).max() if len(si) else 0.0, inj=np.abs(it["injection"] - rit["injection"]).max(),
+                   flow=np.abs(it["flow"] - rit["flow"]).max(), avgU=np.abs(it["avgU"] - rit["avgU"]).max(), lam=np.abs(lam - rl).max(), mu=np.abs(mu - rm).max(), rho=np.abs(rho - rr).max())
+        print((N, L, G, S, T), f"world {world}: {dt / iters * 1e3:.3f} ms/iter (1 GPU: {ref.status.last_step_ms / iters:.3f}) max abs diff vs single GPU:", {k: float('%.2e' % v) for k, v in err.items()}, flush=True)
+        assert max(err.values()) < 1e-6 * max(1.0, np.abs(rit["flow"]).max())
+    dist.barrier()
+dist.destroy_process_group()
