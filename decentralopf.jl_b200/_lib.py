@@ -43,7 +43,7 @@ class DopfStatus(C.Structure):
 
 EXPORTS = ["dopf_version", "dopf_default_config", "dopf_create", "dopf_destroy", "dopf_step", "dopf_get_status",
            "dopf_get_iterate", "dopf_get_duals", "dopf_set_state", "dopf_get_nodal_price", "dopf_get_total_costs",
-           "dopf_comm_unique_id", "dopf_comm_init", "dopf_last_error", "dopf_profile_iteration"]
+           "dopf_set_partition", "dopf_set_stream", "dopf_step_phase", "dopf_exchange_buffer", "dopf_last_error", "dopf_profile_iteration"]
 
 
 def build(force=False, verbose=False):
@@ -52,7 +52,7 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "--shared", "-cudart", "static", "-o", LIB_PATH] + _SRCS + ["-ldl"]
+           "-Xcompiler", "-fPIC", "--shared", "-cudart", "static", "-o", LIB_PATH] + _SRCS
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -87,7 +87,9 @@ def load():
     lib.dopf_get_nodal_price.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     lib.dopf_get_total_costs.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.dopf_profile_iteration.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]
-    lib.dopf_comm_unique_id.argtypes = [C.c_void_p]
-    lib.dopf_comm_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
+    lib.dopf_set_partition.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+    lib.dopf_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.dopf_step_phase.argtypes = [C.c_void_p, C.c_int32]
+    lib.dopf_exchange_buffer.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     _lib = lib
     return lib

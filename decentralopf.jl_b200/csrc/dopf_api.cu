@@ -3,7 +3,6 @@
 #include "../../include/dopf.h"
 #include "dopf_kernels.h"
 
-#include <dlfcn.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -17,39 +16,6 @@ using namespace dopf;
 namespace {
 
 thread_local std::string g_create_error;
-
-// ---- minimal NCCL binding, resolved at run time (torch ships its own libnccl) -----------------
-typedef struct ncclComm *ncclComm_t;
-typedef struct { char internal[128]; } ncclUniqueId;
-enum { ncclSum = 0, ncclMax = 2 };
-enum { ncclFloat64 = 8 };
-struct NcclApi {
-    int (*GetUniqueId)(ncclUniqueId *);
-    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
-    int (*CommDestroy)(ncclComm_t);
-    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
-    const char *(*GetErrorString)(int);
-    bool ok = false;
-};
-NcclApi &nccl()
-{
-    static NcclApi api;
-    static bool tried = false;
-    if (tried) return api;
-    tried = true;
-    void *hnd = nullptr;
-    if (dlsym(RTLD_DEFAULT, "ncclAllReduce")) hnd = RTLD_DEFAULT;
-    if (!hnd) hnd = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!hnd) hnd = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-    if (!hnd) return api;
-    api.GetUniqueId = (int (*)(ncclUniqueId *))dlsym(hnd, "ncclGetUniqueId");
-    api.CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(hnd, "ncclCommInitRank");
-    api.CommDestroy = (int (*)(ncclComm_t))dlsym(hnd, "ncclCommDestroy");
-    api.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(hnd, "ncclAllReduce");
-    api.GetErrorString = (const char *(*)(int))dlsym(hnd, "ncclGetErrorString");
-    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce;
-    return api;
-}
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
@@ -73,10 +39,10 @@ struct dopf_handle {
     std::string err;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_step_ms = 0.0;
-    // multi-GPU
-    ncclComm_t comm = nullptr;
+    // multi-GPU (agent-block partition; exchanges are done by the caller between the phases)
     int rank = 0, nranks = 1;
-    int host_cur = 0;   // host mirror of Ctrl::cur (multi-GPU exchanges)
+    int host_cur = 0;          // host mirror of Ctrl::cur, advanced by phase 3
+    cudaStream_t own_stream = nullptr;
 };
 
 namespace {
@@ -111,18 +77,6 @@ template <class T> int upload(dopf_handle *h, const T **dst, const std::vector<T
     if (!src.empty()) CK(cudaMemcpyAsync(d, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));   // src may be a temporary
     *dst = d;
-    return 0;
-}
-
-// exchange steps between the kernels of one iteration (multi-GPU only)
-int comm_allreduce(dopf_handle *h, const void *src, void *dst, size_t n, int op)
-{
-    if (h->nranks <= 1) return 0;
-    int rc = nccl().AllReduce(src, dst, n, ncclFloat64, op, h->comm, h->stream);
-    if (rc != 0) {
-        h->err = std::string("ncclAllReduce: ") + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "error");
-        return DOPF_E_COMM;
-    }
     return 0;
 }
 
@@ -163,7 +117,6 @@ int check_device_error(dopf_handle *h)
 }  // namespace
 
 namespace dopf {
-static int exchange_cb(void *ctx, int what, cudaStream_t st);
 int enqueue_iteration_comm(dopf_handle *h, cudaStream_t st);
 }
 
@@ -184,14 +137,13 @@ void dopf_destroy(dopf_handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->graph) cudaGraphDestroy(h->graph);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (void *p : h->allocs) cudaFree(p);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
 
@@ -217,6 +169,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->device));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = h->stream;
     CK(cudaMallocHost((void **)&h->h_ctrl, sizeof(Ctrl)));
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
     memset(h->h_ctrl, 0, sizeof(Ctrl));
@@ -555,49 +508,79 @@ int dopf_get_total_costs(dopf_handle *h, double *out)
     return DOPF_OK;
 }
 
-int dopf_comm_unique_id(void *out128)
+int dopf_set_stream(dopf_handle *h, void *cuda_stream)
 {
-    if (!out128) return DOPF_E_ARG;
-    if (!nccl().ok) { g_create_error = "NCCL library not found (libnccl.so.2)"; return DOPF_E_COMM; }
-    ncclUniqueId id;
-    if (nccl().GetUniqueId(&id) != 0) { g_create_error = "ncclGetUniqueId failed"; return DOPF_E_COMM; }
-    memcpy(out128, &id, sizeof id);
+    if (!h) return DOPF_E_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }   // graphs are stream-agnostic, but keep it simple
+    if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
     return DOPF_OK;
 }
 
-int dopf_comm_init(dopf_handle *h, int32_t rank, int32_t nranks, const void *uid, int32_t total_agents)
+int dopf_set_partition(dopf_handle *h, int32_t rank, int32_t nranks, int32_t total_agents)
 {
-    if (!h || !uid || nranks < 1 || rank < 0 || rank >= nranks || total_agents < h->lp.view.A) return DOPF_E_ARG;
-    if (h->h_ctrl->iters_done != 0 || h->graph_exec) { h->err = "dopf_comm_init must precede the first dopf_step"; return DOPF_E_ARG; }
-    if (nranks == 1) return DOPF_OK;
-    if (!nccl().ok) { h->err = "NCCL library not found (libnccl.so.2)"; return DOPF_E_COMM; }
+    if (!h || nranks < 1 || rank < 0 || rank >= nranks || total_agents < h->lp.view.A) return DOPF_E_ARG;
+    if (h->h_ctrl->iters_done != 0) { h->err = "dopf_set_partition must precede the first iteration"; return DOPF_E_ARG; }
     CK(cudaSetDevice(h->device));
-    ncclUniqueId id;
-    memcpy(&id, uid, sizeof id);
-    int rc = nccl().CommInitRank(&h->comm, nranks, id, rank);
-    if (rc != 0) { h->err = std::string("ncclCommInitRank: ") + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "error"); return DOPF_E_COMM; }
     h->rank = rank; h->nranks = nranks;
-    h->use_graph = false;          // exchanges are issued from the host between the kernels
     View &v = h->lp.view;
     v.A = total_agents;
     v.demand_on = rank == 0 ? 1 : 0;
-    for (int k = 0; k < 2; ++k) {
-        double *q = nullptr;
-        int r2 = dev_alloc(h, &q, (size_t)v.Np * v.ldt);
-        if (r2) return r2;
-        v.injloc[k] = q;
+    if (nranks > 1 && v.injloc[0] == v.inj[0]) {
+        for (int k = 0; k < 2; ++k) {
+            double *q = nullptr;
+            int r2 = dev_alloc(h, &q, (size_t)v.Np * v.ldt);
+            if (r2) return r2;
+            v.injloc[k] = q;
+        }
     }
-    // state before iteration 1 with the exchanged injection (-demand from rank 0, agents at 0)
-    if ((rc = sync_ctrl(h))) return rc;
+    h->use_graph = nranks == 1 && h->use_graph;
+    // local part of the state before iteration 1: staged injection (-demand on rank 0) in the inactive
+    // buffers; the caller all-reduces DOPF_XBUF_INJ and then runs dopf_step_phase(h, -1) to finish
+    int rc = sync_ctrl(h);
+    if (rc) return rc;
     h->host_cur = h->h_ctrl->cur;
-    Exchange x{exchange_cb, h};
-    if ((rc = launch_rebuild_derived(h->lp, h->stream, &x)) < 0) return rc;
-    h->host_cur = 1 - h->host_cur;
-    // the local contribution of the *previous* iterate is needed by the slack sums: fill both buffers
-    CK(cudaMemcpyAsync(v.injloc[1 - h->host_cur], v.injloc[h->host_cur], (size_t)v.Np * v.ldt * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    launch_rebuild_derived(h->lp, h->stream, 0);
+    if (nranks > 1) CK(cudaMemcpyAsync(v.inj[1 - h->host_cur], v.injloc[1 - h->host_cur], (size_t)v.Np * v.ldt * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaGetLastError());
-    if ((rc = sync_ctrl(h))) return rc;
-    if (h->h_ctrl->cur != h->host_cur) { h->err = "internal: buffer index mismatch after dopf_comm_init"; return DOPF_E_CUDA; }
+    return DOPF_OK;
+}
+
+int dopf_step_phase(dopf_handle *h, int32_t phase)
+{
+    if (!h || phase < -1 || phase >= DOPF_N_SEGMENTS) return DOPF_E_ARG;
+    CK(cudaSetDevice(h->device));
+    View &v = h->lp.view;
+    if (phase == -1) {   // second half of the initial state after the injection exchange
+        launch_rebuild_derived(h->lp, h->stream, 1);
+        h->host_cur = 1 - h->host_cur;
+        if (h->nranks > 1) CK(cudaMemcpyAsync(v.injloc[1 - h->host_cur], v.injloc[h->host_cur], (size_t)v.Np * v.ldt * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaGetLastError());
+        return DOPF_OK;
+    }
+    const int n = enqueue_iteration(h->lp, h->stream, phase);
+    if (phase == 0) h->launches_per_iter = 0;
+    h->launches_per_iter += n;
+    if (phase == DOPF_X_INJ && h->nranks > 1)   // the exchange runs in place on the global injection
+        CK(cudaMemcpyAsync(v.inj[1 - h->host_cur], v.injloc[1 - h->host_cur], (size_t)v.Np * v.ldt * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (phase == DOPF_N_SEGMENTS - 1) h->host_cur = 1 - h->host_cur;
+    CK(cudaGetLastError());
+    return DOPF_OK;
+}
+
+int dopf_exchange_buffer(dopf_handle *h, int32_t which, void **device_ptr, int64_t *count)
+{
+    if (!h || !device_ptr || !count) return DOPF_E_ARG;
+    View &v = h->lp.view;
+    const int nxt = 1 - h->host_cur;
+    switch (which) {
+    case DOPF_XBUF_DMAX: *device_ptr = v.dmax; *count = v.ldt; break;
+    case DOPF_XBUF_INJ: *device_ptr = v.inj[nxt]; *count = (int64_t)v.Np * v.ldt; break;
+    case DOPF_XBUF_ROWSUM: *device_ptr = v.rowsumU; *count = (int64_t)2 * v.Lp * v.ldt; break;
+    default: return DOPF_E_ARG;
+    }
     return DOPF_OK;
 }
 
@@ -605,30 +588,14 @@ int dopf_comm_init(dopf_handle *h, int32_t rank, int32_t nranks, const void *uid
 
 namespace dopf {
 
-static int exchange_cb(void *ctx, int what, cudaStream_t st)
-{
-    dopf_handle *h = (dopf_handle *)ctx;
-    (void)st;
-    View &v = h->lp.view;
-    const int nxt = 1 - h->host_cur;
-    switch (what) {
-    case DOPF_X_DMAX: return comm_allreduce(h, v.dmax, v.dmax, (size_t)v.ldt, ncclMax);            // bits of non-negative doubles
-    case DOPF_X_INJ: return comm_allreduce(h, v.injloc[nxt], v.inj[nxt], (size_t)v.Np * v.ldt, ncclSum);
-    case DOPF_X_ROWSUM: return comm_allreduce(h, v.rowsumU, v.rowsumU, (size_t)2 * v.Lp * v.ldt, ncclSum);
-    }
-    return 0;
-}
-
-// one iteration including the exchange steps; returns the number of kernel launches or < 0
+// one whole iteration (single-GPU handles); returns the number of kernel launches or < 0
 int enqueue_iteration_comm(dopf_handle *h, cudaStream_t st)
 {
-    if (h->nranks <= 1) return enqueue_iteration(h->lp, st);
-    // the exchanges address the double-buffered arrays from the host, so the host mirrors the buffer
-    // index; it advances by one per enqueued iteration (multi-GPU runs do not stop early on the device)
-    Exchange x{exchange_cb, h};
-    int n = enqueue_iteration(h->lp, st, &x);
-    h->host_cur = 1 - h->host_cur;
-    return n;
+    if (h->nranks > 1) {
+        h->err = "partitioned handles are stepped with dopf_step_phase (the caller does the exchanges)";
+        return DOPF_E_UNSUPPORTED;
+    }
+    return enqueue_iteration(h->lp, st);
 }
 
 }  // namespace dopf

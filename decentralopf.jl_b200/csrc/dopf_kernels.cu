@@ -726,13 +726,15 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 int slack_chunks(int G, int S) { return cdiv(G, SLK_AGENTS) + cdiv(S, SLK_AGENTS); }
 int slack_rows_cap() { return SLK_ROWS; }
 
-int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, const Exchange *x)
+int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
 {
-#define XCHG(what) do { if (x) { int rc_ = x->fn(x->ctx, what, st); if (rc_ < 0) return rc_; } } while (0)
+    int cur_seg = 0;
+#define XCHG(what) do { ++cur_seg; } while (0)
     const View &v = lp.view;
     int launches = 0;
 #define LAUNCH(...)                                                                                \
     do {                                                                                           \
+        if (segment >= 0 && cur_seg != segment) break;                                             \
         const bool prof_ = lp.prof_events && launches < lp.prof_cap;                               \
         if (prof_) cudaEventRecord(lp.prof_events[2 * launches], st);                              \
         __VA_ARGS__;                                                                               \
@@ -838,11 +840,11 @@ __global__ void k_flip(View v) { v.ctrl->cur = 1 - v.ctrl->cur; }
 
 // derived quantities (injection, column sums, flows, levels) of the iterate staged in the
 // inactive buffers, then flip: the staged iterate becomes the "previous iterate"
-int launch_rebuild_derived(const LaunchPlan &lp, cudaStream_t st, const Exchange *x)
+void launch_rebuild_derived(const LaunchPlan &lp, cudaStream_t st, int segment)
 {
     const View &v = lp.view;
-    k_inject<<<cdiv((long long)v.Np * v.ldt, 256), 256, 0, st>>>(v);
-    if (x) { int rc_ = x->fn(x->ctx, DOPF_X_INJ, st); if (rc_ < 0) return rc_; }
+    if (segment <= 0) k_inject<<<cdiv((long long)v.Np * v.ldt, 256), 256, 0, st>>>(v);
+    if (segment == 0) return;
     k_colsum<<<v.ldt / 32, dim3(32, 32), 0, st>>>(v);
     dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);
     if (lp.bm_n == 64) k_gemm<64, false><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n);
@@ -850,7 +852,6 @@ int launch_rebuild_derived(const LaunchPlan &lp, cudaStream_t st, const Exchange
     k_flow_reduce<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, st>>>(v, lp.part, lp.ksplit_n);
     if (v.S > 0) k_levels<<<cdiv(v.S, 128), 128, 0, st>>>(v);
     k_flip<<<1, 1, 0, st>>>(v);
-    return 0;
 }
 
 

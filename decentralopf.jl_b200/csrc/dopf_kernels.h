@@ -23,18 +23,16 @@ struct LaunchPlan {
     cudaEvent_t *prof_events; const char **prof_names; int prof_cap; int *prof_count;
 };
 
-// exchange points of one iteration (multi-GPU): called with the stream between the kernels
-enum { DOPF_X_DMAX = 0, DOPF_X_INJ = 1, DOPF_X_ROWSUM = 2 };
-struct Exchange {
-    int (*fn)(void *ctx, int what, cudaStream_t st);   // returns 0 or a negative error
-    void *ctx;
-};
-int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, const Exchange *x = nullptr);
+// exchange points split one iteration into 4 segments (multi-GPU: the host all-reduces the buffer named
+// by the exchange point between two segments).  segment = -1 enqueues the whole iteration.
+enum { DOPF_X_DMAX = 0, DOPF_X_INJ = 1, DOPF_X_ROWSUM = 2, DOPF_N_SEGMENTS = 4 };
+int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment = -1);
 int slack_chunks(int G, int S);
 int slack_rows_cap();   // returns number of kernel launches
 void launch_total_costs(const View &v, double *d_out, cudaStream_t st);
 void launch_nodal_price(const View &v, int which, double *d_out, cudaStream_t st);
-int launch_rebuild_derived(const LaunchPlan &lp, cudaStream_t st, const Exchange *x = nullptr);  // inj/ssum/flow/E of buffer [cur] from P,D,C
+// segment 0: local injection of the staged iterate; segment 1: column sums, flows, levels, buffer flip
+void launch_rebuild_derived(const LaunchPlan &lp, cudaStream_t st, int segment = -1);  // inj/ssum/flow/E of buffer [cur] from P,D,C
 
 }  // namespace dopf
 #endif

@@ -30,22 +30,62 @@ def shard_problem(prob: Problem, rank: int, world: int) -> Problem:
                    np.ascontiguousarray(prob.sto_node[si])), gi, si
 
 
-def connect(dev, total_agents, dist=None):
-    """join the ranks of a torch.distributed process group into one libdopf communicator"""
-    import torch
-    import torch.distributed as tdist
-    dist = dist or tdist
-    rank, world = dist.get_rank(), dist.get_world_size()
-    uid = np.zeros(128, dtype=np.uint8)
-    if rank == 0:
-        rc = dev.lib.dopf_comm_unique_id(uid.ctypes.data_as(C.c_void_p))
-        if rc != 0:
-            raise RuntimeError("dopf_comm_unique_id failed")
-    backend = dist.get_backend()
-    t = torch.from_numpy(uid)
-    if backend == "nccl":
-        t = t.cuda()
-    dist.broadcast(t, src=0)
-    uid = t.cpu().numpy()
-    dev._check(dev.lib.dopf_comm_init(dev.h, rank, world, uid.ctypes.data_as(C.c_void_p), int(total_agents)), "dopf_comm_init")
-    return rank, world
+class _DevBuf:
+    """wraps a raw device pointer so that torch can view it (__cuda_array_interface__)"""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = dict(shape=(int(n),), typestr="<f8", data=(int(ptr), False), version=2)
+
+
+class PartitionedADMM:
+    """One rank of an agent-partitioned run.  libdopf runs the four phases of an iteration on a torch
+    CUDA stream; torch.distributed (NCCL) all-reduces the exchange buffers in place between them."""
+
+    def __init__(self, prob: Problem, rank, world, device, dist=None, **cfg):
+        import torch
+        import torch.distributed as tdist
+        from .device import DeviceADMM
+        self.torch, self.dist = torch, dist or tdist
+        self.rank, self.world = rank, world
+        self.full = prob
+        self.sub, self.gen_index, self.sto_index = shard_problem(prob, rank, world)
+        self.dev = DeviceADMM(self.sub, device=device, use_graph=False, **cfg)
+        self.stream = torch.cuda.Stream(device=device)
+        d = self.dev
+        d._check(d.lib.dopf_set_stream(d.h, C.c_void_p(self.stream.cuda_stream)), "dopf_set_stream")
+        with torch.cuda.stream(self.stream):
+            d._check(d.lib.dopf_set_partition(d.h, rank, world, prob.G + prob.S), "dopf_set_partition")
+            self._allreduce(1, self.dist.ReduceOp.SUM)
+            d._check(d.lib.dopf_step_phase(d.h, -1), "dopf_step_phase")
+        self.stream.synchronize()
+
+    def _buffer(self, which):
+        ptr, n = C.c_void_p(), C.c_int64()
+        self.dev._check(self.dev.lib.dopf_exchange_buffer(self.dev.h, which, C.byref(ptr), C.byref(n)), "dopf_exchange_buffer")
+        return self.torch.as_tensor(_DevBuf(ptr.value, n.value), device=f"cuda:{self.torch.cuda.current_device()}")
+
+    def _allreduce(self, which, op):
+        if self.world > 1:
+            self.dist.all_reduce(self._buffer(which), op=op)
+
+    def step(self, iters=1, check_every=16):
+        d, lib, R = self.dev, self.dev.lib, self.dist.ReduceOp
+        done = 0
+        with self.torch.cuda.stream(self.stream):
+            while done < iters:
+                n = min(check_every, iters - done)
+                for _ in range(n):
+                    d._check(lib.dopf_step_phase(d.h, 0), "phase 0"); self._allreduce(0, R.MAX)
+                    d._check(lib.dopf_step_phase(d.h, 1), "phase 1"); self._allreduce(1, R.SUM)
+                    d._check(lib.dopf_step_phase(d.h, 2), "phase 2"); self._allreduce(2, R.SUM)
+                    d._check(lib.dopf_step_phase(d.h, 3), "phase 3")
+                done += n
+                d._check(lib.dopf_get_status(d.h, C.byref(d.status)), "dopf_get_status")   # synchronises
+                if d.status.converged:
+                    break
+        return d.status
+
+    def close(self):
+        self.dev.close()
+
+

@@ -111,12 +111,28 @@ int dopf_profile_iteration(dopf_handle *h, int32_t cap, float *ms, const char **
 int dopf_get_nodal_price(dopf_handle *h, int32_t which, double *out /*[N][T]*/);
 int dopf_get_total_costs(dopf_handle *h, double *out);
 
-/* multi-GPU (one process per GPU): agents are partitioned over ranks, the network part is
- * replicated.  `nccl_unique_id` = the 128 bytes of an ncclUniqueId created by rank 0
- * (dopf_comm_unique_id) and distributed by the caller.  demand must be passed on every rank;
- * only rank 0's demand enters the injection.  Call before the first dopf_step. */
-int dopf_comm_unique_id(void *out128);
-int dopf_comm_init(dopf_handle *h, int32_t rank, int32_t nranks, const void *nccl_unique_id, int32_t total_agents);
+/* ---- multi-GPU (one process per GPU; SURVEY.md 8(e) "agent block") ---------------------------------
+ * Every rank creates its handle with the full network data and ITS block of the agents, then calls
+ * dopf_set_partition.  One iteration is run as 4 phases; between two phases the caller all-reduces the
+ * named device buffer IN PLACE over the ranks (torch.distributed / NCCL on the stream given to
+ * dopf_set_stream, so no host synchronisation is needed):
+ *     phase 0 -> all-reduce MAX  DOPF_XBUF_DMAX   (largest agent move per timestep)
+ *     phase 1 -> all-reduce SUM  DOPF_XBUF_INJ    (nodal injection; rank 0 carries the demand)
+ *     phase 2 -> all-reduce SUM  DOPF_XBUF_ROWSUM (exact slack row sums)
+ *     phase 3    (dual update, convergence check, buffer flip)
+ * The network / dual part is replicated, so all ranks hold identical duals and convergence flags. */
+#define DOPF_XBUF_DMAX 0
+#define DOPF_XBUF_INJ 1
+#define DOPF_XBUF_ROWSUM 2
+int dopf_set_partition(dopf_handle *h, int32_t rank, int32_t nranks, int32_t total_agents);
+/* CUDA stream (cudaStream_t) on which the library enqueues all work; NULL = the library's own stream */
+int dopf_set_stream(dopf_handle *h, void *cuda_stream);
+/* enqueue one phase (0..3) of the current iteration; asynchronous.  After phase 3 call dopf_get_status
+ * (synchronises) whenever the host needs the iteration counter / convergence flags. */
+int dopf_step_phase(dopf_handle *h, int32_t phase);
+/* device pointer and element count (float64, or the bit pattern of non-negative float64 for DMAX) of
+ * the buffer to all-reduce after `phase` = which */
+int dopf_exchange_buffer(dopf_handle *h, int32_t which, void **device_ptr, int64_t *count);
 
 const char *dopf_last_error(dopf_handle *h);   /* handle may be NULL: error of the last failed dopf_create */
 const char *dopf_version(void);

@@ -13,10 +13,9 @@ rank, world = dist.get_rank(), dist.get_world_size()
 for (N, L, G, S, T, iters) in [(40, 60, 200, 40, 24, 30), (118, 186, 1000, 200, 24, 25), (2000, 3000, 20000, 5000, 96, 12)]:
     d = pkg.cases.synthetic_arrays(N=N, L=L, G=G, S=S, T=T, seed=1); prob = pkg.Problem.from_arrays(d); A = G + S
     cfg = dict(gamma=0.3 / A, flow_weight=1.0 / A)
-    sub, gi, si = multi.shard_problem(prob, rank, world)
-    dev = DeviceADMM(sub, device=local, hinge_capacity=64, **cfg)
-    multi.connect(dev, A)
-    t0 = time.time(); st = dev.step(iters); dt = time.time() - t0
+    part = multi.PartitionedADMM(prob, rank, world, local, hinge_capacity=64, **cfg)
+    dev, gi, si = part.dev, part.gen_index, part.sto_index
+    torch.cuda.synchronize(); t0 = time.time(); st = part.step(iters); torch.cuda.synchronize(); dt = time.time() - t0
     it = dev.get_iterate(); lam, mu, rho = dev.get_duals(0)
     if rank == 0:
         ref = DeviceADMM(prob, device=local, hinge_capacity=64, **cfg); ref.step(iters)
