@@ -222,7 +222,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
         for (int l = 0; l < L; ++l) for (int n = 0; n < N; ++n) ptdfT[(size_t)n * Lp + l] = ptdf[(size_t)l * Np + n];
         UP(v.ptdfT, ptdfT);
     }
-    UP(v.ptdf, ptdf); UP(v.fmax, fmax); UP(v.demand, demand); UP(v.q, q); UP(v.prow, prow); UP(v.mwide, mwide); UP(v.nagents, nag);
+    UP(v.ptdf, ptdf); UP(v.fmax, fmax); UP(v.demand, demand); UP(v.q, q); UP(v.prow, prow); { const double *t_ = nullptr; UP(t_, mwide); v.mwide = const_cast<double *>(t_); UP(t_, rbox); v.rbox = const_cast<double *>(t_); } UP(v.nagents, nag);
     UP(v.gen_mc, gmc); UP(v.gen_pmax, gpm); UP(v.gen_node, gnode); UP(v.gen_ptr, gptr);
     UP(v.sto_mc, smc); UP(v.sto_pmax, spm); UP(v.sto_emax, sem); UP(v.sto_node, snode); UP(v.sto_ptr, sptr);
 #undef UP
@@ -553,7 +553,8 @@ int dopf_step_phase(dopf_handle *h, int32_t phase)
     if (!h || phase < -1 || phase >= DOPF_N_SEGMENTS) return DOPF_E_ARG;
     CK(cudaSetDevice(h->device));
     View &v = h->lp.view;
-    if (phase == -1) {   // second half of the initial state after the injection exchange
+    if (phase == -1) {   // second half of the initial state after the injection / box-range exchanges
+        launch_mwide(v, h->stream);
         launch_rebuild_derived(h->lp, h->stream, 1);
         h->host_cur = 1 - h->host_cur;
         if (h->nranks > 1) CK(cudaMemcpyAsync(v.injloc[1 - h->host_cur], v.injloc[h->host_cur], (size_t)v.Np * v.ldt * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
@@ -579,6 +580,7 @@ int dopf_exchange_buffer(dopf_handle *h, int32_t which, void **device_ptr, int64
     case DOPF_XBUF_DMAX: *device_ptr = v.dmax; *count = v.ldt; break;
     case DOPF_XBUF_INJ: *device_ptr = v.inj[nxt]; *count = (int64_t)v.Np * v.ldt; break;
     case DOPF_XBUF_ROWSUM: *device_ptr = v.rowsumU; *count = (int64_t)2 * v.Lp * v.ldt; break;
+    case DOPF_XBUF_RBOX: *device_ptr = v.rbox; *count = v.Np; break;
     default: return DOPF_E_ARG;
     }
     return DOPF_OK;

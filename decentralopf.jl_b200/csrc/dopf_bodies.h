@@ -59,7 +59,8 @@ struct View {
     const double *demand;   // [Np][ldt]
     const double *q;        // [Np]  sum_l ptdf[l,n]^2
     const double *prow;     // [Lp]  max_n |ptdf[l,n]|
-    const double *mwide;    // [Lp]  max_n |ptdf[l,n]| * box range of node n
+    double *mwide;          // [Lp]  max_n |ptdf[l,n]| * box range of node n
+    double *rbox;           // [Np]  largest possible |delta| of an agent at node n (max-reduced over ranks)
     const double *nagents;  // [Np]  number of agents at node n
     const double *gen_mc, *gen_pmax; const int *gen_node; const int *gen_ptr;   // sorted by node; ptr [N+1]
     const double *sto_mc, *sto_pmax, *sto_emax; const int *sto_node; const int *sto_ptr;

@@ -823,6 +823,20 @@ void launch_nodal_price(const View &v, int which, double *d_out, cudaStream_t st
     k_nodal_price<<<cdiv((long long)v.N * v.T, 128), 128, 0, st>>>(v, which, d_out);
 }
 
+// static wide-row bound mwide[l] = max_n |ptdf[l,n]| * rbox[n]; one warp per line (re-run after the
+// node box ranges have been max-reduced over the ranks)
+__global__ void k_mwide(View v)
+{
+    const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (l >= v.L) return;
+    double m = 0.0;
+    for (int n = lane; n < v.N; n += 32) m = fmax(m, fabs(v.ptdf[(size_t)l * v.Np + n]) * v.rbox[n]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) v.mwide[l] = m;
+}
+void launch_mwide(const View &v, cudaStream_t st) { k_mwide<<<cdiv((long long)v.L * 32, 128), 128, 0, st>>>(v); }
+
 // levels of the staged iterate and buffer flip, used when a state is injected from the host
 __global__ void k_levels(View v)
 {

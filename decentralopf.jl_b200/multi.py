@@ -55,7 +55,8 @@ class PartitionedADMM:
         d._check(d.lib.dopf_set_stream(d.h, C.c_void_p(self.stream.cuda_stream)), "dopf_set_stream")
         with torch.cuda.stream(self.stream):
             d._check(d.lib.dopf_set_partition(d.h, rank, world, prob.G + prob.S), "dopf_set_partition")
-            self._allreduce(1, self.dist.ReduceOp.SUM)
+            self._allreduce(1, self.dist.ReduceOp.SUM)     # initial injection (-demand from rank 0)
+            self._allreduce(3, self.dist.ReduceOp.MAX)     # per-node box ranges -> identical candidate rows on all ranks
             d._check(d.lib.dopf_step_phase(d.h, -1), "dopf_step_phase")
         self.stream.synchronize()
 

@@ -120,10 +120,12 @@ int dopf_get_total_costs(dopf_handle *h, double *out);
  *     phase 1 -> all-reduce SUM  DOPF_XBUF_INJ    (nodal injection; rank 0 carries the demand)
  *     phase 2 -> all-reduce SUM  DOPF_XBUF_ROWSUM (exact slack row sums)
  *     phase 3    (dual update, convergence check, buffer flip)
+ * Set-up: dopf_set_partition, all-reduce SUM DOPF_XBUF_INJ and MAX DOPF_XBUF_RBOX, dopf_step_phase(h, -1).
  * The network / dual part is replicated, so all ranks hold identical duals and convergence flags. */
 #define DOPF_XBUF_DMAX 0
 #define DOPF_XBUF_INJ 1
 #define DOPF_XBUF_ROWSUM 2
+#define DOPF_XBUF_RBOX 3     /* set-up only: per-node box range, all-reduce MAX before dopf_step_phase(h, -1) */
 int dopf_set_partition(dopf_handle *h, int32_t rank, int32_t nranks, int32_t total_agents);
 /* CUDA stream (cudaStream_t) on which the library enqueues all work; NULL = the library's own stream */
 int dopf_set_stream(dopf_handle *h, void *cuda_stream);

@@ -138,7 +138,7 @@ void *emul_create(int N, int L, int T, int G, int S, const double *ptdf, const d
         }
     }
     for (int n = 0; n < N; ++n) for (int t = 0; t < T; ++t) dm[(size_t)n * ldt + t] = demand[(size_t)n * T + t];
-    v.ptdf = P; v.fmax = f; v.demand = dm; v.q = q; v.prow = prow; v.mwide = mw; v.nagents = na;
+    v.ptdf = P; v.fmax = f; v.demand = dm; v.q = q; v.prow = prow; v.mwide = mw; v.nagents = na; v.rbox = nullptr;
     double *a;
     int *ip;
     a = e->mk(G); std::copy(gmc, gmc + G, a); v.gen_mc = a;
