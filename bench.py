@@ -8,8 +8,12 @@ metric  : agent*timestep updates per second = (G+S)*T*iterations / time (SURVEY.
 workload: "target" = the north_star's synthetic 100k-agent x 96-period case (80k generators +
           20k storages on the 2000-node / 3000-line grid of BASELINE configs[2]); inputs resident in
           HBM; working set (~0.5 GB) exceeds the 126 MB L2, so no explicit L2 flush is needed.
-N > 1   : independent scenarios (BASELINE configs[3] style): every rank runs its own scenario of
-          the same shape, no data-path collective ("weak" scaling); time = max over ranks.
+N > 1   : weak scaling, one process per GPU.  --shard agents (default): ONE case with N x the agents of
+          the workload on the same grid, agents partitioned over the ranks, network/dual part replicated;
+          per iteration torch.distributed (NCCL) all-reduces the per-timestep move maxima, the nodal
+          injection and the exact slack row sums between the phases of libdopf.
+          --shard scenarios: every rank runs an independent scenario (BASELINE configs[3] style), no
+          data-path collective.  Time = max over ranks of the device time.
 --impl reference : the CPU oracle (oracle/, OpenMP on all host cores) on a bounded sample of the
           same workload; the Julia/JuMP/Gurobi reference itself cannot be installed here (no Julia).
 """
@@ -140,8 +144,17 @@ def run_dopf(args):
     from dopf_b200.device import DeviceADMM
     N, L, G, S, T = WORKLOADS[args.workload]
     A = G + S
-    prob, cfg = make_case(pkg, args.workload, seed=rank)   # one independent scenario per rank
-    dev = DeviceADMM(prob, device=local, hinge_capacity=64, **cfg)
+    partitioned = world > 1 and args.shard == "agents"
+    if partitioned:
+        from dopf_b200 import multi
+        prob, cfg = make_case(pkg, args.workload, seed=0, agents=(world * G, world * S))   # same case on every rank
+        part = multi.PartitionedADMM(prob, rank, world, local, hinge_capacity=64, **cfg)
+        dev = part.dev
+        A = world * (G + S) // world      # per-rank agents (value below multiplies by world)
+    else:
+        part = None
+        prob, cfg = make_case(pkg, args.workload, seed=rank)   # one independent scenario per rank
+        dev = DeviceADMM(prob, device=local, hinge_capacity=64, **cfg)
 
     def barrier():
         torch.cuda.synchronize()
@@ -149,15 +162,25 @@ def run_dopf(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    dev.step(args.warmup)
+    (part or dev).step(args.warmup)
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
     if clocks:
         clocks.start()
-    st = dev.step(args.steps)                  # device time by CUDA events on the library's stream
+    if partitioned:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(part.stream):       # libdopf and the collectives run on this stream
+            e0.record(part.stream)
+        st = part.step(args.steps, check_every=args.steps)
+        with torch.cuda.stream(part.stream):
+            e1.record(part.stream)
+        part.stream.synchronize()
+        ms_total = e0.elapsed_time(e1)
+    else:
+        st = dev.step(args.steps)              # device time by CUDA events on the library's stream
+        ms_total = st.last_step_ms
     barrier()
     clk = clocks.stop() if clocks else None
-    ms_total = st.last_step_ms
     tmax = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -167,11 +190,11 @@ def run_dopf(args):
                   tight_rows=st.tight_rows, wide_rows=st.wide_rows, residuals=[st.res_lambda, st.res_mue, st.res_rho])
 
     # ---- per-kernel device times of one iteration (CUDA event pair per launch) -> roofline ----
-    prof = dev.profile_iteration()
+    prof = dev.profile_iteration() if not partitioned else []
     kern = {}
     for name, ms in prof:
         kern[name] = kern.get(name, 0.0) + ms
-    dom = max(kern, key=kern.get)
+    dom = max(kern, key=kern.get) if kern else None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -185,7 +208,9 @@ def run_dopf(args):
                  "k_inject": 8.0 * (G + 2 * S) * T + 16.0 * N * T}
     gemm_flops = {"k_gemm<32, true>": 4.0 * L * N * T, "k_gemm<64, true>": 4.0 * L * N * T,
                   "k_gemm<32, false>": 2.0 * L * N * T, "k_gemm<64, false>": 2.0 * L * N * T}
-    if dom in gemm_flops:
+    if dom is None:
+        roof = None
+    elif dom in gemm_flops:
         ach = gemm_flops[dom] / (kern[dom] * 1e-3) / 1e12
         roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": 37.0, "unit": "TFLOP/s", "frac": ach / 37.0, "traffic": None,
                 "peak_source": "nominal B200 fp64 (DMMA) 37 TFLOP/s - no fp64 figure in MEASURED_PEAKS.json"}
@@ -194,10 +219,11 @@ def run_dopf(args):
         ach = b / (kern[dom] * 1e-3) / 1e9
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": b}
-    roof["kernel_ms"] = kern[dom]
-    roof["kernel_share_of_iteration"] = kern[dom] / sum(kern.values())
+    if roof is not None:
+        roof["kernel_ms"] = kern[dom]
+        roof["kernel_share_of_iteration"] = kern[dom] / sum(kern.values())
     gp = kern.get("k_gen_predict<2>", kern.get("k_gen_predict<1>"))
-    if gp:
+    if gp and roof is not None:
         roof["generator_stream"] = {"kernel_ms": gp, "achieved_GBps": 16.0 * G * T / (gp * 1e-3) / 1e9, "frac": 16.0 * G * T / (gp * 1e-3) / 1e9 / hbm}
 
     # ---- end to end through the C ABI with host buffers (pinned): upload state, iterate, read back ----
@@ -216,9 +242,14 @@ def run_dopf(args):
     iteration = dev.status.iteration
     barrier()
     t0 = time.perf_counter()
+    if partitioned:
+        h2d = 0
     for _ in range(e2e_steps):
-        dev.set_state(iteration, P=hb["P"], D=hb["D"], C_=hb["C"], avgU=hb["avgU"], avgK=hb["avgK"], lam=hl, mu=hm, rho=hr)
-        dev.step(1)
+        if partitioned:
+            part.step(1)                       # state stays on the device; results are read back every step
+        else:
+            dev.set_state(iteration, P=hb["P"], D=hb["D"], C_=hb["C"], avgU=hb["avgU"], avgK=hb["avgK"], lam=hl, mu=hm, rho=hr)
+            dev.step(1)
         dev.get_iterate(("P", "D", "C", "E"), out=hb)
         dev.lib.dopf_get_duals(dev.h, 0, hl.ctypes.data_as(C.c_void_p), hm.ctypes.data_as(C.c_void_p), hr.ctypes.data_as(C.c_void_p))
         iteration = dev.status.iteration
@@ -235,14 +266,16 @@ def run_dopf(args):
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": args.workload, "nodes": N, "lines": L, "generators": G, "storages": S, "timesteps": T,
                            "gamma": cfg["gamma"], "flow_weight": cfg["flow_weight"], "prox_weight": cfg["prox_weight"],
-                           "parallelism": f"{world} independent scenario(s), one per GPU, no collective",
+                           "parallelism": (f"{world} GPUs, agents partitioned ({world}x{G + S} agents on one grid), NCCL all-reduce of move maxima / nodal injection / slack sums per iteration"
+                                           if partitioned else f"{world} independent scenario(s), one per GPU, no collective"),
                            "l2": "working set larger than L2 (no flush)"},
                 "iters_per_s": world * args.steps / (ms_total * 1e-3),
-                "gpu_launches": st.launches_per_iteration * args.steps,
+                "gpu_launches": dev.status.launches_per_iteration * args.steps,
                 "clocks": clk, "roofline": roof,
                 "kernels_ms": {k: round(v, 4) for k, v in kern.items()},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "steps": e2e_steps, "what": "dopf_set_state(host) + dopf_step(1) + dopf_get_iterate/duals(host), pinned buffers"},
+                        "steps": e2e_steps, "what": ("partitioned run: iterate + dopf_get_iterate/duals(host) every step (no per-step upload)" if partitioned
+                                                     else "dopf_set_state(host) + dopf_step(1) + dopf_get_iterate/duals(host), pinned buffers")},
                 "steady_state": steady}
         if world == 1 and not args.no_cpu_baseline:
             v, ms, cores, sample = oracle_rate(pkg, args.workload, 3, 1)
@@ -261,6 +294,7 @@ def main():
     ap.add_argument("--impl", default="dopf", choices=["dopf", "reference"])
     ap.add_argument("--workload", default="target", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="agents", choices=["agents", "scenarios"], help="N>1: partition the agents of one case (NCCL exchanges) or run independent scenarios")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
