@@ -139,6 +139,9 @@ void dopf_destroy(dopf_handle *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->graph) cudaGraphDestroy(h->graph);
+    if (h->lp.ev_fork) cudaEventDestroy(h->lp.ev_fork);
+    if (h->lp.ev_join) cudaEventDestroy(h->lp.ev_join);
+    if (h->lp.side_stream) cudaStreamDestroy(h->lp.side_stream);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (void *p : h->allocs) cudaFree(p);
@@ -172,6 +175,8 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     h->own_stream = h->stream;
     CK(cudaMallocHost((void **)&h->h_ctrl, sizeof(Ctrl)));
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
+    CK(cudaStreamCreateWithFlags(&h->lp.side_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->lp.ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->lp.ev_join, cudaEventDisableTiming));
     memset(h->h_ctrl, 0, sizeof(Ctrl));
 
     LaunchPlan &lp = h->lp;

@@ -729,6 +729,13 @@ int slack_rows_cap() { return SLK_ROWS; }
 int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
 {
     int cur_seg = 0;
+    // independent groups run on a side stream when the whole iteration is enqueued at once and no
+    // per-kernel profiling is requested (works both under graph capture and for direct launches)
+    const bool par = segment < 0 && !lp.prof_events && lp.side_stream;
+    cudaStream_t cs = st;
+#define FORK() do { if (par) { cudaEventRecord(lp.ev_fork, st); cudaStreamWaitEvent(lp.side_stream, lp.ev_fork, 0); cs = lp.side_stream; } } while (0)
+#define MAIN() do { cs = st; } while (0)
+#define JOIN() do { if (par) { cudaEventRecord(lp.ev_join, lp.side_stream); cudaStreamWaitEvent(st, lp.ev_join, 0); } cs = st; } while (0)
 #define XCHG(what) do { ++cur_seg; } while (0)
     const View &v = lp.view;
     int launches = 0;
@@ -736,78 +743,90 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     do {                                                                                           \
         if (segment >= 0 && cur_seg != segment) break;                                             \
         const bool prof_ = lp.prof_events && launches < lp.prof_cap;                               \
-        if (prof_) cudaEventRecord(lp.prof_events[2 * launches], st);                              \
+        if (prof_) cudaEventRecord(lp.prof_events[2 * launches], cs);                              \
         __VA_ARGS__;                                                                               \
-        if (prof_) { cudaEventRecord(lp.prof_events[2 * launches + 1], st); lp.prof_names[launches] = #__VA_ARGS__; } \
+        if (prof_) { cudaEventRecord(lp.prof_events[2 * launches + 1], cs); lp.prof_names[launches] = #__VA_ARGS__; } \
         ++launches;                                                                                \
     } while (0)
-    LAUNCH(k_begin<<<lp.num_sms, 256, 0, st>>>(v));
-    LAUNCH(k_row_prep<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, st>>>(v));
-    LAUNCH(k_compact<<<v.T, 256, 0, st>>>(v, 0));
+    LAUNCH(k_begin<<<lp.num_sms, 256, 0, cs>>>(v));
+    LAUNCH(k_row_prep<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, cs>>>(v));
+    LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 0));
     {   // PTDF^T M and (PTDF.^2)^T W
         dim3 grid(v.Np / lp.bm_t, v.ldt / BN, lp.ksplit_t);
-        if (lp.bm_t == 64) LAUNCH(k_gemm<64, true><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, lp.part2, v.Np, v.Lp, lp.ksplit_t));
-        else LAUNCH(k_gemm<32, true><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, lp.part2, v.Np, v.Lp, lp.ksplit_t));
-        LAUNCH(k_node_prep<<<cdiv((long long)v.Np * v.ldt, 256), 256, 0, st>>>(v, lp.part, lp.part2, lp.ksplit_t));
+        if (lp.bm_t == 64) LAUNCH(k_gemm<64, true><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, lp.part, lp.part2, v.Np, v.Lp, lp.ksplit_t));
+        else LAUNCH(k_gemm<32, true><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, lp.part, lp.part2, v.Np, v.Lp, lp.ksplit_t));
+        LAUNCH(k_node_prep<<<cdiv((long long)v.Np * v.ldt, 256), 256, 0, cs>>>(v, lp.part, lp.part2, lp.ksplit_t));
     }
-    if (v.G > 0) {
-        if (v.T % 2 == 0) LAUNCH(k_gen_predict<2><<<cdiv((long long)v.G * (v.T / 2), 256), 256, 0, st>>>(v));
-        else LAUNCH(k_gen_predict<1><<<cdiv((long long)v.G * v.T, 256), 256, 0, st>>>(v));
-    }
+    FORK();   // storages on the side stream ...
     if (v.S > 0) {
         const int wblocks = min(cdiv(v.S, 4), lp.num_sms * 16);
         switch (lp.sto_j) {
-        case 1: LAUNCH(k_sto_warp<1><<<wblocks, 128, 0, st>>>(v)); break;
-        case 2: LAUNCH(k_sto_warp<2><<<wblocks, 128, 0, st>>>(v)); break;
-        case 3: LAUNCH(k_sto_warp<3><<<wblocks, 128, 0, st>>>(v)); break;
-        case 4: LAUNCH(k_sto_warp<4><<<wblocks, 128, 0, st>>>(v)); break;
-        case 6: LAUNCH(k_sto_warp<6><<<wblocks, 128, 0, st>>>(v)); break;
-        case 8: LAUNCH(k_sto_warp<8><<<wblocks, 128, 0, st>>>(v)); break;
-        default: LAUNCH(k_sto_warm<<<cdiv(v.S, 128), 128, 0, st>>>(v)); break;   // long horizons: sequential warm start
+        case 1: LAUNCH(k_sto_warp<1><<<wblocks, 128, 0, cs>>>(v)); break;
+        case 2: LAUNCH(k_sto_warp<2><<<wblocks, 128, 0, cs>>>(v)); break;
+        case 3: LAUNCH(k_sto_warp<3><<<wblocks, 128, 0, cs>>>(v)); break;
+        case 4: LAUNCH(k_sto_warp<4><<<wblocks, 128, 0, cs>>>(v)); break;
+        case 6: LAUNCH(k_sto_warp<6><<<wblocks, 128, 0, cs>>>(v)); break;
+        case 8: LAUNCH(k_sto_warp<8><<<wblocks, 128, 0, cs>>>(v)); break;
+        default: LAUNCH(k_sto_warm<<<cdiv(v.S, 128), 128, 0, cs>>>(v)); break;   // long horizons: sequential warm start
         }
-        LAUNCH(k_sto_cold<<<min(cdiv(v.S, 64), lp.num_sms * 8), 64, 0, st>>>(v));
+        LAUNCH(k_sto_cold<<<min(cdiv(v.S, 64), lp.num_sms * 8), 64, 0, cs>>>(v));
     }
-    LAUNCH(k_compact<<<v.T, 256, 0, st>>>(v, 1));
+    MAIN();   // ... generators on the main stream
+    if (v.G > 0) {
+        if (v.T % 2 == 0) LAUNCH(k_gen_predict<2><<<cdiv((long long)v.G * (v.T / 2), 256), 256, 0, cs>>>(v));
+        else LAUNCH(k_gen_predict<1><<<cdiv((long long)v.G * v.T, 256), 256, 0, cs>>>(v));
+    }
+    JOIN();
+    LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 1));
     {
         dim3 grid(cdiv(v.N, 32), cdiv(v.T, 8));
-        LAUNCH(k_verify<<<grid, 256, 0, st>>>(v));
+        LAUNCH(k_verify<<<grid, 256, 0, cs>>>(v));
     }
-    if (v.G > 0) LAUNCH(k_gen_fix<<<lp.num_sms * 2, 128, 0, st>>>(v));
+    FORK();
     if (v.S > 0) {
         switch (lp.sto_j) {
-        case 1: LAUNCH(k_sto_fix<1><<<lp.sto_fix_blocks, 256, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 2: LAUNCH(k_sto_fix<2><<<lp.sto_fix_blocks, 256, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 3: LAUNCH(k_sto_fix<3><<<lp.sto_fix_blocks, 256, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 4: LAUNCH(k_sto_fix<4><<<lp.sto_fix_blocks, 256, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 6: LAUNCH(k_sto_fix<6><<<lp.sto_fix_blocks, 256, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 8: LAUNCH(k_sto_fix<8><<<lp.sto_fix_blocks, 256, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        default: LAUNCH(k_sto_fix<0><<<lp.sto_fix_blocks, 256, 0, st>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 1: LAUNCH(k_sto_fix<1><<<lp.sto_fix_blocks, 256, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 2: LAUNCH(k_sto_fix<2><<<lp.sto_fix_blocks, 256, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 3: LAUNCH(k_sto_fix<3><<<lp.sto_fix_blocks, 256, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 4: LAUNCH(k_sto_fix<4><<<lp.sto_fix_blocks, 256, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 6: LAUNCH(k_sto_fix<6><<<lp.sto_fix_blocks, 256, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 8: LAUNCH(k_sto_fix<8><<<lp.sto_fix_blocks, 256, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        default: LAUNCH(k_sto_fix<0><<<lp.sto_fix_blocks, 256, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
         }
     }
+    MAIN();
+    if (v.G > 0) LAUNCH(k_gen_fix<<<lp.num_sms * 2, 128, 0, cs>>>(v));
+    JOIN();
     XCHG(DOPF_X_DMAX);   // all ranks must build the same tight lists
-    LAUNCH(k_compact<<<v.T, 256, 0, st>>>(v, 1));   // moves may have grown
-    LAUNCH(k_inject<<<cdiv((long long)v.Np * v.ldt, 256), 256, 0, st>>>(v));
+    LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 1));   // moves may have grown
+    FORK();   // slack sums need only the new agents and the tight lists ...
+    LAUNCH(k_clear_tflag<<<cdiv((long long)v.Lp * v.ldt / 4, 256), 256, 0, cs>>>(v, lp.tflag));
+    const int ncg = cdiv(v.G, SLK_AGENTS), ncs = cdiv(v.S, SLK_AGENTS);
+    LAUNCH(k_slack_stream<<<dim3(ncg + ncs, v.ldt / 32), SLK_WARPS * 32, 0, cs>>>(v, lp.slack_part, ncg));
+    MAIN();   // ... while the main stream aggregates the injection and computes the flows
+    LAUNCH(k_inject<<<cdiv((long long)v.Np * v.ldt, 256), 256, 0, cs>>>(v));
     XCHG(DOPF_X_INJ);    // nodal injection of all ranks' agents
-    LAUNCH(k_colsum<<<v.ldt / 32, dim3(32, 32), 0, st>>>(v));
+    LAUNCH(k_colsum<<<v.ldt / 32, dim3(32, 32), 0, cs>>>(v));
     {   // flow = PTDF * inj
         dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);
-        if (lp.bm_n == 64) LAUNCH(k_gemm<64, false><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n));
-        else LAUNCH(k_gemm<32, false><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n));
-        LAUNCH(k_flow_reduce<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, st>>>(v, lp.part, lp.ksplit_n));
+        if (lp.bm_n == 64) LAUNCH(k_gemm<64, false><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n));
+        else LAUNCH(k_gemm<32, false><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n));
+        LAUNCH(k_flow_reduce<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, cs>>>(v, lp.part, lp.ksplit_n));
     }
-    LAUNCH(k_clear_tflag<<<cdiv((long long)v.Lp * v.ldt / 4, 256), 256, 0, st>>>(v, lp.tflag));
+    JOIN();
     {
-        const int ncg = cdiv(v.G, SLK_AGENTS), ncs = cdiv(v.S, SLK_AGENTS);
-        LAUNCH(k_slack_stream<<<dim3(ncg + ncs, v.ldt / 32), SLK_WARPS * 32, 0, st>>>(v, lp.slack_part, ncg));
-        LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.T), 128, 0, st>>>(v, lp.tflag));
-        LAUNCH(k_slack_reduce<<<dim3(SLK_ROWS / 4, v.T), 128, 0, st>>>(v, lp.tflag, lp.slack_part, ncg + ncs));
+        LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.T), 128, 0, cs>>>(v, lp.tflag));   // needs the local injection
+        LAUNCH(k_slack_reduce<<<dim3(SLK_ROWS / 4, v.T), 128, 0, cs>>>(v, lp.tflag, lp.slack_part, ncg + ncs));
         XCHG(DOPF_X_ROWSUM); // exact slack sums over all ranks' agents
-        LAUNCH(k_dual<<<cdiv((long long)v.L * v.ldt, 256), 256, 0, st>>>(v, lp.tflag));
+        LAUNCH(k_dual<<<cdiv((long long)v.L * v.ldt, 256), 256, 0, cs>>>(v, lp.tflag));
     }
-    LAUNCH(k_lambda<<<cdiv(v.T, 128), 128, 0, st>>>(v));
-    LAUNCH(k_finish<<<1, 1, 0, st>>>(v));
+    LAUNCH(k_lambda<<<cdiv(v.T, 128), 128, 0, cs>>>(v));
+    LAUNCH(k_finish<<<1, 1, 0, cs>>>(v));
 #undef LAUNCH
 #undef XCHG
+#undef FORK
+#undef MAIN
+#undef JOIN
     if (lp.prof_count) *lp.prof_count = launches;
     return launches;
 }

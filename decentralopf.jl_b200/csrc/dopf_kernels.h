@@ -19,6 +19,8 @@ struct LaunchPlan {
     double *slack_part;       // [agent chunks][ldt][SLK_ROWS] partial slack sums of k_slack_stream
     Hinge *hinge_scratch;     // [sto_fix_blocks][T][hcap]
     int *hcnt_scratch;        // [sto_fix_blocks][T]
+    // fork/join of independent kernel groups on a second stream (whole-iteration mode only)
+    cudaStream_t side_stream; cudaEvent_t ev_fork, ev_join;
     // optional per-kernel profiling (dopf_profile_iteration): event pairs + names in launch order
     cudaEvent_t *prof_events; const char **prof_names; int prof_cap; int *prof_count;
 };

@@ -5,7 +5,8 @@
 //   * anchors  = timesteps whose level is fixed at a bound (kind +1: emax, -1: 0); between two anchors
 //     ("run") the level multiplier eta is constant;
 //   * all runs are solved at once: every lane evaluates y_t(eta) for its timesteps (sto_eval), run sums
-//     come from segmented warp scans, one safeguarded Newton update per run and pass;
+//     come from segmented warp scans, the run's last timestep ("tail") does one safeguarded Newton
+//     update per pass and broadcasts the new multiplier back over its run;
 //   * then the KKT conditions are checked in parallel: levels inside the bounds, and a multiplier
 //     path with the right sign at every anchor (intervals, because saturated runs have a non-unique
 //     multiplier).  Violated levels add an anchor (first violated timestep of the run), anchors with a
@@ -13,6 +14,10 @@
 //   * the result is accepted only when the KKT conditions hold (=> exact optimum of the convex
 //     problem).  Storages that do not verify within the caps go to the sequential exact solver.
 // The initial active set comes from the previous levels (warm start).
+//
+// Scans: the segment structure is turned once per active-set iteration into per-element "reach"
+// counters (how far the element may look towards its run head / tail inside its 32-wide chunk), so a
+// segmented scan step is just shuffle + compare + op, without shuffling flags.
 #ifndef DOPF_STO_WARP_CUH
 #define DOPF_STO_WARP_CUH
 
@@ -23,52 +28,157 @@ namespace dopf {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr double WBIG = 1e300;
 
-// ---- chunked segmented scans over the strided ownership t = lane + 32*j ------------------------------
-// forward inclusive scan, restarting at elements with head[j] == true
-template <int J, class T, class Op>
-__device__ __forceinline__ void seg_scan_fwd(T (&v)[J], const bool (&head)[J], Op op, T identity)
+template <int J>
+struct Reach {
+    int back[J];    // forward scans: steps the element may look back inside its chunk (towards the run head)
+    int fwd[J];     // backward scans: steps it may look ahead (towards the run tail)
+    bool cin[J];    // run head lies in an earlier chunk  -> takes the forward carry
+    bool cout[J];   // run tail lies in a later chunk    -> takes the backward carry
+};
+
+// position of the last head at or before t (plain inclusive max-scan of head ? t : -1)
+template <int J>
+__device__ __forceinline__ void last_flag_pos(const bool (&flag)[J], int (&pos)[J])
 {
     const int lane = threadIdx.x & 31;
-    T carry = identity;
+    int carry = -1;
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-        T x = v[j];
-        bool f = head[j];
+        int x = flag[j] ? lane + 32 * j : -1;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const T xo = __shfl_up_sync(FULL, x, o);
-            const bool fo = __shfl_up_sync(FULL, (int)f, o) != 0;
-            if (lane >= o && !f) { x = op(xo, x); f = fo; }
+            const int xo = __shfl_up_sync(FULL, x, o);
+            if (lane >= o) x = max(x, xo);
         }
-        if (!f) x = op(carry, x);          // no head between the chunk start and this element
-        v[j] = x;
+        x = max(x, carry);
+        pos[j] = x;
         carry = __shfl_sync(FULL, x, 31);
     }
 }
-
-// backward inclusive scan (from larger t to smaller), restarting at elements with tail[j] == true
-template <int J, class T, class Op>
-__device__ __forceinline__ void seg_scan_bwd(T (&v)[J], const bool (&tail)[J], Op op, T identity)
+// position of the first flag at or after t (plain inclusive min-scan from the right)
+template <int J>
+__device__ __forceinline__ void next_flag_pos(const bool (&flag)[J], int (&pos)[J])
 {
     const int lane = threadIdx.x & 31;
-    T carry = identity;
+    int carry = 0x7fffffff;
 #pragma unroll
     for (int j = J - 1; j >= 0; --j) {
-        T x = v[j];
-        bool f = tail[j];
+        int x = flag[j] ? lane + 32 * j : 0x7fffffff;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const T xo = __shfl_down_sync(FULL, x, o);
-            const bool fo = __shfl_down_sync(FULL, (int)f, o) != 0;
-            if (lane + o < 32 && !f) { x = op(xo, x); f = fo; }
+            const int xo = __shfl_down_sync(FULL, x, o);
+            if (lane + o < 32) x = min(x, xo);
         }
-        if (!f) x = op(carry, x);
-        v[j] = x;
+        x = min(x, carry);
+        pos[j] = x;
         carry = __shfl_sync(FULL, x, 0);
     }
 }
 
-// value of the element at t-1 (identity for t = 0)
+template <int J>
+__device__ __forceinline__ void reach_back_from_heads(const bool (&head)[J], int (&back)[J], bool (&cin)[J])
+{
+    const int lane = threadIdx.x & 31;
+    int hp[J];
+    last_flag_pos<J>(head, hp);
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int t = lane + 32 * j, d = t - hp[j];       // hp >= 0 because t = 0 is always a head
+        back[j] = min(lane, d);
+        cin[j] = hp[j] < 32 * j;
+    }
+}
+template <int J>
+__device__ __forceinline__ void reach_fwd_to_tails(const bool (&tail)[J], int (&fwd)[J], bool (&cout)[J])
+{
+    const int lane = threadIdx.x & 31;
+    int tp[J];
+    next_flag_pos<J>(tail, tp);
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int t = lane + 32 * j;
+        const bool none = tp[j] == 0x7fffffff;
+        fwd[j] = none ? 0 : min(31 - lane, tp[j] - t);
+        cout[j] = !none && tp[j] > 32 * j + 31;
+    }
+}
+
+struct OpAdd { __device__ double operator()(double a, double b) const { return a + b; } };
+struct OpMin { __device__ double operator()(double a, double b) const { return a < b ? a : b; } };
+struct OpMax { __device__ double operator()(double a, double b) const { return a > b ? a : b; } };
+
+// forward inclusive segmented scan of two value arrays at once
+template <int J, class OpA, class OpB>
+__device__ __forceinline__ void seg_fwd2(double (&a)[J], double (&b)[J], const int (&back)[J], const bool (&cin)[J],
+                                         OpA opa, OpB opb, double ida, double idb)
+{
+    double ca = ida, cb = idb;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        double x = a[j], y = b[j];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double xo = __shfl_up_sync(FULL, x, o), yo = __shfl_up_sync(FULL, y, o);
+            if (back[j] >= o) { x = opa(xo, x); y = opb(yo, y); }
+        }
+        if (cin[j]) { x = opa(ca, x); y = opb(cb, y); }
+        a[j] = x; b[j] = y;
+        ca = __shfl_sync(FULL, x, 31); cb = __shfl_sync(FULL, y, 31);
+    }
+}
+template <int J>
+__device__ __forceinline__ void seg_fwd_min_int(int (&a)[J], const int (&back)[J], const bool (&cin)[J])
+{
+    int ca = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        int x = a[j];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int xo = __shfl_up_sync(FULL, x, o);
+            if (back[j] >= o) x = min(xo, x);
+        }
+        if (cin[j]) x = min(ca, x);
+        a[j] = x;
+        ca = __shfl_sync(FULL, x, 31);
+    }
+}
+// every element takes the values held by the tail of its run (a double and an int at once)
+template <int J>
+__device__ __forceinline__ void seg_take_tail(double (&a)[J], int (&b)[J], const int (&fwd)[J], const bool (&cout)[J])
+{
+    double ca = 0.0; int cb = 0;
+#pragma unroll
+    for (int j = J - 1; j >= 0; --j) {
+        double x = a[j]; int y = b[j];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double xo = __shfl_down_sync(FULL, x, o); const int yo = __shfl_down_sync(FULL, y, o);
+            if (fwd[j] >= o) { x = xo; y = yo; }
+        }
+        if (cout[j]) { x = ca; y = cb; }
+        a[j] = x; b[j] = y;
+        ca = __shfl_sync(FULL, x, 0); cb = __shfl_sync(FULL, y, 0);
+    }
+}
+template <int J>
+__device__ __forceinline__ void seg_take_tail_int2(int (&a)[J], int (&b)[J], const int (&fwd)[J], const bool (&cout)[J])
+{
+    int ca = 0, cb = 0;
+#pragma unroll
+    for (int j = J - 1; j >= 0; --j) {
+        int x = a[j], y = b[j];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int xo = __shfl_down_sync(FULL, x, o), yo = __shfl_down_sync(FULL, y, o);
+            if (fwd[j] >= o) { x = xo; y = yo; }
+        }
+        if (cout[j]) { x = ca; y = cb; }
+        a[j] = x; b[j] = y;
+        ca = __shfl_sync(FULL, x, 0); cb = __shfl_sync(FULL, y, 0);
+    }
+}
+// value of the element at t-1 / t+1
 template <int J, class T>
 __device__ __forceinline__ void shift_from_prev(const T (&v)[J], T (&out)[J], T first)
 {
@@ -81,7 +191,18 @@ __device__ __forceinline__ void shift_from_prev(const T (&v)[J], T (&out)[J], T 
         carry = __shfl_sync(FULL, v[j], 31);
     }
 }
-
+template <int J>
+__device__ __forceinline__ void shift_from_next(const int (&v)[J], int (&out)[J], int last)
+{
+    const int lane = threadIdx.x & 31;
+    int carry = last;
+#pragma unroll
+    for (int j = J - 1; j >= 0; --j) {
+        const int dn = __shfl_down_sync(FULL, v[j], 1);
+        out[j] = lane == 31 ? carry : dn;
+        carry = __shfl_sync(FULL, v[j], 0);
+    }
+}
 template <int J>
 __device__ __forceinline__ bool any_of(const bool (&p)[J])
 {
@@ -91,12 +212,8 @@ __device__ __forceinline__ bool any_of(const bool (&p)[J])
     return __any_sync(FULL, a);
 }
 
-struct OpAdd { __device__ double operator()(double a, double b) const { return a + b; } };
-struct OpMin { __device__ double operator()(double a, double b) const { return a < b ? a : b; } };
-struct OpMax { __device__ double operator()(double a, double b) const { return a > b ? a : b; } };
-struct OpTakeFirst { template <class T> __device__ T operator()(T a, T) const { return a; } };   // op(incoming, self) = incoming
-struct OpLastNonzero { __device__ int operator()(int a, int b) const { return b != 0 ? b : a; } };
-struct OpMinInt { __device__ int operator()(int a, int b) const { return a < b ? a : b; } };
+// run status bits broadcast from the tail
+enum { RS_CONV = 1, RS_BAD = 2, RS_FLAT = 4, RS_EMPTY = 8, RS_FREEBAD = 16 };
 
 // returns true if the storage was solved and written; false => caller queues it for the exact sequential solver
 template <int J, bool HINGES>
@@ -128,30 +245,33 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
         kind[j] = !valid[j] ? 0 : (Ep >= k.emax - tolA ? 1 : (Ep <= tolA ? -1 : 0));
     }
 
-    double D[J], C[J], E[J];
+    double D[J], C[J], pre[J];
     bool accepted = false;
     for (int as_it = 0; as_it < 24 && !accepted; ++as_it) {
-        // ---- run structure from the anchors -----------------------------------------------------
+        // ---- run structure from the anchors (timesteps beyond T are isolated one-element runs) ------
         bool head[J], tail[J];
         int prevk[J], endk[J];
+        Reach<J> R;
         {
             int kp[J];
-            shift_from_prev<J, int>(kind, kp, 1);                     // kind of t-1 (t = 0 starts a run)
-            int lastnz[J];
-#pragma unroll
-            for (int j = 0; j < J; ++j) { head[j] = kp[j] != 0; lastnz[j] = kind[j]; }
-            bool nohead[J];
-#pragma unroll
-            for (int j = 0; j < J; ++j) nohead[j] = false;
-            seg_scan_fwd<J, int>(lastnz, nohead, OpLastNonzero(), 0);  // last anchor kind at or before t
-            shift_from_prev<J, int>(lastnz, prevk, 0);                // ... strictly before t
+            shift_from_prev<J, int>(kind, kp, 1);                        // kind of t-1 (t = 0 starts a run)
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 const int t = lane + 32 * j;
-                tail[j] = valid[j] && (kind[j] != 0 || t == T - 1);
-                endk[j] = kind[j];
+                head[j] = kp[j] != 0 || !valid[j] || t == T;
+                tail[j] = !valid[j] || kind[j] != 0 || t == T - 1;
             }
-            seg_scan_bwd<J, int>(endk, tail, OpTakeFirst(), 0);       // kind at the end of my run
+            reach_back_from_heads<J>(head, R.back, R.cin);
+            reach_fwd_to_tails<J>(tail, R.fwd, R.cout);
+            // kind of the anchor that closed the previous run = kind at (head position - 1):
+            // heads read it from t-1, then it is spread over the run with a forward "take head" scan
+            double hk[J], dummy[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) { hk[j] = head[j] ? (double)((lane + 32 * j) == 0 ? 0 : kp[j]) : -2.0; dummy[j] = 0.0; }
+            seg_fwd2<J>(hk, dummy, R.back, R.cin, OpMax(), OpAdd(), -2.0, 0.0);   // non-heads hold -2 => max = head's value
+#pragma unroll
+            for (int j = 0; j < J; ++j) { prevk[j] = (int)hk[j]; endk[j] = kind[j]; }
+            seg_take_tail<J>(eta, endk, R.fwd, R.cout);                  // start multiplier and end kind of my run
         }
         double e0[J], target[J];
         bool freeend[J];
@@ -160,17 +280,15 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
             e0[j] = prevk[j] > 0 ? k.emax : 0.0;
             target[j] = (endk[j] > 0 ? k.emax : 0.0) - e0[j];
             freeend[j] = endk[j] == 0;
+            if (freeend[j]) eta[j] = 0.0;
         }
-        // one multiplier per run: start from the previous multiplier at the run end (0 for the free end)
-        seg_scan_bwd<J, double>(eta, tail, OpTakeFirst(), 0.0);
-#pragma unroll
-        for (int j = 0; j < J; ++j) if (freeend[j]) eta[j] = 0.0;
 
-        // ---- simultaneous safeguarded Newton on all runs ------------------------------------------
-        double lo[J], hi[J], rlo[J], rhi[J], toty[J], totd[J], pre[J];
-        bool conv[J], bad[J];          // bad: the run cannot meet its target with this active set
+        // ---- simultaneous safeguarded Newton on all runs (state lives at the tails) -----------------
+        double lo[J], hi[J], totd[J];
+        int rs[J];
 #pragma unroll
-        for (int j = 0; j < J; ++j) { lo[j] = -WBIG; hi[j] = WBIG; rlo[j] = rhi[j] = 0.0; conv[j] = !valid[j]; bad[j] = false; }
+        for (int j = 0; j < J; ++j) { lo[j] = -WBIG; hi[j] = WBIG; totd[j] = 0.0; rs[j] = valid[j] ? 0 : RS_CONV; }
+        bool capped = true;
         for (int it = 0; it < 24; ++it) {
             double dy[J];
 #pragma unroll
@@ -180,182 +298,150 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
                     D[j] = e.D; C[j] = e.C; pre[j] = e.C - e.D; dy[j] = e.dy;
                 } else { D[j] = C[j] = pre[j] = dy[j] = 0.0; }
             }
-            seg_scan_fwd<J, double>(pre, head, OpAdd(), 0.0);
-            seg_scan_fwd<J, double>(dy, head, OpAdd(), 0.0);
-#pragma unroll
-            for (int j = 0; j < J; ++j) { toty[j] = pre[j]; totd[j] = dy[j]; }
-            seg_scan_bwd<J, double>(toty, tail, OpTakeFirst(), 0.0);
-            seg_scan_bwd<J, double>(totd, tail, OpTakeFirst(), 0.0);
-            bool needflat[J], pending[J];
+            seg_fwd2<J>(pre, dy, R.back, R.cin, OpAdd(), OpAdd(), 0.0, 0.0);
+            bool pending[J], needflat[J];
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                const double r = toty[j] - target[j];
-                const double tolS = 1e-13 * (1.0 + fabs(target[j]) + k.pmax);
-                if (valid[j] && !conv[j] && !bad[j]) conv[j] = freeend[j] || fabs(r) <= tolS;
-                pending[j] = valid[j] && !conv[j] && !bad[j];
-                needflat[j] = pending[j] && !(totd[j] < -1e-300);
+                totd[j] = dy[j];
+                pending[j] = false; needflat[j] = false;
+                if (valid[j] && tail[j] && !(rs[j] & (RS_CONV | RS_BAD))) {
+                    const double r = pre[j] - target[j];
+                    const double tolS = 1e-13 * (1.0 + fabs(target[j]) + k.pmax);
+                    if (freeend[j] || fabs(r) <= tolS) rs[j] |= RS_CONV;
+                    else { pending[j] = true; needflat[j] = !(dy[j] < -1e-300); }
+                }
             }
-            if (!any_of<J>(pending)) break;
-            double best[J];
-#pragma unroll
-            for (int j = 0; j < J; ++j) best[j] = 0.0;
+            if (!any_of<J>(pending)) { capped = false; break; }
+            double bu[J], bd[J];
             if (any_of<J>(needflat)) {
-                // saturated runs: nearest clip breakpoint of any step of the run in the needed direction
-                double bu[J], bd[J];
-                bool hard[J];
+                // saturated runs: nearest clip breakpoint of any step of the run in the needed direction;
+                // every element offers its own breakpoints, the tail picks (runs that are not flat ignore it)
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
-                    bu[j] = WBIG; bd[j] = -WBIG; hard[j] = false;
-                    if (needflat[j]) {
-                        if (hl[j].n != 0) hard[j] = true;
+                    bu[j] = WBIG; bd[j] = -WBIG;
+                    if (valid[j]) {
+                        if (hl[j].n != 0) { bu[j] = -WBIG; bd[j] = WBIG; }             // hinge on a flat run: not handled here
                         else { bu[j] = sto_next_break(st[j], k, eta[j], true); bd[j] = sto_next_break(st[j], k, eta[j], false); }
                     }
                 }
-                seg_scan_fwd<J, double>(bu, head, OpMin(), WBIG); seg_scan_bwd<J, double>(bu, tail, OpTakeFirst(), WBIG);
-                seg_scan_fwd<J, double>(bd, head, OpMax(), -WBIG); seg_scan_bwd<J, double>(bd, tail, OpTakeFirst(), -WBIG);
-                double hd[J];
-#pragma unroll
-                for (int j = 0; j < J; ++j) hd[j] = hard[j] ? 1.0 : 0.0;
-                seg_scan_fwd<J, double>(hd, head, OpMax(), 0.0); seg_scan_bwd<J, double>(hd, tail, OpTakeFirst(), 0.0);
-#pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    if (!needflat[j]) continue;
-                    const bool up = toty[j] - target[j] > 0.0;
-                    const double b = up ? bu[j] : bd[j];
-                    if (hd[j] != 0.0 || !(fabs(b) < WBIG)) bad[j] = true;          // unreachable / hinge on a flat run
-                    else best[j] = b + (up ? 1.0 : -1.0) * 1e-11 * (1.0 + fabs(b));
-                }
+                seg_fwd2<J>(bu, bd, R.back, R.cin, OpMin(), OpMax(), WBIG, -WBIG);
             }
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                if (!pending[j] || bad[j]) continue;
-                const double r = toty[j] - target[j];
-                if (r > 0.0) { lo[j] = eta[j]; rlo[j] = r; } else { hi[j] = eta[j]; rhi[j] = r; }
-                double en = needflat[j] ? best[j] : eta[j] - r / totd[j];
+                if (!pending[j]) continue;
+                const double r = pre[j] - target[j];
+                if (r > 0.0) lo[j] = eta[j]; else hi[j] = eta[j];
+                double en;
+                if (!needflat[j]) en = eta[j] - r / dy[j];
+                else {
+                    const bool up = r > 0.0;
+                    const double b = up ? bu[j] : bd[j];
+                    if (!(fabs(b) < WBIG)) { rs[j] |= RS_BAD; continue; }               // unreachable target / hinge on a flat run
+                    en = b + (up ? 1.0 : -1.0) * 1e-11 * (1.0 + fabs(b));
+                }
                 if (!(en > lo[j] && en < hi[j])) {
                     if (lo[j] > -WBIG && hi[j] < WBIG) {
-                        en = lo[j] - rlo[j] * (hi[j] - lo[j]) / (rhi[j] - rlo[j]);
-                        if (!(en > lo[j] && en < hi[j])) en = 0.5 * (lo[j] + hi[j]);
-                        if ((hi[j] - lo[j]) <= 1e-15 * (1.0 + fabs(lo[j]))) conv[j] = true;
-                    } else bad[j] = true;
+                        en = 0.5 * (lo[j] + hi[j]);
+                        if ((hi[j] - lo[j]) <= 1e-15 * (1.0 + fabs(lo[j]))) rs[j] |= RS_CONV;
+                    } else { rs[j] |= RS_BAD; continue; }
                 }
                 eta[j] = en;
             }
+            seg_take_tail<J>(eta, rs, R.fwd, R.cout);
         }
-        {
-            bool pend[J];
+        if (capped) return false;                                             // Newton cap reached
+        // final run state for every element: multiplier, status, "flat" (sum of derivatives at the tail)
 #pragma unroll
-            for (int j = 0; j < J; ++j) pend[j] = valid[j] && !conv[j] && !bad[j];
-            if (any_of<J>(pend)) return false;                         // Newton cap reached
-        }
+        for (int j = 0; j < J; ++j) if (valid[j] && tail[j] && !(totd[j] < -1e-300)) rs[j] |= RS_FLAT;
+        seg_take_tail<J>(eta, rs, R.fwd, R.cout);
 
         // ---- KKT check ------------------------------------------------------------------------------
-        bool vio_up[J], vio_dn[J], change = false;
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            E[j] = e0[j] + pre[j];
-            vio_up[j] = valid[j] && !bad[j] && E[j] > k.emax + tolE;
-            vio_dn[j] = valid[j] && !bad[j] && E[j] < -tolE;
-        }
-        // multiplier interval of every run (flat runs: stretch on which every step keeps its value)
+        bool vio_up[J], vio_dn[J];
         double Ilo[J], Ihi[J];
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-            Ilo[j] = -WBIG; Ihi[j] = WBIG;                              // neutral for min/max over the run
+            const double E = e0[j] + pre[j];
+            const bool ok = valid[j] && !(rs[j] & RS_BAD);
+            vio_up[j] = ok && E > k.emax + tolE;
+            vio_dn[j] = ok && E < -tolE;
+            // multiplier interval of my run, contributed per element: a point unless the whole run is flat
+            Ilo[j] = -WBIG; Ihi[j] = WBIG;
             if (valid[j]) {
-                if (totd[j] < -1e-300 || hl[j].n != 0) { Ilo[j] = eta[j]; Ihi[j] = eta[j]; }
+                if (!(rs[j] & RS_FLAT) || hl[j].n != 0) { Ilo[j] = eta[j]; Ihi[j] = eta[j]; }
                 else sto_flat_interval(st[j], k, eta[j], D[j], C[j], Ilo[j], Ihi[j]);
             }
         }
-        seg_scan_fwd<J, double>(Ilo, head, OpMax(), -WBIG); seg_scan_bwd<J, double>(Ilo, tail, OpTakeFirst(), -WBIG);
-        seg_scan_fwd<J, double>(Ihi, head, OpMin(), WBIG); seg_scan_bwd<J, double>(Ihi, tail, OpTakeFirst(), WBIG);
-        // sign chain: after an upper anchor eta may not rise, after a lower anchor it may not drop.
-        // Fhi = running min of Ihi over consecutive runs linked by upper anchors (restart after a lower
-        // anchor), Flo = running max of Ilo over runs linked by lower anchors.
+        seg_fwd2<J>(Ilo, Ihi, R.back, R.cin, OpMax(), OpMin(), -WBIG, WBIG);      // tails now hold the run interval
+        // sign chain over the runs: after an upper anchor eta may not rise, after a lower anchor it may not
+        // drop.  Only tails carry run values, the other elements are neutral; the chains restart at the
+        // head of a run whose previous anchor has the other kind.
         double Fhi[J], Flo[J];
-        bool hup[J], hdn[J];
+        {
+            bool hup[J], hdn[J];
+            int bup[J], bdn[J]; bool cup[J], cdn[J];
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-            Fhi[j] = Ihi[j]; Flo[j] = Ilo[j];
-            hup[j] = head[j] && prevk[j] <= 0;      // chain of "may not rise" restarts unless the previous anchor was upper
-            hdn[j] = head[j] && prevk[j] >= 0;
+            for (int j = 0; j < J; ++j) {
+                Fhi[j] = (valid[j] && tail[j]) ? Ihi[j] : WBIG;
+                Flo[j] = (valid[j] && tail[j]) ? Ilo[j] : -WBIG;
+                hup[j] = head[j] && prevk[j] <= 0;
+                hdn[j] = head[j] && prevk[j] >= 0;
+            }
+            reach_back_from_heads<J>(hup, bup, cup);
+            reach_back_from_heads<J>(hdn, bdn, cdn);
+            double d1[J], d2[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) { d1[j] = 0.0; d2[j] = 0.0; }
+            seg_fwd2<J>(Fhi, d1, bup, cup, OpMin(), OpAdd(), WBIG, 0.0);
+            seg_fwd2<J>(Flo, d2, bdn, cdn, OpMax(), OpAdd(), -WBIG, 0.0);
         }
-        seg_scan_fwd<J, double>(Fhi, hup, OpMin(), WBIG);
-        seg_scan_fwd<J, double>(Flo, hdn, OpMax(), -WBIG);
-        bool drop_prev[J];                           // the anchor just before my run has the wrong sign
+        int tv[J], flag[J];
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const int t = lane + 32 * j;
-            double a = Flo[j], b = Fhi[j];
-            if (valid[j] && t == T - 1 && kind[j] != 0) {          // end of horizon: eta_{T+1} = 0
-                if (kind[j] > 0) a = a > 0.0 ? a : 0.0; else b = b < 0.0 ? b : 0.0;
+            tv[j] = (vio_up[j] || vio_dn[j]) ? t : 0x7fffffff;
+            flag[j] = 0;
+            if (valid[j] && tail[j] && !(rs[j] & RS_BAD)) {
+                double a = Flo[j], b = Fhi[j];
+                if (t == T - 1 && kind[j] != 0) {                  // end of horizon: eta_{T+1} = 0
+                    if (kind[j] > 0) a = a > 0.0 ? a : 0.0; else b = b < 0.0 ? b : 0.0;
+                }
+                if (a > b) flag[j] |= RS_EMPTY;
+                if (freeend[j] && (Flo[j] > 0.0 || Fhi[j] < 0.0)) flag[j] |= RS_FREEBAD;
             }
-            const bool empty = valid[j] && !bad[j] && a > b;
-            // report at the head of the run (the anchor to drop is the end of the previous run); for the
-            // horizon end the terminal anchor itself is dropped below
-            drop_prev[j] = empty;
+            if (valid[j] && tail[j] && (rs[j] & RS_BAD)) flag[j] |= RS_BAD;
         }
-        // a run is "empty" at all of its elements or none (interval values are run-uniform) except for the
-        // terminal adjustment, which only touches t = T-1; propagate that to the run head
-        {
-            double em[J];
-#pragma unroll
-            for (int j = 0; j < J; ++j) em[j] = drop_prev[j] ? 1.0 : 0.0;
-            seg_scan_bwd<J, double>(em, tail, OpMax(), 0.0);
-#pragma unroll
-            for (int j = 0; j < J; ++j) drop_prev[j] = em[j] != 0.0;
-        }
-        // free end must admit eta = 0
-        bool freebad[J];
-#pragma unroll
-        for (int j = 0; j < J; ++j) freebad[j] = valid[j] && freeend[j] && (Flo[j] > 0.0 || Fhi[j] < 0.0);
+        seg_fwd_min_int<J>(tv, R.back, R.cin);                      // tails hold the first violated timestep
+        seg_take_tail_int2<J>(tv, flag, R.fwd, R.cout);             // ... and tell their run
 
         // ---- repair the active set -----------------------------------------------------------------
-        // (1) first level violation of every run becomes an anchor
-        {
-            int tv[J];
+        bool change = false, anybad = false;
+        int wantdrop[J];                                            // head of a run that wants the previous anchor gone
 #pragma unroll
-            for (int j = 0; j < J; ++j) tv[j] = (vio_up[j] || vio_dn[j]) ? lane + 32 * j : 0x7fffffff;
-            seg_scan_fwd<J, int>(tv, head, OpMinInt(), 0x7fffffff);
-            seg_scan_bwd<J, int>(tv, tail, OpTakeFirst(), 0x7fffffff);
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                if (valid[j] && tv[j] == lane + 32 * j) { kind[j] = vio_up[j] ? 1 : -1; change = true; }
-            }
+        for (int j = 0; j < J; ++j) {
+            const int t = lane + 32 * j;
+            anybad |= valid[j] && (flag[j] != 0 || vio_up[j] || vio_dn[j]);
+            wantdrop[j] = (valid[j] && head[j] && ((flag[j] & (RS_EMPTY | RS_FREEBAD)) || ((flag[j] & RS_BAD) && freeend[j]))) ? 1 : 0;
+            if (valid[j] && tv[j] == t) { kind[j] = vio_up[j] ? 1 : -1; change = true; }       // (1) new anchor
         }
-        // (2) anchors with a wrong multiplier sign (or closing an unsatisfiable run) are dropped:
-        //     drop the anchor that ends the previous run  <=> element t-1 of a head element
-        {
-            bool dropme[J], nexthead_drop[J];
-            // does the run starting at t+1 ask to drop me?  (shift information from t+1 to t)
-            const int lane_ = lane;
-            bool carry = false;
+        int nextwant[J];
+        shift_from_next<J>(wantdrop, nextwant, 0);
 #pragma unroll
-            for (int j = J - 1; j >= 0; --j) {
-                const bool mine = head[j] && (drop_prev[j] || freebad[j] || (bad[j] && freeend[j])) && valid[j];
-                const bool dn = __shfl_down_sync(FULL, (int)mine, 1) != 0;
-                nexthead_drop[j] = lane_ == 31 ? carry : dn;
-                carry = __shfl_sync(FULL, (int)mine, 0) != 0;
-            }
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const int t = lane + 32 * j;
-                dropme[j] = valid[j] && kind[j] != 0 && nexthead_drop[j];
-                // unsatisfiable run: drop its own end anchor; terminal anchor with a wrong sign likewise
-                if (valid[j] && kind[j] != 0 && tail[j] && bad[j]) dropme[j] = true;
-                if (valid[j] && kind[j] != 0 && t == T - 1 && drop_prev[j]) dropme[j] = true;
-                if (dropme[j]) { kind[j] = 0; change = true; }
-            }
+        for (int j = 0; j < J; ++j) {
+            const int t = lane + 32 * j;
+            if (!valid[j] || kind[j] == 0 || tv[j] == t) continue;
+            bool drop = nextwant[j] != 0;                                                       // (2) wrong sign at my anchor
+            if (tail[j] && (flag[j] & RS_BAD)) drop = true;                                     //     my run cannot meet its target
+            if (t == T - 1 && (flag[j] & RS_EMPTY)) drop = true;                                //     wrong sign at the horizon end
+            if (drop) { kind[j] = 0; change = true; }
         }
-        // a run that starts at t = 0 cannot drop a previous anchor: if it is empty/bad without any other
-        // change we cannot repair it here
-        change = __any_sync(FULL, change);
-        bool anybad = false;
-#pragma unroll
-        for (int j = 0; j < J; ++j) anybad |= bad[j] || drop_prev[j] || freebad[j] || vio_up[j] || vio_dn[j];
         anybad = __any_sync(FULL, anybad);
+        change = __any_sync(FULL, change);
         if (!anybad) accepted = true;
         else if (!change) return false;
+        if (accepted) {
+#pragma unroll
+            for (int j = 0; j < J; ++j) pre[j] += e0[j];            // levels
+        }
     }
     if (!accepted) return false;
 
@@ -365,7 +451,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
         const int t = lane + 32 * j;
         if (!valid[j]) continue;
         const size_t o = (size_t)s * T + t;
-        sel(v.D, nxt)[o] = D[j]; sel(v.C, nxt)[o] = C[j]; v.E[o] = E[j]; v.eta[o] = eta[j];
+        sel(v.D, nxt)[o] = D[j]; sel(v.C, nxt)[o] = C[j]; v.E[o] = pre[j]; v.eta[o] = eta[j];
         note_move(v, n, t, (D[j] - st[j].Db) - (C[j] - st[j].Cb));
     }
     return true;
