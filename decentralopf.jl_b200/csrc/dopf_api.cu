@@ -160,6 +160,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     for (int g = 0; g < G; ++g) if (p->gen_node[g] < 0 || p->gen_node[g] >= N) { h->err = "gen_node out of range"; return DOPF_E_ARG; }
     for (int s = 0; s < S; ++s) if (p->sto_node[s] < 0 || p->sto_node[s] >= N) { h->err = "sto_node out of range"; return DOPF_E_ARG; }
     if ((long long)G * T >= (1ll << 31) || (long long)S * T >= (1ll << 31)) { h->err = "G*T or S*T exceeds 2^31"; return DOPF_E_UNSUPPORTED; }
+    if (T / (T % 4 == 0 ? 4 : (T % 2 == 0 ? 2 : 1)) > 1024) { h->err = "horizon too long for this build (T/vec > 1024 timestep slots per block)"; return DOPF_E_UNSUPPORTED; }
 
     int ndev = 0;
     cudaError_t e0 = cudaGetDeviceCount(&ndev);
@@ -240,7 +241,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     }
     AL(v.E, (size_t)S * T); AL(v.eta, (size_t)S * T); AL(v.cold_work, S); AL(v.wide_b, (size_t)T * 2 * L); AL(v.avgU, (size_t)Lp * ldt); AL(v.avgK, (size_t)Lp * ldt);
     AL(v.bplus, (size_t)Lp * ldt); AL(v.bminus, (size_t)Lp * ldt); AL(v.M, (size_t)Lp * ldt); AL(v.Wt, (size_t)Lp * ldt);
-    AL(v.g0, (size_t)Np * ldt); AL(v.s1, (size_t)Np * ldt);
+    AL(v.g0, (size_t)Np * ldt); AL(v.s1, (size_t)Np * ldt); AL(v.rg, (size_t)Np * ldt);
     AL(v.dn, (size_t)Np * ldt); AL(v.dmax, ldt);
     AL(v.flags, (size_t)ldt * Lp);
     AL(v.wide, (size_t)T * 2 * L); AL(v.wcnt, T); AL(v.tight, (size_t)T * 2 * L); AL(v.tcnt, T);

@@ -80,6 +80,7 @@ struct View {
     // per-iteration scratch
     double *bplus, *bminus, *M, *Wt;   // [Lp][ldt]
     double *g0, *s1;                   // [Np][ldt]
+    double *rg;                        // [Np][ldt] 1/(prox + s1): generator step size
     unsigned long long *dn;            // [Np][ldt] max |delta| of the agents at (n,t) (bits)
     unsigned long long *dmax;          // [ldt]
     unsigned char *flags;              // [ldt][Lp] bit0: U side wide candidate, bit1: K side
@@ -119,9 +120,7 @@ DOPF_HD void body_row_prep(const View &v, int l, int t)
 DOPF_HD double body_gen_predict(const View &v, int g, int t, double Pprev, int n, double mc, double pmax)
 {
     const size_t nt = (size_t)n * v.ldt + t;
-    const double a = v.c.prox + v.s1[nt];
-    double d = -(mc + v.g0[nt]) / a;
-    double Pn = Pprev + d;
+    double Pn = Pprev - (mc + v.g0[nt]) * v.rg[nt];
     Pn = Pn < 0.0 ? 0.0 : (Pn > pmax ? pmax : Pn);
     return Pn;
 }
@@ -133,7 +132,8 @@ DOPF_HD void note_move(const View &v, int n, int t, double delta)
     const unsigned long long b = nonneg_bits(ad);
     unsigned long long *pn = v.dn + (size_t)n * v.ldt + t;
     if (b > *pn) DOPF_ATOMIC_MAX_U64(pn, b);
-    if (b > v.dmax[t]) DOPF_ATOMIC_MAX_U64(v.dmax + t, b);
+    // dmax[t] = max_n dn[n][t] is computed by a separate column reduction (k_dmax): updating it here
+    // would serialise every moving agent of a timestep on one address
 }
 
 // ---- storages: accessors over the device layout ------------------------------------------------

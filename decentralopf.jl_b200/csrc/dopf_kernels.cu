@@ -227,7 +227,9 @@ __global__ void k_node_prep(View v, const double *Cpart, const double *C2part, i
     double a = 0.0, b = 0.0;
     for (int z = 0; z < ksplit; ++z) { a += Cpart[(size_t)z * v.Np * v.ldt + i]; b += C2part[(size_t)z * v.Np * v.ldt + i]; }
     v.g0[i] = sel(v.lam, cur)[t] + v.c.gamma * sel(v.ssum, cur)[t] + a;
-    v.s1[i] = v.c.gamma + 2.0 * v.c.kappa * v.q[n] + b;
+    const double s1v = v.c.gamma + 2.0 * v.c.kappa * v.q[n] + b;
+    v.s1[i] = s1v;
+    v.rg[i] = 1.0 / (v.c.prox + s1v);     // generator step: delta = -(mc + g0) * rg
 }
 
 // epilogue of the flow product: line_utilization = ptdf * injection (results.jl:114)
@@ -244,32 +246,70 @@ __global__ void k_flow_reduce(View v, const double *Cpart, int ksplit)
 // ------------------------------------------------------------------------------------------------
 // generator predict: one thread per (agent, VEC consecutive t); streaming, 16 B per unit
 // ------------------------------------------------------------------------------------------------
+// one unit of the generator update: anchor-linearised closed form + box projection
+// (subproblems.jl:63-83 reduced; exact unless a slack hinge lies in (0, delta], which k_verify detects)
+__device__ __forceinline__ double gen_unit(double pp, double mc, double pmax, double g0, double rg)
+{
+    const double x = pp - (mc + g0) * rg;
+    return x < 0.0 ? 0.0 : (x > pmax ? pmax : x);
+}
+
+// Node-major generator update: one block per node, threadIdx.x = timestep slot (VEC timesteps),
+// threadIdx.y = agent row.  g0 and the step size 1/(prox+s1) of (node, t) stay in registers while the
+// block streams through the node's generators (contiguous, agents are node-sorted): per unit one
+// 8-byte load, one 8-byte store and a few flops.  The largest move per (node, t) is accumulated in
+// registers and published with one atomic per thread.
+constexpr int GEN_UNR = 4;
 template <int VEC>
 __global__ void __launch_bounds__(256) k_gen_predict(View v)
 {
     if (!DOPF_ACTIVE(v)) return;
+    const int n = blockIdx.x;
+    const int ga = v.gen_ptr[n], gb = v.gen_ptr[n + 1];
+    if (ga == gb) return;
     const int cur = v.ctrl->cur, nxt = 1 - cur;
-    const int per = v.T / VEC;                      // VEC divides T
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)v.G * per) return;
-    const int g = (int)(idx / per), t = (int)(idx % per) * VEC;
-    const int n = __ldg(v.gen_node + g);
-    const double mc = __ldg(v.gen_mc + g), pmax = __ldg(v.gen_pmax + g);
-    const size_t o = (size_t)g * v.T + t;
-    if (VEC == 2) {
-        const double2 pp = *reinterpret_cast<const double2 *>(sel(v.P, cur) + o);
-        double2 pn;
-        pn.x = body_gen_predict(v, g, t, pp.x, n, mc, pmax);
-        pn.y = body_gen_predict(v, g, t + 1, pp.y, n, mc, pmax);
-        *reinterpret_cast<double2 *>(sel(v.P, nxt) + o) = pn;
-        note_move(v, n, t, pn.x - pp.x);
-        note_move(v, n, t + 1, pn.y - pp.y);
-    } else {
-        const double pp = sel(v.P, cur)[o];
-        const double pn = body_gen_predict(v, g, t, pp, n, mc, pmax);
-        sel(v.P, nxt)[o] = pn;
-        note_move(v, n, t, pn - pp);
+    const double *__restrict__ Pc = sel(v.P, cur);
+    double *__restrict__ Pn = sel(v.P, nxt);
+    const int t = threadIdx.x * VEC, rows = blockDim.y;
+    const size_t nt = (size_t)n * v.ldt + t;
+    double g0[VEC], rg[VEC], mx[VEC];
+#pragma unroll
+    for (int w = 0; w < VEC; ++w) { g0[w] = v.g0[nt + w]; rg[w] = v.rg[nt + w]; mx[w] = 0.0; }
+    for (int g = ga + threadIdx.y; g < gb; g += rows * GEN_UNR) {
+        double pp[GEN_UNR][VEC], mc[GEN_UNR], pm[GEN_UNR];
+#pragma unroll
+        for (int u = 0; u < GEN_UNR; ++u) {                    // all loads first
+            const int gg = min(g + u * rows, gb - 1);
+            mc[u] = __ldg(v.gen_mc + gg); pm[u] = __ldg(v.gen_pmax + gg);
+            const size_t o = (size_t)gg * v.T + t;
+            if (VEC == 4) {
+                const double2 a = *reinterpret_cast<const double2 *>(Pc + o), b = *reinterpret_cast<const double2 *>(Pc + o + 2);
+                pp[u][0] = a.x; pp[u][1 % VEC] = a.y; pp[u][2 % VEC] = b.x; pp[u][3 % VEC] = b.y;
+            } else if (VEC == 2) {
+                const double2 a = *reinterpret_cast<const double2 *>(Pc + o);
+                pp[u][0] = a.x; pp[u][1 % VEC] = a.y;
+            } else pp[u][0] = Pc[o];
+        }
+#pragma unroll
+        for (int u = 0; u < GEN_UNR; ++u) {
+            const int gg = g + u * rows;
+            if (gg >= gb) break;
+            double pn[VEC];
+#pragma unroll
+            for (int w = 0; w < VEC; ++w) {
+                pn[w] = gen_unit(pp[u][w], mc[u], pm[u], g0[w], rg[w]);
+                mx[w] = fmax(mx[w], fabs(pn[w] - pp[u][w]));
+            }
+            const size_t o = (size_t)gg * v.T + t;
+            if (VEC == 4) {
+                *reinterpret_cast<double2 *>(Pn + o) = make_double2(pn[0], pn[1 % VEC]);
+                *reinterpret_cast<double2 *>(Pn + o + 2) = make_double2(pn[2 % VEC], pn[3 % VEC]);
+            } else if (VEC == 2) *reinterpret_cast<double2 *>(Pn + o) = make_double2(pn[0], pn[1 % VEC]);
+            else Pn[o] = pn[0];
+        }
     }
+#pragma unroll
+    for (int w = 0; w < VEC; ++w) note_move(v, n, t + w, mx[w]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -347,10 +387,10 @@ __device__ __forceinline__ int collect_hinges(const View &v, int n, int t, doubl
 }
 
 template <int J>
-__global__ void __launch_bounds__(256) k_sto_fix(View v, Hinge *hinge_scratch, int *hcnt_scratch)
+__global__ void __launch_bounds__(512) k_sto_fix(View v, Hinge *hinge_scratch, int *hcnt_scratch)
 {
     if (!DOPF_ACTIVE(v)) return;
-    // one block per affected storage: the 8 warps collect the hinge lists of different timesteps,
+    // one block per affected storage: the 16 warps collect the hinge lists of different timesteps,
     // then warp 0 re-solves the storage exactly
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int total = v.ctrl->sto_work_cnt;
@@ -434,6 +474,24 @@ __global__ void k_inject(View v)
     body_inject(v, i / v.ldt, i % v.ldt);
 }
 
+// dmax[t] = largest move of any agent at timestep t = column maximum of dn (bit patterns of
+// non-negative doubles compare like integers); block (32,32): 32 timesteps, 32 row groups
+__global__ void k_dmax(View v)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    __shared__ unsigned long long part[32][33];
+    const int t = blockIdx.x * 32 + threadIdx.x;
+    unsigned long long a = 0ull;
+    for (int n = blockIdx.y * 32 + threadIdx.y; n < v.N; n += 32 * gridDim.y) { const unsigned long long b = v.dn[(size_t)n * v.ldt + t]; a = b > a ? b : a; }
+    part[threadIdx.y][threadIdx.x] = a;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        unsigned long long m = 0ull;
+        for (int k = 0; k < 32; ++k) m = part[k][threadIdx.x] > m ? part[k][threadIdx.x] : m;
+        if (m > v.dmax[t]) atomicMax(v.dmax + t, m);     // dmax is zeroed by k_begin and only grows within an iteration
+    }
+}
+
 __global__ void k_colsum(View v)   // block (32,32): 32 timesteps, 32 row groups
 {
     if (!DOPF_ACTIVE(v)) return;
@@ -458,9 +516,12 @@ __global__ void k_colsum(View v)   // block (32,32): 32 timesteps, 32 row groups
 // per-chunk partials are written to slack_part[chunk][t][row] and reduced in fixed order by k_dual
 // (deterministic).  Rows beyond SLK_ROWS per timestep are handled by k_slack_rows below.
 // ------------------------------------------------------------------------------------------------
-constexpr int SLK_ROWS = 16, SLK_AGENTS = 512, SLK_WARPS = 4;
+#ifndef DOPF_SLK_ROWS
+#define DOPF_SLK_ROWS 16
+#endif
+constexpr int SLK_ROWS = DOPF_SLK_ROWS, SLK_GROUPS = 64 / DOPF_SLK_ROWS, SLK_AGENTS = 512, SLK_WARPS = 4;   // SLK_ROWS*SLK_GROUPS rows per timestep
 
-__global__ void __launch_bounds__(SLK_WARPS * 32, 3) k_slack_stream(View v, double *part, int nchunk_gen)
+__global__ void __launch_bounds__(SLK_WARPS * 32, (SLK_ROWS <= 8 ? 6 : 3)) k_slack_stream(View v, double *part, int nchunk_gen)
 {
     if (!DOPF_ACTIVE(v)) return;
     __shared__ double red[SLK_WARPS][SLK_ROWS][33];
@@ -473,9 +534,10 @@ __global__ void __launch_bounds__(SLK_WARPS * 32, 3) k_slack_stream(View v, doub
     const int cur = v.ctrl->cur, nxt = 1 - cur;
     const bool tv = t < v.T;
     const int tt = tv ? t : 0;
-    const int cnt = tv ? min(v.tcnt[t], SLK_ROWS) : 0;
+    const int r0 = blockIdx.z * SLK_ROWS;                       // row group of this block
+    const int cnt = tv ? max(0, min(v.tcnt[t] - r0, SLK_ROWS)) : 0;
     int rl[SLK_ROWS]; double rb[SLK_ROWS], acc[SLK_ROWS];
-    const int *lst = v.tight + (size_t)tt * 2 * v.L;
+    const int *lst = v.tight + (size_t)tt * 2 * v.L + r0;
 #pragma unroll
     for (int j = 0; j < SLK_ROWS; ++j) {
         acc[j] = 0.0; rl[j] = 0; rb[j] = 0.0;
@@ -486,7 +548,8 @@ __global__ void __launch_bounds__(SLK_WARPS * 32, 3) k_slack_stream(View v, doub
         }
     }
     const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
-    if (maxcnt > 0) {
+    if (maxcnt == 0) return;                                    // no row of this group in the tile: the partials are never read
+    {
         // every warp walks a contiguous agent range (consecutive agents share their node, so the PTDF
         // entries of the lane's rows are re-gathered only when the node changes); 4 agents are loaded
         // ahead of their use to keep several memory requests in flight
@@ -542,7 +605,7 @@ __global__ void __launch_bounds__(SLK_WARPS * 32, 3) k_slack_stream(View v, doub
         double sum = 0.0;
 #pragma unroll
         for (int w = 0; w < SLK_WARPS; ++w) sum += red[w][j][lane];
-        if (tv) part[((size_t)chunk * v.ldt + t) * SLK_ROWS + j] = sum;
+        if (tv) part[((size_t)chunk * v.ldt + t) * (SLK_ROWS * SLK_GROUPS) + r0 + j] = sum;
     }
 }
 
@@ -560,7 +623,7 @@ __global__ void __launch_bounds__(128) k_slack_rows(View v, unsigned char *tflag
     const int cur = v.ctrl->cur, nxt = 1 - cur;
     const int cnt = v.tcnt[t];
     const int *lst = v.tight + (size_t)t * 2 * v.L;
-    for (int j = SLK_ROWS + blockIdx.x; j < cnt; j += gridDim.x) {
+    for (int j = SLK_ROWS * SLK_GROUPS + blockIdx.x; j < cnt; j += gridDim.x) {
         const int l = lst[j] >> 1, side = lst[j] & 1;
         const double b = side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t];
         if (threadIdx.x == 0) qcnt = 0;
@@ -615,11 +678,11 @@ __global__ void __launch_bounds__(128) k_slack_reduce(View v, unsigned char *tfl
     if (!DOPF_ACTIVE(v)) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = blockIdx.y;
-    const int cnt = min(v.tcnt[t], SLK_ROWS);
+    const int cnt = min(v.tcnt[t], SLK_ROWS * SLK_GROUPS);
     const int slot = blockIdx.x * 4 + warp;
     if (slot >= cnt) return;
     double sum = 0.0;
-    for (int c = lane; c < nchunks; c += 32) sum += part[((size_t)c * v.ldt + t) * SLK_ROWS + slot];
+    for (int c = lane; c < nchunks; c += 32) sum += part[((size_t)c * v.ldt + t) * (SLK_ROWS * SLK_GROUPS) + slot];
     sum = Group<32>::sum(sum);
     if (lane == 0) {
         const int e = v.tight[(size_t)t * 2 * v.L + slot], l = e >> 1, side = e & 1;
@@ -724,7 +787,7 @@ __global__ void k_nodal_price(View v, int which, double *out /*[N][T]*/)
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 int slack_chunks(int G, int S) { return cdiv(G, SLK_AGENTS) + cdiv(S, SLK_AGENTS); }
-int slack_rows_cap() { return SLK_ROWS; }
+int slack_rows_cap() { return SLK_ROWS * SLK_GROUPS; }
 
 int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
 {
@@ -773,10 +836,15 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     }
     MAIN();   // ... generators on the main stream
     if (v.G > 0) {
-        if (v.T % 2 == 0) LAUNCH(k_gen_predict<2><<<cdiv((long long)v.G * (v.T / 2), 256), 256, 0, cs>>>(v));
-        else LAUNCH(k_gen_predict<1><<<cdiv((long long)v.G * v.T, 256), 256, 0, cs>>>(v));
+        // one block per node: x = timestep slots of `vec` timesteps, y = agent rows
+        const int vec = v.T % 4 == 0 ? 4 : (v.T % 2 == 0 ? 2 : 1), per = v.T / vec;   // per <= 1024 checked at create
+        const dim3 blk(per, max(1, 256 / per)), grd(v.N);
+        if (vec == 4) LAUNCH(k_gen_predict<4><<<grd, blk, 0, cs>>>(v));
+        else if (vec == 2) LAUNCH(k_gen_predict<2><<<grd, blk, 0, cs>>>(v));
+        else LAUNCH(k_gen_predict<1><<<grd, blk, 0, cs>>>(v));
     }
     JOIN();
+    LAUNCH(k_dmax<<<dim3(v.ldt / 32, 16), dim3(32, 32), 0, cs>>>(v));
     LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 1));
     {
         dim3 grid(cdiv(v.N, 32), cdiv(v.T, 8));
@@ -785,24 +853,25 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     FORK();
     if (v.S > 0) {
         switch (lp.sto_j) {
-        case 1: LAUNCH(k_sto_fix<1><<<lp.sto_fix_blocks, 256, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 2: LAUNCH(k_sto_fix<2><<<lp.sto_fix_blocks, 256, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 3: LAUNCH(k_sto_fix<3><<<lp.sto_fix_blocks, 256, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 4: LAUNCH(k_sto_fix<4><<<lp.sto_fix_blocks, 256, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 6: LAUNCH(k_sto_fix<6><<<lp.sto_fix_blocks, 256, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 8: LAUNCH(k_sto_fix<8><<<lp.sto_fix_blocks, 256, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        default: LAUNCH(k_sto_fix<0><<<lp.sto_fix_blocks, 256, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 1: LAUNCH(k_sto_fix<1><<<lp.sto_fix_blocks, 512, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 2: LAUNCH(k_sto_fix<2><<<lp.sto_fix_blocks, 512, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 3: LAUNCH(k_sto_fix<3><<<lp.sto_fix_blocks, 512, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 4: LAUNCH(k_sto_fix<4><<<lp.sto_fix_blocks, 512, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 6: LAUNCH(k_sto_fix<6><<<lp.sto_fix_blocks, 512, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 8: LAUNCH(k_sto_fix<8><<<lp.sto_fix_blocks, 512, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        default: LAUNCH(k_sto_fix<0><<<lp.sto_fix_blocks, 512, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
         }
     }
     MAIN();
     if (v.G > 0) LAUNCH(k_gen_fix<<<lp.num_sms * 2, 128, 0, cs>>>(v));
     JOIN();
+    LAUNCH(k_dmax<<<dim3(v.ldt / 32, 16), dim3(32, 32), 0, cs>>>(v));
     XCHG(DOPF_X_DMAX);   // all ranks must build the same tight lists
     LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 1));   // moves may have grown
     FORK();   // slack sums need only the new agents and the tight lists ...
     LAUNCH(k_clear_tflag<<<cdiv((long long)v.Lp * v.ldt / 4, 256), 256, 0, cs>>>(v, lp.tflag));
     const int ncg = cdiv(v.G, SLK_AGENTS), ncs = cdiv(v.S, SLK_AGENTS);
-    LAUNCH(k_slack_stream<<<dim3(ncg + ncs, v.ldt / 32), SLK_WARPS * 32, 0, cs>>>(v, lp.slack_part, ncg));
+    LAUNCH(k_slack_stream<<<dim3(ncg + ncs, v.ldt / 32, SLK_GROUPS), SLK_WARPS * 32, 0, cs>>>(v, lp.slack_part, ncg));
     MAIN();   // ... while the main stream aggregates the injection and computes the flows
     LAUNCH(k_inject<<<cdiv((long long)v.Np * v.ldt, 256), 256, 0, cs>>>(v));
     XCHG(DOPF_X_INJ);    // nodal injection of all ranks' agents
@@ -816,7 +885,7 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     JOIN();
     {
         LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.T), 128, 0, cs>>>(v, lp.tflag));   // needs the local injection
-        LAUNCH(k_slack_reduce<<<dim3(SLK_ROWS / 4, v.T), 128, 0, cs>>>(v, lp.tflag, lp.slack_part, ncg + ncs));
+        LAUNCH(k_slack_reduce<<<dim3(SLK_ROWS * SLK_GROUPS / 4, v.T), 128, 0, cs>>>(v, lp.tflag, lp.slack_part, ncg + ncs));
         XCHG(DOPF_X_ROWSUM); // exact slack sums over all ranks' agents
         LAUNCH(k_dual<<<cdiv((long long)v.L * v.ldt, 256), 256, 0, cs>>>(v, lp.tflag));
     }

@@ -159,7 +159,7 @@ void *emul_create(int N, int L, int T, int G, int S, const double *ptdf, const d
     { double *pt = e->mk((size_t)Np * Lp); for (int l = 0; l < L; ++l) for (int n = 0; n < N; ++n) pt[(size_t)n * Lp + l] = P[(size_t)l * Np + n]; v.ptdfT = pt; }
     v.avgU = e->mk((size_t)Lp * ldt); v.avgK = e->mk((size_t)Lp * ldt);
     v.bplus = e->mk((size_t)Lp * ldt); v.bminus = e->mk((size_t)Lp * ldt); v.M = e->mk((size_t)Lp * ldt); v.Wt = e->mk((size_t)Lp * ldt);
-    v.g0 = e->mk((size_t)Np * ldt); v.s1 = e->mk((size_t)Np * ldt);
+    v.g0 = e->mk((size_t)Np * ldt); v.s1 = e->mk((size_t)Np * ldt); v.rg = e->mk((size_t)Np * ldt);
     e->dn.assign((size_t)Np * ldt, 0); e->dmax.assign(ldt, 0); v.dn = e->dn.data(); v.dmax = e->dmax.data();
     e->flags.assign((size_t)ldt * Lp, 0); v.flags = e->flags.data(); e->tflag.assign((size_t)Lp * ldt, 0);
     v.wide = e->mki((size_t)T * 2 * L); v.wcnt = e->mki(T); v.tight = e->mki((size_t)T * 2 * L); v.tcnt = e->mki(T);
@@ -184,6 +184,8 @@ void emul_warm_fail(int *out) { for (int i = 0; i < 8; ++i) { out[i] = g_warm_fa
 static void compact(Emul *e, int mode)
 {
     View &v = e->v;
+    if (mode == 1)
+        for (int t = 0; t < v.ldt; ++t) { unsigned long long m = 0; for (int n = 0; n < v.N; ++n) m = std::max(m, v.dn[(size_t)n * v.ldt + t]); v.dmax[t] = m; }
     for (int t = 0; t < v.T; ++t) {
         int cnt = 0;
         if (mode == 0) {
@@ -255,6 +257,7 @@ void emul_iterate(void *h)
         for (int l = 0; l < Lp; ++l) { double p = v.ptdf[(size_t)l * Np + n]; a += p * v.M[(size_t)l * ldt + t]; b += p * p * v.Wt[(size_t)l * ldt + t]; }
         v.g0[(size_t)n * ldt + t] = v.lam[cur][t] + v.c.gamma * v.ssum[cur][t] + a;
         v.s1[(size_t)n * ldt + t] = v.c.gamma + 2.0 * v.c.kappa * v.q[n] + b;
+        v.rg[(size_t)n * ldt + t] = 1.0 / (v.c.prox + v.s1[(size_t)n * ldt + t]);
     }
     for (int g = 0; g < v.G; ++g) for (int t = 0; t < T; ++t) {
         const double pp = v.P[cur][(size_t)g * T + t];
