@@ -275,6 +275,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
             lp.sto_j = 0;
             for (int o : opts) if (o >= need) { lp.sto_j = o; break; }
         }
+        if (lp.sto_j > 0 && set_storage_smem_attr(T) != 0) { h->err = "cudaFuncSetAttribute(shared memory) failed"; return DOPF_E_CUDA; }
         const size_t warps = (size_t)lp.sto_fix_blocks;     // one scratch slot per block
         AL(lp.hinge_scratch, S ? warps * T * v.hcap : 1);
         AL(lp.hcnt_scratch, S ? warps * T : 1);

@@ -338,8 +338,10 @@ __global__ void __launch_bounds__(128, DOPF_STO_MINB) k_sto_warp(View v)
     if (!DOPF_ACTIVE(v)) return;
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    extern __shared__ __align__(16) double sto_smem[];
+    double *tab = sto_smem + (size_t)(threadIdx.x >> 5) * (sto_warp_smem_per_warp(v.T) / sizeof(double));
     for (int s = gw; s < v.S; s += nw) {
-        const bool ok = sto_warp_solve<J, false>(v, s, nullptr, nullptr);
+        const bool ok = sto_warp_solve<J, false>(v, s, nullptr, nullptr, tab);
         if (!ok && lane == 0) v.cold_work[atomicAdd(&v.ctrl->cold_work_cnt, 1)] = s;
         __syncwarp();
     }
@@ -408,8 +410,9 @@ __global__ void __launch_bounds__(512) k_sto_fix(View v, Hinge *hinge_scratch, i
         }
         __syncthreads();
         if (warp == 0) {
+            extern __shared__ __align__(16) double sto_smem[];
             bool ok = false;
-            if (J > 0) ok = sto_warp_solve<(J > 0 ? J : 1), true>(v, s, mylist, mycnt);
+            if (J > 0) ok = sto_warp_solve<(J > 0 ? J : 1), true>(v, s, mylist, mycnt, sto_smem);
             if (lane == 0) {
                 if (!ok) body_sto_cold(v, s, mylist, mycnt);
                 atomicAdd(&v.ctrl->stat_sto_fix, 1);
@@ -786,6 +789,18 @@ __global__ void k_nodal_price(View v, int which, double *out /*[N][T]*/)
 // ------------------------------------------------------------------------------------------------
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+int set_storage_smem_attr(int T)
+{
+    const int bytes = (int)(4 * sto_warp_smem_per_warp(T));
+    if (bytes <= 48 * 1024) return 0;
+    cudaError_t e = cudaSuccess;
+#define SETA(K) do { if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); } while (0)
+    SETA(k_sto_warp<1>); SETA(k_sto_warp<2>); SETA(k_sto_warp<3>); SETA(k_sto_warp<4>); SETA(k_sto_warp<6>); SETA(k_sto_warp<8>);
+    SETA(k_sto_fix<1>); SETA(k_sto_fix<2>); SETA(k_sto_fix<3>); SETA(k_sto_fix<4>); SETA(k_sto_fix<6>); SETA(k_sto_fix<8>);
+#undef SETA
+    return (int)e;
+}
+
 int slack_chunks(int G, int S) { return cdiv(G, SLK_AGENTS) + cdiv(S, SLK_AGENTS); }
 int slack_rows_cap() { return SLK_ROWS * SLK_GROUPS; }
 
@@ -824,12 +839,12 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     if (v.S > 0) {
         const int wblocks = min(cdiv(v.S, 4), lp.num_sms * 16);
         switch (lp.sto_j) {
-        case 1: LAUNCH(k_sto_warp<1><<<wblocks, 128, 0, cs>>>(v)); break;
-        case 2: LAUNCH(k_sto_warp<2><<<wblocks, 128, 0, cs>>>(v)); break;
-        case 3: LAUNCH(k_sto_warp<3><<<wblocks, 128, 0, cs>>>(v)); break;
-        case 4: LAUNCH(k_sto_warp<4><<<wblocks, 128, 0, cs>>>(v)); break;
-        case 6: LAUNCH(k_sto_warp<6><<<wblocks, 128, 0, cs>>>(v)); break;
-        case 8: LAUNCH(k_sto_warp<8><<<wblocks, 128, 0, cs>>>(v)); break;
+        case 1: LAUNCH(k_sto_warp<1><<<wblocks, 128, 4 * sto_warp_smem_per_warp(v.T), cs>>>(v)); break;
+        case 2: LAUNCH(k_sto_warp<2><<<wblocks, 128, 4 * sto_warp_smem_per_warp(v.T), cs>>>(v)); break;
+        case 3: LAUNCH(k_sto_warp<3><<<wblocks, 128, 4 * sto_warp_smem_per_warp(v.T), cs>>>(v)); break;
+        case 4: LAUNCH(k_sto_warp<4><<<wblocks, 128, 4 * sto_warp_smem_per_warp(v.T), cs>>>(v)); break;
+        case 6: LAUNCH(k_sto_warp<6><<<wblocks, 128, 4 * sto_warp_smem_per_warp(v.T), cs>>>(v)); break;
+        case 8: LAUNCH(k_sto_warp<8><<<wblocks, 128, 4 * sto_warp_smem_per_warp(v.T), cs>>>(v)); break;
         default: LAUNCH(k_sto_warm<<<cdiv(v.S, 128), 128, 0, cs>>>(v)); break;   // long horizons: sequential warm start
         }
         LAUNCH(k_sto_cold<<<min(cdiv(v.S, 64), lp.num_sms * 8), 64, 0, cs>>>(v));
@@ -853,13 +868,13 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     FORK();
     if (v.S > 0) {
         switch (lp.sto_j) {
-        case 1: LAUNCH(k_sto_fix<1><<<lp.sto_fix_blocks, 512, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 2: LAUNCH(k_sto_fix<2><<<lp.sto_fix_blocks, 512, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 3: LAUNCH(k_sto_fix<3><<<lp.sto_fix_blocks, 512, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 4: LAUNCH(k_sto_fix<4><<<lp.sto_fix_blocks, 512, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 6: LAUNCH(k_sto_fix<6><<<lp.sto_fix_blocks, 512, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 8: LAUNCH(k_sto_fix<8><<<lp.sto_fix_blocks, 512, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        default: LAUNCH(k_sto_fix<0><<<lp.sto_fix_blocks, 512, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 1: LAUNCH(k_sto_fix<1><<<lp.sto_fix_blocks, 512, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 2: LAUNCH(k_sto_fix<2><<<lp.sto_fix_blocks, 512, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 3: LAUNCH(k_sto_fix<3><<<lp.sto_fix_blocks, 512, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 4: LAUNCH(k_sto_fix<4><<<lp.sto_fix_blocks, 512, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 6: LAUNCH(k_sto_fix<6><<<lp.sto_fix_blocks, 512, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 8: LAUNCH(k_sto_fix<8><<<lp.sto_fix_blocks, 512, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        default: LAUNCH(k_sto_fix<0><<<lp.sto_fix_blocks, 512, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
         }
     }
     MAIN();

@@ -30,6 +30,7 @@ struct LaunchPlan {
 enum { DOPF_X_DMAX = 0, DOPF_X_INJ = 1, DOPF_X_ROWSUM = 2, DOPF_N_SEGMENTS = 4 };
 int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment = -1);
 void launch_mwide(const View &v, cudaStream_t st);
+int set_storage_smem_attr(int T);   // opt in to > 48 KB dynamic shared memory for long horizons
 int slack_chunks(int G, int S);
 int slack_rows_cap();   // returns number of kernel launches
 void launch_total_costs(const View &v, double *d_out, cudaStream_t st);

@@ -1,12 +1,13 @@
-// Warp-parallel storage solve (one warp per storage, lane l owns timesteps l, l+32, ...).
+// Warp-parallel storage solve (one warp per storage; lane l owns the J consecutive timesteps
+// l*J .. l*J+J-1, loads stay fully coalesced because the warp covers one contiguous range).
 //
 // Active-set method on the level bounds 0 <= E_t <= emax (reference problem:
 // /root/reference/src/optimization/subproblems.jl:107-207 after slack elimination):
 //   * anchors  = timesteps whose level is fixed at a bound (kind +1: emax, -1: 0); between two anchors
 //     ("run") the level multiplier eta is constant;
-//   * all runs are solved at once: every lane evaluates y_t(eta) for its timesteps (sto_eval), run sums
-//     come from segmented warp scans, the run's last timestep ("tail") does one safeguarded Newton
-//     update per pass and broadcasts the new multiplier back over its run;
+//   * all runs are solved at once: every lane evaluates y_t(eta) for its timesteps, run sums come from
+//     segmented warp scans, the run's last timestep ("tail") does one safeguarded Newton update per pass
+//     and broadcasts the new multiplier back over its run;
 //   * then the KKT conditions are checked in parallel: levels inside the bounds, and a multiplier
 //     path with the right sign at every anchor (intervals, because saturated runs have a non-unique
 //     multiplier).  Violated levels add an anchor (first violated timestep of the run), anchors with a
@@ -15,9 +16,11 @@
 //     problem).  Storages that do not verify within the caps go to the sequential exact solver.
 // The initial active set comes from the previous levels (warm start).
 //
-// Scans: the segment structure is turned once per active-set iteration into per-element "reach"
-// counters (how far the element may look towards its run head / tail inside its 32-wide chunk), so a
-// segmented scan step is just shuffle + compare + op, without shuffling flags.
+// Cost structure: (a) a segmented scan is an in-register pass over the lane's J elements plus ONE
+// 32-wide cross-lane scan of the lane aggregates; (b) everything of a timestep that does not depend
+// on eta - the sorted clip breakpoints of D(nu), C(nu) and delta at those breakpoints - is tabulated
+// once per storage in shared memory, so an evaluation is four FMAs, a select, one interpolation and
+// one clip.
 #ifndef DOPF_STO_WARP_CUH
 #define DOPF_STO_WARP_CUH
 
@@ -28,180 +31,124 @@ namespace dopf {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr double WBIG = 1e300;
 
-template <int J>
-struct Reach {
-    int back[J];    // forward scans: steps the element may look back inside its chunk (towards the run head)
-    int fwd[J];     // backward scans: steps it may look ahead (towards the run tail)
-    bool cin[J];    // run head lies in an earlier chunk  -> takes the forward carry
-    bool cout[J];   // run tail lies in a later chunk    -> takes the backward carry
-};
-
-// position of the last head at or before t (plain inclusive max-scan of head ? t : -1)
-template <int J>
-__device__ __forceinline__ void last_flag_pos(const bool (&flag)[J], int (&pos)[J])
-{
-    const int lane = threadIdx.x & 31;
-    int carry = -1;
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-        int x = flag[j] ? lane + 32 * j : -1;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int xo = __shfl_up_sync(FULL, x, o);
-            if (lane >= o) x = max(x, xo);
-        }
-        x = max(x, carry);
-        pos[j] = x;
-        carry = __shfl_sync(FULL, x, 31);
-    }
-}
-// position of the first flag at or after t (plain inclusive min-scan from the right)
-template <int J>
-__device__ __forceinline__ void next_flag_pos(const bool (&flag)[J], int (&pos)[J])
-{
-    const int lane = threadIdx.x & 31;
-    int carry = 0x7fffffff;
-#pragma unroll
-    for (int j = J - 1; j >= 0; --j) {
-        int x = flag[j] ? lane + 32 * j : 0x7fffffff;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int xo = __shfl_down_sync(FULL, x, o);
-            if (lane + o < 32) x = min(x, xo);
-        }
-        x = min(x, carry);
-        pos[j] = x;
-        carry = __shfl_sync(FULL, x, 0);
-    }
-}
-
-template <int J>
-__device__ __forceinline__ void reach_back_from_heads(const bool (&head)[J], int (&back)[J], bool (&cin)[J])
-{
-    const int lane = threadIdx.x & 31;
-    int hp[J];
-    last_flag_pos<J>(head, hp);
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-        const int t = lane + 32 * j, d = t - hp[j];       // hp >= 0 because t = 0 is always a head
-        back[j] = min(lane, d);
-        cin[j] = hp[j] < 32 * j;
-    }
-}
-template <int J>
-__device__ __forceinline__ void reach_fwd_to_tails(const bool (&tail)[J], int (&fwd)[J], bool (&cout)[J])
-{
-    const int lane = threadIdx.x & 31;
-    int tp[J];
-    next_flag_pos<J>(tail, tp);
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-        const int t = lane + 32 * j;
-        const bool none = tp[j] == 0x7fffffff;
-        fwd[j] = none ? 0 : min(31 - lane, tp[j] - t);
-        cout[j] = !none && tp[j] > 32 * j + 31;
-    }
-}
-
 struct OpAdd { __device__ double operator()(double a, double b) const { return a + b; } };
 struct OpMin { __device__ double operator()(double a, double b) const { return a < b ? a : b; } };
 struct OpMax { __device__ double operator()(double a, double b) const { return a > b ? a : b; } };
 
-// forward inclusive segmented scan of two value arrays at once
+// lane-level reach for a set of segment heads: how many lanes back a lane may combine
+template <int J>
+__device__ __forceinline__ int lane_reach_back(const bool (&head)[J])
+{
+    const int lane = threadIdx.x & 31;
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < J; ++j) any |= head[j];
+    int x = any ? lane : -1;                      // lane 0 always holds a head (t = 0)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int xo = __shfl_up_sync(FULL, x, o); if (lane >= o) x = max(x, xo); }
+    return lane - x;                              // 0 if this lane holds a head
+}
+template <int J>
+__device__ __forceinline__ int lane_reach_fwd(const bool (&tail)[J])
+{
+    const int lane = threadIdx.x & 31;
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < J; ++j) any |= tail[j];
+    int x = any ? lane : 64;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int xo = __shfl_down_sync(FULL, x, o); if (lane + o < 32) x = min(x, xo); }
+    return x >= 64 ? 0 : x - lane;                // 0 if this lane holds a tail (or none follows)
+}
+
+// forward inclusive segmented scan of two arrays at once (segments start at head[j])
 template <int J, class OpA, class OpB>
-__device__ __forceinline__ void seg_fwd2(double (&a)[J], double (&b)[J], const int (&back)[J], const bool (&cin)[J],
+__device__ __forceinline__ void seg_fwd2(double (&a)[J], double (&b)[J], const bool (&head)[J], int lreach,
                                          OpA opa, OpB opb, double ida, double idb)
 {
-    double ca = ida, cb = idb;
+    const int lane = threadIdx.x & 31;
+    double ra = ida, rb = idb;
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-        double x = a[j], y = b[j];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double xo = __shfl_up_sync(FULL, x, o), yo = __shfl_up_sync(FULL, y, o);
-            if (back[j] >= o) { x = opa(xo, x); y = opb(yo, y); }
-        }
-        if (cin[j]) { x = opa(ca, x); y = opb(cb, y); }
-        a[j] = x; b[j] = y;
-        ca = __shfl_sync(FULL, x, 31); cb = __shfl_sync(FULL, y, 31);
+        if (head[j]) { ra = a[j]; rb = b[j]; } else { ra = opa(ra, a[j]); rb = opb(rb, b[j]); }
+        a[j] = ra; b[j] = rb;
     }
-}
-template <int J>
-__device__ __forceinline__ void seg_fwd_min_int(int (&a)[J], const int (&back)[J], const bool (&cin)[J])
-{
-    int ca = 0x7fffffff;
+    double xa = ra, xb = rb;                      // aggregate of the segment that is open at the lane end
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double ya = __shfl_up_sync(FULL, xa, o), yb = __shfl_up_sync(FULL, xb, o);
+        if (lreach >= o) { xa = opa(ya, xa); xb = opb(yb, xb); }
+    }
+    double ca = __shfl_up_sync(FULL, xa, 1), cb = __shfl_up_sync(FULL, xb, 1);
+    if (lane == 0) { ca = ida; cb = idb; }
+    bool open = true;                             // elements before the lane's first head continue the incoming segment
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-        int x = a[j];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int xo = __shfl_up_sync(FULL, x, o);
-            if (back[j] >= o) x = min(xo, x);
-        }
-        if (cin[j]) x = min(ca, x);
-        a[j] = x;
-        ca = __shfl_sync(FULL, x, 31);
-    }
-}
-// every element takes the values held by the tail of its run (a double and an int at once)
-template <int J>
-__device__ __forceinline__ void seg_take_tail(double (&a)[J], int (&b)[J], const int (&fwd)[J], const bool (&cout)[J])
-{
-    double ca = 0.0; int cb = 0;
-#pragma unroll
-    for (int j = J - 1; j >= 0; --j) {
-        double x = a[j]; int y = b[j];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double xo = __shfl_down_sync(FULL, x, o); const int yo = __shfl_down_sync(FULL, y, o);
-            if (fwd[j] >= o) { x = xo; y = yo; }
-        }
-        if (cout[j]) { x = ca; y = cb; }
-        a[j] = x; b[j] = y;
-        ca = __shfl_sync(FULL, x, 0); cb = __shfl_sync(FULL, y, 0);
+        if (head[j]) open = false;
+        if (open) { a[j] = opa(ca, a[j]); b[j] = opb(cb, b[j]); }
     }
 }
 template <int J>
-__device__ __forceinline__ void seg_take_tail_int2(int (&a)[J], int (&b)[J], const int (&fwd)[J], const bool (&cout)[J])
+__device__ __forceinline__ void seg_fwd_min_int(int (&a)[J], const bool (&head)[J], int lreach)
 {
-    int ca = 0, cb = 0;
+    const int lane = threadIdx.x & 31;
+    int r = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < J; ++j) { r = head[j] ? a[j] : min(r, a[j]); a[j] = r; }
+    int x = r;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, x, o); if (lreach >= o) x = min(y, x); }
+    int c = __shfl_up_sync(FULL, x, 1);
+    if (lane == 0) c = 0x7fffffff;
+    bool open = true;
+#pragma unroll
+    for (int j = 0; j < J; ++j) { if (head[j]) open = false; if (open) a[j] = min(c, a[j]); }
+}
+// every element takes the values held by the tail of its run
+template <int J, class TB>
+__device__ __forceinline__ void seg_take_tail(double (&a)[J], TB (&b)[J], const bool (&tail)[J], int lreach)
+{
+    const int lane = threadIdx.x & 31;
+    double fa = 0.0; TB fb = TB();               // values at the lane's FIRST tail (what lanes to the left need)
+    {
+        double ca = 0.0; TB cb = TB(); bool seen = false;
+#pragma unroll
+        for (int j = J - 1; j >= 0; --j) {
+            if (tail[j]) { ca = a[j]; cb = b[j]; seen = true; } else if (seen) { a[j] = ca; b[j] = cb; }
+        }
+        fa = ca; fb = cb;                        // after the loop: the left-most tail of the lane (if any)
+    }
+    double xa = fa; TB xb = fb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double ya = __shfl_down_sync(FULL, xa, o); const TB yb = __shfl_down_sync(FULL, xb, o);
+        if (lreach >= o) { xa = ya; xb = yb; }
+    }
+    const double ca = __shfl_down_sync(FULL, xa, 1); const TB cb = __shfl_down_sync(FULL, xb, 1);
+    bool seen = false;                           // elements to the right of the lane's last tail take the carry
 #pragma unroll
     for (int j = J - 1; j >= 0; --j) {
-        int x = a[j], y = b[j];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int xo = __shfl_down_sync(FULL, x, o), yo = __shfl_down_sync(FULL, y, o);
-            if (fwd[j] >= o) { x = xo; y = yo; }
-        }
-        if (cout[j]) { x = ca; y = cb; }
-        a[j] = x; b[j] = y;
-        ca = __shfl_sync(FULL, x, 0); cb = __shfl_sync(FULL, y, 0);
+        if (tail[j]) seen = true;
+        if (!seen && lane < 31) { a[j] = ca; b[j] = cb; }
     }
 }
-// value of the element at t-1 / t+1
 template <int J, class T>
 __device__ __forceinline__ void shift_from_prev(const T (&v)[J], T (&out)[J], T first)
 {
     const int lane = threadIdx.x & 31;
-    T carry = first;
+    const T up = __shfl_up_sync(FULL, v[J - 1], 1);
+    out[0] = lane == 0 ? first : up;
 #pragma unroll
-    for (int j = 0; j < J; ++j) {
-        const T up = __shfl_up_sync(FULL, v[j], 1);
-        out[j] = lane == 0 ? carry : up;
-        carry = __shfl_sync(FULL, v[j], 31);
-    }
+    for (int j = 1; j < J; ++j) out[j] = v[j - 1];
 }
-template <int J>
-__device__ __forceinline__ void shift_from_next(const int (&v)[J], int (&out)[J], int last)
+template <int J, class T>
+__device__ __forceinline__ void shift_from_next(const T (&v)[J], T (&out)[J], T last)
 {
     const int lane = threadIdx.x & 31;
-    int carry = last;
+    const T dn = __shfl_down_sync(FULL, v[0], 1);
+    out[J - 1] = lane == 31 ? last : dn;
 #pragma unroll
-    for (int j = J - 1; j >= 0; --j) {
-        const int dn = __shfl_down_sync(FULL, v[j], 1);
-        out[j] = lane == 31 ? carry : dn;
-        carry = __shfl_sync(FULL, v[j], 0);
-    }
+    for (int j = 0; j < J - 1; ++j) out[j] = v[j + 1];
 }
 template <int J>
 __device__ __forceinline__ bool any_of(const bool (&p)[J])
@@ -212,14 +159,97 @@ __device__ __forceinline__ bool any_of(const bool (&p)[J])
     return __any_sync(FULL, a);
 }
 
+// ---- per-timestep clip table (independent of eta) ---------------------------------------------------------
+// bb[0..3]: sorted breakpoints of D(nu), C(nu);  dl[0..3]: delta = (D-Db)-(C-Cb) at those breakpoints.
+// Stored component-major in shared memory: comp c of timestep t at tab[c*tstride + t] (conflict-free).
+struct ClipTab { double bb[4], dl[4]; };
+
+__device__ __forceinline__ void clip_tab_build(const StoStep &st, const StoConst &k, ClipTab &c)
+{
+    double b0 = k.prox * (st.Db - k.pmax) - k.mc, b1 = k.prox * st.Db - k.mc;
+    double b2 = k.mc - k.prox * st.Cb, b3 = k.mc + k.prox * (k.pmax - st.Cb);
+    double t;
+    if (b0 > b2) { t = b0; b0 = b2; b2 = t; }
+    if (b1 > b3) { t = b1; b1 = b3; b3 = t; }
+    if (b1 > b2) { t = b1; b1 = b2; b2 = t; }
+    c.bb[0] = b0; c.bb[1] = b1; c.bb[2] = b2; c.bb[3] = b3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double D, C; int nf;
+        sto_dc_of_nu(st, k, c.bb[i], D, C, nf);
+        c.dl[i] = (D - st.Db) - (C - st.Cb);
+    }
+}
+__device__ __forceinline__ ClipTab clip_tab_load(const double *tab, int tstride, int t)
+{
+    ClipTab c;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { c.bb[i] = tab[i * tstride + t]; c.dl[i] = tab[(4 + i) * tstride + t]; }
+    return c;
+}
+// same result as sto_eval() for a hinge-free step
+__device__ __forceinline__ StoEval eval_tab(const StoStep &st, const StoConst &k, const ClipTab &c, double eta)
+{
+    const double base = st.g0 - eta;
+    double psi[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) psi[i] = c.bb[i] - base - st.s1 * c.dl[i];
+    double nu;
+    if (psi[0] >= 0.0) nu = c.bb[0] - psi[0];
+    else if (psi[3] <= 0.0) nu = c.bb[3] - psi[3];
+    else {
+        const int f = psi[1] >= 0.0 ? 0 : (psi[2] >= 0.0 ? 1 : 2);
+        const double pl = c.bb[f], pv = psi[f], ql = c.bb[f + 1], qv = psi[f + 1];
+        nu = (qv == pv) ? pl : pl - pv * (ql - pl) / (qv - pv);
+    }
+    StoEval r; int nf;
+    sto_dc_of_nu(st, k, nu, r.D, r.C, nf);
+    r.dy = -(double)nf / (k.prox + st.s1 * nf);
+    return r;
+}
+// nearest eta-breakpoint strictly beyond eta (same as sto_next_break)
+__device__ __forceinline__ void next_breaks_tab(const StoStep &st, const ClipTab &c, double eta, double &up, double &dn)
+{
+    up = WBIG; dn = -WBIG;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double e = st.g0 + st.s1 * c.dl[i] - c.bb[i];
+        if (e > eta && e < up) up = e;
+        if (e < eta && e > dn) dn = e;
+    }
+}
+// maximal eta-interval around eta on which y_t stays constant (same as sto_flat_interval)
+__device__ __forceinline__ void flat_interval_tab(const StoStep &st, const ClipTab &c, double eta, double D, double C, double &ilo, double &ihi)
+{
+    ilo = ihi = eta;
+    const double nu = st.g0 - eta + st.s1 * ((D - st.Db) - (C - st.Cb));
+    const double tol = 1e-10 * (1.0 + fabs(nu));
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const bool linf = j == 0, rinf = j == 4;
+        const double plo = linf ? 0.0 : c.bb[j - 1], phi = rinf ? 0.0 : c.bb[j];
+        if (!linf && nu < plo - tol) continue;
+        if (!rinf && nu > phi + tol) continue;
+        if (!linf && !rinf && (!(phi > plo) || c.dl[j - 1] != c.dl[j])) continue;   // a variable is free on this piece
+        const double dl = linf ? c.dl[0] : c.dl[j - 1];
+        const double eh = linf ? WBIG : st.g0 + st.s1 * dl - plo;
+        const double el = rinf ? -WBIG : st.g0 + st.s1 * dl - phi;
+        ilo = el < ilo ? el : ilo; ihi = eh > ihi ? eh : ihi;
+    }
+}
+
 // run status bits broadcast from the tail
 enum { RS_CONV = 1, RS_BAD = 2, RS_FLAT = 4, RS_EMPTY = 8, RS_FREEBAD = 16 };
 
+// shared memory per warp: 8 doubles per timestep (clip table)
+__host__ __device__ inline size_t sto_warp_smem_per_warp(int T) { return (size_t)8 * (size_t)((T + 1) | 1) * sizeof(double); }
+
 // returns true if the storage was solved and written; false => caller queues it for the exact sequential solver
 template <int J, bool HINGES>
-__device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const int *hcnt)
+__device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const int *hcnt, double *tab)
 {
     const int lane = threadIdx.x & 31, T = v.T;
+    const int tstride = (T + 1) | 1;
     const int cur = v.ctrl->cur, nxt = 1 - cur, n = v.sto_node[s];
     StoConst k;
     k.mc = v.sto_mc[s]; k.pmax = v.sto_pmax[s]; k.emax = v.sto_emax[s]; k.prox = v.c.prox; k.iprox = 1.0 / v.c.prox;
@@ -230,20 +260,41 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
     bool valid[J];
     int kind[J];          // anchor at the end of t: +1 level = emax, -1 level = 0, 0 none
     double eta[J];
+    // coalesced loads: element e = lane + 32*i of the warp's contiguous range is staged through the
+    // shared table area and re-read in blocked order (lane owns timesteps lane*J .. lane*J+J-1)
+    __syncwarp();
+    for (int t = lane; t < T; t += 32) {
+        const size_t o = (size_t)s * T + t;
+        tab[0 * tstride + t] = sel(v.D, cur)[o]; tab[1 * tstride + t] = sel(v.C, cur)[o];
+        tab[2 * tstride + t] = v.g0[(size_t)n * v.ldt + t]; tab[3 * tstride + t] = v.s1[(size_t)n * v.ldt + t];
+        tab[4 * tstride + t] = v.eta[o]; tab[5 * tstride + t] = v.E[o];
+    }
+    __syncwarp();
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-        const int t = lane + 32 * j;
+        const int t = lane * J + j;
         valid[j] = t < T;
         const int tt = valid[j] ? t : T - 1;
-        const size_t o = (size_t)s * T + tt;
-        st[j].Db = sel(v.D, cur)[o]; st[j].Cb = sel(v.C, cur)[o];
-        st[j].g0 = v.g0[(size_t)n * v.ldt + tt]; st[j].s1 = v.s1[(size_t)n * v.ldt + tt];
+        st[j].Db = tab[0 * tstride + tt]; st[j].Cb = tab[1 * tstride + tt];
+        st[j].g0 = tab[2 * tstride + tt]; st[j].s1 = tab[3 * tstride + tt];
+        eta[j] = tab[4 * tstride + tt];
+        const double Ep = tab[5 * tstride + tt];
         hl[j].h = HINGES ? hinges + (size_t)tt * v.hcap : nullptr;
         hl[j].n = HINGES ? hcnt[tt] : 0;
-        eta[j] = v.eta[o];
-        const double Ep = v.E[o];
         kind[j] = !valid[j] ? 0 : (Ep >= k.emax - tolA ? 1 : (Ep <= tolA ? -1 : 0));
     }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < J; ++j) {                  // clip tables (overwrite the staging area)
+        ClipTab c;
+        clip_tab_build(st[j], k, c);
+        const int t = lane * J + j;
+        if (valid[j]) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { tab[i * tstride + t] = c.bb[i]; tab[(4 + i) * tstride + t] = c.dl[i]; }
+        }
+    }
+    __syncwarp();
 
     double D[J], C[J], pre[J];
     bool accepted = false;
@@ -251,27 +302,28 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
         // ---- run structure from the anchors (timesteps beyond T are isolated one-element runs) ------
         bool head[J], tail[J];
         int prevk[J], endk[J];
-        Reach<J> R;
         {
             int kp[J];
             shift_from_prev<J, int>(kind, kp, 1);                        // kind of t-1 (t = 0 starts a run)
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                const int t = lane + 32 * j;
-                head[j] = kp[j] != 0 || !valid[j] || t == T;
+                const int t = lane * J + j;
+                head[j] = kp[j] != 0 || !valid[j];
                 tail[j] = !valid[j] || kind[j] != 0 || t == T - 1;
             }
-            reach_back_from_heads<J>(head, R.back, R.cin);
-            reach_fwd_to_tails<J>(tail, R.fwd, R.cout);
-            // kind of the anchor that closed the previous run = kind at (head position - 1):
-            // heads read it from t-1, then it is spread over the run with a forward "take head" scan
+        }
+        const int rb = lane_reach_back<J>(head), rf = lane_reach_fwd<J>(tail);
+        {
+            // kind of the anchor that closed the previous run: heads read it at t-1 and spread it forward
+            int kp[J];
+            shift_from_prev<J, int>(kind, kp, 0);
             double hk[J], dummy[J];
 #pragma unroll
-            for (int j = 0; j < J; ++j) { hk[j] = head[j] ? (double)((lane + 32 * j) == 0 ? 0 : kp[j]) : -2.0; dummy[j] = 0.0; }
-            seg_fwd2<J>(hk, dummy, R.back, R.cin, OpMax(), OpAdd(), -2.0, 0.0);   // non-heads hold -2 => max = head's value
+            for (int j = 0; j < J; ++j) { hk[j] = head[j] ? (double)kp[j] : -2.0; dummy[j] = 0.0; }
+            seg_fwd2<J>(hk, dummy, head, rb, OpMax(), OpAdd(), -2.0, 0.0);   // non-heads hold -2 => max = the head's value
 #pragma unroll
             for (int j = 0; j < J; ++j) { prevk[j] = (int)hk[j]; endk[j] = kind[j]; }
-            seg_take_tail<J>(eta, endk, R.fwd, R.cout);                  // start multiplier and end kind of my run
+            seg_take_tail<J, int>(eta, endk, tail, rf);                  // start multiplier and end kind of my run
         }
         double e0[J], target[J];
         bool freeend[J];
@@ -294,11 +346,13 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 if (valid[j]) {
-                    const StoEval e = sto_eval(st[j], k, hl[j], eta[j]);
+                    StoEval e;
+                    if (HINGES && hl[j].n != 0) e = sto_eval(st[j], k, hl[j], eta[j]);
+                    else e = eval_tab(st[j], k, clip_tab_load(tab, tstride, lane * J + j), eta[j]);
                     D[j] = e.D; C[j] = e.C; pre[j] = e.C - e.D; dy[j] = e.dy;
                 } else { D[j] = C[j] = pre[j] = dy[j] = 0.0; }
             }
-            seg_fwd2<J>(pre, dy, R.back, R.cin, OpAdd(), OpAdd(), 0.0, 0.0);
+            seg_fwd2<J>(pre, dy, head, rb, OpAdd(), OpAdd(), 0.0, 0.0);
             bool pending[J], needflat[J];
 #pragma unroll
             for (int j = 0; j < J; ++j) {
@@ -321,10 +375,10 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
                     bu[j] = WBIG; bd[j] = -WBIG;
                     if (valid[j]) {
                         if (hl[j].n != 0) { bu[j] = -WBIG; bd[j] = WBIG; }             // hinge on a flat run: not handled here
-                        else { bu[j] = sto_next_break(st[j], k, eta[j], true); bd[j] = sto_next_break(st[j], k, eta[j], false); }
+                        else next_breaks_tab(st[j], clip_tab_load(tab, tstride, lane * J + j), eta[j], bu[j], bd[j]);
                     }
                 }
-                seg_fwd2<J>(bu, bd, R.back, R.cin, OpMin(), OpMax(), WBIG, -WBIG);
+                seg_fwd2<J>(bu, bd, head, rb, OpMin(), OpMax(), WBIG, -WBIG);
             }
 #pragma unroll
             for (int j = 0; j < J; ++j) {
@@ -347,13 +401,13 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
                 }
                 eta[j] = en;
             }
-            seg_take_tail<J>(eta, rs, R.fwd, R.cout);
+            seg_take_tail<J, int>(eta, rs, tail, rf);
         }
         if (capped) return false;                                             // Newton cap reached
         // final run state for every element: multiplier, status, "flat" (sum of derivatives at the tail)
 #pragma unroll
         for (int j = 0; j < J; ++j) if (valid[j] && tail[j] && !(totd[j] < -1e-300)) rs[j] |= RS_FLAT;
-        seg_take_tail<J>(eta, rs, R.fwd, R.cout);
+        seg_take_tail<J, int>(eta, rs, tail, rf);
 
         // ---- KKT check ------------------------------------------------------------------------------
         bool vio_up[J], vio_dn[J];
@@ -368,17 +422,16 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
             Ilo[j] = -WBIG; Ihi[j] = WBIG;
             if (valid[j]) {
                 if (!(rs[j] & RS_FLAT) || hl[j].n != 0) { Ilo[j] = eta[j]; Ihi[j] = eta[j]; }
-                else sto_flat_interval(st[j], k, eta[j], D[j], C[j], Ilo[j], Ihi[j]);
+                else flat_interval_tab(st[j], clip_tab_load(tab, tstride, lane * J + j), eta[j], D[j], C[j], Ilo[j], Ihi[j]);
             }
         }
-        seg_fwd2<J>(Ilo, Ihi, R.back, R.cin, OpMax(), OpMin(), -WBIG, WBIG);      // tails now hold the run interval
+        seg_fwd2<J>(Ilo, Ihi, head, rb, OpMax(), OpMin(), -WBIG, WBIG);          // tails now hold the run interval
         // sign chain over the runs: after an upper anchor eta may not rise, after a lower anchor it may not
         // drop.  Only tails carry run values, the other elements are neutral; the chains restart at the
         // head of a run whose previous anchor has the other kind.
         double Fhi[J], Flo[J];
         {
             bool hup[J], hdn[J];
-            int bup[J], bdn[J]; bool cup[J], cdn[J];
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 Fhi[j] = (valid[j] && tail[j]) ? Ihi[j] : WBIG;
@@ -386,18 +439,17 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
                 hup[j] = head[j] && prevk[j] <= 0;
                 hdn[j] = head[j] && prevk[j] >= 0;
             }
-            reach_back_from_heads<J>(hup, bup, cup);
-            reach_back_from_heads<J>(hdn, bdn, cdn);
+            const int rup = lane_reach_back<J>(hup), rdn = lane_reach_back<J>(hdn);
             double d1[J], d2[J];
 #pragma unroll
             for (int j = 0; j < J; ++j) { d1[j] = 0.0; d2[j] = 0.0; }
-            seg_fwd2<J>(Fhi, d1, bup, cup, OpMin(), OpAdd(), WBIG, 0.0);
-            seg_fwd2<J>(Flo, d2, bdn, cdn, OpMax(), OpAdd(), -WBIG, 0.0);
+            seg_fwd2<J>(Fhi, d1, hup, rup, OpMin(), OpAdd(), WBIG, 0.0);
+            seg_fwd2<J>(Flo, d2, hdn, rdn, OpMax(), OpAdd(), -WBIG, 0.0);
         }
         int tv[J], flag[J];
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-            const int t = lane + 32 * j;
+            const int t = lane * J + j;
             tv[j] = (vio_up[j] || vio_dn[j]) ? t : 0x7fffffff;
             flag[j] = 0;
             if (valid[j] && tail[j] && !(rs[j] & RS_BAD)) {
@@ -410,24 +462,31 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
             }
             if (valid[j] && tail[j] && (rs[j] & RS_BAD)) flag[j] |= RS_BAD;
         }
-        seg_fwd_min_int<J>(tv, R.back, R.cin);                      // tails hold the first violated timestep
-        seg_take_tail_int2<J>(tv, flag, R.fwd, R.cout);             // ... and tell their run
+        seg_fwd_min_int<J>(tv, head, rb);                           // tails hold the first violated timestep
+        {
+            double tvd[J];                                          // ... and tell their run (timestep as double, flags as int)
+#pragma unroll
+            for (int j = 0; j < J; ++j) tvd[j] = (double)tv[j];
+            seg_take_tail<J, int>(tvd, flag, tail, rf);
+#pragma unroll
+            for (int j = 0; j < J; ++j) tv[j] = (int)tvd[j];
+        }
 
         // ---- repair the active set -----------------------------------------------------------------
         bool change = false, anybad = false;
         int wantdrop[J];                                            // head of a run that wants the previous anchor gone
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-            const int t = lane + 32 * j;
+            const int t = lane * J + j;
             anybad |= valid[j] && (flag[j] != 0 || vio_up[j] || vio_dn[j]);
             wantdrop[j] = (valid[j] && head[j] && ((flag[j] & (RS_EMPTY | RS_FREEBAD)) || ((flag[j] & RS_BAD) && freeend[j]))) ? 1 : 0;
             if (valid[j] && tv[j] == t) { kind[j] = vio_up[j] ? 1 : -1; change = true; }       // (1) new anchor
         }
         int nextwant[J];
-        shift_from_next<J>(wantdrop, nextwant, 0);
+        shift_from_next<J, int>(wantdrop, nextwant, 0);
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-            const int t = lane + 32 * j;
+            const int t = lane * J + j;
             if (!valid[j] || kind[j] == 0 || tv[j] == t) continue;
             bool drop = nextwant[j] != 0;                                                       // (2) wrong sign at my anchor
             if (tail[j] && (flag[j] & RS_BAD)) drop = true;                                     //     my run cannot meet its target
@@ -445,15 +504,23 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
     }
     if (!accepted) return false;
 
-    // ---- emit ------------------------------------------------------------------------------------------
+    // ---- emit: stage the results in shared memory and write them out coalesced ---------------------------
+    __syncwarp();
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-        const int t = lane + 32 * j;
+        const int t = lane * J + j;
         if (!valid[j]) continue;
-        const size_t o = (size_t)s * T + t;
-        sel(v.D, nxt)[o] = D[j]; sel(v.C, nxt)[o] = C[j]; v.E[o] = pre[j]; v.eta[o] = eta[j];
-        note_move(v, n, t, (D[j] - st[j].Db) - (C[j] - st[j].Cb));
+        tab[0 * tstride + t] = D[j]; tab[1 * tstride + t] = C[j]; tab[2 * tstride + t] = pre[j]; tab[3 * tstride + t] = eta[j];
+        tab[4 * tstride + t] = (D[j] - st[j].Db) - (C[j] - st[j].Cb);
     }
+    __syncwarp();
+    for (int t = lane; t < T; t += 32) {
+        const size_t o = (size_t)s * T + t;
+        sel(v.D, nxt)[o] = tab[0 * tstride + t]; sel(v.C, nxt)[o] = tab[1 * tstride + t];
+        v.E[o] = tab[2 * tstride + t]; v.eta[o] = tab[3 * tstride + t];
+        note_move(v, n, t, tab[4 * tstride + t]);
+    }
+    __syncwarp();
     return true;
 }
 
