@@ -203,26 +203,32 @@ def run_dopf(args):
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     # algorithmic bytes per launch
-    alg_bytes = {"k_gen_predict<2>": 16.0 * G * T, "k_gen_predict<1>": 16.0 * G * T,
-                 "k_sto_warm": 40.0 * S * T, "k_sto_cold": 40.0 * S * T, "k_sto_fix": 40.0 * S * T,
-                 "k_inject": 8.0 * (G + 2 * S) * T + 16.0 * N * T}
-    gemm_flops = {"k_gemm<32, true>": 4.0 * L * N * T, "k_gemm<64, true>": 4.0 * L * N * T,
-                  "k_gemm<32, false>": 2.0 * L * N * T, "k_gemm<64, false>": 2.0 * L * N * T}
+    def alg_bytes_of(name):
+        if name.startswith("k_gen_predict"): return 16.0 * G * T
+        if name.startswith("k_sto_"): return 40.0 * S * T
+        if name.startswith("k_slack_stream"): return 16.0 * G * T + 32.0 * S * T      # re-reads both iterates of every agent
+        if name.startswith("k_inject"): return 8.0 * (G + 2 * S) * T + 16.0 * N * T
+        return None
+
+    def gemm_flops_of(name):
+        if name.startswith("k_gemm") and "true" in name: return 4.0 * L * N * T          # PTDF^T M and (PTDF.^2)^T W
+        if name.startswith("k_gemm"): return 2.0 * L * N * T
+        return None
     if dom is None:
         roof = None
-    elif dom in gemm_flops:
-        ach = gemm_flops[dom] / (kern[dom] * 1e-3) / 1e12
+    elif gemm_flops_of(dom):
+        ach = gemm_flops_of(dom) / (kern[dom] * 1e-3) / 1e12
         roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": 37.0, "unit": "TFLOP/s", "frac": ach / 37.0, "traffic": None,
                 "peak_source": "nominal B200 fp64 (DMMA) 37 TFLOP/s - no fp64 figure in MEASURED_PEAKS.json"}
     else:
-        b = alg_bytes.get(dom, 40.0 * S * T)
+        b = alg_bytes_of(dom) or 40.0 * S * T
         ach = b / (kern[dom] * 1e-3) / 1e9
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": b}
     if roof is not None:
         roof["kernel_ms"] = kern[dom]
         roof["kernel_share_of_iteration"] = kern[dom] / sum(kern.values())
-    gp = kern.get("k_gen_predict<2>", kern.get("k_gen_predict<1>"))
+    gp = next((v for k_, v in kern.items() if k_.startswith("k_gen_predict")), None)
     if gp and roof is not None:
         roof["generator_stream"] = {"kernel_ms": gp, "achieved_GBps": 16.0 * G * T / (gp * 1e-3) / 1e9, "frac": 16.0 * G * T / (gp * 1e-3) / 1e9 / hbm}
 

@@ -38,7 +38,8 @@ class DopfStatus(C.Structure):
                 ("res_lambda", C.c_double), ("res_mue", C.c_double), ("res_rho", C.c_double),
                 ("gen_corrected", C.c_int32), ("sto_corrected", C.c_int32),
                 ("tight_rows", C.c_int32), ("wide_rows", C.c_int32),
-                ("launches_per_iteration", C.c_int32), ("sto_cold", C.c_int32), ("last_step_ms", C.c_double)]
+                ("launches_per_iteration", C.c_int32), ("sto_cold", C.c_int32), ("last_step_ms", C.c_double),
+                ("fix_sequential", C.c_int32), ("reserved3", C.c_int32)]
 
 
 EXPORTS = ["dopf_version", "dopf_default_config", "dopf_create", "dopf_destroy", "dopf_step", "dopf_get_status",

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -98,6 +99,8 @@ void fill_status(dopf_handle *h, dopf_status *s)
     s->tight_rows = c.stat_tight_rows; s->wide_rows = c.stat_wide_rows;
     s->launches_per_iteration = h->launches_per_iter;
     s->sto_cold = c.stat_sto_cold;
+    s->reserved2 = c.stat_fix_seq;
+    if (getenv("DOPF_DEBUG")) fprintf(stderr, "[dopf] k_sto_fix cycles: collect max %llu solve max %llu | sums %llu %llu | work %d\n", c.dbg_cyc[0], c.dbg_cyc[1], c.dbg_cyc[2], c.dbg_cyc[3], c.sto_work_cnt);
     s->last_step_ms = h->last_step_ms;
 }
 

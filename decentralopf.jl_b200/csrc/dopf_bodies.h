@@ -38,6 +38,8 @@ struct Ctrl {
     int iters_done;     // iterations executed since create
     int gen_work_cnt, sto_work_cnt, cold_work_cnt;
     int stat_sto_cold;                   // storages solved by the cold funnel in the last iteration
+    int stat_fix_seq;                    // cumulated correction-pass storages that needed the sequential solver
+    unsigned long long dbg_cyc[4];       // debug: max cycles of the k_sto_fix phases (collect, solve) and totals
     int stat_gen_fix, stat_sto_fix;      // cumulated corrected agents (statistics)
     int stat_tight_rows, stat_wide_rows; // of the last iteration
     unsigned long long res_bits[3];      // max |dual_{k+1}-dual_k| for lambda, mue, rho (bits)
@@ -139,13 +141,14 @@ DOPF_HD void note_move(const View &v, int n, int t, double delta)
 // ---- storages: accessors over the device layout ------------------------------------------------
 struct GlobalSteps {     // previous iterate and anchor linearisation of one storage, read in place
     const double *Db, *Cb, *g0, *s1;
-    const Hinge *hinges; const int *hcnt; int hcap;
+    const Hinge *hinges; const int *hcnt; int hcap; bool sorted;
     DOPF_HD StoStep step(int t) const { StoStep st; st.Db = Db[t]; st.Cb = Cb[t]; st.g0 = g0[t]; st.s1 = s1[t]; return st; }
     DOPF_HD HingeList list(int t) const
     {
         HingeList l;
         l.h = hinges ? hinges + (size_t)t * hcap : nullptr;
         l.n = hinges ? hcnt[t] : 0;
+        l.sorted = sorted;
         return l;
     }
 };
@@ -171,7 +174,7 @@ DOPF_HD void sto_setup(const View &v, int s, StoConst &k, GlobalSteps &sp)
     k.mc = v.sto_mc[s]; k.pmax = v.sto_pmax[s]; k.emax = v.sto_emax[s]; k.prox = v.c.prox; k.iprox = 1.0 / v.c.prox;
     sp.Db = sel(v.D, cur) + (size_t)s * v.T; sp.Cb = sel(v.C, cur) + (size_t)s * v.T;
     sp.g0 = v.g0 + (size_t)n * v.ldt; sp.s1 = v.s1 + (size_t)n * v.ldt;
-    sp.hinges = nullptr; sp.hcnt = nullptr; sp.hcap = 0;
+    sp.hinges = nullptr; sp.hcnt = nullptr; sp.hcap = 0; sp.sorted = false;
 }
 
 // record the moves of a finished storage (after its final emit pass)
@@ -197,11 +200,11 @@ DOPF_HD void body_sto_warm(const View &v, int s)
     else v.cold_work[DOPF_ATOMIC_ADD_I32(&v.ctrl->cold_work_cnt, 1)] = s;
 }
 
-DOPF_HD void body_sto_cold(const View &v, int s, const Hinge *hinges, const int *hcnt)
+DOPF_HD void body_sto_cold(const View &v, int s, const Hinge *hinges, const int *hcnt, bool sorted = false)
 {
     StoConst k; GlobalSteps sp;
     sto_setup(v, s, k, sp);
-    sp.hinges = hinges; sp.hcnt = hcnt; sp.hcap = v.hcap;
+    sp.hinges = hinges; sp.hcnt = hcnt; sp.hcap = v.hcap; sp.sorted = sorted;
     StoEmit emit(v, sp, k, s, v.sto_node[s]);
     bool done = false;
     if (hinges) {

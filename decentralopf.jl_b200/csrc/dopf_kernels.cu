@@ -22,6 +22,7 @@ __global__ void k_begin(View v)
     if (i == 0) {
         v.ctrl->gen_work_cnt = 0; v.ctrl->sto_work_cnt = 0; v.ctrl->cold_work_cnt = 0;
         v.ctrl->res_bits[0] = v.ctrl->res_bits[1] = v.ctrl->res_bits[2] = 0ull;
+        v.ctrl->dbg_cyc[0] = v.ctrl->dbg_cyc[1] = v.ctrl->dbg_cyc[2] = v.ctrl->dbg_cyc[3] = 0ull;
     }
     for (int k = i; k < v.Np * v.ldt; k += gridDim.x * blockDim.x) v.dn[k] = 0ull;
     for (int k = i; k < v.ldt; k += gridDim.x * blockDim.x) v.dmax[k] = 0ull;
@@ -366,19 +367,24 @@ __device__ __forceinline__ int collect_hinges(const View &v, int n, int t, doubl
     const double *lb = v.wide_b + (size_t)t * 2 * v.L;
     const double *prow = v.ptdfT + (size_t)n * v.Lp;
     int cnt = 0;
-    for (int b0 = 0; b0 < cnt_in; b0 += 64) {
-        Hinge h[2]; bool ok[2];
+    constexpr int U = 8;                          // 256 list entries per iteration, all loads issued before use
+    for (int b0 = 0; b0 < cnt_in; b0 += 32 * U) {
+        int e[U]; double b[U], p[U];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int j = b0 + u * 32 + lane;
-            ok[u] = false; h[u].bp = 0.0; h[u].sg = 0.0;
-            if (j < cnt_in) {
-                const int e = lst[j];
-                ok[u] = make_hinge(v.c, prow[e >> 1], lb[j], e & 1, h[u]) && h[u].bp > lo && h[u].bp < hi;
-            }
+        for (int u = 0; u < U; ++u) {
+            const int j = min(b0 + u * 32 + lane, cnt_in - 1);
+            e[u] = lst[j]; b[u] = lb[j];
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) p[u] = prow[e[u] >> 1];
+        Hinge h[U]; bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            h[u].bp = 0.0; h[u].sg = 0.0;
+            ok[u] = (b0 + u * 32 + lane < cnt_in) && make_hinge(v.c, p[u], b[u], e[u] & 1, h[u]) && h[u].bp > lo && h[u].bp < hi;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
             const unsigned m = __ballot_sync(0xffffffffu, ok[u]);
             const int pos = cnt + __popc(m & ((1u << lane) - 1));
             if (ok[u] && pos < cap) out[pos] = h[u];
@@ -386,6 +392,25 @@ __device__ __forceinline__ int collect_hinges(const View &v, int n, int t, doubl
         }
     }
     return cnt;
+}
+
+// sort a hinge list of at most 64 entries by |bp| ascending (rank sort, one warp, 2 entries per lane)
+__device__ __forceinline__ void sort_hinges(Hinge *lst, int n)
+{
+    const int lane = threadIdx.x & 31;
+    if (n <= 1 || n > 64) return;
+    Hinge h0 = lane < n ? lst[lane] : Hinge{1e308, 0.0}, h1 = lane + 32 < n ? lst[lane + 32] : Hinge{1e308, 0.0};
+    const double k0 = fabs(h0.bp), k1 = fabs(h1.bp);
+    int r0 = 0, r1 = 0;
+    for (int i = 0; i < n; ++i) {
+        const double ki = __shfl_sync(0xffffffffu, i < 32 ? k0 : k1, i & 31);
+        r0 += (ki < k0) || (ki == k0 && i < lane);
+        r1 += (ki < k1) || (ki == k1 && i < lane + 32);
+    }
+    __syncwarp();
+    if (lane < n) lst[r0] = h0;
+    if (lane + 32 < n) lst[r1] = h1;
+    __syncwarp();
 }
 
 template <int J>
@@ -401,21 +426,28 @@ __global__ void __launch_bounds__(512) k_sto_fix(View v, Hinge *hinge_scratch, i
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int s = v.sto_work[w], n = v.sto_node[s];
         const double pm = v.sto_pmax[s];
+        const long long c0 = clock64();
         for (int t = warp; t < v.T; t += nwarps) {
             // delta = (D-Db)-(C-Cb) with 0<=D,C<=pmax  =>  delta in [-Db-(pmax-Cb), (pmax-Db)+Cb]
             const double Db = sel(v.D, v.ctrl->cur)[(size_t)s * v.T + t], Cb = sel(v.C, v.ctrl->cur)[(size_t)s * v.T + t];
             int cnt = collect_hinges(v, n, t, -Db - (pm - Cb), (pm - Db) + Cb, mylist + (size_t)t * v.hcap, v.hcap);
             if (cnt > v.hcap) { if (lane == 0) v.ctrl->error = DOPF_ERR_HINGE_CAP; cnt = v.hcap; }
             if (lane == 0) mycnt[t] = cnt;
+            __syncwarp();
+            sort_hinges(mylist + (size_t)t * v.hcap, cnt);     // evaluations exit at the first hinge beyond |delta|
         }
         __syncthreads();
+        const long long c1 = clock64();
         if (warp == 0) {
             extern __shared__ __align__(16) double sto_smem[];
             bool ok = false;
             if (J > 0) ok = sto_warp_solve<(J > 0 ? J : 1), true>(v, s, mylist, mycnt, sto_smem);
             if (lane == 0) {
-                if (!ok) body_sto_cold(v, s, mylist, mycnt);
+                if (!ok) { body_sto_cold(v, s, mylist, mycnt, v.hcap <= 64); atomicAdd(&v.ctrl->stat_fix_seq, 1); }
                 atomicAdd(&v.ctrl->stat_sto_fix, 1);
+                const long long c2 = clock64();
+                atomicMax(&v.ctrl->dbg_cyc[0], (unsigned long long)(c1 - c0)); atomicMax(&v.ctrl->dbg_cyc[1], (unsigned long long)(c2 - c1));
+                atomicAdd(&v.ctrl->dbg_cyc[2], (unsigned long long)(c1 - c0)); atomicAdd(&v.ctrl->dbg_cyc[3], (unsigned long long)(c2 - c1));
             }
         }
         __syncthreads();
@@ -453,7 +485,7 @@ __global__ void k_gen_fix(View v)
         __syncwarp();
         if (cnt > CAP) { if (lane == 0) v.ctrl->error = DOPF_ERR_HINGE_CAP; cnt = CAP; }
         if (lane == 0) {
-            HingeList hl; hl.h = lists[wib]; hl.n = cnt;
+            HingeList hl; hl.h = lists[wib]; hl.n = cnt; hl.sorted = false;
             const size_t nt = (size_t)n * v.ldt + t;
             const double d = root_monotone_pl(v.gen_mc[g] + v.g0[nt], v.c.prox + v.s1[nt], hl, lo, hi);
             double Pn = Pb + d;

@@ -54,10 +54,15 @@ DOPF_HD void hinge_accum(const Hinge h, double delta, double &val, double &slope
 struct HingeList {
     const Hinge *h;
     int n;
+    bool sorted;   // entries ordered by |bp| ascending: hinges beyond |delta| keep their anchor state => early exit
     DOPF_HD void eval(double delta, double &val, double &slope) const
     {
         val = 0.0; slope = 0.0;
-        for (int i = 0; i < n; ++i) hinge_accum(h[i], delta, val, slope);
+        const double ad = fabs(delta);
+        for (int i = 0; i < n; ++i) {
+            if (sorted && fabs(h[i].bp) > ad) break;
+            hinge_accum(h[i], delta, val, slope);
+        }
     }
 };
 
@@ -166,15 +171,10 @@ DOPF_HD StoEval sto_eval(const StoStep &st, const StoConst &k, const HingeList &
         double v;
         hl.eval((D - st.Db) - (C - st.Cb), v, sl);
         if (v != 0.0 || sl != 0.0) {
-            // a hinge differs from its anchor state at this delta: safeguarded Newton on Psi with hinges
-            const double big = k.mc + k.prox * k.pmax + 1.0;
-            double lo = -big + base - 1.0, hi = big + base + 1.0;
-            {
-                double v2, s2;
-                hl.eval(2.0 * k.pmax, v2, s2);  hi += st.s1 * 2.0 * k.pmax + fabs(v2);
-                hl.eval(-2.0 * k.pmax, v2, s2); lo -= st.s1 * 2.0 * k.pmax + fabs(v2);
-            }
-            double flo = -1.0, fhi = 1.0;
+            // a hinge differs from its anchor state at this delta: safeguarded Newton on Psi with hinges,
+            // started at the hinge-free solution; the bracket is built lazily from the iterates (Psi is
+            // increasing with slope >= 1, so |Psi| bounds the distance to the root)
+            double lo = -1e300, hi = 1e300, flo = 0.0, fhi = 0.0;
             bool have_lo = false, have_hi = false;
             for (int it = 0; it < 200; ++it) {
                 sto_dc_of_nu(st, k, nu, D, C, nf);
@@ -186,8 +186,10 @@ DOPF_HD StoEval sto_eval(const StoStep &st, const StoConst &k, const HingeList &
                 const double slope = 1.0 + (st.s1 + sl) * nf * k.iprox;
                 double nn = nu - psi / slope;
                 if (!(nn > lo && nn < hi)) {
-                    nn = (have_lo && have_hi) ? lo - flo * (hi - lo) / (fhi - flo) : 0.5 * (lo + hi);
-                    if (!(nn > lo && nn < hi)) nn = 0.5 * (lo + hi);
+                    if (have_lo && have_hi) {
+                        nn = lo - flo * (hi - lo) / (fhi - flo);
+                        if (!(nn > lo && nn < hi)) nn = 0.5 * (lo + hi);
+                    } else nn = nu - psi;          // slope >= 1: the root lies within |psi| of nu
                 }
                 if (fabs(nn - nu) <= 1e-15 * (1.0 + fabs(nu))) { nu = nn; break; }
                 nu = nn;
@@ -322,6 +324,7 @@ struct StoProblem {
         HingeList l;
         l.h = hinges ? hinges + (size_t)t * hcap : nullptr;
         l.n = hinges ? hcnt[t] : 0;
+        l.sorted = false;
         return l;
     }
 };

@@ -281,6 +281,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
         const double Ep = tab[5 * tstride + tt];
         hl[j].h = HINGES ? hinges + (size_t)tt * v.hcap : nullptr;
         hl[j].n = HINGES ? hcnt[tt] : 0;
+        hl[j].sorted = HINGES && v.hcap <= 64;   // k_sto_fix sorts lists of up to 64 entries by |bp|
         kind[j] = !valid[j] ? 0 : (Ep >= k.emax - tolA ? 1 : (Ep <= tolA ? -1 : 0));
     }
     __syncwarp();
@@ -346,9 +347,13 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 if (valid[j]) {
-                    StoEval e;
-                    if (HINGES && hl[j].n != 0) e = sto_eval(st[j], k, hl[j], eta[j]);
-                    else e = eval_tab(st[j], k, clip_tab_load(tab, tstride, lane * J + j), eta[j]);
+                    StoEval e = eval_tab(st[j], k, clip_tab_load(tab, tstride, lane * J + j), eta[j]);
+                    if (HINGES && hl[j].n != 0) {
+                        // the hinge-free solution is exact unless a hinge differs from its anchor state at this delta
+                        double hv, hs;
+                        hl[j].eval((e.D - st[j].Db) - (e.C - st[j].Cb), hv, hs);
+                        if (hv != 0.0 || hs != 0.0) e = sto_eval(st[j], k, hl[j], eta[j]);
+                    }
                     D[j] = e.D; C[j] = e.C; pre[j] = e.C - e.D; dy[j] = e.dy;
                 } else { D[j] = C[j] = pre[j] = dy[j] = 0.0; }
             }

@@ -32,6 +32,7 @@ mutable struct DopfStatus   # struct dopf_status
     res_lambda::Cdouble; res_mue::Cdouble; res_rho::Cdouble
     gen_corrected::Cint; sto_corrected::Cint; tight_rows::Cint; wide_rows::Cint
     launches_per_iteration::Cint; sto_cold::Cint; last_step_ms::Cdouble
+    fix_sequential::Cint; reserved3::Cint
     DopfStatus() = new()
 end
 

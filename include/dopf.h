@@ -83,6 +83,8 @@ typedef struct dopf_status {
     int32_t launches_per_iteration;        /* kernels enqueued per iteration                  */
     int32_t sto_cold;                      /* storages that needed the cold solve in the last iteration */
     double last_step_ms;                   /* device time of the last dopf_step (CUDA events on the library stream) */
+    int32_t reserved2;                     /* cumulated correction-pass storages that fell back to the sequential solver */
+    int32_t reserved3;
 } dopf_status;
 
 int dopf_create(const dopf_problem *p, const dopf_config *c, dopf_handle **out);

@@ -81,7 +81,7 @@ double emul_gen_root(double c, double a, int n, const double *hbp, const double 
 {
     std::vector<Hinge> h(n > 0 ? n : 1);
     for (int i = 0; i < n; ++i) { h[i].bp = hbp[i]; h[i].sg = hsg[i]; }
-    HingeList l; l.h = h.data(); l.n = n;
+    HingeList l; l.h = h.data(); l.n = n; l.sorted = false;
     return root_monotone_pl(c, a, l, lo, hi);
 }
 }
@@ -276,7 +276,7 @@ void emul_iterate(void *h)
             int en = v.wide[(size_t)t * 2 * v.L + j]; int l = en >> 1, side = en & 1; Hinge hh;
             if (make_hinge(v.c, v.ptdf[(size_t)l * Np + n], side ? v.bminus[(size_t)l * ldt + t] : v.bplus[(size_t)l * ldt + t], side, hh) && hh.bp > lo && hh.bp < hi) lst.push_back(hh);
         }
-        HingeList hl; hl.h = lst.data(); hl.n = (int)lst.size();
+        HingeList hl; hl.h = lst.data(); hl.n = (int)lst.size(); hl.sorted = false;
         const size_t nt = (size_t)n * ldt + t;
         double dd = root_monotone_pl(v.gen_mc[g] + v.g0[nt], v.c.prox + v.s1[nt], hl, lo, hi);
         double Pn = Pb + dd; Pn = Pn < 0 ? 0 : (Pn > pmax ? pmax : Pn);
