@@ -53,7 +53,8 @@ def make_case(pkg, workload, seed, agents=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons; started before the warm-up, samples are time-stamped and only
+    those inside the timed region are reported (nearest ones if the region is shorter than the period)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -62,7 +63,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -70,21 +71,31 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def wait_for_samples(self, n=2, timeout=3.0):
+        t0 = time.time()
+        while len(self.rows) < n and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def stop(self, t_begin, t_end):
+        time.sleep(0.05)
         if self.proc:
             self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        good = [(ts, r) for ts, r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        inside = [r for ts, r in good if t_begin <= ts <= t_end + 0.03]
+        note = "samples inside the timed region"
+        if not inside and good:
+            inside = [r for ts, r in sorted(good, key=lambda x: abs(x[0] - 0.5 * (t_begin + t_end)))[:3]]
+            note = "timed region shorter than the sampling period: nearest samples"
+        sm = [float(r[0]) for r in inside]; mx = [float(r[1]) for r in inside if r[1].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 7:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "note": note}
 
 
 def oracle_rate(pkg, workload, steps, warmup, budget_s=150.0):
@@ -162,11 +173,14 @@ def run_dopf(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    (part or dev).step(args.warmup)
-    barrier()
     clocks = ClockSampler(local) if rank == 0 else None
     if clocks:
         clocks.start()
+    (part or dev).step(args.warmup)
+    if clocks:
+        clocks.wait_for_samples()
+    barrier()
+    t_begin = time.time()
     if partitioned:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(part.stream):       # libdopf and the collectives run on this stream
@@ -180,7 +194,7 @@ def run_dopf(args):
         st = dev.step(args.steps)              # device time by CUDA events on the library's stream
         ms_total = st.last_step_ms
     barrier()
-    clk = clocks.stop() if clocks else None
+    clk = clocks.stop(t_begin, time.time()) if clocks else None
     tmax = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -295,7 +309,7 @@ def run_dopf(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="dopf", choices=["dopf", "reference"])
     ap.add_argument("--workload", default="target", choices=sorted(WORKLOADS))

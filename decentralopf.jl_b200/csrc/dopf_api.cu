@@ -100,7 +100,7 @@ void fill_status(dopf_handle *h, dopf_status *s)
     s->launches_per_iteration = h->launches_per_iter;
     s->sto_cold = c.stat_sto_cold;
     s->reserved2 = c.stat_fix_seq;
-    if (getenv("DOPF_DEBUG")) fprintf(stderr, "[dopf] k_sto_fix cycles: collect max %llu solve max %llu | sums %llu %llu | work %d\n", c.dbg_cyc[0], c.dbg_cyc[1], c.dbg_cyc[2], c.dbg_cyc[3], c.sto_work_cnt);
+    if (getenv("DOPF_DEBUG")) fprintf(stderr, "[dopf] slack rows: %llu rows, queued nodes total %llu max/row %llu | sto_fix max cycles %llu work %d\n", c.dbg_cyc[3], (unsigned long long)c.pair_cnt, c.dbg_cyc[0], c.dbg_cyc[1], c.sto_work_cnt);
     s->last_step_ms = h->last_step_ms;
 }
 
@@ -246,15 +246,18 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     AL(v.bplus, (size_t)Lp * ldt); AL(v.bminus, (size_t)Lp * ldt); AL(v.M, (size_t)Lp * ldt); AL(v.Wt, (size_t)Lp * ldt);
     AL(v.g0, (size_t)Np * ldt); AL(v.s1, (size_t)Np * ldt); AL(v.rg, (size_t)Np * ldt);
     AL(v.dn, (size_t)Np * ldt); AL(v.dmax, ldt);
+    for (int k = 0; k < 8; ++k) AL(v.nst[k], (size_t)Np * ldt);
     AL(v.flags, (size_t)ldt * Lp);
     AL(v.wide, (size_t)T * 2 * L); AL(v.wcnt, T); AL(v.tight, (size_t)T * 2 * L); AL(v.tcnt, T);
     v.gen_work_cap = (int)std::min<long long>((long long)G * T, 1ll << 30);
     AL(v.gen_work, (size_t)std::max(v.gen_work_cap, 1)); AL(v.sto_work, S); AL(v.sto_flag, S);
+    if (N >= (1 << 20) || T >= (1 << 11)) { h->err = "N >= 2^20 or T >= 2^11 not supported by the pair queue encoding"; return DOPF_E_UNSUPPORTED; }
+    v.pair_cap = 1 << 20;
+    AL(v.pair_row, v.pair_cap); AL(v.pair_node, v.pair_cap);
     AL(v.rowsumU, (size_t)2 * Lp * ldt); v.rowsumK = v.rowsumU + (size_t)Lp * ldt;   // contiguous: one exchange
     AL(v.ctrl, 1);
     AL(lp.tflag, (size_t)Lp * ldt);
-    AL(v.tslot, (size_t)2 * Lp * ldt);
-    AL(lp.slack_part, (size_t)slack_chunks(G, S) * ldt * slack_rows_cap());
+
     AL(h->d_scalar, 4);
     AL(h->d_nodal, (size_t)N * T);
 
@@ -283,7 +286,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
         AL(lp.hinge_scratch, S ? warps * T * v.hcap : 1);
         AL(lp.hcnt_scratch, S ? warps * T : 1);
     }
-    lp.slack_blocks_x = std::max(1, std::min(64, (4 * lp.num_sms + T - 1) / T));
+    lp.slack_blocks_x = std::max(1, std::min(64, (8 * lp.num_sms + T - 1) / T));
 
     // ---- state before iteration 1 (admm.jl:29-36; helpers/results.jl:14-73 "zeros") ----------
     Ctrl c0;

@@ -11,14 +11,18 @@ namespace dopf {
 
 #if defined(__CUDA_ARCH__)
 #define DOPF_ATOMIC_MAX_U64(addr, v) atomicMax((unsigned long long *)(addr), (unsigned long long)(v))
+#define DOPF_ATOMIC_MIN_U64(addr, v) atomicMin((unsigned long long *)(addr), (unsigned long long)(v))
 #define DOPF_ATOMIC_ADD_I32(addr, v) atomicAdd((int *)(addr), (int)(v))
 #define DOPF_ATOMIC_EXCH_I32(addr, v) atomicExch((int *)(addr), (int)(v))
 #else
 static inline unsigned long long dopf_host_max_u64(unsigned long long *a, unsigned long long v)
 { unsigned long long o = *a; if (v > o) *a = v; return o; }
+static inline unsigned long long dopf_host_min_u64(unsigned long long *a, unsigned long long v)
+{ unsigned long long o = *a; if (v < o) *a = v; return o; }
 static inline int dopf_host_add_i32(int *a, int v) { int o = *a; *a = o + v; return o; }
 static inline int dopf_host_exch_i32(int *a, int v) { int o = *a; *a = v; return o; }
 #define DOPF_ATOMIC_MAX_U64(addr, v) dopf_host_max_u64((unsigned long long *)(addr), (unsigned long long)(v))
+#define DOPF_ATOMIC_MIN_U64(addr, v) dopf_host_min_u64((unsigned long long *)(addr), (unsigned long long)(v))
 #define DOPF_ATOMIC_ADD_I32(addr, v) dopf_host_add_i32((int *)(addr), (int)(v))
 #define DOPF_ATOMIC_EXCH_I32(addr, v) dopf_host_exch_i32((int *)(addr), (int)(v))
 #endif
@@ -36,7 +40,7 @@ struct Ctrl {
     int conv_lambda, conv_mue, conv_rho;
     int error;          // DOPF_ERR_*; set => every later kernel is a no-op, state stays valid
     int iters_done;     // iterations executed since create
-    int gen_work_cnt, sto_work_cnt, cold_work_cnt;
+    int gen_work_cnt, sto_work_cnt, cold_work_cnt, pair_cnt;
     int stat_sto_cold;                   // storages solved by the cold funnel in the last iteration
     int stat_fix_seq;                    // cumulated correction-pass storages that needed the sequential solver
     unsigned long long dbg_cyc[4];       // debug: max cycles of the k_sto_fix phases (collect, solve) and totals
@@ -84,6 +88,11 @@ struct View {
     double *g0, *s1;                   // [Np][ldt]
     double *rg;                        // [Np][ldt] 1/(prox + s1): generator step size
     unsigned long long *dn;            // [Np][ldt] max |delta| of the agents at (n,t) (bits)
+    // node statistics of the moves delta_i of this rank's agents at (n,t), written by body_inject:
+    //   nst[0] = min delta (<= 0), nst[1] = max delta (>= 0), nst[2] = largest negative delta (-inf if none),
+    //   nst[3] = smallest positive delta (+inf if none), nst[4] = sum of negative deltas, nst[5] = sum of
+    //   positive deltas, nst[6] = number of negative movers, nst[7] = number of positive movers
+    double *nst[8];                    // each [ldt][Np] (timestep-major: the slack rows scan over the nodes of one t)
     unsigned long long *dmax;          // [ldt]
     unsigned char *flags;              // [ldt][Lp] bit0: U side wide candidate, bit1: K side
     int *wide, *wcnt;                  // [T][2L] entries l*2+side ; [T]
@@ -91,10 +100,10 @@ struct View {
     const double *ptdfT;               // [Np][Lp] transposed PTDF (node-major) for per-agent hinge collection
     int *cold_work;                    // [S] storages whose warm start did not verify
     int *tight, *tcnt;                 // [T][2L] ; [T]
-    int *tslot;                        // [2][Lp][ldt] position of (side,l,t) in the tight list of t (stale unless verified)
     int *gen_work;                     // [gen_work_cap] g*T+t
     int *sto_work, *sto_flag;          // [S], [S]
     double *rowsumU, *rowsumK;         // [Lp][ldt] exact sum_i (b -+ p delta_i)_+ of tight rows
+    int *pair_row, *pair_node; int pair_cap;   // (tight row, node) pairs whose agents must be summed one by one
     Ctrl *ctrl;
 };
 
@@ -262,15 +271,70 @@ DOPF_HD void body_verify(const View &v, int n, int t)
 // ---- nodal injection of the new iterate (results.jl:64,88-106) --------------------------------
 DOPF_HD void body_inject(const View &v, int n, int t)
 {
-    const int nxt = 1 - v.ctrl->cur;
+    const int cur = v.ctrl->cur, nxt = 1 - cur;
     double a = 0.0;
+    double lo = 0.0, hi = 0.0, inneg = -INFINITY, inpos = INFINITY, sneg = 0.0, spos = 0.0, cneg = 0.0, cpos = 0.0;
     if (n < v.N && t < v.T) {
         a = v.demand_on ? -v.demand[(size_t)n * v.ldt + t] : 0.0;
-        for (int g = v.gen_ptr[n]; g < v.gen_ptr[n + 1]; ++g) a += sel(v.P, nxt)[(size_t)g * v.T + t];
-        for (int s = v.sto_ptr[n]; s < v.sto_ptr[n + 1]; ++s)
-            a += sel(v.D, nxt)[(size_t)s * v.T + t] - sel(v.C, nxt)[(size_t)s * v.T + t];
+        for (int g = v.gen_ptr[n]; g < v.gen_ptr[n + 1]; ++g) {
+            const size_t o = (size_t)g * v.T + t;
+            const double pn = sel(v.P, nxt)[o], d = pn - sel(v.P, cur)[o];
+            a += pn;
+            if (d < 0.0) { lo = d < lo ? d : lo; inneg = d > inneg ? d : inneg; sneg += d; cneg += 1.0; }
+            else if (d > 0.0) { hi = d > hi ? d : hi; inpos = d < inpos ? d : inpos; spos += d; cpos += 1.0; }
+        }
+        for (int s = v.sto_ptr[n]; s < v.sto_ptr[n + 1]; ++s) {
+            const size_t o = (size_t)s * v.T + t;
+            const double dn_ = sel(v.D, nxt)[o], cn_ = sel(v.C, nxt)[o];
+            const double d = (dn_ - sel(v.D, cur)[o]) - (cn_ - sel(v.C, cur)[o]);
+            a += dn_ - cn_;
+            if (d < 0.0) { lo = d < lo ? d : lo; inneg = d > inneg ? d : inneg; sneg += d; cneg += 1.0; }
+            else if (d > 0.0) { hi = d > hi ? d : hi; inpos = d < inpos ? d : inpos; spos += d; cpos += 1.0; }
+        }
     }
     sel(v.injloc, nxt)[(size_t)n * v.ldt + t] = a;
+    const size_t i = (size_t)t * v.Np + n;
+    v.nst[0][i] = lo; v.nst[1][i] = hi; v.nst[2][i] = inneg; v.nst[3][i] = inpos;
+    v.nst[4][i] = sneg; v.nst[5][i] = spos; v.nst[6][i] = cneg; v.nst[7][i] = cpos;
+}
+
+// closed form of sum_i (b + sp*delta_i)_+ over the agents of node n at time t from the node statistics;
+// ok = false if the hinge threshold falls strictly between two movers on one side (then the caller sums
+// over the agents).  Resting agents (delta = 0) contribute (b)_+ each.
+DOPF_HD double slack_node_closed(const View &v, double b, double sp, int n, int t, bool &ok)
+{
+    const size_t i = (size_t)t * v.Np + n;
+    const double na = v.nagents[n];
+    ok = true;
+    if (na == 0.0) return 0.0;
+    if (sp == 0.0) return na * pospart(b);
+    const double lo = v.nst[0][i], hi = v.nst[1][i];
+    const double f0 = b + sp * lo, f1 = b + sp * hi;
+    const double sall = v.nst[4][i] + v.nst[5][i];
+    if (f0 >= 0.0 && f1 >= 0.0) return na * b + sp * sall;            // nobody is clipped
+    if (f0 <= 0.0 && f1 <= 0.0 && b <= 0.0) return 0.0;               // everybody is clipped (resting agents: b <= 0)
+    // movers that push the term down are the negative ones for sp > 0, the positive ones for sp < 0
+    const bool downneg = sp > 0.0;
+    const double in_dn = downneg ? v.nst[2][i] : v.nst[3][i];         // the "down" mover closest to zero
+    const double in_up = downneg ? v.nst[3][i] : v.nst[2][i];         // the "up" mover closest to zero
+    const double s_up = downneg ? v.nst[5][i] : v.nst[4][i], c_up = downneg ? v.nst[7][i] : v.nst[6][i];
+    const double s_dn = downneg ? v.nst[4][i] : v.nst[5][i], c_dn = downneg ? v.nst[6][i] : v.nst[7][i];
+    if (b >= 0.0) {
+        // resting and "up" movers keep a non-negative term; are ALL "down" movers clipped?
+        if (c_dn == 0.0 || b + sp * in_dn <= 0.0) return (na - c_dn) * b + sp * s_up;
+        // is NO "down" mover clipped?  (then f0/f1 test above would have caught it, kept for clarity)
+        const double out_dn = downneg ? lo : hi;
+        if (b + sp * out_dn >= 0.0) return na * b + sp * sall;
+    } else {
+        // resting and "down" movers are clipped; are ALL "up" movers unclipped?
+        if (c_up == 0.0) return 0.0;
+        if (b + sp * in_up >= 0.0) return c_up * b + sp * s_up;
+        const double out_up = downneg ? hi : lo;
+        if (b + sp * out_up <= 0.0) return 0.0;
+    }
+    (void)s_dn;
+    ok = false;
+    return 0.0;
 }
 
 // ---- exact slack sums of one tight row at one node (results.jl:83-84,110-112) ------------------
@@ -278,18 +342,12 @@ DOPF_HD void body_inject(const View &v, int n, int t)
 DOPF_HD double body_slack_row_node(const View &v, int l, int side, int n, int t)
 {
     const int cur = v.ctrl->cur, nxt = 1 - cur;
-    const double na = v.nagents[n];
-    if (na == 0.0) return 0.0;
     const double p = v.ptdf[(size_t)l * v.Np + n];
     const double b = side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t];
     const double sp = side ? p : -p;   // term is (b + sp*delta)_+
-    const size_t nt = (size_t)n * v.ldt + t;
-    if (p == 0.0) return na * pospart(b);
-    const double dnt = bits_nonneg(v.dn[nt]);
-    if (fabs(b) > fabs(p) * dnt) {   // nobody at this node crosses the hinge
-        if (b <= 0.0) return 0.0;
-        return na * b + sp * (sel(v.injloc, nxt)[nt] - sel(v.injloc, cur)[nt]);
-    }
+    bool ok;
+    const double c = slack_node_closed(v, b, sp, n, t, ok);
+    if (ok) return c;
     double a = 0.0;
     for (int g = v.gen_ptr[n]; g < v.gen_ptr[n + 1]; ++g) {
         const double d = sel(v.P, nxt)[(size_t)g * v.T + t] - sel(v.P, cur)[(size_t)g * v.T + t];

@@ -20,7 +20,7 @@ __global__ void k_begin(View v)
     if (!DOPF_ACTIVE(v)) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
-        v.ctrl->gen_work_cnt = 0; v.ctrl->sto_work_cnt = 0; v.ctrl->cold_work_cnt = 0;
+        v.ctrl->gen_work_cnt = 0; v.ctrl->sto_work_cnt = 0; v.ctrl->cold_work_cnt = 0; v.ctrl->pair_cnt = 0;
         v.ctrl->res_bits[0] = v.ctrl->res_bits[1] = v.ctrl->res_bits[2] = 0ull;
         v.ctrl->dbg_cyc[0] = v.ctrl->dbg_cyc[1] = v.ctrl->dbg_cyc[2] = v.ctrl->dbg_cyc[3] = 0ull;
     }
@@ -86,7 +86,6 @@ __global__ void __launch_bounds__(256) k_compact(View v, int mode)
                 if (pass == 1 && p) {
                     const int pos = cnt + __popc(m & ((1u << lane) - 1));
                     out[pos] = e;
-                    v.tslot[((size_t)(e & 1) * v.Lp + (e >> 1)) * v.ldt + t] = pos;
                 }
                 cnt += __popc(m);
             }
@@ -446,8 +445,7 @@ __global__ void __launch_bounds__(512) k_sto_fix(View v, Hinge *hinge_scratch, i
                 if (!ok) { body_sto_cold(v, s, mylist, mycnt, v.hcap <= 64); atomicAdd(&v.ctrl->stat_fix_seq, 1); }
                 atomicAdd(&v.ctrl->stat_sto_fix, 1);
                 const long long c2 = clock64();
-                atomicMax(&v.ctrl->dbg_cyc[0], (unsigned long long)(c1 - c0)); atomicMax(&v.ctrl->dbg_cyc[1], (unsigned long long)(c2 - c1));
-                atomicAdd(&v.ctrl->dbg_cyc[2], (unsigned long long)(c1 - c0)); atomicAdd(&v.ctrl->dbg_cyc[3], (unsigned long long)(c2 - c1));
+                atomicMax(&v.ctrl->dbg_cyc[1], (unsigned long long)(c2 - c0));
             }
         }
         __syncthreads();
@@ -544,153 +542,31 @@ __global__ void k_colsum(View v)   // block (32,32): 32 timesteps, 32 row groups
 }
 
 // ------------------------------------------------------------------------------------------------
-// exact average-slack sums of the tight rows, agent-streaming form (results.jl:83-84,110-112):
-//   rowsum[l,t,side] = sum over ALL agents i of (b_lt -+ p_{l,n(i)} * delta_it)_+
-// Block = 32 timesteps x SLK_AGENTS agents; lane = timestep (coalesced along t), the 8 warps walk the
-// agents of the chunk.  Every lane accumulates the first SLK_ROWS tight rows of its own timestep;
-// per-chunk partials are written to slack_part[chunk][t][row] and reduced in fixed order by k_dual
-// (deterministic).  Rows beyond SLK_ROWS per timestep are handled by k_slack_rows below.
-// ------------------------------------------------------------------------------------------------
-#ifndef DOPF_SLK_ROWS
-#define DOPF_SLK_ROWS 16
-#endif
-constexpr int SLK_ROWS = DOPF_SLK_ROWS, SLK_GROUPS = 64 / DOPF_SLK_ROWS, SLK_AGENTS = 512, SLK_WARPS = 4;   // SLK_ROWS*SLK_GROUPS rows per timestep
-
-__global__ void __launch_bounds__(SLK_WARPS * 32, (SLK_ROWS <= 8 ? 6 : 3)) k_slack_stream(View v, double *part, int nchunk_gen)
-{
-    if (!DOPF_ACTIVE(v)) return;
-    __shared__ double red[SLK_WARPS][SLK_ROWS][33];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t = blockIdx.y * 32 + lane;
-    const int chunk = blockIdx.x;
-    const bool gens = chunk < nchunk_gen;
-    const int a0 = (gens ? chunk : chunk - nchunk_gen) * SLK_AGENTS;
-    const int a1 = min(a0 + SLK_AGENTS, gens ? v.G : v.S);
-    const int cur = v.ctrl->cur, nxt = 1 - cur;
-    const bool tv = t < v.T;
-    const int tt = tv ? t : 0;
-    const int r0 = blockIdx.z * SLK_ROWS;                       // row group of this block
-    const int cnt = tv ? max(0, min(v.tcnt[t] - r0, SLK_ROWS)) : 0;
-    int rl[SLK_ROWS]; double rb[SLK_ROWS], acc[SLK_ROWS];
-    const int *lst = v.tight + (size_t)tt * 2 * v.L + r0;
-#pragma unroll
-    for (int j = 0; j < SLK_ROWS; ++j) {
-        acc[j] = 0.0; rl[j] = 0; rb[j] = 0.0;
-        if (j < cnt) {
-            const int e = lst[j], l = e >> 1;
-            rl[j] = e;
-            rb[j] = (e & 1) ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t];
-        }
-    }
-    const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
-    if (maxcnt == 0) return;                                    // no row of this group in the tile: the partials are never read
-    {
-        // every warp walks a contiguous agent range (consecutive agents share their node, so the PTDF
-        // entries of the lane's rows are re-gathered only when the node changes); 4 agents are loaded
-        // ahead of their use to keep several memory requests in flight
-        const int per = SLK_AGENTS / SLK_WARPS;
-        const int w0 = a0 + warp * per, w1 = min(w0 + per, a1);
-        const double *An = gens ? sel(v.P, nxt) : sel(v.D, nxt), *Ap = gens ? sel(v.P, cur) : sel(v.D, cur);
-        const double *Cn = sel(v.C, nxt), *Cp = sel(v.C, cur);
-        const int *nodes = gens ? v.gen_node : v.sto_node;
-        int ncur = -1, nrest = 0;
-        double pj[SLK_ROWS];
-#pragma unroll
-        for (int j = 0; j < SLK_ROWS; ++j) pj[j] = 0.0;
-        for (int a = w0; a < w1; a += 4) {
-            double d[4]; int nn[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int aa = min(a + u, w1 - 1);
-                const size_t o = (size_t)aa * v.T + tt;
-                nn[u] = nodes[aa];
-                d[u] = An[o] - Ap[o];
-                if (!gens) d[u] -= Cn[o] - Cp[o];
-                if (a + u >= w1 || !tv) d[u] = 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (a + u >= w1) break;
-                // agents resting at a bound over the whole tile (delta = 0 for all 32 timesteps) add the
-                // constant (b)_+ to every row: count them instead of evaluating the rows
-                if (__all_sync(0xffffffffu, d[u] == 0.0)) { ++nrest; continue; }
-                if (nn[u] != ncur) {
-                    ncur = nn[u];
-                    const double *pcol = v.ptdfT + (size_t)ncur * v.Lp;
-#pragma unroll
-                    for (int j = 0; j < SLK_ROWS; ++j)
-                        if (j < cnt) { const double p = pcol[rl[j] >> 1]; pj[j] = (rl[j] & 1) ? p : -p; }
-                }
-                // rows beyond the lane's own count have rb = pj = 0 and add exactly 0: no per-lane predicate,
-                // only a warp-uniform cut at the largest count of the warp
-#pragma unroll
-                for (int j = 0; j < SLK_ROWS; ++j) {
-                    if (j >= maxcnt) break;
-                    acc[j] += fmax(fma(pj[j], d[u], rb[j]), 0.0);
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < SLK_ROWS; ++j) acc[j] += (double)nrest * fmax(rb[j], 0.0);
-    }
-#pragma unroll
-    for (int j = 0; j < SLK_ROWS; ++j) red[warp][j][lane] = acc[j];
-    __syncthreads();
-    for (int j = warp; j < SLK_ROWS; j += SLK_WARPS) {   // fixed-order reduction over the warps
-        double sum = 0.0;
-#pragma unroll
-        for (int w = 0; w < SLK_WARPS; ++w) sum += red[w][j][lane];
-        if (tv) part[((size_t)chunk * v.ldt + t) * (SLK_ROWS * SLK_GROUPS) + r0 + j] = sum;
-    }
-}
-
-// rows beyond SLK_ROWS per timestep (rare): one block per (t, row).  Threads classify the nodes;
-// nodes nobody crosses contribute in closed form, the (rare) crossed nodes are queued in shared
-// memory and summed by the warps with the lanes over the agents of the node.
+// exact average-slack sums of the tight rows (results.jl:83-84,110-112):
+//   rowsum[l,t,side] = sum over all agents i of (b_lt -+ p_{l,n(i)} * delta_it)_+
+// one block per (t, row).  Threads classify the nodes with the signed move range [dlo,dhi] of (n,t):
+// nodes whose agents all keep the hinge on one side contribute in closed form (node sums), the mixed
+// nodes are queued in shared memory and summed by the warps with the lanes over the agents of the node.
 __global__ void __launch_bounds__(128) k_slack_rows(View v, unsigned char *tflag)
 {
     if (!DOPF_ACTIVE(v)) return;
-    constexpr int QCAP = 512;
     __shared__ double red[4];
-    __shared__ int queue[QCAP];
-    __shared__ int qcnt;
     const int t = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cur = v.ctrl->cur, nxt = 1 - cur;
     const int cnt = v.tcnt[t];
     const int *lst = v.tight + (size_t)t * 2 * v.L;
-    for (int j = SLK_ROWS * SLK_GROUPS + blockIdx.x; j < cnt; j += gridDim.x) {
+    for (int j = blockIdx.x; j < cnt; j += gridDim.x) {
         const int l = lst[j] >> 1, side = lst[j] & 1;
         const double b = side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t];
-        if (threadIdx.x == 0) qcnt = 0;
-        __syncthreads();
         double a = 0.0;
         for (int n = threadIdx.x; n < v.N; n += blockDim.x) {
-            const double na = v.nagents[n];
-            if (na == 0.0) continue;
             const double p = v.ptdf[(size_t)l * v.Np + n];
-            const size_t nt = (size_t)n * v.ldt + t;
-            if (p == 0.0) { a += na * pospart(b); continue; }
-            if (fabs(b) > fabs(p) * bits_nonneg(v.dn[nt])) {      // nobody at this node crosses the hinge
-                if (b > 0.0) a += na * b + (side ? p : -p) * (sel(v.injloc, nxt)[nt] - sel(v.injloc, cur)[nt]);
-                continue;
-            }
-            const int q = atomicAdd(&qcnt, 1);
-            if (q < QCAP) queue[q] = n; else a += body_slack_row_node(v, l, side, n, t);   // overflow: serial path
-        }
-        __syncthreads();
-        const int nq = min(qcnt, QCAP);
-        for (int q = warp; q < nq; q += (blockDim.x >> 5)) {
-            const int n = queue[q];
-            const double sp = side ? v.ptdf[(size_t)l * v.Np + n] : -v.ptdf[(size_t)l * v.Np + n];
-            const int g0 = v.gen_ptr[n], g1 = v.gen_ptr[n + 1], s0 = v.sto_ptr[n], s1 = v.sto_ptr[n + 1];
-            for (int g = g0 + lane; g < g1; g += 32) {
-                const size_t o = (size_t)g * v.T + t;
-                a += pospart(b + sp * (sel(v.P, nxt)[o] - sel(v.P, cur)[o]));
-            }
-            for (int s = s0 + lane; s < s1; s += 32) {
-                const size_t o = (size_t)s * v.T + t;
-                a += pospart(b + sp * ((sel(v.D, nxt)[o] - sel(v.D, cur)[o]) - (sel(v.C, nxt)[o] - sel(v.C, cur)[o])));
-            }
+            bool ok;
+            const double c = slack_node_closed(v, b, side ? p : -p, n, t, ok);
+            if (ok) { a += c; continue; }
+            // mixed node: its agents are summed one by one by k_slack_pairs (whole-GPU parallelism)
+            const int q = atomicAdd(&v.ctrl->pair_cnt, 1);
+            if (q < v.pair_cap) { v.pair_row[q] = lst[j]; v.pair_node[q] = n | (t << 20); }
+            else a += body_slack_row_node(v, l, side, n, t);      // queue full: serial path
         }
         a = Group<32>::sum(a);
         if (lane == 0) red[warp] = a;
@@ -706,24 +582,30 @@ __global__ void __launch_bounds__(128) k_slack_rows(View v, unsigned char *tflag
     }
 }
 
-// fixed-order sum of the per-chunk partials of k_slack_stream into rowsumU / rowsumK: one warp per
-// (t, tight row slot), lanes over the chunks (shuffle tree => deterministic)
-__global__ void __launch_bounds__(128) k_slack_reduce(View v, unsigned char *tflag, const double *part, int nchunks)
+// mixed (row, node) pairs: one warp per pair, lanes over the agents of the node
+__global__ void __launch_bounds__(256) k_slack_pairs(View v)
 {
     if (!DOPF_ACTIVE(v)) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t = blockIdx.y;
-    const int cnt = min(v.tcnt[t], SLK_ROWS * SLK_GROUPS);
-    const int slot = blockIdx.x * 4 + warp;
-    if (slot >= cnt) return;
-    double sum = 0.0;
-    for (int c = lane; c < nchunks; c += 32) sum += part[((size_t)c * v.ldt + t) * (SLK_ROWS * SLK_GROUPS) + slot];
-    sum = Group<32>::sum(sum);
-    if (lane == 0) {
-        const int e = v.tight[(size_t)t * 2 * v.L + slot], l = e >> 1, side = e & 1;
-        const size_t i = (size_t)l * v.ldt + t;
-        (side ? v.rowsumK : v.rowsumU)[i] = sum;
-        atomicOr(reinterpret_cast<unsigned int *>(tflag) + (i >> 2), (unsigned)(1u << side) << (8 * (i & 3)));
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int total = min(v.ctrl->pair_cnt, v.pair_cap);
+    const int cur = v.ctrl->cur, nxt = 1 - cur;
+    for (int q = gw; q < total; q += nw) {
+        const int e = v.pair_row[q], l = e >> 1, side = e & 1;
+        const int n = v.pair_node[q] & 0xfffff, t = v.pair_node[q] >> 20;
+        const double b = side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t];
+        const double p = v.ptdf[(size_t)l * v.Np + n], sp = side ? p : -p;
+        double a = 0.0;
+        for (int g = v.gen_ptr[n] + lane; g < v.gen_ptr[n + 1]; g += 32) {
+            const size_t o = (size_t)g * v.T + t;
+            a += pospart(b + sp * (sel(v.P, nxt)[o] - sel(v.P, cur)[o]));
+        }
+        for (int s = v.sto_ptr[n] + lane; s < v.sto_ptr[n + 1]; s += 32) {
+            const size_t o = (size_t)s * v.T + t;
+            a += pospart(b + sp * ((sel(v.D, nxt)[o] - sel(v.D, cur)[o]) - (sel(v.C, nxt)[o] - sel(v.C, cur)[o])));
+        }
+        a = Group<32>::sum(a);
+        if (lane == 0) atomicAdd((side ? v.rowsumK : v.rowsumU) + (size_t)l * v.ldt + t, a);
     }
 }
 
@@ -833,8 +715,6 @@ int set_storage_smem_attr(int T)
     return (int)e;
 }
 
-int slack_chunks(int G, int S) { return cdiv(G, SLK_AGENTS) + cdiv(S, SLK_AGENTS); }
-int slack_rows_cap() { return SLK_ROWS * SLK_GROUPS; }
 
 int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
 {
@@ -915,13 +795,13 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     LAUNCH(k_dmax<<<dim3(v.ldt / 32, 16), dim3(32, 32), 0, cs>>>(v));
     XCHG(DOPF_X_DMAX);   // all ranks must build the same tight lists
     LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 1));   // moves may have grown
-    FORK();   // slack sums need only the new agents and the tight lists ...
     LAUNCH(k_clear_tflag<<<cdiv((long long)v.Lp * v.ldt / 4, 256), 256, 0, cs>>>(v, lp.tflag));
-    const int ncg = cdiv(v.G, SLK_AGENTS), ncs = cdiv(v.S, SLK_AGENTS);
-    LAUNCH(k_slack_stream<<<dim3(ncg + ncs, v.ldt / 32, SLK_GROUPS), SLK_WARPS * 32, 0, cs>>>(v, lp.slack_part, ncg));
-    MAIN();   // ... while the main stream aggregates the injection and computes the flows
     LAUNCH(k_inject<<<cdiv((long long)v.Np * v.ldt, 256), 256, 0, cs>>>(v));
     XCHG(DOPF_X_INJ);    // nodal injection of all ranks' agents
+    FORK();   // the slack sums need the local injection, not the flows: they overlap the flow product
+    LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.T), 128, 0, cs>>>(v, lp.tflag));
+    LAUNCH(k_slack_pairs<<<lp.num_sms * 2, 256, 0, cs>>>(v));
+    MAIN();
     LAUNCH(k_colsum<<<v.ldt / 32, dim3(32, 32), 0, cs>>>(v));
     {   // flow = PTDF * inj
         dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);
@@ -930,12 +810,8 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
         LAUNCH(k_flow_reduce<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, cs>>>(v, lp.part, lp.ksplit_n));
     }
     JOIN();
-    {
-        LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.T), 128, 0, cs>>>(v, lp.tflag));   // needs the local injection
-        LAUNCH(k_slack_reduce<<<dim3(SLK_ROWS * SLK_GROUPS / 4, v.T), 128, 0, cs>>>(v, lp.tflag, lp.slack_part, ncg + ncs));
-        XCHG(DOPF_X_ROWSUM); // exact slack sums over all ranks' agents
-        LAUNCH(k_dual<<<cdiv((long long)v.L * v.ldt, 256), 256, 0, cs>>>(v, lp.tflag));
-    }
+    XCHG(DOPF_X_ROWSUM); // exact slack sums over all ranks' agents
+    LAUNCH(k_dual<<<cdiv((long long)v.L * v.ldt, 256), 256, 0, cs>>>(v, lp.tflag));
     LAUNCH(k_lambda<<<cdiv(v.T, 128), 128, 0, cs>>>(v));
     LAUNCH(k_finish<<<1, 1, 0, cs>>>(v));
 #undef LAUNCH

@@ -16,7 +16,6 @@ struct LaunchPlan {
     int slack_blocks_x;
     double *part, *part2;     // split-K partial tiles
     unsigned char *tflag;     // [Lp][ldt] bit0/bit1: exact row sums present (U/K side)
-    double *slack_part;       // [agent chunks][ldt][SLK_ROWS] partial slack sums of k_slack_stream
     Hinge *hinge_scratch;     // [sto_fix_blocks][T][hcap]
     int *hcnt_scratch;        // [sto_fix_blocks][T]
     // fork/join of independent kernel groups on a second stream (whole-iteration mode only)
@@ -31,7 +30,6 @@ enum { DOPF_X_DMAX = 0, DOPF_X_INJ = 1, DOPF_X_ROWSUM = 2, DOPF_N_SEGMENTS = 4 }
 int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment = -1);
 void launch_mwide(const View &v, cudaStream_t st);
 int set_storage_smem_attr(int T);   // opt in to > 48 KB dynamic shared memory for long horizons
-int slack_chunks(int G, int S);
 int slack_rows_cap();   // returns number of kernel launches
 void launch_total_costs(const View &v, double *d_out, cudaStream_t st);
 void launch_nodal_price(const View &v, int which, double *d_out, cudaStream_t st);

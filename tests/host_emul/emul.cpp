@@ -161,9 +161,9 @@ void *emul_create(int N, int L, int T, int G, int S, const double *ptdf, const d
     v.bplus = e->mk((size_t)Lp * ldt); v.bminus = e->mk((size_t)Lp * ldt); v.M = e->mk((size_t)Lp * ldt); v.Wt = e->mk((size_t)Lp * ldt);
     v.g0 = e->mk((size_t)Np * ldt); v.s1 = e->mk((size_t)Np * ldt); v.rg = e->mk((size_t)Np * ldt);
     e->dn.assign((size_t)Np * ldt, 0); e->dmax.assign(ldt, 0); v.dn = e->dn.data(); v.dmax = e->dmax.data();
+    for (int k = 0; k < 8; ++k) v.nst[k] = e->mk((size_t)Np * ldt);
     e->flags.assign((size_t)ldt * Lp, 0); v.flags = e->flags.data(); e->tflag.assign((size_t)Lp * ldt, 0);
     v.wide = e->mki((size_t)T * 2 * L); v.wcnt = e->mki(T); v.tight = e->mki((size_t)T * 2 * L); v.tcnt = e->mki(T);
-    v.tslot = e->mki((size_t)2 * Lp * ldt);
     v.gen_work = e->mki(v.gen_work_cap); v.sto_work = e->mki(S); v.sto_flag = e->mki(S);
     v.rowsumU = e->mk((size_t)Lp * ldt); v.rowsumK = e->mk((size_t)Lp * ldt);
     memset(&e->ctrl, 0, sizeof e->ctrl); e->ctrl.iteration = 1; v.ctrl = &e->ctrl;
