@@ -100,7 +100,7 @@ void fill_status(dopf_handle *h, dopf_status *s)
     s->launches_per_iteration = h->launches_per_iter;
     s->sto_cold = c.stat_sto_cold;
     s->reserved2 = c.stat_fix_seq;
-    if (getenv("DOPF_DEBUG")) fprintf(stderr, "[dopf] slack rows: %llu rows, queued nodes total %llu max/row %llu | sto_fix max cycles %llu work %d\n", c.dbg_cyc[3], (unsigned long long)c.pair_cnt, c.dbg_cyc[0], c.dbg_cyc[1], c.sto_work_cnt);
+    if (getenv("DOPF_DEBUG")) fprintf(stderr, "[dopf] pairs %d | sto_fix max cycles collect %llu total %llu work %d | gen_fix max cycles total %llu work %d maxhinges %d | sto_fix solve: max AS %d newton passes %d slow evals %d cycles(loop) %llu\n", c.pair_cnt, c.dbg_cyc[0], c.dbg_cyc[1], c.sto_work_cnt, c.dbg_cyc[3], c.gen_work_cnt, c.dbg_hmax, c.dbg_i[0], c.dbg_i[1], c.dbg_i[2], c.dbg_cyc[2]);
     s->last_step_ms = h->last_step_ms;
 }
 
@@ -274,7 +274,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     AL(lp.part, (size_t)std::max(lp.ksplit_t * Np, lp.ksplit_n * Lp) * ldt);
     AL(lp.part2, (size_t)lp.ksplit_t * Np * ldt);
     {
-        lp.sto_fix_blocks = std::max(1, std::min(lp.num_sms * 2, S));
+        lp.sto_fix_blocks = std::max(1, std::min(lp.num_sms * 8, S));
         {
             const int need = (T + 31) / 32;
             const int opts[6] = {1, 2, 3, 4, 6, 8};
@@ -282,7 +282,10 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
             for (int o : opts) if (o >= need) { lp.sto_j = o; break; }
         }
         if (lp.sto_j > 0 && set_storage_smem_attr(T) != 0) { h->err = "cudaFuncSetAttribute(shared memory) failed"; return DOPF_E_CUDA; }
-        const size_t warps = (size_t)lp.sto_fix_blocks;     // one scratch slot per block
+        // scratch: one slot per collected work item (up to 512 MB) + one per solver block for the overflow
+        const size_t slot_bytes = (size_t)T * v.hcap * sizeof(Hinge) + (size_t)T * sizeof(int);
+        lp.sto_fix_slots = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(S, 1), ((size_t)512 << 20) / slot_bytes));
+        const size_t warps = (size_t)lp.sto_fix_slots + (size_t)lp.sto_fix_blocks;
         AL(lp.hinge_scratch, S ? warps * T * v.hcap : 1);
         AL(lp.hcnt_scratch, S ? warps * T : 1);
     }

@@ -22,7 +22,7 @@ __global__ void k_begin(View v)
     if (i == 0) {
         v.ctrl->gen_work_cnt = 0; v.ctrl->sto_work_cnt = 0; v.ctrl->cold_work_cnt = 0; v.ctrl->pair_cnt = 0;
         v.ctrl->res_bits[0] = v.ctrl->res_bits[1] = v.ctrl->res_bits[2] = 0ull;
-        v.ctrl->dbg_cyc[0] = v.ctrl->dbg_cyc[1] = v.ctrl->dbg_cyc[2] = v.ctrl->dbg_cyc[3] = 0ull;
+        v.ctrl->dbg_cyc[0] = v.ctrl->dbg_cyc[1] = v.ctrl->dbg_cyc[2] = v.ctrl->dbg_cyc[3] = 0ull; v.ctrl->dbg_hmax = 0; v.ctrl->dbg_i[0] = v.ctrl->dbg_i[1] = v.ctrl->dbg_i[2] = v.ctrl->dbg_i[3] = 0;
     }
     for (int k = i; k < v.Np * v.ldt; k += gridDim.x * blockDim.x) v.dn[k] = 0ull;
     for (int k = i; k < v.ldt; k += gridDim.x * blockDim.x) v.dmax[k] = 0ull;
@@ -379,8 +379,12 @@ __device__ __forceinline__ int collect_hinges(const View &v, int n, int t, doubl
         Hinge h[U]; bool ok[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
+            // breakpoint b/q inside (lo,hi), tested without the division (only the few accepted entries divide)
+            const double q = (e[u] & 1) ? -p[u] : p[u];
+            const double x0 = (q > 0.0 ? lo : hi) * q, x1 = (q > 0.0 ? hi : lo) * q;
+            ok[u] = (b0 + u * 32 + lane < cnt_in) && q != 0.0 && b[u] > x0 && b[u] < x1;
             h[u].bp = 0.0; h[u].sg = 0.0;
-            ok[u] = (b0 + u * 32 + lane < cnt_in) && make_hinge(v.c, p[u], b[u], e[u] & 1, h[u]) && h[u].bp > lo && h[u].bp < hi;
+            if (ok[u]) ok[u] = make_hinge(v.c, p[u], b[u], e[u] & 1, h[u]) && h[u].bp > lo && h[u].bp < hi;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -412,43 +416,56 @@ __device__ __forceinline__ void sort_hinges(Hinge *lst, int n)
     __syncwarp();
 }
 
-template <int J>
-__global__ void __launch_bounds__(512) k_sto_fix(View v, Hinge *hinge_scratch, int *hcnt_scratch)
+// hinge lists of the affected storages: one warp per (work item, timestep); items beyond the scratch
+// capacity are collected by k_sto_fix itself
+__device__ __forceinline__ void sto_collect_one(const View &v, int s, int t, Hinge *list, int *cnt_out)
+{
+    const int lane = threadIdx.x & 31, n = v.sto_node[s];
+    const double pm = v.sto_pmax[s];
+    // delta = (D-Db)-(C-Cb) with 0<=D,C<=pmax  =>  delta in [-Db-(pmax-Cb), (pmax-Db)+Cb]
+    const double Db = sel(v.D, v.ctrl->cur)[(size_t)s * v.T + t], Cb = sel(v.C, v.ctrl->cur)[(size_t)s * v.T + t];
+    int cnt = collect_hinges(v, n, t, -Db - (pm - Cb), (pm - Db) + Cb, list, v.hcap);
+    if (cnt > v.hcap) { if (lane == 0) v.ctrl->error = DOPF_ERR_HINGE_CAP; cnt = v.hcap; }
+    if (lane == 0) *cnt_out = cnt;
+    __syncwarp();
+    sort_hinges(list, cnt);                       // evaluations exit at the first hinge beyond |delta|
+}
+
+__global__ void __launch_bounds__(128) k_sto_collect(View v, Hinge *hinge_scratch, int *hcnt_scratch, int slots)
 {
     if (!DOPF_ACTIVE(v)) return;
-    // one block per affected storage: the 16 warps collect the hinge lists of different timesteps,
-    // then warp 0 re-solves the storage exactly
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const long long tasks = (long long)min(v.ctrl->sto_work_cnt, slots) * v.T;
+    for (long long k = gw; k < tasks; k += nw) {
+        const int w = (int)(k / v.T), t = (int)(k % v.T);
+        sto_collect_one(v, v.sto_work[w], t, hinge_scratch + ((size_t)w * v.T + t) * v.hcap, hcnt_scratch + (size_t)w * v.T + t);
+    }
+}
+
+// one warp (= one block, so the solver may use the whole register file) per affected storage
+template <int J>
+__global__ void __launch_bounds__(32) k_sto_fix(View v, Hinge *hinge_scratch, int *hcnt_scratch, int slots)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    extern __shared__ __align__(16) double sto_smem[];
+    const int lane = threadIdx.x & 31;
     const int total = v.ctrl->sto_work_cnt;
-    Hinge *mylist = hinge_scratch + (size_t)blockIdx.x * v.T * v.hcap;
-    int *mycnt = hcnt_scratch + (size_t)blockIdx.x * v.T;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        const int s = v.sto_work[w], n = v.sto_node[s];
-        const double pm = v.sto_pmax[s];
-        const long long c0 = clock64();
-        for (int t = warp; t < v.T; t += nwarps) {
-            // delta = (D-Db)-(C-Cb) with 0<=D,C<=pmax  =>  delta in [-Db-(pmax-Cb), (pmax-Db)+Cb]
-            const double Db = sel(v.D, v.ctrl->cur)[(size_t)s * v.T + t], Cb = sel(v.C, v.ctrl->cur)[(size_t)s * v.T + t];
-            int cnt = collect_hinges(v, n, t, -Db - (pm - Cb), (pm - Db) + Cb, mylist + (size_t)t * v.hcap, v.hcap);
-            if (cnt > v.hcap) { if (lane == 0) v.ctrl->error = DOPF_ERR_HINGE_CAP; cnt = v.hcap; }
-            if (lane == 0) mycnt[t] = cnt;
+        const int s = v.sto_work[w];
+        const int slot = w < slots ? w : slots + blockIdx.x;
+        Hinge *mylist = hinge_scratch + (size_t)slot * v.T * v.hcap;
+        int *mycnt = hcnt_scratch + (size_t)slot * v.T;
+        if (w >= slots) {
+            for (int t = 0; t < v.T; ++t) sto_collect_one(v, s, t, mylist + (size_t)t * v.hcap, mycnt + t);
             __syncwarp();
-            sort_hinges(mylist + (size_t)t * v.hcap, cnt);     // evaluations exit at the first hinge beyond |delta|
         }
-        __syncthreads();
-        const long long c1 = clock64();
-        if (warp == 0) {
-            extern __shared__ __align__(16) double sto_smem[];
-            bool ok = false;
-            if (J > 0) ok = sto_warp_solve<(J > 0 ? J : 1), true>(v, s, mylist, mycnt, sto_smem);
-            if (lane == 0) {
-                if (!ok) { body_sto_cold(v, s, mylist, mycnt, v.hcap <= 64); atomicAdd(&v.ctrl->stat_fix_seq, 1); }
-                atomicAdd(&v.ctrl->stat_sto_fix, 1);
-                const long long c2 = clock64();
-                atomicMax(&v.ctrl->dbg_cyc[1], (unsigned long long)(c2 - c0));
-            }
+        bool ok = false;
+        if (J > 0) ok = sto_warp_solve<(J > 0 ? J : 1), true>(v, s, mylist, mycnt, sto_smem);
+        if (lane == 0) {
+            if (!ok) { body_sto_cold(v, s, mylist, mycnt, v.hcap <= 64); atomicAdd(&v.ctrl->stat_fix_seq, 1); }
+            atomicAdd(&v.ctrl->stat_sto_fix, 1);
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -475,12 +492,14 @@ __global__ void k_gen_fix(View v)
     const int gw = blockIdx.x * (blockDim.x >> 5) + wib, nw = gridDim.x * (blockDim.x >> 5);
     const int total = min(v.ctrl->gen_work_cnt, v.gen_work_cap);
     for (int w = gw; w < total; w += nw) {
+        const long long c0 = clock64();
         const int g = v.gen_work[w] / v.T, t = v.gen_work[w] % v.T;
         const int n = v.gen_node[g];
         const double Pb = sel(v.P, cur)[(size_t)g * v.T + t], pmax = v.gen_pmax[g];
         const double lo = -Pb, hi = pmax - Pb;
         int cnt = collect_hinges(v, n, t, lo, hi, lists[wib], CAP);
         __syncwarp();
+        const long long c1 = clock64();
         if (cnt > CAP) { if (lane == 0) v.ctrl->error = DOPF_ERR_HINGE_CAP; cnt = CAP; }
         if (lane == 0) {
             HingeList hl; hl.h = lists[wib]; hl.n = cnt; hl.sorted = false;
@@ -491,6 +510,8 @@ __global__ void k_gen_fix(View v)
             sel(v.P, nxt)[(size_t)g * v.T + t] = Pn;
             note_move(v, n, t, Pn - Pb);
             atomicAdd(&v.ctrl->stat_gen_fix, 1);
+            atomicMax(&v.ctrl->dbg_cyc[3], (unsigned long long)(clock64() - c0));
+            atomicMax(&v.ctrl->dbg_hmax, cnt);
         }
         __syncwarp();
     }
@@ -779,14 +800,15 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     }
     FORK();
     if (v.S > 0) {
+        LAUNCH(k_sto_collect<<<lp.num_sms * 8, 128, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch, lp.sto_fix_slots));
         switch (lp.sto_j) {
-        case 1: LAUNCH(k_sto_fix<1><<<lp.sto_fix_blocks, 512, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 2: LAUNCH(k_sto_fix<2><<<lp.sto_fix_blocks, 512, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 3: LAUNCH(k_sto_fix<3><<<lp.sto_fix_blocks, 512, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 4: LAUNCH(k_sto_fix<4><<<lp.sto_fix_blocks, 512, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 6: LAUNCH(k_sto_fix<6><<<lp.sto_fix_blocks, 512, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        case 8: LAUNCH(k_sto_fix<8><<<lp.sto_fix_blocks, 512, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
-        default: LAUNCH(k_sto_fix<0><<<lp.sto_fix_blocks, 512, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch)); break;
+        case 1: LAUNCH(k_sto_fix<1><<<lp.sto_fix_blocks, 32, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch, lp.sto_fix_slots)); break;
+        case 2: LAUNCH(k_sto_fix<2><<<lp.sto_fix_blocks, 32, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch, lp.sto_fix_slots)); break;
+        case 3: LAUNCH(k_sto_fix<3><<<lp.sto_fix_blocks, 32, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch, lp.sto_fix_slots)); break;
+        case 4: LAUNCH(k_sto_fix<4><<<lp.sto_fix_blocks, 32, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch, lp.sto_fix_slots)); break;
+        case 6: LAUNCH(k_sto_fix<6><<<lp.sto_fix_blocks, 32, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch, lp.sto_fix_slots)); break;
+        case 8: LAUNCH(k_sto_fix<8><<<lp.sto_fix_blocks, 32, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch, lp.sto_fix_slots)); break;
+        default: LAUNCH(k_sto_fix<0><<<lp.sto_fix_blocks, 32, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch, lp.sto_fix_slots)); break;
         }
     }
     MAIN();

@@ -11,13 +11,14 @@ struct LaunchPlan {
     int num_sms;
     int bm_t, ksplit_t;       // tile rows / split-K of the transposed product (PTDF^T M)
     int bm_n, ksplit_n;       // ... of the flow product (PTDF * inj)
-    int sto_fix_blocks;       // grid of the storage correction pass (one block = one affected storage; sizes the scratch)
+    int sto_fix_blocks;       // grid of the storage correction pass (one 32-thread block = one affected storage)
+    int sto_fix_slots;        // work items whose hinge lists k_sto_collect gathers (one scratch slot each)
     int sto_j;                // timesteps per lane of the warp-parallel storage solve (0: horizon too long)
     int slack_blocks_x;
     double *part, *part2;     // split-K partial tiles
     unsigned char *tflag;     // [Lp][ldt] bit0/bit1: exact row sums present (U/K side)
-    Hinge *hinge_scratch;     // [sto_fix_blocks][T][hcap]
-    int *hcnt_scratch;        // [sto_fix_blocks][T]
+    Hinge *hinge_scratch;     // [sto_fix_slots + sto_fix_blocks][T][hcap]
+    int *hcnt_scratch;        // [sto_fix_slots + sto_fix_blocks][T]
     // fork/join of independent kernel groups on a second stream (whole-iteration mode only)
     cudaStream_t side_stream; cudaEvent_t ev_fork, ev_join;
     // optional per-kernel profiling (dopf_profile_iteration): event pairs + names in launch order

@@ -27,6 +27,13 @@
 
 namespace dopf {
 
+#if !defined(__CUDACC__) && defined(DOPF_COUNT_ITERS)
+static long dopf_iters_root[202], dopf_iters_sto[202];   // test-only iteration histograms
+#define DOPF_COUNT(arr, it) (++arr[(it) > 200 ? 200 : (it)])
+#else
+#define DOPF_COUNT(arr, it) ((void)0)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // Hinges.  One hinge = one (line, side) whose per-agent slack clips at 0 when the agent moves:
 //   term(delta) = s*(delta-bp)  on the active side  dir*(delta-bp) > 0,  0 otherwise.
@@ -64,6 +71,39 @@ struct HingeList {
             hinge_accum(h[i], delta, val, slope);
         }
     }
+    // value, the slopes on both sides of delta and the nearest breakpoints strictly beyond delta on both
+    // sides.  A breakpoint within rounding distance of delta counts as reached: on each side the hinge is
+    // in the state it has beyond the breakpoint.  For sorted lists the first hinge beyond |delta| bounds
+    // the distance to every remaining breakpoint (a conservative `next` on both sides).
+    DOPF_HD void eval2(double delta, double &val, double &sL, double &sR, double &nL, double &nR, double xtol = 0.0) const
+    {
+        val = 0.0; sL = 0.0; sR = 0.0; nL = -1e300; nR = 1e300;
+        const double ad = fabs(delta), tol = 1e-14 * (1.0 + ad) + xtol;
+        for (int i = 0; i < n; ++i) {
+            const double bp = h[i].bp, abp = fabs(bp);
+            if (sorted && abp > ad + tol) {
+                if (abp < nR) nR = abp;
+                if (-abp > nL) nL = -abp;
+                break;
+            }
+            const double dir = h[i].sg > 0.0 ? 1.0 : -1.0, s = fabs(h[i].sg);
+            const bool anchored = dir * bp < 0.0;
+            const double w = delta - bp;
+            const bool at = fabs(w) <= tol;
+            if (!at) { if (bp > delta) { if (bp < nR) nR = bp; } else { if (bp > nL) nL = bp; } }
+            const bool pos = dir * w > 0.0;                         // side of the hinge delta is on (if not at it)
+            const bool actR = at ? dir > 0.0 : pos, actL = at ? dir < 0.0 : pos;
+            if (!anchored) {
+                if (actR) sR += s;
+                if (actL) sL += s;
+                if (!at && pos) val += s * w;
+            } else {
+                if (!actR) sR -= s;
+                if (!actL) sL -= s;
+                if (!at && !pos) val -= s * w;
+            }
+        }
+    }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -86,17 +126,26 @@ DOPF_HD double root_monotone_pl(double c, double a, const HingeList &hl, double 
     if (fhi <= 0.0) return hi;
     double x = -c / a;
     if (!(x > lo && x < hi)) x = 0.5 * (lo + hi);
-    for (int it = 0; it < 200; ++it) {
-        hl.eval(x, v, s);
+    // walk piece by piece towards the root: f is linear between x and the next breakpoint on the side
+    // the root lies on, so either the Newton step of that piece is the exact root or the root lies
+    // beyond the breakpoint.  The direction never changes => at most n+1 evaluations.
+    const int cap = 2 * hl.n + 8;
+    for (int it = 0; it < cap; ++it) {
+        double sL, sR, nL, nR;
+        hl.eval2(x, v, sL, sR, nL, nR);
         const double f = c + a * x + v;
-        if (f == 0.0) return x;
-        if (f < 0.0) { lo = x; flo = f; } else { hi = x; fhi = f; }
-        double xn = x - f / (a + s);
-        if (!(xn > lo && xn < hi)) xn = lo - flo * (hi - lo) / (fhi - flo);   // secant inside bracket
-        if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
-        if (fabs(xn - x) <= 1e-15 * (1.0 + fabs(x))) return xn;
-        x = xn;
+        if (f == 0.0) { DOPF_COUNT(dopf_iters_root, it + 1); return x; }
+        if (f < 0.0) {
+            const double xn = x - f / (a + sR);
+            if (xn <= nR) { DOPF_COUNT(dopf_iters_root, it + 1); return xn < hi ? xn : hi; }
+            x = nR;
+        } else {
+            const double xn = x - f / (a + sL);
+            if (xn >= nL) { DOPF_COUNT(dopf_iters_root, it + 1); return xn > lo ? xn : lo; }
+            x = nL;
+        }
     }
+    DOPF_COUNT(dopf_iters_root, 201);
     return x;
 }
 
@@ -174,26 +223,46 @@ DOPF_HD StoEval sto_eval(const StoStep &st, const StoConst &k, const HingeList &
             // a hinge differs from its anchor state at this delta: safeguarded Newton on Psi with hinges,
             // started at the hinge-free solution; the bracket is built lazily from the iterates (Psi is
             // increasing with slope >= 1, so |Psi| bounds the distance to the root)
-            double lo = -1e300, hi = 1e300, flo = 0.0, fhi = 0.0;
-            bool have_lo = false, have_hi = false;
-            for (int it = 0; it < 200; ++it) {
+            // Same walk as root_monotone_pl, in nu: Psi is linear up to the next clip breakpoint of D, C
+            // or the next hinge breakpoint (delta falls when nu rises), whichever comes first.
+            const double bD0 = k.prox * (st.Db - k.pmax) - k.mc, bD1 = k.prox * st.Db - k.mc;
+            const double bC0 = k.mc - k.prox * st.Cb, bC1 = k.mc + k.prox * (k.pmax - st.Cb);
+            const double cb[4] = { bD0, bD1, bC0, bC1 };
+            const int cap = 2 * hl.n + 16;
+            int it = 0;
+            for (; it < cap; ++it) {
                 sto_dc_of_nu(st, k, nu, D, C, nf);
                 const double delta = (D - st.Db) - (C - st.Cb);
-                hl.eval(delta, v, sl);
+                double sLd, sRd, nLd, nRd;
+                hl.eval2(delta, v, sLd, sRd, nLd, nRd, 1e-15 * (1.0 + fabs(nu)) * k.iprox);   // a step to a hinge always moves nu
                 const double psi = nu - base - st.s1 * delta - v;
                 if (psi == 0.0) break;
-                if (psi < 0.0) { lo = nu; flo = psi; have_lo = true; } else { hi = nu; fhi = psi; have_hi = true; }
-                const double slope = 1.0 + (st.s1 + sl) * nf * k.iprox;
-                double nn = nu - psi / slope;
-                if (!(nn > lo && nn < hi)) {
-                    if (have_lo && have_hi) {
-                        nn = lo - flo * (hi - lo) / (fhi - flo);
-                        if (!(nn > lo && nn < hi)) nn = 0.5 * (lo + hi);
-                    } else nn = nu - psi;          // slope >= 1: the root lies within |psi| of nu
+                const bool up = psi < 0.0;                           // nu has to rise
+                const double tn = 1e-14 * (1.0 + fabs(nu));
+                int nfd = 0;                                         // free variables on the side of travel
+                double nb = up ? 1e300 : -1e300;                     // next breakpoint in nu on that side
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int q = 0; q < 2; ++q) {
+                    const double b0 = cb[2 * q], b1 = cb[2 * q + 1];
+                    const bool at0 = fabs(nu - b0) <= tn, at1 = fabs(nu - b1) <= tn;
+                    if (at0 && at1) continue;                        // pmax = 0: never free
+                    nfd += at0 ? up : (at1 ? !up : (nu > b0 && nu < b1));
+                    if (!at0 && (up ? (b0 > nu && b0 < nb) : (b0 < nu && b0 > nb))) nb = b0;
+                    if (!at1 && (up ? (b1 > nu && b1 < nb) : (b1 < nu && b1 > nb))) nb = b1;
                 }
-                if (fabs(nn - nu) <= 1e-15 * (1.0 + fabs(nu))) { nu = nn; break; }
-                nu = nn;
+                const double sld = up ? sLd : sRd, nbd = up ? nLd : nRd;
+                if (nfd > 0 && fabs(nbd) < 1e300) {
+                    const double nh = nu + (delta - nbd) * k.prox / nfd;
+                    if (up ? (nh > nu && nh < nb) : (nh < nu && nh > nb)) nb = nh;
+                }
+                const double slope = 1.0 + (st.s1 + sld) * nfd * k.iprox;
+                const double nn = nu - psi / slope;
+                if (up ? nn <= nb : nn >= nb) { nu = nn; break; }
+                nu = nb;
             }
+            DOPF_COUNT(dopf_iters_sto, it + 1);
             sto_dc_of_nu(st, k, nu, D, C, nf);
             hl.eval((D - st.Db) - (C - st.Cb), v, sl);
         }
