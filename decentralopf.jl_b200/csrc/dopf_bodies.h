@@ -230,57 +230,95 @@ DOPF_HD void body_sto_cold(const View &v, int s, const Hinge *hinges, const int 
 }
 
 // ---- verify: which agents at (n,t) moved across a slack hinge? --------------------------------
-DOPF_HD void body_verify(const View &v, int n, int t)
+// nearest hinge breakpoints (lo < 0 < hi) of the tight rows around delta = 0 that an agent of (n,t) can
+// have reached; false if there is none within the largest move of the node
+DOPF_HD bool verify_bounds(const View &v, int n, int t, double &lo, double &hi)
 {
-    const int cur = v.ctrl->cur, nxt = 1 - cur;
     const size_t nt = (size_t)n * v.ldt + t;
     const double dnt = bits_nonneg(v.dn[nt]);
-    if (dnt == 0.0) return;
-    double lo = -INFINITY, hi = INFINITY;   // nearest hinge breakpoints around delta = 0
+    if (dnt == 0.0) return false;
+    lo = -INFINITY; hi = INFINITY;
     const int cnt = v.tcnt[t];
     const int *lst = v.tight + (size_t)t * 2 * v.L;
     for (int j = 0; j < cnt; ++j) {
         const int l = lst[j] >> 1, side = lst[j] & 1;
         const double p = v.ptdf[(size_t)l * v.Np + n];
+        const double b = side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t];
+        if (fabs(b) > fabs(p) * dnt * (1.0 + 1e-12)) continue;      // |b/p| > dnt (without the division)
         Hinge h;
-        if (!make_hinge(v.c, p, side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t], side, h)) continue;
+        if (!make_hinge(v.c, p, b, side, h)) continue;
         if (fabs(h.bp) > dnt) continue;
         if (h.bp > 0.0) { if (h.bp < hi) hi = h.bp; }
         else if (h.bp < 0.0) { if (h.bp > lo) lo = h.bp; }
         else { if (h.sg > 0.0) hi = 0.0; else lo = 0.0; }
     }
-    if (lo == -INFINITY && hi == INFINITY) return;
-    for (int g = v.gen_ptr[n]; g < v.gen_ptr[n + 1]; ++g) {
-        const double d = sel(v.P, nxt)[(size_t)g * v.T + t] - sel(v.P, cur)[(size_t)g * v.T + t];
-        if (d > hi || d < lo) {
-            const int slot = DOPF_ATOMIC_ADD_I32(&v.ctrl->gen_work_cnt, 1);
-            if (slot < v.gen_work_cap) v.gen_work[slot] = g * v.T + t;
-            else v.ctrl->error = DOPF_ERR_WORK_CAP;
-        }
+    return !(lo == -INFINITY && hi == INFINITY);
+}
+DOPF_HD void verify_note_gen(const View &v, int g, int t)
+{
+    const int slot = DOPF_ATOMIC_ADD_I32(&v.ctrl->gen_work_cnt, 1);
+    if (slot < v.gen_work_cap) v.gen_work[slot] = g * v.T + t;
+    else v.ctrl->error = DOPF_ERR_WORK_CAP;
+}
+DOPF_HD void verify_note_sto(const View &v, int s)
+{
+    if (DOPF_ATOMIC_EXCH_I32(&v.sto_flag[s], 1) == 0) {
+        const int slot = DOPF_ATOMIC_ADD_I32(&v.ctrl->sto_work_cnt, 1);
+        v.sto_work[slot] = s;
     }
-    for (int s = v.sto_ptr[n]; s < v.sto_ptr[n + 1]; ++s) {
-        const size_t i = (size_t)s * v.T + t;
-        const double d = (sel(v.D, nxt)[i] - sel(v.D, cur)[i]) - (sel(v.C, nxt)[i] - sel(v.C, cur)[i]);
-        if (d > hi || d < lo) {
-            if (DOPF_ATOMIC_EXCH_I32(&v.sto_flag[s], 1) == 0) {
-                const int slot = DOPF_ATOMIC_ADD_I32(&v.ctrl->sto_work_cnt, 1);
-                v.sto_work[slot] = s;
-            }
-        }
-    }
+}
+DOPF_HD bool verify_gen_moved(const View &v, int g, int t, double lo, double hi)
+{
+    const int cur = v.ctrl->cur;
+    const double d = sel(v.P, 1 - cur)[(size_t)g * v.T + t] - sel(v.P, cur)[(size_t)g * v.T + t];
+    return d > hi || d < lo;
+}
+DOPF_HD bool verify_sto_moved(const View &v, int s, int t, double lo, double hi)
+{
+    const int cur = v.ctrl->cur, nxt = 1 - cur;
+    const size_t i = (size_t)s * v.T + t;
+    const double d = (sel(v.D, nxt)[i] - sel(v.D, cur)[i]) - (sel(v.C, nxt)[i] - sel(v.C, cur)[i]);
+    return d > hi || d < lo;
+}
+DOPF_HD void body_verify(const View &v, int n, int t)
+{
+    double lo, hi;
+    if (!verify_bounds(v, n, t, lo, hi)) return;
+    for (int g = v.gen_ptr[n]; g < v.gen_ptr[n + 1]; ++g) if (verify_gen_moved(v, g, t, lo, hi)) verify_note_gen(v, g, t);
+    for (int s = v.sto_ptr[n]; s < v.sto_ptr[n + 1]; ++s) if (verify_sto_moved(v, s, t, lo, hi)) verify_note_sto(v, s);
 }
 
 // ---- nodal injection of the new iterate (results.jl:64,88-106) --------------------------------
-DOPF_HD void body_inject(const View &v, int n, int t)
+// injection of (n,t) and the node statistics st[0..7] of the moves (see View::nst)
+DOPF_HD double inject_compute(const View &v, int n, int t, double (&st)[8])
 {
     const int cur = v.ctrl->cur, nxt = 1 - cur;
     double a = 0.0;
     double lo = 0.0, hi = 0.0, inneg = -INFINITY, inpos = INFINITY, sneg = 0.0, spos = 0.0, cneg = 0.0, cpos = 0.0;
     if (n < v.N && t < v.T) {
         a = v.demand_on ? -v.demand[(size_t)n * v.ldt + t] : 0.0;
-        for (int g = v.gen_ptr[n]; g < v.gen_ptr[n + 1]; ++g) {
+        const double *Pn = sel(v.P, nxt), *Pc = sel(v.P, cur);
+        const int g1 = v.gen_ptr[n + 1];
+        int g = v.gen_ptr[n];
+        for (; g + 4 <= g1; g += 4) {                 // all 8 loads in flight before the dependent chain
+            double pn[4], pc[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int u = 0; u < 4; ++u) { pn[u] = Pn[(size_t)(g + u) * v.T + t]; pc[u] = Pc[(size_t)(g + u) * v.T + t]; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int u = 0; u < 4; ++u) {
+                const double d = pn[u] - pc[u];
+                a += pn[u];
+                if (d < 0.0) { lo = d < lo ? d : lo; inneg = d > inneg ? d : inneg; sneg += d; cneg += 1.0; }
+                else if (d > 0.0) { hi = d > hi ? d : hi; inpos = d < inpos ? d : inpos; spos += d; cpos += 1.0; }
+            }
+        }
+        for (; g < g1; ++g) {
             const size_t o = (size_t)g * v.T + t;
-            const double pn = sel(v.P, nxt)[o], d = pn - sel(v.P, cur)[o];
+            const double pn = Pn[o], d = pn - Pc[o];
             a += pn;
             if (d < 0.0) { lo = d < lo ? d : lo; inneg = d > inneg ? d : inneg; sneg += d; cneg += 1.0; }
             else if (d > 0.0) { hi = d > hi ? d : hi; inpos = d < inpos ? d : inpos; spos += d; cpos += 1.0; }
@@ -294,10 +332,15 @@ DOPF_HD void body_inject(const View &v, int n, int t)
             else if (d > 0.0) { hi = d > hi ? d : hi; inpos = d < inpos ? d : inpos; spos += d; cpos += 1.0; }
         }
     }
-    sel(v.injloc, nxt)[(size_t)n * v.ldt + t] = a;
+    st[0] = lo; st[1] = hi; st[2] = inneg; st[3] = inpos; st[4] = sneg; st[5] = spos; st[6] = cneg; st[7] = cpos;
+    return a;
+}
+DOPF_HD void body_inject(const View &v, int n, int t)
+{
+    double st[8];
+    sel(v.injloc, 1 - v.ctrl->cur)[(size_t)n * v.ldt + t] = inject_compute(v, n, t, st);
     const size_t i = (size_t)t * v.Np + n;
-    v.nst[0][i] = lo; v.nst[1][i] = hi; v.nst[2][i] = inneg; v.nst[3][i] = inpos;
-    v.nst[4][i] = sneg; v.nst[5][i] = spos; v.nst[6][i] = cneg; v.nst[7][i] = cpos;
+    for (int k = 0; k < 8; ++k) v.nst[k][i] = st[k];
 }
 
 // closed form of sum_i (b + sp*delta_i)_+ over the agents of node n at time t from the node statistics;

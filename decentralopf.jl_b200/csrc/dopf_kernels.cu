@@ -472,13 +472,35 @@ __global__ void __launch_bounds__(32) k_sto_fix(View v, Hinge *hinge_scratch, in
 // ------------------------------------------------------------------------------------------------
 // verify: lanes along nodes (PTDF rows are node-contiguous), 8 timesteps per block
 // ------------------------------------------------------------------------------------------------
-__global__ void k_verify(View v)
+__global__ void __launch_bounds__(256) k_verify(View v)
 {
     if (!DOPF_ACTIVE(v)) return;
-    const int n = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int t = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (n >= v.N || t >= v.T) return;
-    body_verify(v, n, t);
+    // phase 1 (lanes along the nodes): hinge bounds of (n,t); phase 2: the few (n,t) with a hinge in reach
+    // are queued and their agents checked with the lanes along the agents
+    __shared__ int qn[256], qcnt;
+    __shared__ double qlo[256], qhi[256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + lane;
+    const int t = blockIdx.y * (blockDim.x >> 5) + warp;
+    if (threadIdx.x == 0) qcnt = 0;
+    __syncthreads();
+    if (n < v.N && t < v.T) {
+        double lo, hi;
+        if (verify_bounds(v, n, t, lo, hi)) {
+            const int q = atomicAdd(&qcnt, 1);
+            qn[q] = n * 8 + warp; qlo[q] = lo; qhi[q] = hi;
+        }
+    }
+    __syncthreads();
+    const int total = qcnt;
+    for (int q = warp; q < total; q += (blockDim.x >> 5)) {
+        const int nn = qn[q] >> 3, tt = blockIdx.y * (blockDim.x >> 5) + (qn[q] & 7);
+        const double lo = qlo[q], hi = qhi[q];
+        for (int g = v.gen_ptr[nn] + lane; g < v.gen_ptr[nn + 1]; g += 32)
+            if (verify_gen_moved(v, g, tt, lo, hi)) verify_note_gen(v, g, tt);
+        for (int s = v.sto_ptr[nn] + lane; s < v.sto_ptr[nn + 1]; s += 32)
+            if (verify_sto_moved(v, s, tt, lo, hi)) verify_note_sto(v, s);
+    }
 }
 
 // exact re-solve of the generators on the work list: one warp per (agent, t)
@@ -520,12 +542,25 @@ __global__ void k_gen_fix(View v)
 // ------------------------------------------------------------------------------------------------
 // aggregation ("coordinator gather", results.jl:55-106): injection and its column sums
 // ------------------------------------------------------------------------------------------------
-__global__ void k_inject(View v)
+// block = 8 nodes x 32 timesteps: warp w sums the agents of node 8*blockIdx.x+w with the lanes along t (the
+// agent arrays are t-contiguous); the node statistics are stored timestep-major ([ldt][Np], read along the
+// nodes by k_slack_rows), so they go through a shared-memory transpose and leave as 64-byte runs.
+__global__ void __launch_bounds__(256) k_inject(View v)
 {
     if (!DOPF_ACTIVE(v)) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= v.Np * v.ldt) return;
-    body_inject(v, i / v.ldt, i % v.ldt);
+    __shared__ double tile[8][32][9];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n = blockIdx.x * 8 + w, t = blockIdx.y * 32 + lane;
+    double st[8];
+    const double a = inject_compute(v, n, t, st);
+    sel(v.injloc, 1 - v.ctrl->cur)[(size_t)n * v.ldt + t] = a;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tile[k][lane][w] = st[k];
+    __syncthreads();
+    const int tt = threadIdx.x >> 3, nn = threadIdx.x & 7;
+    const size_t o = (size_t)(blockIdx.y * 32 + tt) * v.Np + blockIdx.x * 8 + nn;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.nst[k][o] = tile[k][tt][nn];
 }
 
 // dmax[t] = largest move of any agent at timestep t = column maximum of dn (bit patterns of
@@ -818,7 +853,7 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     XCHG(DOPF_X_DMAX);   // all ranks must build the same tight lists
     LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 1));   // moves may have grown
     LAUNCH(k_clear_tflag<<<cdiv((long long)v.Lp * v.ldt / 4, 256), 256, 0, cs>>>(v, lp.tflag));
-    LAUNCH(k_inject<<<cdiv((long long)v.Np * v.ldt, 256), 256, 0, cs>>>(v));
+    LAUNCH(k_inject<<<dim3(v.Np / 8, v.ldt / 32), 256, 0, cs>>>(v));
     XCHG(DOPF_X_INJ);    // nodal injection of all ranks' agents
     FORK();   // the slack sums need the local injection, not the flows: they overlap the flow product
     LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.T), 128, 0, cs>>>(v, lp.tflag));
@@ -890,7 +925,7 @@ __global__ void k_flip(View v) { v.ctrl->cur = 1 - v.ctrl->cur; }
 void launch_rebuild_derived(const LaunchPlan &lp, cudaStream_t st, int segment)
 {
     const View &v = lp.view;
-    if (segment <= 0) k_inject<<<cdiv((long long)v.Np * v.ldt, 256), 256, 0, st>>>(v);
+    if (segment <= 0) k_inject<<<dim3(v.Np / 8, v.ldt / 32), 256, 0, st>>>(v);
     if (segment == 0) return;
     k_colsum<<<v.ldt / 32, dim3(32, 32), 0, st>>>(v);
     dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);
