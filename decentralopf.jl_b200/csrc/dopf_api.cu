@@ -100,7 +100,6 @@ void fill_status(dopf_handle *h, dopf_status *s)
     s->launches_per_iteration = h->launches_per_iter;
     s->sto_cold = c.stat_sto_cold;
     s->reserved2 = c.stat_fix_seq;
-    if (getenv("DOPF_DEBUG")) fprintf(stderr, "[dopf] pairs %d | sto_fix max cycles collect %llu total %llu work %d | gen_fix max cycles total %llu work %d maxhinges %d | sto_fix solve: max AS %d newton passes %d slow evals %d cycles(loop) %llu\n", c.pair_cnt, c.dbg_cyc[0], c.dbg_cyc[1], c.sto_work_cnt, c.dbg_cyc[3], c.gen_work_cnt, c.dbg_hmax, c.dbg_i[0], c.dbg_i[1], c.dbg_i[2], c.dbg_cyc[2]);
     s->last_step_ms = h->last_step_ms;
 }
 

@@ -43,9 +43,6 @@ struct Ctrl {
     int gen_work_cnt, sto_work_cnt, cold_work_cnt, pair_cnt;
     int stat_sto_cold;                   // storages solved by the cold funnel in the last iteration
     int stat_fix_seq;                    // cumulated correction-pass storages that needed the sequential solver
-    int dbg_hmax, dbg_pad;
-    int dbg_i[4];
-    unsigned long long dbg_cyc[4];       // debug: max cycles of the k_sto_fix phases (collect, solve) and totals
     int stat_gen_fix, stat_sto_fix;      // cumulated corrected agents (statistics)
     int stat_tight_rows, stat_wide_rows; // of the last iteration
     unsigned long long res_bits[3];      // max |dual_{k+1}-dual_k| for lambda, mue, rho (bits)

@@ -13,31 +13,15 @@ namespace dopf {
 #define DOPF_ACTIVE(v) ((v).ctrl->converged == 0 && (v).ctrl->error == 0)
 
 // ------------------------------------------------------------------------------------------------
-// iteration prologue: reset per-iteration counters
-// ------------------------------------------------------------------------------------------------
-__global__ void k_begin(View v)
-{
-    if (!DOPF_ACTIVE(v)) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) {
-        v.ctrl->gen_work_cnt = 0; v.ctrl->sto_work_cnt = 0; v.ctrl->cold_work_cnt = 0; v.ctrl->pair_cnt = 0;
-        v.ctrl->res_bits[0] = v.ctrl->res_bits[1] = v.ctrl->res_bits[2] = 0ull;
-        v.ctrl->dbg_cyc[0] = v.ctrl->dbg_cyc[1] = v.ctrl->dbg_cyc[2] = v.ctrl->dbg_cyc[3] = 0ull; v.ctrl->dbg_hmax = 0; v.ctrl->dbg_i[0] = v.ctrl->dbg_i[1] = v.ctrl->dbg_i[2] = v.ctrl->dbg_i[3] = 0;
-    }
-    for (int k = i; k < v.Np * v.ldt; k += gridDim.x * blockDim.x) v.dn[k] = 0ull;
-    for (int k = i; k < v.ldt; k += gridDim.x * blockDim.x) v.dmax[k] = 0ull;
-    for (int k = i; k < v.S; k += gridDim.x * blockDim.x) v.sto_flag[k] = 0;
-}
-
-// ------------------------------------------------------------------------------------------------
 // row preparation over the padded [Lp][ldt] grid (coalesced along t)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_row_prep(View v)
+__global__ void k_row_prep(View v, unsigned char *tflag)
 {
     if (!DOPF_ACTIVE(v)) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= v.Lp * v.ldt) return;
     body_row_prep(v, i / v.ldt, i % v.ldt);
+    tflag[i] = 0; v.rowsumU[i] = 0.0; v.rowsumK[i] = 0.0;      // exact-slack-sum marks of this iteration (k_slack_rows)
 }
 
 // ordered compaction of the candidate rows of one timestep; one block (8 warps) per t: every warp
@@ -222,7 +206,16 @@ __global__ void k_node_prep(View v, const double *Cpart, const double *C2part, i
 {
     if (!DOPF_ACTIVE(v)) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // iteration prologue: reset the per-iteration counters, move maxima and work flags (nothing before this
+    // kernel in the iteration touches them)
+    if (i == 0) {
+        v.ctrl->gen_work_cnt = 0; v.ctrl->sto_work_cnt = 0; v.ctrl->cold_work_cnt = 0; v.ctrl->pair_cnt = 0;
+        v.ctrl->res_bits[0] = v.ctrl->res_bits[1] = v.ctrl->res_bits[2] = 0ull;
+    }
+    if (i < v.ldt) v.dmax[i] = 0ull;
+    for (int k = i; k < v.S; k += gridDim.x * blockDim.x) v.sto_flag[k] = 0;
     if (i >= v.Np * v.ldt) return;
+    v.dn[i] = 0ull;
     const int n = i / v.ldt, t = i % v.ldt, cur = v.ctrl->cur;
     double a = 0.0, b = 0.0;
     for (int z = 0; z < ksplit; ++z) { a += Cpart[(size_t)z * v.Np * v.ldt + i]; b += C2part[(size_t)z * v.Np * v.ldt + i]; }
@@ -514,14 +507,12 @@ __global__ void k_gen_fix(View v)
     const int gw = blockIdx.x * (blockDim.x >> 5) + wib, nw = gridDim.x * (blockDim.x >> 5);
     const int total = min(v.ctrl->gen_work_cnt, v.gen_work_cap);
     for (int w = gw; w < total; w += nw) {
-        const long long c0 = clock64();
         const int g = v.gen_work[w] / v.T, t = v.gen_work[w] % v.T;
         const int n = v.gen_node[g];
         const double Pb = sel(v.P, cur)[(size_t)g * v.T + t], pmax = v.gen_pmax[g];
         const double lo = -Pb, hi = pmax - Pb;
         int cnt = collect_hinges(v, n, t, lo, hi, lists[wib], CAP);
         __syncwarp();
-        const long long c1 = clock64();
         if (cnt > CAP) { if (lane == 0) v.ctrl->error = DOPF_ERR_HINGE_CAP; cnt = CAP; }
         if (lane == 0) {
             HingeList hl; hl.h = lists[wib]; hl.n = cnt; hl.sorted = false;
@@ -532,8 +523,6 @@ __global__ void k_gen_fix(View v)
             sel(v.P, nxt)[(size_t)g * v.T + t] = Pn;
             note_move(v, n, t, Pn - Pb);
             atomicAdd(&v.ctrl->stat_gen_fix, 1);
-            atomicMax(&v.ctrl->dbg_cyc[3], (unsigned long long)(clock64() - c0));
-            atomicMax(&v.ctrl->dbg_hmax, cnt);
         }
         __syncwarp();
     }
@@ -577,7 +566,7 @@ __global__ void k_dmax(View v)
     if (threadIdx.y == 0) {
         unsigned long long m = 0ull;
         for (int k = 0; k < 32; ++k) m = part[k][threadIdx.x] > m ? part[k][threadIdx.x] : m;
-        if (m > v.dmax[t]) atomicMax(v.dmax + t, m);     // dmax is zeroed by k_begin and only grows within an iteration
+        if (m > v.dmax[t]) atomicMax(v.dmax + t, m);     // dmax is zeroed by k_node_prep and only grows within an iteration
     }
 }
 
@@ -665,14 +654,6 @@ __global__ void __launch_bounds__(256) k_slack_pairs(View v)
     }
 }
 
-__global__ void k_clear_tflag(View v, unsigned char *tflag)
-{
-    if (!DOPF_ACTIVE(v)) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < v.Lp * v.ldt / 4) reinterpret_cast<unsigned int *>(tflag)[i] = 0u;
-    for (int k = i; k < v.Lp * v.ldt; k += gridDim.x * blockDim.x) { v.rowsumU[k] = 0.0; v.rowsumK[k] = 0.0; }
-}
-
 // dual update + residual maxima (update_duals.jl, convergence.jl:3-12)
 __global__ void __launch_bounds__(256) k_dual(View v, const unsigned char *tflag)
 {
@@ -702,24 +683,32 @@ __global__ void __launch_bounds__(256) k_dual(View v, const unsigned char *tflag
     }
 }
 
-__global__ void k_lambda(View v)
+// lambda update (update_duals.jl:2-9) with its residual, then the convergence check and the buffer flip
+__global__ void __launch_bounds__(256) k_lambda_finish(View v)
 {
     if (!DOPF_ACTIVE(v)) return;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= v.T) return;
-    const double r = body_lambda(v, t);
-    if (r > 0.0) atomicMax(&v.ctrl->res_bits[0], nonneg_bits(r));
-}
-
-__global__ void k_finish(View v)
-{
-    if (!DOPF_ACTIVE(v)) return;
-    v.ctrl->stat_tight_rows = 0;
-    for (int t = 0; t < v.T; ++t) { v.ctrl->stat_tight_rows += v.tcnt[t]; }
-    int wr = 0;
-    for (int t = 0; t < v.T; ++t) wr += v.wcnt[t];
-    v.ctrl->stat_wide_rows = wr;
-    body_finish(v);
+    __shared__ unsigned long long rb[8];
+    __shared__ int ct[8], cw[8];
+    unsigned long long r = 0ull;
+    int nt = 0, nw = 0;
+    for (int t = threadIdx.x; t < v.T; t += blockDim.x) {
+        const double x = body_lambda(v, t);
+        if (x > 0.0) { const unsigned long long b = nonneg_bits(x); r = b > r ? b : r; }
+        nt += v.tcnt[t]; nw += v.wcnt[t];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long ro = __shfl_xor_sync(0xffffffffu, r, o);
+        r = ro > r ? ro : r;
+        nt += __shfl_xor_sync(0xffffffffu, nt, o); nw += __shfl_xor_sync(0xffffffffu, nw, o);
+    }
+    if ((threadIdx.x & 31) == 0) { rb[threadIdx.x >> 5] = r; ct[threadIdx.x >> 5] = nt; cw[threadIdx.x >> 5] = nw; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) { r = rb[k] > r ? rb[k] : r; nt += ct[k]; nw += cw[k]; }
+        v.ctrl->res_bits[0] = r;
+        v.ctrl->stat_tight_rows = nt; v.ctrl->stat_wide_rows = nw;
+        body_finish(v);
+    }
 }
 
 // total_costs (results.jl:95-105) - on demand only
@@ -794,8 +783,7 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
         if (prof_) { cudaEventRecord(lp.prof_events[2 * launches + 1], cs); lp.prof_names[launches] = #__VA_ARGS__; } \
         ++launches;                                                                                \
     } while (0)
-    LAUNCH(k_begin<<<lp.num_sms, 256, 0, cs>>>(v));
-    LAUNCH(k_row_prep<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, cs>>>(v));
+    LAUNCH(k_row_prep<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, cs>>>(v, lp.tflag));
     LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 0));
     {   // PTDF^T M and (PTDF.^2)^T W
         dim3 grid(v.Np / lp.bm_t, v.ldt / BN, lp.ksplit_t);
@@ -852,7 +840,6 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     LAUNCH(k_dmax<<<dim3(v.ldt / 32, 16), dim3(32, 32), 0, cs>>>(v));
     XCHG(DOPF_X_DMAX);   // all ranks must build the same tight lists
     LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 1));   // moves may have grown
-    LAUNCH(k_clear_tflag<<<cdiv((long long)v.Lp * v.ldt / 4, 256), 256, 0, cs>>>(v, lp.tflag));
     LAUNCH(k_inject<<<dim3(v.Np / 8, v.ldt / 32), 256, 0, cs>>>(v));
     XCHG(DOPF_X_INJ);    // nodal injection of all ranks' agents
     FORK();   // the slack sums need the local injection, not the flows: they overlap the flow product
@@ -869,8 +856,7 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     JOIN();
     XCHG(DOPF_X_ROWSUM); // exact slack sums over all ranks' agents
     LAUNCH(k_dual<<<cdiv((long long)v.L * v.ldt, 256), 256, 0, cs>>>(v, lp.tflag));
-    LAUNCH(k_lambda<<<cdiv(v.T, 128), 128, 0, cs>>>(v));
-    LAUNCH(k_finish<<<1, 1, 0, cs>>>(v));
+    LAUNCH(k_lambda_finish<<<1, 256, 0, cs>>>(v));
 #undef LAUNCH
 #undef XCHG
 #undef FORK

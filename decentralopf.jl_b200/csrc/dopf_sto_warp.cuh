@@ -299,10 +299,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
 
     double D[J], C[J], pre[J];
     bool accepted = false;
-    int dbg_newton = 0, dbg_slow = 0;
-    const long long dbg_c0 = clock64();
     for (int as_it = 0; as_it < 24 && !accepted; ++as_it) {
-        if (HINGES && lane == 0) atomicMax(&v.ctrl->dbg_i[0], as_it + 1);
         // ---- run structure from the anchors (timesteps beyond T are isolated one-element runs) ------
         bool head[J], tail[J];
         int prevk[J], endk[J];
@@ -346,7 +343,6 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
         for (int j = 0; j < J; ++j) { lo[j] = -WBIG; hi[j] = WBIG; totd[j] = 0.0; rs[j] = valid[j] ? 0 : RS_CONV; }
         bool capped = true;
         for (int it = 0; it < 24; ++it) {
-            ++dbg_newton;
             double dy[J];
 #pragma unroll
             for (int j = 0; j < J; ++j) {
@@ -356,7 +352,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
                         // the hinge-free solution is exact unless a hinge differs from its anchor state at this delta
                         double hv, hs;
                         hl[j].eval((e.D - st[j].Db) - (e.C - st[j].Cb), hv, hs);
-                        if (hv != 0.0 || hs != 0.0) { e = sto_eval(st[j], k, hl[j], eta[j]); ++dbg_slow; }
+                        if (hv != 0.0 || hs != 0.0) e = sto_eval(st[j], k, hl[j], eta[j]);
                     }
                     D[j] = e.D; C[j] = e.C; pre[j] = e.C - e.D; dy[j] = e.dy;
                 } else { D[j] = C[j] = pre[j] = dy[j] = 0.0; }
@@ -512,7 +508,6 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
         }
     }
     if (!accepted) return false;
-    if (HINGES) { dbg_slow = __reduce_add_sync(FULL, dbg_slow); if (lane == 0) { atomicMax(&v.ctrl->dbg_i[1], dbg_newton); atomicMax(&v.ctrl->dbg_i[2], dbg_slow); atomicMax(&v.ctrl->dbg_cyc[2], (unsigned long long)(clock64() - dbg_c0)); } }
 
     // ---- emit: stage the results in shared memory and write them out coalesced ---------------------------
     __syncwarp();
