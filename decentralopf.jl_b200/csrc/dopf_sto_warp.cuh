@@ -18,9 +18,9 @@
 //
 // Cost structure: (a) a segmented scan is an in-register pass over the lane's J elements plus ONE
 // 32-wide cross-lane scan of the lane aggregates; (b) everything of a timestep that does not depend
-// on eta - the sorted clip breakpoints of D(nu), C(nu) and delta at those breakpoints - is tabulated
-// once per storage in shared memory, so an evaluation is four FMAs, a select, one interpolation and
-// one clip.
+// on eta - the sorted clip breakpoints of D(nu), C(nu), the eta-thresholds at which nu(eta) passes them
+// and the inverse slopes in between - is tabulated once per storage in shared memory, so an evaluation
+// is four comparisons, one interpolation (no division) and one clip.
 #ifndef DOPF_STO_WARP_CUH
 #define DOPF_STO_WARP_CUH
 
@@ -160,80 +160,87 @@ __device__ __forceinline__ bool any_of(const bool (&p)[J])
 }
 
 // ---- per-timestep clip table (independent of eta) ---------------------------------------------------------
-// bb[0..3]: sorted breakpoints of D(nu), C(nu);  dl[0..3]: delta = (D-Db)-(C-Cb) at those breakpoints.
-// Stored component-major in shared memory: comp c of timestep t at tab[c*tstride + t] (conflict-free).
-struct ClipTab { double bb[4], dl[4]; };
+// Psi(nu) = nu - (g0 - eta) - s1*delta(nu) is piecewise linear with the four clip breakpoints bb[0..3] of
+// D(nu), C(nu); Psi(bb[i]) = eta - e[i] with the eta-thresholds e[i] = g0 + s1*dl[i] - bb[i] (non-increasing in
+// i, dl[i] = delta at bb[i]).  An evaluation therefore is: compare eta with e[0..3], interpolate nu on that
+// piece with the tabulated inverse slope, clip D and C.  Components (component-major in shared memory, comp c
+// of timestep t at tab[c*tstride + t], conflict-free):
+//   0-3 e | 4-7 bb | 8-10 isl (inverse slope of Psi on the inner pieces) | 11,12 dy for 1, 2 free variables
+//   13-16 dl | 17 g0 | 18 s1
+constexpr int TAB_E = 0, TAB_BB = 4, TAB_ISL = 8, TAB_DY = 11, TAB_DL = 13, TAB_G0 = 17, TAB_S1 = 18, TAB_COMPS = 19;
 
-__device__ __forceinline__ void clip_tab_build(const StoStep &st, const StoConst &k, ClipTab &c)
+__device__ __forceinline__ void clip_tab_build(const StoStep &st, const StoConst &k, double *tab, int tstride, int t)
 {
     double b0 = k.prox * (st.Db - k.pmax) - k.mc, b1 = k.prox * st.Db - k.mc;
     double b2 = k.mc - k.prox * st.Cb, b3 = k.mc + k.prox * (k.pmax - st.Cb);
-    double t;
-    if (b0 > b2) { t = b0; b0 = b2; b2 = t; }
-    if (b1 > b3) { t = b1; b1 = b3; b3 = t; }
-    if (b1 > b2) { t = b1; b1 = b2; b2 = t; }
-    c.bb[0] = b0; c.bb[1] = b1; c.bb[2] = b2; c.bb[3] = b3;
+    double x;
+    if (b0 > b2) { x = b0; b0 = b2; b2 = x; }
+    if (b1 > b3) { x = b1; b1 = b3; b3 = x; }
+    if (b1 > b2) { x = b1; b1 = b2; b2 = x; }
+    const double bb[4] = { b0, b1, b2, b3 };
+    double e[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         double D, C; int nf;
-        sto_dc_of_nu(st, k, c.bb[i], D, C, nf);
-        c.dl[i] = (D - st.Db) - (C - st.Cb);
+        sto_dc_of_nu(st, k, bb[i], D, C, nf);
+        const double dl = (D - st.Db) - (C - st.Cb);
+        e[i] = st.g0 + st.s1 * dl - bb[i];
+        tab[(TAB_E + i) * tstride + t] = e[i]; tab[(TAB_BB + i) * tstride + t] = bb[i]; tab[(TAB_DL + i) * tstride + t] = dl;
     }
-}
-__device__ __forceinline__ ClipTab clip_tab_load(const double *tab, int tstride, int t)
-{
-    ClipTab c;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { c.bb[i] = tab[i * tstride + t]; c.dl[i] = tab[(4 + i) * tstride + t]; }
-    return c;
+    for (int f = 0; f < 3; ++f)
+        tab[(TAB_ISL + f) * tstride + t] = (e[f] == e[f + 1]) ? 0.0 : (bb[f + 1] - bb[f]) / (e[f] - e[f + 1]);
+    tab[(TAB_DY + 0) * tstride + t] = -1.0 / (k.prox + st.s1);
+    tab[(TAB_DY + 1) * tstride + t] = -2.0 / (k.prox + 2.0 * st.s1);
+    tab[TAB_G0 * tstride + t] = st.g0; tab[TAB_S1 * tstride + t] = st.s1;
 }
 // same result as sto_eval() for a hinge-free step
-__device__ __forceinline__ StoEval eval_tab(const StoStep &st, const StoConst &k, const ClipTab &c, double eta)
+__device__ __forceinline__ StoEval eval_tab(const StoStep &st, const StoConst &k, const double *tab, int tstride, int t, double eta)
 {
-    const double base = st.g0 - eta;
-    double psi[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) psi[i] = c.bb[i] - base - st.s1 * c.dl[i];
-    double nu;
-    if (psi[0] >= 0.0) nu = c.bb[0] - psi[0];
-    else if (psi[3] <= 0.0) nu = c.bb[3] - psi[3];
-    else {
-        const int f = psi[1] >= 0.0 ? 0 : (psi[2] >= 0.0 ? 1 : 2);
-        const double pl = c.bb[f], pv = psi[f], ql = c.bb[f + 1], qv = psi[f + 1];
-        nu = (qv == pv) ? pl : pl - pv * (ql - pl) / (qv - pv);
-    }
+    const double e0 = tab[(TAB_E + 0) * tstride + t], e1 = tab[(TAB_E + 1) * tstride + t];
+    const double e2 = tab[(TAB_E + 2) * tstride + t], e3 = tab[(TAB_E + 3) * tstride + t];
+    // anchor breakpoint a and piece: left of all (slope 1), right of all (slope 1), inner piece f = a
+    const bool left = eta >= e0, right = !left && eta <= e3;
+    const int a = left ? 0 : (right ? 3 : (eta >= e1 ? 0 : (eta >= e2 ? 1 : 2)));
+    const double ae = a == 0 ? e0 : (a == 1 ? e1 : (a == 2 ? e2 : e3));
+    const double ab = tab[(TAB_BB + a) * tstride + t];
+    const double as = (left || right) ? 1.0 : tab[(TAB_ISL + a) * tstride + t];
+    const double nu = ab - (eta - ae) * as;
     StoEval r; int nf;
     sto_dc_of_nu(st, k, nu, r.D, r.C, nf);
-    r.dy = -(double)nf / (k.prox + st.s1 * nf);
+    r.dy = nf == 0 ? 0.0 : tab[(TAB_DY + nf - 1) * tstride + t];
     return r;
 }
 // nearest eta-breakpoint strictly beyond eta (same as sto_next_break)
-__device__ __forceinline__ void next_breaks_tab(const StoStep &st, const ClipTab &c, double eta, double &up, double &dn)
+__device__ __forceinline__ void next_breaks_tab(const double *tab, int tstride, int t, double eta, double &up, double &dn)
 {
     up = WBIG; dn = -WBIG;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const double e = st.g0 + st.s1 * c.dl[i] - c.bb[i];
+        const double e = tab[(TAB_E + i) * tstride + t];
         if (e > eta && e < up) up = e;
         if (e < eta && e > dn) dn = e;
     }
 }
 // maximal eta-interval around eta on which y_t stays constant (same as sto_flat_interval)
-__device__ __forceinline__ void flat_interval_tab(const StoStep &st, const ClipTab &c, double eta, double D, double C, double &ilo, double &ihi)
+__device__ __forceinline__ void flat_interval_tab(const StoStep &st, const double *tab, int tstride, int t, double eta, double D, double C, double &ilo, double &ihi)
 {
     ilo = ihi = eta;
-    const double nu = st.g0 - eta + st.s1 * ((D - st.Db) - (C - st.Cb));
+    const double g0 = tab[TAB_G0 * tstride + t], s1 = tab[TAB_S1 * tstride + t];
+    const double nu = g0 - eta + s1 * ((D - st.Db) - (C - st.Cb));
     const double tol = 1e-10 * (1.0 + fabs(nu));
+    double bb[4], dl[4], e[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { bb[i] = tab[(TAB_BB + i) * tstride + t]; dl[i] = tab[(TAB_DL + i) * tstride + t]; e[i] = tab[(TAB_E + i) * tstride + t]; }
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         const bool linf = j == 0, rinf = j == 4;
-        const double plo = linf ? 0.0 : c.bb[j - 1], phi = rinf ? 0.0 : c.bb[j];
+        const double plo = linf ? 0.0 : bb[j - 1], phi = rinf ? 0.0 : bb[j];
         if (!linf && nu < plo - tol) continue;
         if (!rinf && nu > phi + tol) continue;
-        if (!linf && !rinf && (!(phi > plo) || c.dl[j - 1] != c.dl[j])) continue;   // a variable is free on this piece
-        const double dl = linf ? c.dl[0] : c.dl[j - 1];
-        const double eh = linf ? WBIG : st.g0 + st.s1 * dl - plo;
-        const double el = rinf ? -WBIG : st.g0 + st.s1 * dl - phi;
+        if (!linf && !rinf && (!(phi > plo) || dl[j - 1] != dl[j])) continue;   // a variable is free on this piece
+        const double eh = linf ? WBIG : e[j - 1];
+        const double el = rinf ? -WBIG : e[j];
         ilo = el < ilo ? el : ilo; ihi = eh > ihi ? eh : ihi;
     }
 }
@@ -241,8 +248,8 @@ __device__ __forceinline__ void flat_interval_tab(const StoStep &st, const ClipT
 // run status bits broadcast from the tail
 enum { RS_CONV = 1, RS_BAD = 2, RS_FLAT = 4, RS_EMPTY = 8, RS_FREEBAD = 16 };
 
-// shared memory per warp: 8 doubles per timestep (clip table)
-__host__ __device__ inline size_t sto_warp_smem_per_warp(int T) { return (size_t)8 * (size_t)((T + 1) | 1) * sizeof(double); }
+// shared memory per warp: the clip table (19 doubles per timestep)
+__host__ __device__ inline size_t sto_warp_smem_per_warp(int T) { return (size_t)19 * (size_t)((T + 1) | 1) * sizeof(double); }
 
 // returns true if the storage was solved and written; false => caller queues it for the exact sequential solver
 template <int J, bool HINGES>
@@ -286,15 +293,8 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
     }
     __syncwarp();
 #pragma unroll
-    for (int j = 0; j < J; ++j) {                  // clip tables (overwrite the staging area)
-        ClipTab c;
-        clip_tab_build(st[j], k, c);
-        const int t = lane * J + j;
-        if (valid[j]) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { tab[i * tstride + t] = c.bb[i]; tab[(4 + i) * tstride + t] = c.dl[i]; }
-        }
-    }
+    for (int j = 0; j < J; ++j)                    // clip tables (overwrite the staging area)
+        if (valid[j]) clip_tab_build(st[j], k, tab, tstride, lane * J + j);
     __syncwarp();
 
     double D[J], C[J], pre[J];
@@ -347,7 +347,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 if (valid[j]) {
-                    StoEval e = eval_tab(st[j], k, clip_tab_load(tab, tstride, lane * J + j), eta[j]);
+                    StoEval e = eval_tab(st[j], k, tab, tstride, lane * J + j, eta[j]);
                     if (HINGES && hl[j].n != 0) {
                         // the hinge-free solution is exact unless a hinge differs from its anchor state at this delta
                         double hv, hs;
@@ -380,7 +380,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
                     bu[j] = WBIG; bd[j] = -WBIG;
                     if (valid[j]) {
                         if (hl[j].n != 0) { bu[j] = -WBIG; bd[j] = WBIG; }             // hinge on a flat run: not handled here
-                        else next_breaks_tab(st[j], clip_tab_load(tab, tstride, lane * J + j), eta[j], bu[j], bd[j]);
+                        else next_breaks_tab(tab, tstride, lane * J + j, eta[j], bu[j], bd[j]);
                     }
                 }
                 seg_fwd2<J>(bu, bd, head, rb, OpMin(), OpMax(), WBIG, -WBIG);
@@ -427,7 +427,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
             Ilo[j] = -WBIG; Ihi[j] = WBIG;
             if (valid[j]) {
                 if (!(rs[j] & RS_FLAT) || hl[j].n != 0) { Ilo[j] = eta[j]; Ihi[j] = eta[j]; }
-                else flat_interval_tab(st[j], clip_tab_load(tab, tstride, lane * J + j), eta[j], D[j], C[j], Ilo[j], Ihi[j]);
+                else flat_interval_tab(st[j], tab, tstride, lane * J + j, eta[j], D[j], C[j], Ilo[j], Ihi[j]);
             }
         }
         seg_fwd2<J>(Ilo, Ihi, head, rb, OpMax(), OpMin(), -WBIG, WBIG);          // tails now hold the run interval
