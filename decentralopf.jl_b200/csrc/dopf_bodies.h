@@ -297,37 +297,51 @@ DOPF_HD double inject_compute(const View &v, int n, int t, double (&st)[8])
         const double *Pn = sel(v.P, nxt), *Pc = sel(v.P, cur);
         const int g1 = v.gen_ptr[n + 1];
         int g = v.gen_ptr[n];
-        for (; g + 4 <= g1; g += 4) {                 // all 8 loads in flight before the dependent chain
-            double pn[4], pc[4];
+#define DOPF_NOTE_MOVE(d)                                                                                   \
+        if ((d) < 0.0) { lo = (d) < lo ? (d) : lo; inneg = (d) > inneg ? (d) : inneg; sneg += (d); cneg += 1.0; } \
+        else if ((d) > 0.0) { hi = (d) > hi ? (d) : hi; inpos = (d) < inpos ? (d) : inpos; spos += (d); cpos += 1.0; }
+        for (; g + 8 <= g1; g += 8) {                 // 16 loads in flight before the dependent chain
+            double pn[8], pc[8];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-            for (int u = 0; u < 4; ++u) { pn[u] = Pn[(size_t)(g + u) * v.T + t]; pc[u] = Pc[(size_t)(g + u) * v.T + t]; }
+            for (int u = 0; u < 8; ++u) { pn[u] = Pn[(size_t)(g + u) * v.T + t]; pc[u] = Pc[(size_t)(g + u) * v.T + t]; }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-            for (int u = 0; u < 4; ++u) {
-                const double d = pn[u] - pc[u];
-                a += pn[u];
-                if (d < 0.0) { lo = d < lo ? d : lo; inneg = d > inneg ? d : inneg; sneg += d; cneg += 1.0; }
-                else if (d > 0.0) { hi = d > hi ? d : hi; inpos = d < inpos ? d : inpos; spos += d; cpos += 1.0; }
-            }
+            for (int u = 0; u < 8; ++u) { const double d = pn[u] - pc[u]; a += pn[u]; DOPF_NOTE_MOVE(d) }
         }
         for (; g < g1; ++g) {
             const size_t o = (size_t)g * v.T + t;
             const double pn = Pn[o], d = pn - Pc[o];
             a += pn;
-            if (d < 0.0) { lo = d < lo ? d : lo; inneg = d > inneg ? d : inneg; sneg += d; cneg += 1.0; }
-            else if (d > 0.0) { hi = d > hi ? d : hi; inpos = d < inpos ? d : inpos; spos += d; cpos += 1.0; }
+            DOPF_NOTE_MOVE(d)
         }
-        for (int s = v.sto_ptr[n]; s < v.sto_ptr[n + 1]; ++s) {
+        const double *Dn = sel(v.D, nxt), *Dc = sel(v.D, cur), *Cn = sel(v.C, nxt), *Cc = sel(v.C, cur);
+        const int s1 = v.sto_ptr[n + 1];
+        int s = v.sto_ptr[n];
+        for (; s + 4 <= s1; s += 4) {
+            double dn_[4], dc_[4], cn_[4], cc_[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int u = 0; u < 4; ++u) {
+                const size_t o = (size_t)(s + u) * v.T + t;
+                dn_[u] = Dn[o]; dc_[u] = Dc[o]; cn_[u] = Cn[o]; cc_[u] = Cc[o];
+            }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int u = 0; u < 4; ++u) { const double d = (dn_[u] - dc_[u]) - (cn_[u] - cc_[u]); a += dn_[u] - cn_[u]; DOPF_NOTE_MOVE(d) }
+        }
+        for (; s < s1; ++s) {
             const size_t o = (size_t)s * v.T + t;
-            const double dn_ = sel(v.D, nxt)[o], cn_ = sel(v.C, nxt)[o];
-            const double d = (dn_ - sel(v.D, cur)[o]) - (cn_ - sel(v.C, cur)[o]);
+            const double dn_ = Dn[o], cn_ = Cn[o];
+            const double d = (dn_ - Dc[o]) - (cn_ - Cc[o]);
             a += dn_ - cn_;
-            if (d < 0.0) { lo = d < lo ? d : lo; inneg = d > inneg ? d : inneg; sneg += d; cneg += 1.0; }
-            else if (d > 0.0) { hi = d > hi ? d : hi; inpos = d < inpos ? d : inpos; spos += d; cpos += 1.0; }
+            DOPF_NOTE_MOVE(d)
         }
+#undef DOPF_NOTE_MOVE
     }
     st[0] = lo; st[1] = hi; st[2] = inneg; st[3] = inpos; st[4] = sneg; st[5] = spos; st[6] = cneg; st[7] = cpos;
     return a;

@@ -35,7 +35,9 @@ __global__ void __launch_bounds__(256) k_compact(View v, int mode)
     __shared__ int wcount[8];
     const int t = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_in = mode == 0 ? v.L : v.wcnt[t];
-    const int per = ((n_in + 8 * 32 - 1) / (8 * 32)) * 32;       // slice length per warp (multiple of 32)
+    // slice length per warp: a multiple of 128 rows in mode 0 (4 flag bytes per lane), of 32 entries in mode 1
+    const int gran = mode == 0 ? 128 : 32;
+    const int per = ((n_in + 8 * gran - 1) / (8 * gran)) * gran;
     const int i0 = warp * per, i1 = min(i0 + per, n_in);
     const unsigned char *fl = v.flags + (size_t)t * v.Lp;
     const int *in = v.wide + (size_t)t * 2 * v.L;
@@ -44,22 +46,36 @@ __global__ void __launch_bounds__(256) k_compact(View v, int mode)
     for (int pass = 0; pass < 2; ++pass) {
         int cnt = 0;
         if (pass == 1) { for (int w = 0; w < warp; ++w) cnt += wcount[w]; }
-        for (int base = i0; base < i1; base += 32) {
-            const int i = base + lane;
-            if (mode == 0) {
-                const unsigned char f = i < i1 ? fl[i] : 0;
+        if (mode == 0) {
+            // lane owns rows base+4*lane .. +3 (one 32-bit load; Lp is a multiple of 64, rows >= L carry no flags);
+            // list order = row order: exclusive prefix of the lane counts, then the lane writes its entries in order
+            for (int base = i0; base < i1; base += 128) {
+                const int r0 = base + 4 * lane;
+                const unsigned w4 = r0 < i1 ? *reinterpret_cast<const unsigned *>(fl + r0) : 0u;
+                unsigned bits = 0;                                   // bit 2*k+side of row r0+k
 #pragma unroll
-                for (int side = 0; side < 2; ++side) {
-                    const bool p = (f >> side) & 1;
-                    const unsigned m = __ballot_sync(0xffffffffu, p);
-                    if (pass == 1 && p) {
-                        const int pos = cnt + __popc(m & ((1u << lane) - 1));
-                        out[pos] = i * 2 + side;
-                        v.wide_b[(size_t)t * 2 * v.L + pos] = side ? v.bminus[(size_t)i * v.ldt + t] : v.bplus[(size_t)i * v.ldt + t];
+                for (int k = 0; k < 4; ++k) if (r0 + k < i1) bits |= ((w4 >> (8 * k)) & 3u) << (2 * k);
+                const int mine = __popc(bits);
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+                if (pass == 1) {
+                    int pos = cnt + incl - mine;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if ((bits >> q) & 1u) {
+                            const int i = r0 + (q >> 1), side = q & 1;
+                            out[pos] = i * 2 + side;
+                            v.wide_b[(size_t)t * 2 * v.L + pos] = side ? v.bminus[(size_t)i * v.ldt + t] : v.bplus[(size_t)i * v.ldt + t];
+                            ++pos;
+                        }
                     }
-                    cnt += __popc(m);
                 }
-            } else {
+                cnt += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        } else {
+            for (int base = i0; base < i1; base += 32) {
+                const int i = base + lane;
                 bool p = false;
                 int e = 0;
                 if (i < i1) {
