@@ -266,7 +266,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
     HingeList hl[J];
     bool valid[J];
     int kind[J];          // anchor at the end of t: +1 level = emax, -1 level = 0, 0 none
-    double eta[J];
+    double eta[J], hmin[J];
     // coalesced loads: element e = lane + 32*i of the warp's contiguous range is staged through the
     // shared table area and re-read in blocked order (lane owns timesteps lane*J .. lane*J+J-1)
     __syncwarp();
@@ -289,6 +289,8 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
         hl[j].h = HINGES ? hinges + (size_t)tt * v.hcap : nullptr;
         hl[j].n = HINGES ? hcnt[tt] : 0;
         hl[j].sorted = HINGES && v.hcap <= 64;   // k_sto_fix sorts lists of up to 64 entries by |bp|
+        // smallest |breakpoint| of the step: moves below it leave every hinge in its anchor state (no list access)
+        hmin[j] = (HINGES && hl[j].n != 0 && hl[j].sorted) ? fabs(hl[j].h[0].bp) : 0.0;
         kind[j] = !valid[j] ? 0 : (Ep >= k.emax - tolA ? 1 : (Ep <= tolA ? -1 : 0));
     }
     __syncwarp();
@@ -318,12 +320,12 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
             // kind of the anchor that closed the previous run: heads read it at t-1 and spread it forward
             int kp[J];
             shift_from_prev<J, int>(kind, kp, 0);
-            double hk[J], dummy[J];
+            int hk[J];
 #pragma unroll
-            for (int j = 0; j < J; ++j) { hk[j] = head[j] ? (double)kp[j] : -2.0; dummy[j] = 0.0; }
-            seg_fwd2<J>(hk, dummy, head, rb, OpMax(), OpAdd(), -2.0, 0.0);   // non-heads hold -2 => max = the head's value
+            for (int j = 0; j < J; ++j) hk[j] = head[j] ? -kp[j] : 2;       // non-heads hold 2 => min = minus the head's value
+            seg_fwd_min_int<J>(hk, head, rb);
 #pragma unroll
-            for (int j = 0; j < J; ++j) { prevk[j] = (int)hk[j]; endk[j] = kind[j]; }
+            for (int j = 0; j < J; ++j) { prevk[j] = -hk[j]; endk[j] = kind[j]; }
             seg_take_tail<J, int>(eta, endk, tail, rf);                  // start multiplier and end kind of my run
         }
         double e0[J], target[J];
@@ -350,9 +352,12 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
                     StoEval e = eval_tab(st[j], k, tab, tstride, lane * J + j, eta[j]);
                     if (HINGES && hl[j].n != 0) {
                         // the hinge-free solution is exact unless a hinge differs from its anchor state at this delta
-                        double hv, hs;
-                        hl[j].eval((e.D - st[j].Db) - (e.C - st[j].Cb), hv, hs);
-                        if (hv != 0.0 || hs != 0.0) e = sto_eval(st[j], k, hl[j], eta[j]);
+                        const double dl = (e.D - st[j].Db) - (e.C - st[j].Cb);
+                        if (fabs(dl) >= hmin[j]) {
+                            double hv, hs;
+                            hl[j].eval(dl, hv, hs);
+                            if (hv != 0.0 || hs != 0.0) e = sto_eval(st[j], k, hl[j], eta[j]);
+                        }
                     }
                     D[j] = e.D; C[j] = e.C; pre[j] = e.C - e.D; dy[j] = e.dy;
                 } else { D[j] = C[j] = pre[j] = dy[j] = 0.0; }
