@@ -219,8 +219,7 @@ def run_dopf(args):
     # algorithmic bytes per launch
     def alg_bytes_of(name):
         if name.startswith("k_gen_predict"): return 16.0 * G * T
-        if name.startswith("k_sto_"): return 40.0 * S * T
-        if name.startswith("k_slack_stream"): return 16.0 * G * T + 32.0 * S * T      # re-reads both iterates of every agent
+        if name.startswith("k_sto_warp") or name.startswith("k_sto_warm"): return 40.0 * S * T
         if name.startswith("k_inject"): return 8.0 * (G + 2 * S) * T + 16.0 * N * T
         return None
 
@@ -240,6 +239,12 @@ def run_dopf(args):
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": b}
     if roof is not None:
+        # DRAM bytes (read + write) per launch of that kernel from the committed ncu --set full capture of this workload
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+            roof["traffic"] = tr.get(args.workload, {}).get(dom)
+        except Exception:
+            pass
         roof["kernel_ms"] = kern[dom]
         roof["kernel_share_of_iteration"] = kern[dom] / sum(kern.values())
     gp = next((v for k_, v in kern.items() if k_.startswith("k_gen_predict")), None)
