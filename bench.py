@@ -102,6 +102,7 @@ def oracle_rate(pkg, workload, steps, warmup, budget_s=150.0):
     """agent*timestep updates/s of the CPU oracle on a bounded sample of the workload: the sample's
     agent count is scaled (from a one-iteration probe) so that warmup+steps fit `budget_s`."""
     from oracle import oracle
+    oracle.set_num_threads(len(os.sched_getaffinity(0)))      # all host cores, whatever OMP_NUM_THREADS the launcher exported
     g_s, s_s = SAMPLE_AGENTS[workload]
     prob, cfg = make_case(pkg, workload, seed=0, agents=(max(g_s // 5, 8), max(s_s // 5, 2)))
     ora = oracle.OracleADMM(prob, cfg["gamma"], flow_weight=cfg["flow_weight"], prox_weight=cfg["prox_weight"])

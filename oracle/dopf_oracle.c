@@ -30,6 +30,16 @@ int oracle_num_threads(void)
 #endif
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the timed baseline asks for all host cores explicitly */
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 typedef struct {
     const oracle_problem *p;
     const oracle_state *s;

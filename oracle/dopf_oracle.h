@@ -77,6 +77,7 @@ void oracle_nodal_price(const oracle_problem *p, const double *lam, const double
                         const double *rho, double *out);
 
 int oracle_num_threads(void);
+void oracle_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

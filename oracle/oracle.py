@@ -89,6 +89,10 @@ def num_threads():
     return int(lib().oracle_num_threads())
 
 
+def set_num_threads(n):
+    lib().oracle_set_num_threads(int(n))
+
+
 def ptdf(N, line_from, line_to, susceptance, slack):
     """calculate_ptdf (src/helpers/ptdf.jl:1-41); 0-based indices; returns [L][N]."""
     fr = np.ascontiguousarray(line_from, dtype=np.int32)
