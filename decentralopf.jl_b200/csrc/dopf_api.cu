@@ -465,6 +465,10 @@ int dopf_set_state(dopf_handle *h, int32_t iteration, const double *P, const dou
                    const double *avgU, const double *avgK, const double *lam, const double *mu, const double *rho)
 {
     if (!h || iteration < 1) return DOPF_E_ARG;
+    if (h->nranks > 1) {     // the derived network state would need the exchanges of the partitioned mode
+        h->err = "dopf_set_state is not supported after dopf_set_partition";
+        return DOPF_E_UNSUPPORTED;
+    }
     CK(cudaSetDevice(h->device));
     View &v = h->lp.view;
     int rc;
@@ -491,10 +495,6 @@ int dopf_set_state(dopf_handle *h, int32_t iteration, const double *P, const dou
     c.iters_done = 0;
     *h->h_ctrl = c;
     CK(cudaMemcpyAsync(v.ctrl, h->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, h->stream));
-    if (h->nranks > 1) {
-        h->err = "dopf_set_state is not supported after dopf_comm_init";
-        return DOPF_E_UNSUPPORTED;
-    }
     launch_rebuild_derived(h->lp, h->stream);
     CK(cudaGetLastError());
     if ((rc = sync_ctrl(h))) return rc;

@@ -799,20 +799,5 @@ DOPF_HD double bits_nonneg(unsigned long long u)
     return x.d;
 }
 
-// order-preserving map of a double onto uint64 (for atomicMin / atomicMax on signed values)
-DOPF_HD unsigned long long ordered_bits(double v)
-{
-    union { double d; unsigned long long u; } x;
-    x.d = v;
-    return (x.u >> 63) ? ~x.u : (x.u | 0x8000000000000000ull);
-}
-DOPF_HD double ordered_value(unsigned long long k)
-{
-    union { double d; unsigned long long u; } x;
-    x.u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
-    return x.d;
-}
-#define DOPF_ORDERED_ZERO 0x8000000000000000ull
-
 }  // namespace dopf
 #endif
