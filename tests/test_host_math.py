@@ -108,6 +108,58 @@ def test_generator_root_with_hinges(emul):
             assert f(hi) <= 1e-9
 
 
+@pytest.mark.parametrize("fn", ["emul_storage_solve", "emul_storage_solve_seq"])
+def test_storage_with_hinges_minimises_the_true_objective(emul, fn):
+    """storage solve with explicit slack hinges (the correction pass): the result must minimise
+    sum_t mc(D+C) + prox/2((D-Db)^2+(C-Cb)^2) + phi_t(delta_t) over the boxes and level bounds, where
+    phi_t' = g0 + s1*delta + sum of hinge terms; checked against SLSQP on the C1 objective."""
+    from scipy.optimize import minimize
+    lib = emul.lib()
+    rng = np.random.default_rng(11)
+    hcap = 6
+    for trial in range(60):
+        T = int(rng.choice([1, 2, 3, 5]))
+        mc = float(rng.choice([0.0, 1.0])); pmax = float(rng.integers(5, 30)); emax = pmax * float(rng.choice([0.5, 1, 2])); prox = float(rng.choice([1.0, 0.5]))
+        Db = rng.uniform(0, pmax, T) * (rng.random(T) < 0.5); Cb = rng.uniform(0, pmax, T) * (rng.random(T) < 0.5)
+        g0 = rng.normal(0, 15, T)
+        hcnt = rng.integers(0, hcap + 1, T).astype(np.int32)
+        hbp = rng.normal(0, 0.4 * pmax, (T, hcap)); hs = rng.uniform(0.1, 5, (T, hcap)); hsg = hs * rng.choice([-1.0, 1.0], (T, hcap))
+        s1 = np.zeros(T)
+        for t in range(T):
+            k = hcnt[t]
+            anchored = (np.sign(hsg[t, :k]) * hbp[t, :k]) < 0
+            s1[t] = float(rng.uniform(0.0, 1.0)) + hs[t, :k][anchored].sum()
+        D = np.zeros(T); Cc = np.zeros(T); eta = np.zeros(T); st = np.zeros(4, dtype=np.int32)
+        getattr(lib, fn)(T, C.c_double(mc), C.c_double(pmax), C.c_double(emax), C.c_double(prox), d_(Db), d_(Cb), d_(g0), d_(s1),
+                         hcap, hcnt.ctypes.data_as(ip), d_(np.ascontiguousarray(hbp)), d_(np.ascontiguousarray(hsg)),
+                         d_(D), d_(Cc), d_(eta), st.ctypes.data_as(ip))
+
+        def phi(t, z):
+            v = g0[t] * z + 0.5 * s1[t] * z * z
+            for b, w in zip(hbp[t, :hcnt[t]], hsg[t, :hcnt[t]]):
+                dirn = 1.0 if w > 0 else -1.0
+                e = dirn * (z - b)
+                if dirn * b < 0:
+                    v -= 0.5 * abs(w) * (z - b) ** 2 if e < 0 else 0.0
+                else:
+                    v += 0.5 * abs(w) * (z - b) ** 2 if e > 0 else 0.0
+            return v
+
+        def obj(x):
+            d, c = x[:T], x[T:]
+            return sum(mc * (d[t] + c[t]) + 0.5 * prox * ((d[t] - Db[t]) ** 2 + (c[t] - Cb[t]) ** 2) + phi(t, (d[t] - Db[t]) - (c[t] - Cb[t])) for t in range(T))
+        lev = lambda x: np.cumsum(x[T:] - x[:T])
+        cons = [{"type": "ineq", "fun": lambda x: lev(x)}, {"type": "ineq", "fun": lambda x: emax - lev(x)}]
+        x0 = np.concatenate([D, Cc])
+        assert lev(x0).min() >= -1e-9 and lev(x0).max() <= emax + 1e-9 and x0.min() >= -1e-12 and x0.max() <= pmax + 1e-12
+        best = obj(x0)
+        for start in (x0, np.zeros(2 * T), np.concatenate([Db, Cb]) * 0.5):
+            r = minimize(obj, start, method="SLSQP", bounds=[(0, pmax)] * (2 * T), constraints=cons, options={"ftol": 1e-14, "maxiter": 500})
+            feas = lev(r.x).min() >= -1e-7 and lev(r.x).max() <= emax + 1e-7
+            if r.success and feas:
+                assert best <= r.fun + 1e-6 * (1 + abs(r.fun)), (trial, T, best, r.fun)
+
+
 @pytest.mark.parametrize("name", GOLDEN)
 def test_pipeline_emulation_reproduces_reference_trace(emul, oracle_mod, three_node_sorted, name):
     prob, order = three_node_sorted
