@@ -780,13 +780,16 @@ int set_storage_smem_attr(int T)
 int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
 {
     int cur_seg = 0;
-    // independent groups run on a side stream when the whole iteration is enqueued at once and no
-    // per-kernel profiling is requested (works both under graph capture and for direct launches)
-    const bool par = segment < 0 && !lp.prof_events && lp.side_stream;
+    // the storage and the generator kernels of the predict and of the correction pass are independent: they run on
+    // two streams unless per-kernel profiling is requested (works both under graph capture and for direct launches;
+    // both fork/join pairs lie inside phase 0 of the partitioned mode).  Measured: anything forked beside the PTDF
+    // products (wide-list compaction, slack sums) slows the iteration down, so those stay in stream order.
+    const bool par = !lp.prof_events && lp.side_stream;
     cudaStream_t cs = st;
-#define FORK() do { if (par) { cudaEventRecord(lp.ev_fork, st); cudaStreamWaitEvent(lp.side_stream, lp.ev_fork, 0); cs = lp.side_stream; } } while (0)
+#define SEG_ON() (segment < 0 || cur_seg == segment)
+#define FORK() do { if (par && SEG_ON()) { cudaEventRecord(lp.ev_fork, st); cudaStreamWaitEvent(lp.side_stream, lp.ev_fork, 0); cs = lp.side_stream; } } while (0)
 #define MAIN() do { cs = st; } while (0)
-#define JOIN() do { if (par) { cudaEventRecord(lp.ev_join, lp.side_stream); cudaStreamWaitEvent(st, lp.ev_join, 0); } cs = st; } while (0)
+#define JOIN() do { if (par && SEG_ON()) { cudaEventRecord(lp.ev_join, lp.side_stream); cudaStreamWaitEvent(st, lp.ev_join, 0); } cs = st; } while (0)
 #define XCHG(what) do { ++cur_seg; } while (0)
     const View &v = lp.view;
     int launches = 0;
@@ -858,10 +861,8 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 1));   // moves may have grown
     LAUNCH(k_inject<<<dim3(v.Np / 8, v.ldt / 32), 256, 0, cs>>>(v));
     XCHG(DOPF_X_INJ);    // nodal injection of all ranks' agents
-    FORK();   // the slack sums need the local injection, not the flows: they overlap the flow product
-    LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.T), 128, 0, cs>>>(v, lp.tflag));
+    LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.T), 128, 0, cs>>>(v, lp.tflag));   // needs the local injection statistics only
     LAUNCH(k_slack_pairs<<<lp.num_sms * 2, 256, 0, cs>>>(v));
-    MAIN();
     LAUNCH(k_colsum<<<v.ldt / 32, dim3(32, 32), 0, cs>>>(v));
     {   // flow = PTDF * inj
         dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);
@@ -869,13 +870,13 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
         else LAUNCH(k_gemm<32, false><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n));
         LAUNCH(k_flow_reduce<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, cs>>>(v, lp.part, lp.ksplit_n));
     }
-    JOIN();
     XCHG(DOPF_X_ROWSUM); // exact slack sums over all ranks' agents
     LAUNCH(k_dual<<<cdiv((long long)v.L * v.ldt, 256), 256, 0, cs>>>(v, lp.tflag));
     LAUNCH(k_lambda_finish<<<1, 256, 0, cs>>>(v));
 #undef LAUNCH
 #undef XCHG
 #undef FORK
+#undef SEG_ON
 #undef MAIN
 #undef JOIN
     if (lp.prof_count) *lp.prof_count = launches;
