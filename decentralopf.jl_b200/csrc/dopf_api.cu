@@ -266,7 +266,15 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
         const int ct = ldt / 32;
         bm = ((Mp / 64) * ct >= lp.num_sms) ? 64 : 32;
         const int tiles = (Mp / bm) * ct;
-        ks = std::max(1, std::min({8, (2 * lp.num_sms + tiles - 1) / tiles, Kp / 16 / 8 > 0 ? Kp / 16 / 8 : 1}));
+        // split-K: the kernel runs in waves of num_sms blocks per resident slot, so pick the split with the
+        // fewest waves per unit of work among those that give every SM at least two blocks
+        const int ksmax = std::max(1, std::min(8, Kp / 16 / 8));
+        double best = 1e300; ks = 1;
+        for (int k = 1; k <= ksmax; ++k) {
+            const int blocks = tiles * k;
+            const double cost = (double)((blocks + lp.num_sms - 1) / lp.num_sms) / k + (blocks < 2 * lp.num_sms ? 1.0 : 0.0);
+            if (cost < best - 1e-12) { best = cost; ks = k; }
+        }
     };
     plan_gemm(Np, Lp, lp.bm_t, lp.ksplit_t);
     plan_gemm(Lp, Np, lp.bm_n, lp.ksplit_n);
