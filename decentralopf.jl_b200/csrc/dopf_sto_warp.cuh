@@ -245,8 +245,27 @@ __device__ __forceinline__ void flat_interval_tab(const StoStep &st, const doubl
     }
 }
 
+// clipped step with hinges: D, C, delta and therefore the hinge force are constant while nu stays inside the clip
+// piece [plo, phi] that holds it, so eta may move by (nu - plo) upwards and (phi - nu) downwards without changing y_t
+__device__ __forceinline__ void flat_range_hinge(const StoStep &st, const HingeList &hl, double hmin, const double *tab, int tstride, int t,
+                                                 double eta, double D, double C, double &elo, double &ehi)
+{
+    const double dl = (D - st.Db) - (C - st.Cb);
+    double hv = 0.0, hs = 0.0;
+    if (fabs(dl) >= hmin) hl.eval(dl, hv, hs);
+    const double nu = st.g0 - eta + st.s1 * dl + hv;
+    double plo = -WBIG, phi = WBIG;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double b = tab[(TAB_BB + i) * tstride + t];
+        if (b <= nu) plo = b; else if (phi == WBIG) phi = b;
+    }
+    ehi = plo > -WBIG ? eta + (nu - plo) : WBIG;
+    elo = phi < WBIG ? eta - (phi - nu) : -WBIG;
+}
+
 // run status bits broadcast from the tail
-enum { RS_CONV = 1, RS_BAD = 2, RS_FLAT = 4, RS_EMPTY = 8, RS_FREEBAD = 16 };
+enum { RS_CONV = 1, RS_BAD = 2, RS_FLAT = 4, RS_EMPTY = 8, RS_FREEBAD = 16, RS_ENDBAD = 32 };
 
 // shared memory per warp: the clip table (19 doubles per timestep)
 __host__ __device__ inline size_t sto_warp_smem_per_warp(int T) { return (size_t)19 * (size_t)((T + 1) | 1) * sizeof(double); }
@@ -301,7 +320,8 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
 
     double D[J], C[J], pre[J];
     bool accepted = false;
-    for (int as_it = 0; as_it < 24 && !accepted; ++as_it) {
+    const int as_cap = 24 + T / 2;                 // one new anchor per run and round: long horizons need more rounds from a cold start
+    for (int as_it = 0; as_it < as_cap && !accepted; ++as_it) {
         // ---- run structure from the anchors (timesteps beyond T are isolated one-element runs) ------
         bool head[J], tail[J];
         int prevk[J], endk[J];
@@ -384,8 +404,11 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
                 for (int j = 0; j < J; ++j) {
                     bu[j] = WBIG; bd[j] = -WBIG;
                     if (valid[j]) {
-                        if (hl[j].n != 0) { bu[j] = -WBIG; bd[j] = WBIG; }             // hinge on a flat run: not handled here
-                        else next_breaks_tab(tab, tstride, lane * J + j, eta[j], bu[j], bd[j]);
+                        if (HINGES && hl[j].n != 0) {
+                            double elo, ehi;
+                            flat_range_hinge(st[j], hl[j], hmin[j], tab, tstride, lane * J + j, eta[j], D[j], C[j], elo, ehi);
+                            bu[j] = ehi; bd[j] = elo;
+                        } else next_breaks_tab(tab, tstride, lane * J + j, eta[j], bu[j], bd[j]);
                     }
                 }
                 seg_fwd2<J>(bu, bd, head, rb, OpMin(), OpMax(), WBIG, -WBIG);
@@ -431,7 +454,8 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
             // multiplier interval of my run, contributed per element: a point unless the whole run is flat
             Ilo[j] = -WBIG; Ihi[j] = WBIG;
             if (valid[j]) {
-                if (!(rs[j] & RS_FLAT) || hl[j].n != 0) { Ilo[j] = eta[j]; Ihi[j] = eta[j]; }
+                if (!(rs[j] & RS_FLAT)) { Ilo[j] = eta[j]; Ihi[j] = eta[j]; }
+                else if (HINGES && hl[j].n != 0) flat_range_hinge(st[j], hl[j], hmin[j], tab, tstride, lane * J + j, eta[j], D[j], C[j], Ilo[j], Ihi[j]);
                 else flat_interval_tab(st[j], tab, tstride, lane * J + j, eta[j], D[j], C[j], Ilo[j], Ihi[j]);
             }
         }
@@ -463,12 +487,17 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
             tv[j] = (vio_up[j] || vio_dn[j]) ? t : 0x7fffffff;
             flag[j] = 0;
             if (valid[j] && tail[j] && !(rs[j] & RS_BAD)) {
-                double a = Flo[j], b = Fhi[j];
-                if (t == T - 1 && kind[j] != 0) {                  // end of horizon: eta_{T+1} = 0
-                    if (kind[j] > 0) a = a > 0.0 ? a : 0.0; else b = b < 0.0 ? b : 0.0;
+                const double a = Flo[j], b = Fhi[j];
+                // multiplier signs up to rounding: a weakly active bound (multiplier ~ 0) must not flip between
+                // "wrong sign => drop" and "violated => add" for ever
+                const double tolM = 1e-10 * (1.0 + fabs(a) + fabs(b));
+                if (a > b + tolM) flag[j] |= RS_EMPTY;                       // wrong sign at the anchor before this run
+                else if (t == T - 1 && kind[j] != 0) {                       // end of horizon: eta_{T+1} = 0
+                    // only if the chain itself is consistent the end anchor is the one to go: dropping both
+                    // anchors of a one-element last run re-creates them one by one and cycles
+                    if (kind[j] > 0 ? (b < -tolM) : (a > tolM)) flag[j] |= RS_ENDBAD;
                 }
-                if (a > b) flag[j] |= RS_EMPTY;
-                if (freeend[j] && (Flo[j] > 0.0 || Fhi[j] < 0.0)) flag[j] |= RS_FREEBAD;
+                if (freeend[j] && (Flo[j] > tolM || Fhi[j] < -tolM)) flag[j] |= RS_FREEBAD;
             }
             if (valid[j] && tail[j] && (rs[j] & RS_BAD)) flag[j] |= RS_BAD;
         }
@@ -500,7 +529,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
             if (!valid[j] || kind[j] == 0 || tv[j] == t) continue;
             bool drop = nextwant[j] != 0;                                                       // (2) wrong sign at my anchor
             if (tail[j] && (flag[j] & RS_BAD)) drop = true;                                     //     my run cannot meet its target
-            if (t == T - 1 && (flag[j] & RS_EMPTY)) drop = true;                                //     wrong sign at the horizon end
+            if (t == T - 1 && (flag[j] & RS_ENDBAD)) drop = true;                               //     wrong sign at the horizon end
             if (drop) { kind[j] = 0; change = true; }
         }
         anybad = __any_sync(FULL, anybad);
