@@ -249,7 +249,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     AL(v.flags, (size_t)ldt * Lp);
     AL(v.wide, (size_t)T * 2 * L); AL(v.wcnt, T); AL(v.tight, (size_t)T * 2 * L); AL(v.tcnt, T);
     v.gen_work_cap = (int)std::min<long long>((long long)G * T, 1ll << 30);
-    AL(v.gen_work, (size_t)std::max(v.gen_work_cap, 1)); AL(v.sto_work, S); AL(v.sto_flag, S);
+    AL(v.gen_work, (size_t)std::max(v.gen_work_cap, 1)); AL(v.gen_grp, (size_t)2 * std::max(v.gen_work_cap, 1)); AL(v.sto_work, S); AL(v.sto_flag, S);
     if (N >= (1 << 20) || T >= (1 << 11)) { h->err = "N >= 2^20 or T >= 2^11 not supported by the pair queue encoding"; return DOPF_E_UNSUPPORTED; }
     v.pair_cap = 1 << 20;
     AL(v.pair_row, v.pair_cap); AL(v.pair_node, v.pair_cap);

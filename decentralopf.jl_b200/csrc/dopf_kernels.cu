@@ -225,7 +225,7 @@ __global__ void k_node_prep(View v, const double *Cpart, const double *C2part, i
     // iteration prologue: reset the per-iteration counters, move maxima and work flags (nothing before this
     // kernel in the iteration touches them)
     if (i == 0) {
-        v.ctrl->gen_work_cnt = 0; v.ctrl->sto_work_cnt = 0; v.ctrl->cold_work_cnt = 0; v.ctrl->pair_cnt = 0;
+        v.ctrl->gen_work_cnt = 0; v.ctrl->sto_work_cnt = 0; v.ctrl->cold_work_cnt = 0; v.ctrl->pair_cnt = 0; v.ctrl->gen_grp_cnt = 0;
         v.ctrl->res_bits[0] = v.ctrl->res_bits[1] = v.ctrl->res_bits[2] = 0ull;
     }
     if (i < v.ldt) v.dmax[i] = 0ull;
@@ -505,41 +505,83 @@ __global__ void __launch_bounds__(256) k_verify(View v)
     for (int q = warp; q < total; q += (blockDim.x >> 5)) {
         const int nn = qn[q] >> 3, tt = blockIdx.y * (blockDim.x >> 5) + (qn[q] & 7);
         const double lo = qlo[q], hi = qhi[q];
-        for (int g = v.gen_ptr[nn] + lane; g < v.gen_ptr[nn + 1]; g += 32)
-            if (verify_gen_moved(v, g, tt, lo, hi)) verify_note_gen(v, g, tt);
+        // the flagged generators of one (n,t) share their hinge candidates: they are appended as one group of
+        // consecutive work entries (one atomic per group) so that k_gen_fix collects the hinges once per group
+        for (int g0 = v.gen_ptr[nn]; g0 < v.gen_ptr[nn + 1]; g0 += 32) {
+            const int g = g0 + lane;
+            const bool hit = g < v.gen_ptr[nn + 1] && verify_gen_moved(v, g, tt, lo, hi);
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m == 0u) continue;
+            int base = 0;
+            if (lane == 0) {
+                base = atomicAdd(&v.ctrl->gen_work_cnt, __popc(m));
+                if (base + __popc(m) <= v.gen_work_cap) {
+                    const int k = atomicAdd(&v.ctrl->gen_grp_cnt, 1);
+                    v.gen_grp[2 * k] = base; v.gen_grp[2 * k + 1] = __popc(m);
+                } else v.ctrl->error = DOPF_ERR_WORK_CAP;
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (hit && base + __popc(m) <= v.gen_work_cap) v.gen_work[base + __popc(m & ((1u << lane) - 1))] = g * v.T + tt;
+        }
         for (int s = v.sto_ptr[nn] + lane; s < v.sto_ptr[nn + 1]; s += 32)
             if (verify_sto_moved(v, s, tt, lo, hi)) verify_note_sto(v, s);
     }
 }
 
 // exact re-solve of the generators on the work list: one warp per (agent, t)
-__global__ void k_gen_fix(View v)
+__global__ void __launch_bounds__(128) k_gen_fix(View v)
 {
     if (!DOPF_ACTIVE(v)) return;
-    constexpr int CAP = 96;
+    // one warp per group (= the flagged generators of one (n,t), at most 32): the hinge candidates inside the
+    // union of the agents' boxes are collected once, then every lane solves its own agent.  A hinge outside an
+    // agent's own box never changes state inside it, so the shared list gives the same root.
+    constexpr int CAP = 128;
     __shared__ Hinge lists[4][CAP];
     const int cur = v.ctrl->cur, nxt = 1 - cur;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gw = blockIdx.x * (blockDim.x >> 5) + wib, nw = gridDim.x * (blockDim.x >> 5);
-    const int total = min(v.ctrl->gen_work_cnt, v.gen_work_cap);
-    for (int w = gw; w < total; w += nw) {
-        const int g = v.gen_work[w] / v.T, t = v.gen_work[w] % v.T;
-        const int n = v.gen_node[g];
+    const int groups = v.ctrl->gen_grp_cnt;
+    for (int k = gw; k < groups; k += nw) {
+        const int base = v.gen_grp[2 * k], cnt_g = v.gen_grp[2 * k + 1];
+        const bool mine = lane < cnt_g;
+        const int e = v.gen_work[base + (mine ? lane : 0)];
+        const int g = e / v.T, t = e % v.T, n = v.gen_node[g];
         const double Pb = sel(v.P, cur)[(size_t)g * v.T + t], pmax = v.gen_pmax[g];
         const double lo = -Pb, hi = pmax - Pb;
-        int cnt = collect_hinges(v, n, t, lo, hi, lists[wib], CAP);
+        double ulo = mine ? lo : 0.0, uhi = mine ? hi : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { ulo = fmin(ulo, __shfl_xor_sync(0xffffffffu, ulo, o)); uhi = fmax(uhi, __shfl_xor_sync(0xffffffffu, uhi, o)); }
+        int cnt = collect_hinges(v, n, t, ulo, uhi, lists[wib], CAP);
         __syncwarp();
-        if (cnt > CAP) { if (lane == 0) v.ctrl->error = DOPF_ERR_HINGE_CAP; cnt = CAP; }
-        if (lane == 0) {
-            HingeList hl; hl.h = lists[wib]; hl.n = cnt; hl.sorted = false;
-            const size_t nt = (size_t)n * v.ldt + t;
-            const double d = root_monotone_pl(v.gen_mc[g] + v.g0[nt], v.c.prox + v.s1[nt], hl, lo, hi);
-            double Pn = Pb + d;
-            Pn = Pn < 0.0 ? 0.0 : (Pn > pmax ? pmax : Pn);
-            sel(v.P, nxt)[(size_t)g * v.T + t] = Pn;
-            note_move(v, n, t, Pn - Pb);
-            atomicAdd(&v.ctrl->stat_gen_fix, 1);
+        const size_t nt = (size_t)n * v.ldt + t;
+        if (cnt <= CAP) {
+            if (mine) {
+                HingeList hl; hl.h = lists[wib]; hl.n = cnt; hl.sorted = false;
+                const double d = root_monotone_pl(v.gen_mc[g] + v.g0[nt], v.c.prox + v.s1[nt], hl, lo, hi);
+                double Pn = Pb + d;
+                Pn = Pn < 0.0 ? 0.0 : (Pn > pmax ? pmax : Pn);
+                sel(v.P, nxt)[(size_t)g * v.T + t] = Pn;
+                note_move(v, n, t, Pn - Pb);
+            }
+        } else {
+            // the union box holds more candidates than the list: one agent at a time with its own box
+            for (int a = 0; a < cnt_g; ++a) {
+                const double alo = __shfl_sync(0xffffffffu, lo, a), ahi = __shfl_sync(0xffffffffu, hi, a);
+                __syncwarp();
+                int c1 = collect_hinges(v, n, t, alo, ahi, lists[wib], CAP);
+                __syncwarp();
+                if (c1 > CAP) { if (lane == 0) v.ctrl->error = DOPF_ERR_HINGE_CAP; c1 = CAP; }
+                if (lane == a) {
+                    HingeList hl; hl.h = lists[wib]; hl.n = c1; hl.sorted = false;
+                    const double d = root_monotone_pl(v.gen_mc[g] + v.g0[nt], v.c.prox + v.s1[nt], hl, lo, hi);
+                    double Pn = Pb + d;
+                    Pn = Pn < 0.0 ? 0.0 : (Pn > pmax ? pmax : Pn);
+                    sel(v.P, nxt)[(size_t)g * v.T + t] = Pn;
+                    note_move(v, n, t, Pn - Pb);
+                }
+            }
         }
+        if (lane == 0) atomicAdd(&v.ctrl->stat_gen_fix, cnt_g);
         __syncwarp();
     }
 }
