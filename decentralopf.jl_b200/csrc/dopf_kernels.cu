@@ -650,10 +650,10 @@ __global__ void k_colsum(View v)   // block (32,32): 32 timesteps, 32 row groups
 // one block per (t, row).  Threads classify the nodes with the signed move range [dlo,dhi] of (n,t):
 // nodes whose agents all keep the hinge on one side contribute in closed form (node sums), the mixed
 // nodes are queued in shared memory and summed by the warps with the lanes over the agents of the node.
-__global__ void __launch_bounds__(128) k_slack_rows(View v, unsigned char *tflag)
+__global__ void __launch_bounds__(512) k_slack_rows(View v, unsigned char *tflag)
 {
     if (!DOPF_ACTIVE(v)) return;
-    __shared__ double red[4];
+    __shared__ double red[16];
     const int t = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cnt = v.tcnt[t];
     const int *lst = v.tight + (size_t)t * 2 * v.L;
@@ -903,7 +903,7 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 1));   // moves may have grown
     LAUNCH(k_inject<<<dim3(v.Np / 8, v.ldt / 32), 256, 0, cs>>>(v));
     XCHG(DOPF_X_INJ);    // nodal injection of all ranks' agents
-    LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.T), 128, 0, cs>>>(v, lp.tflag));   // needs the local injection statistics only
+    LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.T), 512, 0, cs>>>(v, lp.tflag));   // needs the local injection statistics only
     LAUNCH(k_slack_pairs<<<lp.num_sms * 2, 256, 0, cs>>>(v));
     LAUNCH(k_colsum<<<v.ldt / 32, dim3(32, 32), 0, cs>>>(v));
     {   // flow = PTDF * inj
