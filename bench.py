@@ -303,6 +303,17 @@ def run_dopf(args):
                         "steps": e2e_steps, "what": ("partitioned run: iterate + dopf_get_iterate/duals(host) every step (no per-step upload)" if partitioned
                                                      else "dopf_set_state(host) + dopf_step(1) + dopf_get_iterate/duals(host), pinned buffers")},
                 "steady_state": steady}
+        if world == 1:
+            # time to tolerance on the reference's own case (three_node, gamma 0.3, literal weights, eps 1e-3: stops at
+            # iteration 476 like src/opf_admm_decentral.jl) - SURVEY.md 8(d) "time-to-tolerance"
+            try:
+                tn = DeviceADMM(pkg.Problem.from_structs(*pkg.cases.three_node()), gamma=0.3, device=local)
+                t0 = time.perf_counter(); st3 = tn.step(2000); wall = time.perf_counter() - t0
+                line["three_node_to_tolerance"] = {"iterations": int(st3.iteration), "converged": bool(st3.converged),
+                                                   "device_ms": st3.last_step_ms, "wall_ms": wall * 1e3}
+                tn.close()
+            except Exception as e:      # additional information only
+                line["three_node_to_tolerance"] = {"error": str(e)}
         if world == 1 and not args.no_cpu_baseline:
             v, ms, cores, sample = oracle_rate(pkg, args.workload, 3, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_iteration_of_sample": ms}

@@ -250,6 +250,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     AL(v.wide, (size_t)T * 2 * L); AL(v.wcnt, T); AL(v.tight, (size_t)T * 2 * L); AL(v.tcnt, T);
     v.gen_work_cap = (int)std::min<long long>((long long)G * T, 1ll << 30);
     AL(v.gen_work, (size_t)std::max(v.gen_work_cap, 1)); AL(v.gen_grp, (size_t)2 * std::max(v.gen_work_cap, 1)); AL(v.sto_work, S); AL(v.sto_flag, S);
+    AL(v.fix_node_flag, Np); AL(v.fix_node_list, Np); AL(v.fix_node_slot, Np);
     if (N >= (1 << 20) || T >= (1 << 11)) { h->err = "N >= 2^20 or T >= 2^11 not supported by the pair queue encoding"; return DOPF_E_UNSUPPORTED; }
     v.pair_cap = 1 << 20;
     AL(v.pair_row, v.pair_cap); AL(v.pair_node, v.pair_cap);
@@ -289,9 +290,9 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
             for (int o : opts) if (o >= need) { lp.sto_j = o; break; }
         }
         if (lp.sto_j > 0 && set_storage_smem_attr(T) != 0) { h->err = "cudaFuncSetAttribute(shared memory) failed"; return DOPF_E_CUDA; }
-        // scratch: one slot per collected work item (up to 512 MB) + one per solver block for the overflow
+        // scratch: one slot per node with a storage on the work list (up to 512 MB) + one per solver block for the overflow
         const size_t slot_bytes = (size_t)T * v.hcap * sizeof(Hinge) + (size_t)T * sizeof(int);
-        lp.sto_fix_slots = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(S, 1), ((size_t)512 << 20) / slot_bytes));
+        lp.sto_fix_slots = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(N, 1), ((size_t)512 << 20) / slot_bytes));
         const size_t warps = (size_t)lp.sto_fix_slots + (size_t)lp.sto_fix_blocks;
         AL(lp.hinge_scratch, S ? warps * T * v.hcap : 1);
         AL(lp.hcnt_scratch, S ? warps * T : 1);

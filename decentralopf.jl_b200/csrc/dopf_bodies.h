@@ -40,7 +40,7 @@ struct Ctrl {
     int conv_lambda, conv_mue, conv_rho;
     int error;          // DOPF_ERR_*; set => every later kernel is a no-op, state stays valid
     int iters_done;     // iterations executed since create
-    int gen_work_cnt, sto_work_cnt, cold_work_cnt, pair_cnt, gen_grp_cnt;
+    int gen_work_cnt, sto_work_cnt, cold_work_cnt, pair_cnt, gen_grp_cnt, fix_node_cnt;
     int stat_sto_cold;                   // storages solved by the cold funnel in the last iteration
     int stat_fix_seq;                    // cumulated correction-pass storages that needed the sequential solver
     int stat_gen_fix, stat_sto_fix;      // cumulated corrected agents (statistics)
@@ -102,6 +102,7 @@ struct View {
     int *gen_work;                     // [gen_work_cap] g*T+t
     int *gen_grp;                      // [gen_work_cap][2] groups of consecutive work entries of one (n,t): first entry, count
     int *sto_work, *sto_flag;          // [S], [S]
+    int *fix_node_flag, *fix_node_list, *fix_node_slot;   // [Np] nodes with a storage on the work list (device path only)
     double *rowsumU, *rowsumK;         // [Lp][ldt] exact sum_i (b -+ p delta_i)_+ of tight rows
     int *pair_row, *pair_node; int pair_cap;   // (tight row, node) pairs whose agents must be summed one by one
     Ctrl *ctrl;

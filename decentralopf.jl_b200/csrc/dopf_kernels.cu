@@ -225,11 +225,12 @@ __global__ void k_node_prep(View v, const double *Cpart, const double *C2part, i
     // iteration prologue: reset the per-iteration counters, move maxima and work flags (nothing before this
     // kernel in the iteration touches them)
     if (i == 0) {
-        v.ctrl->gen_work_cnt = 0; v.ctrl->sto_work_cnt = 0; v.ctrl->cold_work_cnt = 0; v.ctrl->pair_cnt = 0; v.ctrl->gen_grp_cnt = 0;
+        v.ctrl->gen_work_cnt = 0; v.ctrl->sto_work_cnt = 0; v.ctrl->cold_work_cnt = 0; v.ctrl->pair_cnt = 0; v.ctrl->gen_grp_cnt = 0; v.ctrl->fix_node_cnt = 0;
         v.ctrl->res_bits[0] = v.ctrl->res_bits[1] = v.ctrl->res_bits[2] = 0ull;
     }
     if (i < v.ldt) v.dmax[i] = 0ull;
     for (int k = i; k < v.S; k += gridDim.x * blockDim.x) v.sto_flag[k] = 0;
+    if (i < v.Np) v.fix_node_flag[i] = 0;
     if (i >= v.Np * v.ldt) return;
     v.dn[i] = 0ull;
     const int n = i / v.ldt, t = i % v.ldt, cur = v.ctrl->cur;
@@ -425,15 +426,20 @@ __device__ __forceinline__ void sort_hinges(Hinge *lst, int n)
     __syncwarp();
 }
 
-// hinge lists of the affected storages: one warp per (work item, timestep); items beyond the scratch
-// capacity are collected by k_sto_fix itself
-__device__ __forceinline__ void sto_collect_one(const View &v, int s, int t, Hinge *list, int *cnt_out)
+// hinge lists for the storage correction.  All storages of a node see the same hinge candidates (same PTDF column);
+// only their boxes differ, and a hinge outside a storage's own box never changes state inside it.  So the lists are
+// collected once per (node with a flagged storage, timestep) for the union of the flagged storages' boxes.
+__device__ __forceinline__ void sto_collect_box(const View &v, int s, int t, double &lo, double &hi)
 {
-    const int lane = threadIdx.x & 31, n = v.sto_node[s];
-    const double pm = v.sto_pmax[s];
     // delta = (D-Db)-(C-Cb) with 0<=D,C<=pmax  =>  delta in [-Db-(pmax-Cb), (pmax-Db)+Cb]
+    const double pm = v.sto_pmax[s];
     const double Db = sel(v.D, v.ctrl->cur)[(size_t)s * v.T + t], Cb = sel(v.C, v.ctrl->cur)[(size_t)s * v.T + t];
-    int cnt = collect_hinges(v, n, t, -Db - (pm - Cb), (pm - Db) + Cb, list, v.hcap);
+    lo = -Db - (pm - Cb); hi = (pm - Db) + Cb;
+}
+__device__ __forceinline__ void sto_collect_lists(const View &v, int n, int t, double lo, double hi, Hinge *list, int *cnt_out)
+{
+    const int lane = threadIdx.x & 31;
+    int cnt = collect_hinges(v, n, t, lo, hi, list, v.hcap);
     if (cnt > v.hcap) { if (lane == 0) v.ctrl->error = DOPF_ERR_HINGE_CAP; cnt = v.hcap; }
     if (lane == 0) *cnt_out = cnt;
     __syncwarp();
@@ -443,11 +449,21 @@ __device__ __forceinline__ void sto_collect_one(const View &v, int s, int t, Hin
 __global__ void __launch_bounds__(128) k_sto_collect(View v, Hinge *hinge_scratch, int *hcnt_scratch, int slots)
 {
     if (!DOPF_ACTIVE(v)) return;
+    const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    const long long tasks = (long long)min(v.ctrl->sto_work_cnt, slots) * v.T;
+    const long long tasks = (long long)min(v.ctrl->fix_node_cnt, slots) * v.T;
     for (long long k = gw; k < tasks; k += nw) {
-        const int w = (int)(k / v.T), t = (int)(k % v.T);
-        sto_collect_one(v, v.sto_work[w], t, hinge_scratch + ((size_t)w * v.T + t) * v.hcap, hcnt_scratch + (size_t)w * v.T + t);
+        const int slot = (int)(k / v.T), t = (int)(k % v.T), n = v.fix_node_list[slot];
+        double lo = 0.0, hi = 0.0;                // union of the flagged storages' boxes (both contain 0)
+        for (int s = v.sto_ptr[n] + lane; s < v.sto_ptr[n + 1]; s += 32) {
+            if (!v.sto_flag[s]) continue;
+            double l1, h1;
+            sto_collect_box(v, s, t, l1, h1);
+            lo = fmin(lo, l1); hi = fmax(hi, h1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+        sto_collect_lists(v, n, t, lo, hi, hinge_scratch + ((size_t)slot * v.T + t) * v.hcap, hcnt_scratch + (size_t)slot * v.T + t);
     }
 }
 
@@ -460,12 +476,17 @@ __global__ void __launch_bounds__(32) k_sto_fix(View v, Hinge *hinge_scratch, in
     const int lane = threadIdx.x & 31;
     const int total = v.ctrl->sto_work_cnt;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        const int s = v.sto_work[w];
-        const int slot = w < slots ? w : slots + blockIdx.x;
+        const int s = v.sto_work[w], n = v.sto_node[s];
+        const int nslot = v.fix_node_slot[n];
+        const int slot = nslot < slots ? nslot : slots + blockIdx.x;
         Hinge *mylist = hinge_scratch + (size_t)slot * v.T * v.hcap;
         int *mycnt = hcnt_scratch + (size_t)slot * v.T;
-        if (w >= slots) {
-            for (int t = 0; t < v.T; ++t) sto_collect_one(v, s, t, mylist + (size_t)t * v.hcap, mycnt + t);
+        if (nslot >= slots) {                     // more flagged nodes than scratch slots: own lists, own box
+            for (int t = 0; t < v.T; ++t) {
+                double lo, hi;
+                sto_collect_box(v, s, t, lo, hi);
+                sto_collect_lists(v, n, t, lo, hi, mylist + (size_t)t * v.hcap, mycnt + t);
+            }
             __syncwarp();
         }
         bool ok = false;
@@ -524,7 +545,13 @@ __global__ void __launch_bounds__(256) k_verify(View v)
             if (hit && base + __popc(m) <= v.gen_work_cap) v.gen_work[base + __popc(m & ((1u << lane) - 1))] = g * v.T + tt;
         }
         for (int s = v.sto_ptr[nn] + lane; s < v.sto_ptr[nn + 1]; s += 32)
-            if (verify_sto_moved(v, s, tt, lo, hi)) verify_note_sto(v, s);
+            if (verify_sto_moved(v, s, tt, lo, hi)) {
+                verify_note_sto(v, s);
+                if (atomicExch(&v.fix_node_flag[nn], 1) == 0) {      // the storages of a node share one set of hinge lists
+                    const int k = atomicAdd(&v.ctrl->fix_node_cnt, 1);
+                    v.fix_node_list[k] = nn; v.fix_node_slot[nn] = k;
+                }
+            }
     }
 }
 

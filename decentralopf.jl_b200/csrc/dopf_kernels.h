@@ -12,7 +12,7 @@ struct LaunchPlan {
     int bm_t, ksplit_t;       // tile rows / split-K of the transposed product (PTDF^T M)
     int bm_n, ksplit_n;       // ... of the flow product (PTDF * inj)
     int sto_fix_blocks;       // grid of the storage correction pass (one 32-thread block = one affected storage)
-    int sto_fix_slots;        // work items whose hinge lists k_sto_collect gathers (one scratch slot each)
+    int sto_fix_slots;        // nodes whose hinge lists k_sto_collect gathers (one scratch slot each, shared by the node's storages)
     int sto_j;                // timesteps per lane of the warp-parallel storage solve (0: horizon too long)
     int slack_blocks_x;
     double *part, *part2;     // split-K partial tiles
