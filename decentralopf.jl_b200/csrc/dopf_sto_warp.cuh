@@ -444,13 +444,14 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
 
         // ---- KKT check ------------------------------------------------------------------------------
         bool vio_up[J], vio_dn[J];
-        double Ilo[J], Ihi[J];
+        double Ilo[J], Ihi[J], vmag[J];
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const double E = e0[j] + pre[j];
             const bool ok = valid[j] && !(rs[j] & RS_BAD);
             vio_up[j] = ok && E > k.emax + tolE;
             vio_dn[j] = ok && E < -tolE;
+            vmag[j] = vio_up[j] ? E - k.emax : (vio_dn[j] ? -E : -1.0);
             // multiplier interval of my run, contributed per element: a point unless the whole run is flat
             Ilo[j] = -WBIG; Ihi[j] = WBIG;
             if (valid[j]) {
@@ -480,11 +481,30 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
             seg_fwd2<J>(Fhi, d1, hup, rup, OpMin(), OpAdd(), WBIG, 0.0);
             seg_fwd2<J>(Flo, d2, hdn, rdn, OpMax(), OpAdd(), -WBIG, 0.0);
         }
+        // the new anchor of a run is its most violated timestep (the level path peaks where the bound finally
+        // binds; anchoring the first violated step instead needs one round per step of a long violated stretch)
+        {
+            bool anyv[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) anyv[j] = vio_up[j] || vio_dn[j];
+            if (any_of<J>(anyv)) {
+                double m[J], z[J];
+#pragma unroll
+                for (int j = 0; j < J; ++j) { m[j] = vmag[j]; z[j] = 0.0; }
+                seg_fwd2<J>(m, z, head, rb, OpMax(), OpAdd(), -1.0, 0.0);      // tails hold the largest violation of the run
+                int zi[J];
+#pragma unroll
+                for (int j = 0; j < J; ++j) zi[j] = 0;
+                seg_take_tail<J, int>(m, zi, tail, rf);
+#pragma unroll
+                for (int j = 0; j < J; ++j) vmag[j] = (anyv[j] && vmag[j] >= m[j]) ? 1.0 : -1.0;
+            }
+        }
         int tv[J], flag[J];
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const int t = lane * J + j;
-            tv[j] = (vio_up[j] || vio_dn[j]) ? t : 0x7fffffff;
+            tv[j] = ((vio_up[j] || vio_dn[j]) && vmag[j] > 0.0) ? t : 0x7fffffff;
             flag[j] = 0;
             if (valid[j] && tail[j] && !(rs[j] & RS_BAD)) {
                 const double a = Flo[j], b = Fhi[j];

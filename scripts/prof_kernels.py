@@ -14,7 +14,7 @@ for rep in range(3):
     prof = dev.profile_iteration()
     tot = sum(ms for _, ms in prof)
     print(f"--- {wl} iteration {dev.iteration}: total {tot*1e3:.1f} us; cold {dev.status.sto_cold} fixes(cum) {dev.status.gen_corrected}/{dev.status.sto_corrected} (sequential {dev.status.fix_sequential}) rows {dev.status.tight_rows}/{dev.status.wide_rows}")
-    if rep == 2:
+    if rep == 2 or (len(sys.argv) > 3 and sys.argv[3] == 'all'):
         for name, ms in prof:
             print(f"   {name:24s} {ms*1e3:9.1f} us  {100*ms/tot:5.1f}%")
     dev.step(10)
