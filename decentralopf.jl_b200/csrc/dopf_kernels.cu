@@ -134,9 +134,11 @@ __global__ void __launch_bounds__(128) k_gemm(View v, const double *__restrict__
     constexpr int MT = BM / 32;                       // m8 tiles per warp (4 warps along M)
     constexpr int AROW = TRANS ? (BM + 4) : (BK + 4); // padded smem row of the A tile
     constexpr int AROWS = TRANS ? BK : BM;
-    __shared__ __align__(16) double As[2][AROWS][AROW];
-    __shared__ __align__(16) double Bs[2][BK][BN + 4];
-    __shared__ __align__(16) double B2s[TRANS ? 2 : 1][TRANS ? BK : 1][TRANS ? BN + 4 : 2];
+    // cp.async pipeline depth: 3 stages (one barrier per k-step, two tile loads in flight) where the static 48 KB allow it
+    constexpr int ST = (TRANS && BM == 64) ? 2 : 3;
+    __shared__ __align__(16) double As[ST][AROWS][AROW];
+    __shared__ __align__(16) double Bs[ST][BK][BN + 4];
+    __shared__ __align__(16) double B2s[TRANS ? ST : 1][TRANS ? BK : 1][TRANS ? BN + 4 : 2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, z = blockIdx.z;
@@ -175,11 +177,20 @@ __global__ void __launch_bounds__(128) k_gemm(View v, const double *__restrict__
     };
 
     if (ks0 < ks1) load_tiles(0, ks0);
+    if (ST == 3 && ks0 + 1 < ks1) load_tiles(1, ks0 + 1);
     for (int ks = ks0; ks < ks1; ++ks) {
-        const int buf = (ks - ks0) & 1;
-        if (ks + 1 < ks1) { load_tiles(buf ^ 1, ks + 1); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        __syncthreads();
+        const int buf = (ks - ks0) % ST;
+        if (ST == 3) {
+            // tile ks has landed when at most one younger group is still in flight; the barrier also tells that every
+            // warp is done with tile ks-1, whose buffer the load of tile ks+2 reuses
+            if (ks + 1 < ks1) cp_async_wait<1>(); else cp_async_wait<0>();
+            __syncthreads();
+            if (ks + 2 < ks1) load_tiles((ks + 2 - ks0) % ST, ks + 2);
+        } else {
+            if (ks + 1 < ks1) { load_tiles(buf ^ 1, ks + 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            __syncthreads();
+        }
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 4) {
             double a[MT], b[4], b2[4];
@@ -201,7 +212,7 @@ __global__ void __launch_bounds__(128) k_gemm(View v, const double *__restrict__
                     if (TRANS) dmma(acc2[i][j][0], acc2[i][j][1], a[i] * a[i], b2[j]);
                 }
         }
-        __syncthreads();
+        if (ST == 2) __syncthreads();
     }
     // partial tile store
 #pragma unroll
