@@ -286,25 +286,19 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
     bool valid[J];
     int kind[J];          // anchor at the end of t: +1 level = emax, -1 level = 0, 0 none
     double eta[J], hmin[J];
-    // coalesced loads: element e = lane + 32*i of the warp's contiguous range is staged through the
-    // shared table area and re-read in blocked order (lane owns timesteps lane*J .. lane*J+J-1)
-    __syncwarp();
-    for (int t = lane; t < T; t += 32) {
-        const size_t o = (size_t)s * T + t;
-        tab[0 * tstride + t] = sel(v.D, cur)[o]; tab[1 * tstride + t] = sel(v.C, cur)[o];
-        tab[2 * tstride + t] = v.g0[(size_t)n * v.ldt + t]; tab[3 * tstride + t] = v.s1[(size_t)n * v.ldt + t];
-        tab[4 * tstride + t] = v.eta[o]; tab[5 * tstride + t] = v.E[o];
-    }
+    // blocked ownership (lane owns timesteps lane*J .. lane*J+J-1): the warp reads one contiguous range per array,
+    // J strided passes of 8 bytes per lane that hit the same L1 lines
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < J; ++j) {
         const int t = lane * J + j;
         valid[j] = t < T;
         const int tt = valid[j] ? t : T - 1;
-        st[j].Db = tab[0 * tstride + tt]; st[j].Cb = tab[1 * tstride + tt];
-        st[j].g0 = tab[2 * tstride + tt]; st[j].s1 = tab[3 * tstride + tt];
-        eta[j] = tab[4 * tstride + tt];
-        const double Ep = tab[5 * tstride + tt];
+        const size_t o = (size_t)s * T + tt, on = (size_t)n * v.ldt + tt;
+        st[j].Db = sel(v.D, cur)[o]; st[j].Cb = sel(v.C, cur)[o];
+        st[j].g0 = v.g0[on]; st[j].s1 = v.s1[on];
+        eta[j] = v.eta[o];
+        const double Ep = v.E[o];
         hl[j].h = HINGES ? hinges + (size_t)tt * v.hcap : nullptr;
         hl[j].n = HINGES ? hcnt[tt] : 0;
         hl[j].sorted = HINGES && v.hcap <= 64;   // k_sto_fix sorts lists of up to 64 entries by |bp|
@@ -563,21 +557,15 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
     }
     if (!accepted) return false;
 
-    // ---- emit: stage the results in shared memory and write them out coalesced ---------------------------
-    __syncwarp();
+    // ---- emit (blocked, same access pattern as the loads) --------------------------------------------------
 #pragma unroll
     for (int j = 0; j < J; ++j) {
         const int t = lane * J + j;
         if (!valid[j]) continue;
-        tab[0 * tstride + t] = D[j]; tab[1 * tstride + t] = C[j]; tab[2 * tstride + t] = pre[j]; tab[3 * tstride + t] = eta[j];
-        tab[4 * tstride + t] = (D[j] - st[j].Db) - (C[j] - st[j].Cb);
-    }
-    __syncwarp();
-    for (int t = lane; t < T; t += 32) {
         const size_t o = (size_t)s * T + t;
-        sel(v.D, nxt)[o] = tab[0 * tstride + t]; sel(v.C, nxt)[o] = tab[1 * tstride + t];
-        v.E[o] = tab[2 * tstride + t]; v.eta[o] = tab[3 * tstride + t];
-        note_move(v, n, t, tab[4 * tstride + t]);
+        sel(v.D, nxt)[o] = D[j]; sel(v.C, nxt)[o] = C[j];
+        v.E[o] = pre[j]; v.eta[o] = eta[j];
+        note_move(v, n, t, (D[j] - st[j].Db) - (C[j] - st[j].Cb));
     }
     __syncwarp();
     return true;
