@@ -277,7 +277,15 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
             if (cost < best - 1e-12) { best = cost; ks = k; }
         }
     };
-    plan_gemm(Np, Lp, lp.bm_t, lp.ksplit_t);
+    // the transposed product is only needed at the nodes that carry agents of this handle (all of them on one GPU,
+    // a contiguous node range per rank in the agent-partitioned mode): restrict it to the 64-row tiles of that range
+    int nmin = N, nmax = -1;
+    for (int g = 0; g < G; ++g) { nmin = std::min(nmin, (int)p->gen_node[g]); nmax = std::max(nmax, (int)p->gen_node[g]); }
+    for (int s2 = 0; s2 < S; ++s2) { nmin = std::min(nmin, (int)p->sto_node[s2]); nmax = std::max(nmax, (int)p->sto_node[s2]); }
+    if (nmax < 0) { nmin = 0; nmax = 0; }
+    lp.mt_base = (nmin / 64) * 64;
+    lp.mt_rows = (nmax / 64 + 1) * 64 - lp.mt_base;
+    plan_gemm(lp.mt_rows, Lp, lp.bm_t, lp.ksplit_t);
     plan_gemm(Lp, Np, lp.bm_n, lp.ksplit_n);
     AL(lp.part, (size_t)std::max(lp.ksplit_t * Np, lp.ksplit_n * Lp) * ldt);
     AL(lp.part2, (size_t)lp.ksplit_t * Np * ldt);

@@ -125,7 +125,7 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 template <int BM, bool TRANS>
 __global__ void __launch_bounds__(128) k_gemm(View v, const double *__restrict__ A, int lda, int ldb,
                                               double *__restrict__ Cpart, double *__restrict__ C2part,
-                                              int Mp, int Kp, int ksplit)
+                                              int Mp, int Kp, int ksplit, int m_base)
 {
     if (!DOPF_ACTIVE(v)) return;
     // B operand: M (and W) for the transposed product, the new injection for the flow product
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(128) k_gemm(View v, const double *__restrict__
     __shared__ __align__(16) double B2s[TRANS ? ST : 1][TRANS ? BK : 1][TRANS ? BN + 4 : 2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, z = blockIdx.z;
+    const int m0 = m_base + blockIdx.x * BM, n0 = blockIdx.y * BN, z = blockIdx.z;
     const int ksteps_total = Kp / BK;
     const int per = (ksteps_total + ksplit - 1) / ksplit;
     const int ks0 = z * per, ks1 = min(ksteps_total, ks0 + per);
@@ -885,9 +885,9 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     LAUNCH(k_row_prep<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, cs>>>(v, lp.tflag));
     LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 0));
     {   // PTDF^T M and (PTDF.^2)^T W
-        dim3 grid(v.Np / lp.bm_t, v.ldt / BN, lp.ksplit_t);
-        if (lp.bm_t == 64) LAUNCH(k_gemm<64, true><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, lp.part, lp.part2, v.Np, v.Lp, lp.ksplit_t));
-        else LAUNCH(k_gemm<32, true><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, lp.part, lp.part2, v.Np, v.Lp, lp.ksplit_t));
+        dim3 grid(lp.mt_rows / lp.bm_t, v.ldt / BN, lp.ksplit_t);
+        if (lp.bm_t == 64) LAUNCH(k_gemm<64, true><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, lp.part, lp.part2, v.Np, v.Lp, lp.ksplit_t, lp.mt_base));
+        else LAUNCH(k_gemm<32, true><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, lp.part, lp.part2, v.Np, v.Lp, lp.ksplit_t, lp.mt_base));
         LAUNCH(k_node_prep<<<cdiv((long long)v.Np * v.ldt, 256), 256, 0, cs>>>(v, lp.part, lp.part2, lp.ksplit_t));
     }
     FORK();   // storages on the side stream ...
@@ -946,8 +946,8 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     LAUNCH(k_colsum<<<v.ldt / 32, dim3(32, 32), 0, cs>>>(v));
     {   // flow = PTDF * inj
         dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);
-        if (lp.bm_n == 64) LAUNCH(k_gemm<64, false><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n));
-        else LAUNCH(k_gemm<32, false><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n));
+        if (lp.bm_n == 64) LAUNCH(k_gemm<64, false><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n, 0));
+        else LAUNCH(k_gemm<32, false><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n, 0));
         LAUNCH(k_flow_reduce<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, cs>>>(v, lp.part, lp.ksplit_n));
     }
     XCHG(DOPF_X_ROWSUM); // exact slack sums over all ranks' agents
@@ -1012,8 +1012,8 @@ void launch_rebuild_derived(const LaunchPlan &lp, cudaStream_t st, int segment)
     if (segment == 0) return;
     k_colsum<<<v.ldt / 32, dim3(32, 32), 0, st>>>(v);
     dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);
-    if (lp.bm_n == 64) k_gemm<64, false><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n);
-    else k_gemm<32, false><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n);
+    if (lp.bm_n == 64) k_gemm<64, false><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n, 0);
+    else k_gemm<32, false><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n, 0);
     k_flow_reduce<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, st>>>(v, lp.part, lp.ksplit_n);
     if (v.S > 0) k_levels<<<cdiv(v.S, 128), 128, 0, st>>>(v);
     k_flip<<<1, 1, 0, st>>>(v);

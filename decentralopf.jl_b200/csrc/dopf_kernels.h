@@ -10,6 +10,7 @@ struct LaunchPlan {
     View view;
     int num_sms;
     int bm_t, ksplit_t;       // tile rows / split-K of the transposed product (PTDF^T M)
+    int mt_base, mt_rows;     // node rows [mt_base, mt_base + mt_rows) the transposed product is computed for (multiples of 64)
     int bm_n, ksplit_n;       // ... of the flow product (PTDF * inj)
     int sto_fix_blocks;       // grid of the storage correction pass (one 32-thread block = one affected storage)
     int sto_fix_slots;        // nodes whose hinge lists k_sto_collect gathers (one scratch slot each, shared by the node's storages)
