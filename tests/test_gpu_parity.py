@@ -115,6 +115,21 @@ def test_unsorted_agents_and_edge_cases(pkg, DeviceADMM, oracle_mod):
         _compare(dev, ora, 1e-6)
 
 
+def test_agents_on_a_node_subrange(pkg, DeviceADMM, oracle_mod):
+    """all agents sit on the upper nodes: the PTDF^T product is then restricted to the row tiles of that node range
+    (what every rank of the agent-partitioned mode does); many storages per node share their hinge lists"""
+    d = pkg.cases.synthetic_arrays(N=150, L=220, G=300, S=90, T=12, seed=6)
+    d["gen_node"] = (70 + d["gen_node"] % 80).astype(d["gen_node"].dtype)
+    d["sto_node"] = (128 + d["sto_node"] % 20).astype(d["sto_node"].dtype)
+    prob = pkg.Problem.from_arrays(d); A = 390
+    dev = DeviceADMM(prob, gamma=0.3 / A, flow_weight=1.0 / A, device=0, hinge_capacity=64)
+    ora = oracle_mod.OracleADMM(prob, 0.3 / A, flow_weight=1.0 / A)
+    for _ in range(20):
+        dev.step(1); ora.iterate(0)
+        _compare(dev, ora, 1e-6)
+    assert dev.status.gen_corrected > 0 and dev.status.sto_corrected > 0
+
+
 def test_generators_only_and_storages_only(pkg, DeviceADMM, oracle_mod):
     for G, S in ((8, 0), (0, 6)):
         d = pkg.cases.synthetic_arrays(N=6, L=8, G=max(G, 1), S=max(S, 1), T=6, seed=G + S)
