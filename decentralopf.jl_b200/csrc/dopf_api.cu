@@ -247,7 +247,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     AL(v.dn, (size_t)Np * ldt); AL(v.dmax, ldt);
     for (int k = 0; k < 8; ++k) AL(v.nst[k], (size_t)Np * ldt);
     AL(v.flags, (size_t)ldt * Lp);
-    AL(v.wide, (size_t)T * 2 * L); AL(v.wcnt, T); AL(v.tight, (size_t)T * 2 * L); AL(v.tcnt, T);
+    AL(v.wide, (size_t)T * 2 * L); AL(v.wcnt, T); AL(v.tight, (size_t)T * 2 * L); AL(v.tight_b, (size_t)T * 2 * std::max(L, 1)); AL(v.tcnt, T);
     v.gen_work_cap = (int)std::min<long long>((long long)G * T, 1ll << 30);
     AL(v.gen_work, (size_t)std::max(v.gen_work_cap, 1)); AL(v.gen_grp, (size_t)2 * std::max(v.gen_work_cap, 1)); AL(v.sto_work, S); AL(v.sto_flag, S);
     AL(v.fix_node_flag, Np); AL(v.fix_node_list, Np); AL(v.fix_node_slot, Np);

@@ -99,6 +99,7 @@ struct View {
     const double *ptdfT;               // [Np][Lp] transposed PTDF (node-major) for per-agent hinge collection
     int *cold_work;                    // [S] storages whose warm start did not verify
     int *tight, *tcnt;                 // [T][2L] ; [T]
+    double *tight_b;                   // [T][2L] b of the tight entries (device path: k_verify reads it beside the list)
     int *gen_work;                     // [gen_work_cap] g*T+t
     int *gen_grp;                      // [gen_work_cap][2] groups of consecutive work entries of one (n,t): first entry, count
     int *sto_work, *sto_flag;          // [S], [S]

@@ -78,14 +78,17 @@ __global__ void __launch_bounds__(256) k_compact(View v, int mode)
                 const int i = base + lane;
                 bool p = false;
                 int e = 0;
+                double be = 0.0;
                 if (i < i1) {
                     e = in[i];
-                    p = fabs(v.wide_b[(size_t)t * 2 * v.L + i]) <= v.prow[e >> 1] * dm;
+                    be = v.wide_b[(size_t)t * 2 * v.L + i];
+                    p = fabs(be) <= v.prow[e >> 1] * dm;
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, p);
                 if (pass == 1 && p) {
                     const int pos = cnt + __popc(m & ((1u << lane) - 1));
                     out[pos] = e;
+                    v.tight_b[(size_t)t * 2 * v.L + pos] = be;
                 }
                 cnt += __popc(m);
             }
@@ -513,6 +516,35 @@ __global__ void __launch_bounds__(32) k_sto_fix(View v, Hinge *hinge_scratch, in
 // ------------------------------------------------------------------------------------------------
 // verify: lanes along nodes (PTDF rows are node-contiguous), 8 timesteps per block
 // ------------------------------------------------------------------------------------------------
+// verify_bounds() with the b values read beside the list (one dependent load less per row) and two rows in flight
+__device__ __forceinline__ bool verify_bounds_dev(const View &v, int n, int t, double &lo, double &hi)
+{
+    const double dnt = bits_nonneg(v.dn[(size_t)n * v.ldt + t]);
+    if (dnt == 0.0) return false;
+    lo = -INFINITY; hi = INFINITY;
+    const int cnt = v.tcnt[t];
+    const int *lst = v.tight + (size_t)t * 2 * v.L;
+    const double *lb = v.tight_b + (size_t)t * 2 * v.L;
+    auto one = [&](int e, double b, double p) {
+        if (fabs(b) > fabs(p) * dnt * (1.0 + 1e-12)) return;        // |b/p| > dnt (without the division)
+        Hinge h;
+        if (!make_hinge(v.c, p, b, e & 1, h)) return;
+        if (fabs(h.bp) > dnt) return;
+        if (h.bp > 0.0) { if (h.bp < hi) hi = h.bp; }
+        else if (h.bp < 0.0) { if (h.bp > lo) lo = h.bp; }
+        else { if (h.sg > 0.0) hi = 0.0; else lo = 0.0; }
+    };
+    int j = 0;
+    for (; j + 2 <= cnt; j += 2) {
+        const int e0 = lst[j], e1 = lst[j + 1];
+        const double b0 = lb[j], b1 = lb[j + 1];
+        const double p0 = v.ptdf[(size_t)(e0 >> 1) * v.Np + n], p1 = v.ptdf[(size_t)(e1 >> 1) * v.Np + n];
+        one(e0, b0, p0); one(e1, b1, p1);
+    }
+    if (j < cnt) { const int e0 = lst[j]; one(e0, lb[j], v.ptdf[(size_t)(e0 >> 1) * v.Np + n]); }
+    return !(lo == -INFINITY && hi == INFINITY);
+}
+
 __global__ void __launch_bounds__(256) k_verify(View v)
 {
     if (!DOPF_ACTIVE(v)) return;
@@ -527,7 +559,7 @@ __global__ void __launch_bounds__(256) k_verify(View v)
     __syncthreads();
     if (n < v.N && t < v.T) {
         double lo, hi;
-        if (verify_bounds(v, n, t, lo, hi)) {
+        if (verify_bounds_dev(v, n, t, lo, hi)) {
             const int q = atomicAdd(&qcnt, 1);
             qn[q] = n * 8 + warp; qlo[q] = lo; qhi[q] = hi;
         }
