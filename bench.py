@@ -7,7 +7,10 @@ metric  : agent*timestep updates per second = (G+S)*T*iterations / time (SURVEY.
           whole-job aggregate over all ranks; `iters_per_s` is reported beside it.
 workload: "target" = the north_star's synthetic 100k-agent x 96-period case (80k generators +
           20k storages on the 2000-node / 3000-line grid of BASELINE configs[2]); inputs resident in
-          HBM; working set (~0.5 GB) exceeds the 126 MB L2, so no explicit L2 flush is needed.
+          HBM; working set (~0.5 GB) exceeds the 126 MB L2, so no explicit L2 flush is needed.  It is the case the
+          north_star's target sentence names ("a synthetic 100k-agent x 96-period case ... on 1 B200") and the largest
+          single-GPU case of the list; "cfg2" = BASELINE configs[1] (118 nodes, 1k generators + 200 storages, 24 periods),
+          "cfg3" = BASELINE configs[2] (2k nodes, 20k generators + 5k storages, 96 periods) - see profiles/ for their lines.
 N > 1   : weak scaling, one process per GPU.  --shard agents (default): ONE case with N x the agents of
           the workload on the same grid, agents partitioned over the ranks, network/dual part replicated;
           per iteration torch.distributed (NCCL) all-reduces the per-timestep move maxima, the nodal

@@ -389,6 +389,7 @@ int dopf_profile_iteration(dopf_handle *h, int32_t cap, float *ms, const char **
     int n = 0;
     LaunchPlan lp = h->lp;
     lp.prof_events = ev.data(); lp.prof_names = nm.data(); lp.prof_cap = cap; lp.prof_count = &n;
+    launch_profile_warm(lp, h->stream);
     enqueue_iteration(lp, h->stream);
     CK(cudaGetLastError());
     int rc = sync_ctrl(h);

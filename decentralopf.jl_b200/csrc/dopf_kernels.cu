@@ -995,6 +995,15 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     return launches;
 }
 
+// profiling aid: keeps the stream busy while the first timed launch is queued (k_row_prep only depends on the
+// previous iterate, so running it twice changes nothing); without it the first event pair also times the host's
+// launch latency
+void launch_profile_warm(const LaunchPlan &lp, cudaStream_t st)
+{
+    const View &v = lp.view;
+    k_row_prep<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, st>>>(v, lp.tflag);
+}
+
 void launch_total_costs(const View &v, double *d_out, cudaStream_t st)
 {
     cudaMemsetAsync(d_out, 0, sizeof(double), st);

@@ -34,6 +34,7 @@ void launch_mwide(const View &v, cudaStream_t st);
 int set_storage_smem_attr(int T);   // opt in to > 48 KB dynamic shared memory for long horizons
 int slack_rows_cap();   // returns number of kernel launches
 void launch_total_costs(const View &v, double *d_out, cudaStream_t st);
+void launch_profile_warm(const LaunchPlan &lp, cudaStream_t st);
 void launch_nodal_price(const View &v, int which, double *d_out, cudaStream_t st);
 // segment 0: local injection of the staged iterate; segment 1: column sums, flows, levels, buffer flip
 void launch_rebuild_derived(const LaunchPlan &lp, cudaStream_t st, int segment = -1);  // inj/ssum/flow/E of buffer [cur] from P,D,C
