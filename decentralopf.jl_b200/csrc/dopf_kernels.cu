@@ -29,11 +29,27 @@ __global__ void k_row_prep(View v, unsigned char *tflag)
 // written in order (deterministic list order).
 //  mode 0: wide list from the flag bytes;  mode 1: tight list = wide entries with
 //  |b| <= max_n|ptdf[l,n]| * (largest move of any agent at t)
-__global__ void __launch_bounds__(256) k_compact(View v, int mode)
+__global__ void __launch_bounds__(256) k_compact(View v, int mode, int inline_dmax)
 {
     if (!DOPF_ACTIVE(v)) return;
     __shared__ int wcount[8];
+    __shared__ unsigned long long wmax[8];
     const int t = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (mode == 1 && inline_dmax) {
+        // dmax[t] = column maximum of dn (largest move of any agent at t); the separate k_dmax is only needed when
+        // the maxima are exchanged between ranks before the lists are built
+        unsigned long long a = 0ull;
+        for (int n = threadIdx.x; n < v.N; n += blockDim.x) { const unsigned long long b = v.dn[(size_t)n * v.ldt + t]; a = b > a ? b : a; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long y = __shfl_xor_sync(0xffffffffu, a, o); a = y > a ? y : a; }
+        if (lane == 0) wmax[warp] = a;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int k = 1; k < 8; ++k) a = wmax[k] > a ? wmax[k] : a;
+            v.dmax[t] = a;
+        }
+        __syncthreads();
+    }
     const int n_in = mode == 0 ? v.L : v.wcnt[t];
     // slice length per warp: a multiple of 128 rows in mode 0 (4 flag bytes per lane), of 32 entries in mode 1
     const int gran = mode == 0 ? 128 : 32;
@@ -783,7 +799,7 @@ __global__ void __launch_bounds__(256) k_slack_pairs(View v)
 }
 
 // dual update + residual maxima (update_duals.jl, convergence.jl:3-12)
-__global__ void __launch_bounds__(256) k_dual(View v, const unsigned char *tflag)
+__global__ void __launch_bounds__(256) k_dual(View v, const unsigned char *tflag, const double *Cpart, int ksplit)
 {
     if (!DOPF_ACTIVE(v)) return;
     __shared__ double rm[8], rr[8];
@@ -791,6 +807,11 @@ __global__ void __launch_bounds__(256) k_dual(View v, const unsigned char *tflag
     double a = 0.0, b = 0.0;
     if (i < v.L * v.ldt) {
         const int l = i / v.ldt, t = i % v.ldt;
+        {   // epilogue of the flow product: line_utilization = ptdf * injection (results.jl:114), split-K partials in order
+            double f = 0.0;
+            for (int z = 0; z < ksplit; ++z) f += Cpart[(size_t)z * v.Lp * v.ldt + i];
+            sel(v.flow, 1 - v.ctrl->cur)[i] = f;
+        }
         if (t < v.T) {
             const int flag = tflag[i];
             body_dual(v, l, t, flag, a, b);
@@ -915,7 +936,7 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
         ++launches;                                                                                \
     } while (0)
     LAUNCH(k_row_prep<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, cs>>>(v, lp.tflag));
-    LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 0));
+    LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 0, 0));
     {   // PTDF^T M and (PTDF.^2)^T W
         dim3 grid(lp.mt_rows / lp.bm_t, v.ldt / BN, lp.ksplit_t);
         if (lp.bm_t == 64) LAUNCH(k_gemm<64, true><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, lp.part, lp.part2, v.Np, v.Lp, lp.ksplit_t, lp.mt_base));
@@ -946,8 +967,7 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
         else LAUNCH(k_gen_predict<1><<<grd, blk, 0, cs>>>(v));
     }
     JOIN();
-    LAUNCH(k_dmax<<<dim3(v.ldt / 32, 16), dim3(32, 32), 0, cs>>>(v));
-    LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 1));
+    LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 1, 1));   // with the column maxima of the moves computed in place
     {
         dim3 grid(cdiv(v.N, 32), cdiv(v.T, 8));
         LAUNCH(k_verify<<<grid, 256, 0, cs>>>(v));
@@ -968,9 +988,9 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     MAIN();
     if (v.G > 0) LAUNCH(k_gen_fix<<<lp.num_sms * 2, 128, 0, cs>>>(v));
     JOIN();
-    LAUNCH(k_dmax<<<dim3(v.ldt / 32, 16), dim3(32, 32), 0, cs>>>(v));
+    if (segment >= 0) LAUNCH(k_dmax<<<dim3(v.ldt / 32, 16), dim3(32, 32), 0, cs>>>(v));   // partitioned mode: maxima are exchanged
     XCHG(DOPF_X_DMAX);   // all ranks must build the same tight lists
-    LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 1));   // moves may have grown
+    LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 1, segment < 0));   // moves may have grown
     LAUNCH(k_inject<<<dim3(v.Np / 8, v.ldt / 32), 256, 0, cs>>>(v));
     XCHG(DOPF_X_INJ);    // nodal injection of all ranks' agents
     LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.T), 512, 0, cs>>>(v, lp.tflag));   // needs the local injection statistics only
@@ -980,10 +1000,9 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
         dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);
         if (lp.bm_n == 64) LAUNCH(k_gemm<64, false><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n, 0));
         else LAUNCH(k_gemm<32, false><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n, 0));
-        LAUNCH(k_flow_reduce<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, cs>>>(v, lp.part, lp.ksplit_n));
     }
     XCHG(DOPF_X_ROWSUM); // exact slack sums over all ranks' agents
-    LAUNCH(k_dual<<<cdiv((long long)v.L * v.ldt, 256), 256, 0, cs>>>(v, lp.tflag));
+    LAUNCH(k_dual<<<cdiv((long long)v.L * v.ldt, 256), 256, 0, cs>>>(v, lp.tflag, lp.part, lp.ksplit_n));
     LAUNCH(k_lambda_finish<<<1, 256, 0, cs>>>(v));
 #undef LAUNCH
 #undef XCHG
