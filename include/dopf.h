@@ -37,7 +37,7 @@ extern "C" {
 #define DOPF_E_ARG (-1)       /* invalid argument / dimension                         */
 #define DOPF_E_CUDA (-2)      /* CUDA runtime error (incl. "no device")               */
 #define DOPF_E_CAPACITY (-3)  /* a device work list / hinge list capacity was exceeded */
-#define DOPF_E_COMM (-4)      /* NCCL error                                            */
+#define DOPF_E_COMM (-4)      /* reserved (the collectives of the partitioned mode are the caller's) */
 #define DOPF_E_UNSUPPORTED (-5)
 
 typedef struct dopf_handle dopf_handle;
