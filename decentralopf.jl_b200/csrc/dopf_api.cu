@@ -1,5 +1,5 @@
 // C ABI of libdopf (include/dopf.h): instance set-up, SoA packing, CUDA-graph driven stepping,
-// state transfer, optional NCCL exchange.  No CPU compute path exists in this library.
+// state transfer, phase-wise stepping for the partitioned (multi-GPU) mode.  No CPU compute path exists in this library.
 #include "../../include/dopf.h"
 #include "dopf_kernels.h"
 
@@ -34,6 +34,7 @@ struct dopf_handle {
     Ctrl *h_ctrl = nullptr;          // pinned mirror of the device control block
     double *d_scalar = nullptr;
     double *d_nodal = nullptr;
+    double *d_pen = nullptr;               // lazily allocated: 3*T penalty values + U,K [L][T] of one unit
     std::vector<int> gen_perm, sto_perm;   // sorted position -> caller's index
     bool gen_identity = true, sto_identity = true;
     std::vector<double> stage;             // host staging for permutation / padding
@@ -99,7 +100,7 @@ void fill_status(dopf_handle *h, dopf_status *s)
     s->tight_rows = c.stat_tight_rows; s->wide_rows = c.stat_wide_rows;
     s->launches_per_iteration = h->launches_per_iter;
     s->sto_cold = c.stat_sto_cold;
-    s->reserved2 = c.stat_fix_seq;
+    s->fix_sequential = c.stat_fix_seq;
     s->last_step_ms = h->last_step_ms;
 }
 
@@ -129,7 +130,7 @@ const char *dopf_version(void) { return "libdopf 0.1 (sm_100a)"; }
 void dopf_default_config(dopf_config *c)
 {
     c->gamma = 0.3; c->flow_weight = 10.0; c->prox_weight = 1.0; c->slack_mask_tol = 1e-2; c->eps = 1e-3;
-    c->device = -1; c->hinge_capacity = 0; c->use_graph = 1; c->reserved = 0;
+    c->device = -1; c->hinge_capacity = 0; c->use_graph = 1; c->debug_flags = 0;
 }
 
 const char *dopf_last_error(dopf_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -189,6 +190,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     v.hcap = cfg->hinge_capacity > 0 ? cfg->hinge_capacity : 32;
     v.c = Coef::make(cfg->gamma, cfg->flow_weight, cfg->prox_weight, cfg->slack_mask_tol, cfg->eps);
     v.demand_on = 1;
+    v.debug = cfg->debug_flags;
     const int ldt = v.ldt, Np = v.Np, Lp = v.Lp;
     h->use_graph = cfg->use_graph != 0;
 
@@ -408,7 +410,10 @@ int dopf_get_status(dopf_handle *h, dopf_status *out)
     int rc = sync_ctrl(h);
     if (rc) return rc;
     fill_status(h, out);
-    return DOPF_OK;
+    // partitioned handles are never stepped through dopf_step: this is where a device-side capacity error surfaces.
+    // After an error the device stops flipping its buffers, so the host mirror of the buffer index is re-read too.
+    h->host_cur = h->h_ctrl->cur;
+    return check_device_error(h);
 }
 
 // copy a padded device matrix [rows][ldt] to a dense host matrix [rows][T]
@@ -525,8 +530,73 @@ int dopf_get_nodal_price(dopf_handle *h, int32_t which, double *out)
     CK(cudaSetDevice(h->device));
     const View &v = h->lp.view;
     const int k = which == 0 ? h->h_ctrl->cur : 1 - h->h_ctrl->cur;
-    launch_nodal_price(v, k, h->d_nodal, h->stream);
+    launch_nodal_price(v, v.lam[k], v.mu[k], v.rho[k], h->d_nodal, h->stream);
     CK(cudaMemcpyAsync(out, h->d_nodal, (size_t)v.N * v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DOPF_OK;
+}
+
+int dopf_nodal_price_from(dopf_handle *h, const double *lam, const double *mu, const double *rho, double *out)
+{
+    if (!h || !lam || !mu || !rho || !out) return DOPF_E_ARG;
+    CK(cudaSetDevice(h->device));
+    const View &v = h->lp.view;
+    // staging in per-iteration scratch (M, Wt, first row of g0): all three are rewritten at the start of every iteration
+    int rc;
+    CK(cudaMemcpyAsync(v.g0, lam, (size_t)v.T * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = h2d_matrix(h, v.M, mu, v.L, v.T, v.ldt))) return rc;
+    if ((rc = h2d_matrix(h, v.Wt, rho, v.L, v.T, v.ldt))) return rc;
+    launch_nodal_price(v, v.g0, v.M, v.Wt, h->d_nodal, h->stream);
+    CK(cudaMemcpyAsync(out, h->d_nodal, (size_t)v.N * v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DOPF_OK;
+}
+
+static int need_iteration_done(dopf_handle *h, const char *what)
+{
+    if (h->h_ctrl->iters_done < 1) { h->err = std::string(what) + ": no iteration has run yet"; return DOPF_E_ARG; }
+    if (h->nranks > 1) { h->err = std::string(what) + ": single-GPU handles only"; return DOPF_E_UNSUPPORTED; }
+    return 0;
+}
+
+int dopf_get_unit_penalty(dopf_handle *h, int32_t kind, int32_t index, double *eb, double *upper, double *lower, double *U, double *K)
+{
+    if (!h || kind < 0 || kind > 1 || !eb || !upper || !lower) return DOPF_E_ARG;
+    const View &v = h->lp.view;
+    if (index < 0 || index >= (kind == 0 ? v.G : v.S)) return DOPF_E_ARG;
+    CK(cudaSetDevice(h->device));
+    int rc = need_iteration_done(h, "dopf_get_unit_penalty");
+    if (rc) return rc;
+    if (!h->d_pen) { if ((rc = dev_alloc(h, &h->d_pen, (size_t)3 * v.T + (size_t)2 * v.L * v.T))) return rc; }
+    // caller's index -> position in the node-sorted device order
+    const std::vector<int> &perm = kind == 0 ? h->gen_perm : h->sto_perm;
+    int pos = index;
+    if (!(kind == 0 ? h->gen_identity : h->sto_identity)) pos = (int)(std::find(perm.begin(), perm.end(), index) - perm.begin());
+    double *dU = h->d_pen + (size_t)3 * v.T, *dK = dU + (size_t)v.L * v.T;
+    launch_unit_penalty(v, kind, pos, h->d_pen, h->d_pen + v.T, h->d_pen + 2 * v.T, U ? dU : nullptr, K ? dK : nullptr, h->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(eb, h->d_pen, (size_t)v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(upper, h->d_pen + v.T, (size_t)v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(lower, h->d_pen + 2 * v.T, (size_t)v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (U) CK(cudaMemcpyAsync(U, dU, (size_t)v.L * v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (K) CK(cudaMemcpyAsync(K, dK, (size_t)v.L * v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DOPF_OK;
+}
+
+int dopf_get_penalty_totals(dopf_handle *h, double *eb, double *upper, double *lower)
+{
+    if (!h || !eb || !upper || !lower) return DOPF_E_ARG;
+    const View &v = h->lp.view;
+    CK(cudaSetDevice(h->device));
+    int rc = need_iteration_done(h, "dopf_get_penalty_totals");
+    if (rc) return rc;
+    if (!h->d_pen) { if ((rc = dev_alloc(h, &h->d_pen, (size_t)3 * v.T + (size_t)2 * v.L * v.T))) return rc; }
+    launch_penalty_totals(v, h->d_pen, h->d_pen + v.T, h->d_pen + 2 * v.T, h->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(eb, h->d_pen, (size_t)v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(upper, h->d_pen + v.T, (size_t)v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(lower, h->d_pen + 2 * v.T, (size_t)v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return DOPF_OK;
 }

@@ -57,6 +57,7 @@ struct View {
     int Np, Lp;       // padded row counts (multiples of 64) of the node / line matrices
     int hcap;         // hinge capacity per (agent, t) in the correction pass
     int gen_work_cap;
+    int debug;        // dopf_config.debug_flags: bit0 correction pass of the storages uses the sequential solver, bit1 predict pass too
     Coef c;
     // static problem data
     const double *ptdf;     // [Lp][Np] zero padded                               admm.ptdf

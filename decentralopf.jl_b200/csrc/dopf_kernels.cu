@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(128, DOPF_STO_MINB) k_sto_warp(View v)
     extern __shared__ __align__(16) double sto_smem[];
     double *tab = sto_smem + (size_t)(threadIdx.x >> 5) * (sto_warp_smem_per_warp(v.T) / sizeof(double));
     for (int s = gw; s < v.S; s += nw) {
-        const bool ok = sto_warp_solve<J, false>(v, s, nullptr, nullptr, tab);
+        const bool ok = (v.debug & 2) ? false : sto_warp_solve<J, false>(v, s, nullptr, nullptr, tab);
         if (!ok && lane == 0) v.cold_work[atomicAdd(&v.ctrl->cold_work_cnt, 1)] = s;
         __syncwarp();
     }
@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(32) k_sto_fix(View v, Hinge *hinge_scratch, in
             __syncwarp();
         }
         bool ok = false;
-        if (J > 0) ok = sto_warp_solve<(J > 0 ? J : 1), true>(v, s, mylist, mycnt, sto_smem);
+        if (J > 0 && !(v.debug & 1)) ok = sto_warp_solve<(J > 0 ? J : 1), true>(v, s, mylist, mycnt, sto_smem);
         if (lane == 0) {
             if (!ok) { body_sto_cold(v, s, mylist, mycnt, v.hcap <= 64); atomicAdd(&v.ctrl->stat_fix_seq, 1); }
             atomicAdd(&v.ctrl->stat_sto_fix, 1);
@@ -881,15 +881,80 @@ __global__ void k_total_costs(View v, double *out)
 }
 
 // nodal price (network_elements.jl:16-25): lambda_t + sum_l (mu+rho)[l,t] ptdf[l,n]
-__global__ void k_nodal_price(View v, int which, double *out /*[N][T]*/)
+__global__ void k_nodal_price(View v, const double *lam, const double *mu, const double *rho, double *out /*[N][T]*/)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= v.N * v.T) return;
     const int n = i / v.T, t = i % v.T;
-    double a = sel(v.lam, which)[t];
+    double a = lam[t];
     for (int l = 0; l < v.L; ++l)
-        a += (sel(v.mu, which)[(size_t)l * v.ldt + t] + sel(v.rho, which)[(size_t)l * v.ldt + t]) * v.ptdf[(size_t)l * v.Np + n];
+        a += (mu[(size_t)l * v.ldt + t] + rho[(size_t)l * v.ldt + t]) * v.ptdf[(size_t)l * v.Np + n];
     out[i] = a;
+}
+
+// per-unit report of the newest iterate (subproblems.jl:89-102): the unit's private slacks
+//   U*[l,t] = (2w/k) (b+ - p delta)_+ ,  K*[l,t] = (2w/k) (b- + p delta)_+        
+// and the values of its penalty expressions (penalty_terms.jl:3-37)
+//   energy_balance[t] = (Sbar_t + delta_t)^2, upper_flow[t] = sum_l (Fbar + p delta + U - f)^2, lower_flow[t] = sum_l (K - Fbar - p delta - f)^2.
+// Valid after an iteration has finished: [cur] holds the newest iterate, [1-cur] the previous one and bplus/bminus
+// are still those of that iteration.  One block per timestep, threads over the lines.
+__global__ void __launch_bounds__(128) k_unit_penalty(View v, int kind, int idx, double *eb, double *up, double *lo, double *U, double *K)
+{
+    __shared__ double ru[4], rl[4];
+    const int t = blockIdx.x, newest = v.ctrl->cur, prev = 1 - newest;
+    const int n = kind == 0 ? v.gen_node[idx] : v.sto_node[idx];
+    const size_t o = (size_t)idx * v.T + t;
+    const double delta = kind == 0 ? sel(v.P, newest)[o] - sel(v.P, prev)[o]
+                                   : (sel(v.D, newest)[o] - sel(v.D, prev)[o]) - (sel(v.C, newest)[o] - sel(v.C, prev)[o]);
+    const double sc = v.c.w2 / v.c.kk;
+    double au = 0.0, al = 0.0;
+    for (int l = threadIdx.x; l < v.L; l += blockDim.x) {
+        const size_t i = (size_t)l * v.ldt + t;
+        const double p = v.ptdf[(size_t)l * v.Np + n], pd = p * delta, F = sel(v.flow, prev)[i], f = v.fmax[l];
+        const double u = sc * pospart(v.bplus[i] - pd), k = sc * pospart(v.bminus[i] + pd);
+        if (U) U[(size_t)l * v.T + t] = u;
+        if (K) K[(size_t)l * v.T + t] = k;
+        const double a = F + pd + u - f, b = k - F - pd - f;
+        au += a * a; al += b * b;
+    }
+    au = Group<32>::sum(au); al = Group<32>::sum(al);
+    if ((threadIdx.x & 31) == 0) { ru[threadIdx.x >> 5] = au; rl[threadIdx.x >> 5] = al; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double s = sel(v.ssum, prev)[t] + delta;
+        eb[t] = s * s; up[t] = ru[0] + ru[1] + ru[2] + ru[3]; lo[t] = rl[0] + rl[1] + rl[2] + rl[3];
+    }
+}
+
+// the same three penalty values summed over ALL units (result.penalty_term, results.jl:73-76): one thread per
+// (line, t) walks the nodes and their agents (on demand only: A*L*T terms)
+__global__ void __launch_bounds__(128) k_penalty_totals(View v, double *eb, double *up, double *lo)
+{
+    const int t = blockIdx.x * 32 + (threadIdx.x & 31), l = blockIdx.y * 4 + (threadIdx.x >> 5);
+    if (t >= v.T || l >= v.L) return;
+    const int newest = v.ctrl->cur, prev = 1 - newest;
+    const size_t i = (size_t)l * v.ldt + t;
+    const double sc = v.c.w2 / v.c.kk, F = sel(v.flow, prev)[i], f = v.fmax[l], bp = v.bplus[i], bm = v.bminus[i], S = sel(v.ssum, prev)[t];
+    double au = 0.0, al = 0.0, ae = 0.0;
+    for (int n = 0; n < v.N; ++n) {
+        const double p = v.ptdf[(size_t)l * v.Np + n];
+        for (int g = v.gen_ptr[n]; g < v.gen_ptr[n + 1]; ++g) {
+            const size_t o = (size_t)g * v.T + t;
+            const double d = sel(v.P, newest)[o] - sel(v.P, prev)[o], pd = p * d;
+            const double a = F + pd + sc * pospart(bp - pd) - f, b = sc * pospart(bm + pd) - F - pd - f;
+            au += a * a; al += b * b;
+            if (l == 0) ae += (S + d) * (S + d);
+        }
+        for (int s = v.sto_ptr[n]; s < v.sto_ptr[n + 1]; ++s) {
+            const size_t o = (size_t)s * v.T + t;
+            const double d = (sel(v.D, newest)[o] - sel(v.D, prev)[o]) - (sel(v.C, newest)[o] - sel(v.C, prev)[o]), pd = p * d;
+            const double a = F + pd + sc * pospart(bp - pd) - f, b = sc * pospart(bm + pd) - F - pd - f;
+            au += a * a; al += b * b;
+            if (l == 0) ae += (S + d) * (S + d);
+        }
+    }
+    atomicAdd(up + t, au); atomicAdd(lo + t, al);
+    if (l == 0) eb[t] = ae;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -982,7 +1047,7 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
         case 4: LAUNCH(k_sto_fix<4><<<lp.sto_fix_blocks, 32, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch, lp.sto_fix_slots)); break;
         case 6: LAUNCH(k_sto_fix<6><<<lp.sto_fix_blocks, 32, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch, lp.sto_fix_slots)); break;
         case 8: LAUNCH(k_sto_fix<8><<<lp.sto_fix_blocks, 32, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch, lp.sto_fix_slots)); break;
-        default: LAUNCH(k_sto_fix<0><<<lp.sto_fix_blocks, 32, sto_warp_smem_per_warp(v.T), cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch, lp.sto_fix_slots)); break;
+        default: LAUNCH(k_sto_fix<0><<<lp.sto_fix_blocks, 32, 0, cs>>>(v, lp.hinge_scratch, lp.hcnt_scratch, lp.sto_fix_slots)); break;
         }
     }
     MAIN();
@@ -1029,9 +1094,20 @@ void launch_total_costs(const View &v, double *d_out, cudaStream_t st)
     k_total_costs<<<296, 256, 0, st>>>(v, d_out);
 }
 
-void launch_nodal_price(const View &v, int which, double *d_out, cudaStream_t st)
+void launch_nodal_price(const View &v, const double *lam, const double *mu, const double *rho, double *d_out, cudaStream_t st)
 {
-    k_nodal_price<<<cdiv((long long)v.N * v.T, 128), 128, 0, st>>>(v, which, d_out);
+    k_nodal_price<<<cdiv((long long)v.N * v.T, 128), 128, 0, st>>>(v, lam, mu, rho, d_out);
+}
+
+void launch_unit_penalty(const View &v, int kind, int idx, double *eb, double *up, double *lo, double *U, double *K, cudaStream_t st)
+{
+    k_unit_penalty<<<v.T, 128, 0, st>>>(v, kind, idx, eb, up, lo, U, K);
+}
+
+void launch_penalty_totals(const View &v, double *eb, double *up, double *lo, cudaStream_t st)
+{
+    cudaMemsetAsync(up, 0, sizeof(double) * v.T, st); cudaMemsetAsync(lo, 0, sizeof(double) * v.T, st);
+    k_penalty_totals<<<dim3(cdiv(v.T, 32), cdiv(v.L, 4)), 128, 0, st>>>(v, eb, up, lo);
 }
 
 // static wide-row bound mwide[l] = max_n |ptdf[l,n]| * rbox[n]; one warp per line (re-run after the

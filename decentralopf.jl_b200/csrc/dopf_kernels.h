@@ -35,7 +35,9 @@ int set_storage_smem_attr(int T);   // opt in to > 48 KB dynamic shared memory f
 int slack_rows_cap();   // returns number of kernel launches
 void launch_total_costs(const View &v, double *d_out, cudaStream_t st);
 void launch_profile_warm(const LaunchPlan &lp, cudaStream_t st);
-void launch_nodal_price(const View &v, int which, double *d_out, cudaStream_t st);
+void launch_nodal_price(const View &v, const double *lam, const double *mu, const double *rho, double *d_out, cudaStream_t st);
+void launch_unit_penalty(const View &v, int kind, int idx, double *eb, double *up, double *lo, double *U, double *K, cudaStream_t st);
+void launch_penalty_totals(const View &v, double *eb, double *up, double *lo, cudaStream_t st);
 // segment 0: local injection of the staged iterate; segment 1: column sums, flows, levels, buffer flip
 void launch_rebuild_derived(const LaunchPlan &lp, cudaStream_t st, int segment = -1);  // inj/ssum/flow/E of buffer [cur] from P,D,C
 

@@ -245,9 +245,12 @@ __device__ __forceinline__ void flat_interval_tab(const StoStep &st, const doubl
     }
 }
 
-// clipped step with hinges: D, C, delta and therefore the hinge force are constant while nu stays inside the clip
-// piece [plo, phi] that holds it, so eta may move by (nu - plo) upwards and (phi - nu) downwards without changing y_t
-__device__ __forceinline__ void flat_range_hinge(const StoStep &st, const HingeList &hl, double hmin, const double *tab, int tstride, int t,
+// clipped step with hinges: D, C, delta and therefore the hinge force are constant while nu stays inside the range
+// [plo, phi] on which both variables keep their clip state, so eta may move by (nu - plo) upwards and (phi - nu)
+// downwards without changing y_t.  The range is derived from the clip STATE of D and C, not from the position of nu:
+// on a saturated run the Newton update lands on a clip breakpoint, and locating nu among the breakpoints would
+// pick the neighbouring (free) piece as often as the flat one.
+__device__ __forceinline__ void flat_range_hinge(const StoStep &st, const StoConst &k, const HingeList &hl, double hmin,
                                                  double eta, double D, double C, double &elo, double &ehi)
 {
     const double dl = (D - st.Db) - (C - st.Cb);
@@ -255,13 +258,17 @@ __device__ __forceinline__ void flat_range_hinge(const StoStep &st, const HingeL
     if (fabs(dl) >= hmin) hl.eval(dl, hv, hs);
     const double nu = st.g0 - eta + st.s1 * dl + hv;
     double plo = -WBIG, phi = WBIG;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const double b = tab[(TAB_BB + i) * tstride + t];
-        if (b <= nu) plo = b; else if (phi == WBIG) phi = b;
+    if (k.pmax > 0.0) {
+        // D = clip(Db - (mc + nu)/prox) falls with nu, C = clip(Cb - (mc - nu)/prox) rises with nu
+        if (D <= 0.0) plo = fmax(plo, k.prox * st.Db - k.mc);                     // D stays 0 for nu above
+        else if (D >= k.pmax) phi = fmin(phi, k.prox * (st.Db - k.pmax) - k.mc);  // D stays pmax for nu below
+        else { plo = nu; phi = nu; }                                              // free variable: no slack at all
+        if (C <= 0.0) phi = fmin(phi, k.mc - k.prox * st.Cb);                     // C stays 0 for nu below
+        else if (C >= k.pmax) plo = fmax(plo, k.mc + k.prox * (k.pmax - st.Cb));  // C stays pmax for nu above
+        else { plo = nu; phi = nu; }
     }
-    ehi = plo > -WBIG ? eta + (nu - plo) : WBIG;
-    elo = phi < WBIG ? eta - (phi - nu) : -WBIG;
+    ehi = plo > -WBIG ? eta + fmax(nu - plo, 0.0) : WBIG;
+    elo = phi < WBIG ? eta - fmax(phi - nu, 0.0) : -WBIG;
 }
 
 // run status bits broadcast from the tail
@@ -400,7 +407,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
                     if (valid[j]) {
                         if (HINGES && hl[j].n != 0) {
                             double elo, ehi;
-                            flat_range_hinge(st[j], hl[j], hmin[j], tab, tstride, lane * J + j, eta[j], D[j], C[j], elo, ehi);
+                            flat_range_hinge(st[j], k, hl[j], hmin[j], eta[j], D[j], C[j], elo, ehi);
                             bu[j] = ehi; bd[j] = elo;
                         } else next_breaks_tab(tab, tstride, lane * J + j, eta[j], bu[j], bd[j]);
                     }
@@ -450,7 +457,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
             Ilo[j] = -WBIG; Ihi[j] = WBIG;
             if (valid[j]) {
                 if (!(rs[j] & RS_FLAT)) { Ilo[j] = eta[j]; Ihi[j] = eta[j]; }
-                else if (HINGES && hl[j].n != 0) flat_range_hinge(st[j], hl[j], hmin[j], tab, tstride, lane * J + j, eta[j], D[j], C[j], Ilo[j], Ihi[j]);
+                else if (HINGES && hl[j].n != 0) flat_range_hinge(st[j], k, hl[j], hmin[j], eta[j], D[j], C[j], Ilo[j], Ihi[j]);
                 else flat_interval_tab(st[j], tab, tstride, lane * J + j, eta[j], D[j], C[j], Ilo[j], Ihi[j]);
             }
         }
@@ -525,6 +532,12 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
             for (int j = 0; j < J; ++j) tv[j] = (int)tvd[j];
         }
 
+#ifdef DOPF_DEBUG_STO
+        if (HINGES && (v.debug & 4) && s == ((v.debug >> 8) & 0xfff) && v.ctrl->iteration == (v.debug >> 20)) {
+            for (int j = 0; j < J; ++j)
+                if (valid[j]) printf("r%d t%d kind %d h%d tl%d eta %.9g D %.9g C %.9g E %.9g rs %d I[%.9g,%.9g] F[%.9g,%.9g] flag %d tv %d hn %d hmin %.6g prevk %d endk %d\n", as_it, lane * J + j, kind[j], (int)head[j], (int)tail[j], eta[j], D[j], C[j], e0[j] + pre[j], rs[j], Ilo[j], Ihi[j], Flo[j], Fhi[j], flag[j], tv[j], hl[j].n, hmin[j], prevk[j], endk[j]);
+        }
+#endif
         // ---- repair the active set -----------------------------------------------------------------
         bool change = false, anybad = false;
         int wantdrop[J];                                            // head of a run that wants the previous anchor gone

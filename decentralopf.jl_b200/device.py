@@ -19,7 +19,7 @@ class DeviceADMM:
     """Owns a `dopf_handle`.  Arrays are numpy float64, row-major, timestep contiguous."""
 
     def __init__(self, prob: Problem, gamma=0.3, flow_weight=10.0, prox_weight=1.0, slack_mask_tol=1e-2, eps=1e-3,
-                 device=-1, hinge_capacity=0, use_graph=True):
+                 device=-1, hinge_capacity=0, use_graph=True, debug_flags=0):
         self.lib = _lib.load()
         self.prob = prob
         p = prob
@@ -34,6 +34,7 @@ class DeviceADMM:
         cfg.gamma, cfg.flow_weight, cfg.prox_weight = float(gamma), float(flow_weight), float(prox_weight)
         cfg.slack_mask_tol, cfg.eps = float(slack_mask_tol), float(eps)
         cfg.device, cfg.hinge_capacity, cfg.use_graph = int(device), int(hinge_capacity), int(bool(use_graph))
+        cfg.debug_flags = int(debug_flags)
         self.h = C.c_void_p()
         rc = self.lib.dopf_create(C.byref(cp), C.byref(cfg), C.byref(self.h))
         if rc != 0:
@@ -114,6 +115,28 @@ class DeviceADMM:
         out = np.empty((self.prob.N, self.prob.T))
         self._check(self.lib.dopf_get_nodal_price(self.h, int(which), _ptr(out)), "dopf_get_nodal_price")
         return out
+
+    def nodal_price_of(self, lam, mu, rho):
+        """get_nodal_price for an arbitrary dual set of the caller's history"""
+        out = np.empty((self.prob.N, self.prob.T))
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in (lam, mu, rho)]
+        self._check(self.lib.dopf_nodal_price_from(self.h, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(out)), "dopf_nodal_price_from")
+        return out
+
+    def unit_penalty(self, kind, index, with_slacks=True):
+        """penalty_term and private slacks U, K of one unit in the newest iterate (kind 0 generator, 1 storage)"""
+        p = self.prob
+        eb, up, lo = np.empty(p.T), np.empty(p.T), np.empty(p.T)
+        U = np.empty((p.L, p.T)) if with_slacks else None
+        K = np.empty((p.L, p.T)) if with_slacks else None
+        self._check(self.lib.dopf_get_unit_penalty(self.h, int(kind), int(index), _ptr(eb), _ptr(up), _ptr(lo), _ptr(U), _ptr(K)), "dopf_get_unit_penalty")
+        return dict(energy_balance=eb, upper_flow=up, lower_flow=lo, U=U, K=K)
+
+    def penalty_totals(self):
+        p = self.prob
+        eb, up, lo = np.empty(p.T), np.empty(p.T), np.empty(p.T)
+        self._check(self.lib.dopf_get_penalty_totals(self.h, _ptr(eb), _ptr(up), _ptr(lo)), "dopf_get_penalty_totals")
+        return dict(energy_balance=eb, upper_flow=up, lower_flow=lo)
 
     def total_costs(self):
         v = C.c_double()

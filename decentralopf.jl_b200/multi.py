@@ -2,8 +2,9 @@
 
 Every rank keeps the full network data (PTDF, limits, demand) and a contiguous, node-sorted block of
 the generators and of the storages (so a storage's whole horizon stays on one GPU).  Per iteration the
-ranks exchange (NCCL all-reduce inside libdopf): the per-timestep maximum move, the nodal injection
-and the exact slack row sums - SURVEY.md section 8(e) "agent block".
+ranks all-reduce three device buffers of libdopf in place (the caller owns the collective:
+torch.distributed / NCCL on the stream the library runs on): the per-timestep maximum move, the nodal
+injection and the exact slack row sums - SURVEY.md section 8(e) "agent block".
 """
 import ctypes as C
 
@@ -81,12 +82,76 @@ class PartitionedADMM:
                     d._check(lib.dopf_step_phase(d.h, 2), "phase 2"); self._allreduce(2, R.SUM)
                     d._check(lib.dopf_step_phase(d.h, 3), "phase 3")
                 done += n
-                d._check(lib.dopf_get_status(d.h, C.byref(d.status)), "dopf_get_status")   # synchronises
+                rc = lib.dopf_get_status(d.h, C.byref(d.status))      # synchronises; < 0: device-side capacity error
+                if self.world > 1:       # a failing rank must stop ALL ranks (the others would all-reduce its stale buffers)
+                    flag = self.torch.tensor([rc], dtype=self.torch.int32, device=f"cuda:{self.torch.cuda.current_device()}")
+                    self.dist.all_reduce(flag, op=R.MIN)
+                    worst = int(flag.item())
+                    if worst != 0 and rc == 0:
+                        raise RuntimeError(f"partitioned run stopped: another rank reported rc={worst}")
+                d._check(rc, "dopf_get_status")
                 if d.status.converged:
                     break
         return d.status
 
     def close(self):
         self.dev.close()
+
+
+class LocalPartitionGroup:
+    """`world` partition handles inside ONE process on ONE device, stepped in lockstep with the all-reduces done by
+    plain torch ops on the exchange buffers.  It drives exactly the library code of the multi-GPU mode
+    (dopf_set_partition / dopf_step_phase / dopf_exchange_buffer) without NCCL, so the partitioned path can be
+    checked against a single handle on a one-GPU box (tests/test_gpu_partition.py)."""
+
+    def __init__(self, prob: Problem, world, device=0, **cfg):
+        import torch
+        from .device import DeviceADMM
+        self.torch, self.world, self.full = torch, world, prob
+        self.stream = torch.cuda.Stream(device=device)
+        self.members = []
+        for r in range(world):
+            sub, gi, si = shard_problem(prob, r, world)
+            dev = DeviceADMM(sub, device=device, use_graph=False, **cfg)
+            dev._check(dev.lib.dopf_set_stream(dev.h, C.c_void_p(self.stream.cuda_stream)), "dopf_set_stream")
+            self.members.append((dev, gi, si))
+        with torch.cuda.stream(self.stream):
+            for r, (dev, _, _) in enumerate(self.members):
+                dev._check(dev.lib.dopf_set_partition(dev.h, r, world, prob.G + prob.S), "dopf_set_partition")
+            self._allreduce(1, "sum"); self._allreduce(3, "max")
+            for dev, _, _ in self.members:
+                dev._check(dev.lib.dopf_step_phase(dev.h, -1), "dopf_step_phase")
+        self.stream.synchronize()
+
+    def _buffers(self, which):
+        out = []
+        for dev, _, _ in self.members:
+            ptr, n = C.c_void_p(), C.c_int64()
+            dev._check(dev.lib.dopf_exchange_buffer(dev.h, which, C.byref(ptr), C.byref(n)), "dopf_exchange_buffer")
+            out.append(self.torch.as_tensor(_DevBuf(ptr.value, n.value), device=f"cuda:{self.torch.cuda.current_device()}"))
+        return out
+
+    def _allreduce(self, which, op):
+        bufs = self._buffers(which)
+        st = self.torch.stack(bufs)
+        red = st.sum(0) if op == "sum" else st.max(0).values
+        for b in bufs:
+            b.copy_(red)
+
+    def step(self, iters=1):
+        with self.torch.cuda.stream(self.stream):
+            for _ in range(iters):
+                for phase, (which, op) in enumerate(((0, "max"), (1, "sum"), (2, "sum"), (None, None))):
+                    for dev, _, _ in self.members:
+                        dev._check(dev.lib.dopf_step_phase(dev.h, phase), f"phase {phase}")
+                    if which is not None:
+                        self._allreduce(which, op)
+        for dev, _, _ in self.members:
+            dev._check(dev.lib.dopf_get_status(dev.h, C.byref(dev.status)), "dopf_get_status")
+        return self.members[0][0].status
+
+    def close(self):
+        for dev, _, _ in self.members:
+            dev.close()
 
 

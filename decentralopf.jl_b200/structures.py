@@ -59,27 +59,75 @@ class Convergence:  # structures/convergence.jl:1-20
 
 
 @dataclass(eq=False)
-class ResultGenerator:  # structures/results.jl:11-17 (U,K per agent are never materialised)
-    generator: Generator
-    generation: np.ndarray
+class PenaltyTerm:  # structures/penalty_terms.jl:1-5 - values of the three penalty expressions per timestep
+    energy_balance: np.ndarray
+    upper_flow: np.ndarray
+    lower_flow: np.ndarray
+
+
+class _UnitResult:
+    """penalty_term, U, K of a unit result (subproblems.jl:89-102) are evaluated on the device on first access
+    (dopf_get_unit_penalty) instead of being copied for every agent in every iteration: U, K are L x T per agent."""
+    _source = None
+    _cache = None
+
+    def _detail(self):
+        if self._cache is None:
+            if self._source is None:
+                raise RuntimeError("no device source attached to this unit result")
+            self._cache = self._source()
+        return self._cache
+
+    @property
+    def penalty_term(self):
+        d = self._detail()
+        return PenaltyTerm(d["energy_balance"], d["upper_flow"], d["lower_flow"])
+
+    @property
+    def U(self):
+        return self._detail()["U"]
+
+    @property
+    def K(self):
+        return self._detail()["K"]
+
+
+class ResultGenerator(_UnitResult):  # structures/results.jl:11-17
+    def __init__(self, generator, generation, source=None):
+        self.generator, self.generation, self._source = generator, generation, source
+
+
+class ResultStorage(_UnitResult):  # structures/results.jl:1-9
+    def __init__(self, storage, discharge, charge, level, source=None):
+        self.storage, self.discharge, self.charge, self.level, self._source = storage, discharge, charge, level, source
 
 
 @dataclass(eq=False)
-class ResultStorage:  # structures/results.jl:1-9
-    storage: Storage
+class ResultNode:  # structures/results.jl:19-34 (the node's penalty terms are the sums over its units; not materialised)
+    node: Node
+    generation: np.ndarray
     discharge: np.ndarray
     charge: np.ndarray
-    level: np.ndarray
 
 
-@dataclass(eq=False)
-class Result:  # structures/results.jl:36-48 (fields that the iteration or its readers use)
-    unit_to_result: dict
-    generation: np.ndarray      # [T]
-    discharge: np.ndarray       # [T]
-    charge: np.ndarray          # [T]
-    avg_U: np.ndarray           # [L,T]
-    avg_K: np.ndarray           # [L,T]
-    total_costs: float
-    injection: np.ndarray       # [N,T]
-    line_utilization: np.ndarray  # [L,T]
+class Result:  # structures/results.jl:36-48
+    def __init__(self, unit_to_result, node_to_result, generation, discharge, charge, avg_U, avg_K, total_costs,
+                 injection, line_utilization, totals_source=None):
+        self.unit_to_result = unit_to_result        # unit object -> ResultGenerator | ResultStorage
+        self.node_to_result = node_to_result        # Node -> ResultNode
+        self.generation, self.discharge, self.charge = generation, discharge, charge      # [T]
+        self.avg_U, self.avg_K = avg_U, avg_K                                              # [L,T]
+        self.total_costs = total_costs
+        self.injection = injection                  # [N,T]
+        self.line_utilization = line_utilization    # [L,T]
+        self._totals_source, self._totals = totals_source, None
+
+    @property
+    def penalty_term(self):
+        """sum of the units' penalty terms (results.jl:73-76), evaluated on the device on first access"""
+        if self._totals is None:
+            if self._totals_source is None:
+                raise RuntimeError("no device source attached to this result")
+            self._totals = self._totals_source()
+        t = self._totals
+        return PenaltyTerm(t["energy_balance"], t["upper_flow"], t["lower_flow"])

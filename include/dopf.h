@@ -16,6 +16,8 @@
  *   dopf_set_state     <- (no reference counterpart) resume / inject a mid-trace state
  *   dopf_get_nodal_price <- get_nodal_price(iteration)                      src/helpers/network_elements.jl:16-25
  *   dopf_get_total_costs <- result.total_costs                              src/structures/results.jl:95-105
+ *   dopf_get_unit_penalty <- unit_to_result[u].{penalty_term,U,K}           src/optimization/subproblems.jl:89-102
+ *   dopf_get_penalty_totals <- result.penalty_term                          src/structures/results.jl:73-76
  *
  * Conventions: every matrix is row-major with the timestep index contiguous ([agent][t],
  * [node][t], [line][t]; ptdf is [line][node]).  Julia callers pass permutedims(...) of their
@@ -65,7 +67,7 @@ typedef struct dopf_config {
     int32_t device;          /* CUDA device ordinal, -1 = current device                   */
     int32_t hinge_capacity;  /* per (agent,t) hinge list capacity of the correction pass; 0 = default 32 */
     int32_t use_graph;       /* 1 = replay one captured CUDA graph per iteration           */
-    int32_t reserved;
+    int32_t debug_flags;     /* 0; diagnostics: bit0 storage correction pass by the sequential solver, bit1 storage predict pass too */
 } dopf_config;
 
 /* fills the reference's literals: gamma 0.3, flow_weight 10, prox 1, mask 1e-2, eps 1e-3 */
@@ -83,7 +85,7 @@ typedef struct dopf_status {
     int32_t launches_per_iteration;        /* kernels enqueued per iteration                  */
     int32_t sto_cold;                      /* storages that needed the cold solve in the last iteration */
     double last_step_ms;                   /* device time of the last dopf_step (CUDA events on the library stream) */
-    int32_t reserved2;                     /* cumulated correction-pass storages that fell back to the sequential solver */
+    int32_t fix_sequential;                /* cumulated correction-pass storages that fell back to the sequential solver */
     int32_t reserved3;
 } dopf_status;
 
@@ -111,7 +113,17 @@ int dopf_set_state(dopf_handle *h, int32_t iteration, const double *P, const dou
 int dopf_profile_iteration(dopf_handle *h, int32_t cap, float *ms, const char **names, int32_t *count);
 
 int dopf_get_nodal_price(dopf_handle *h, int32_t which, double *out /*[N][T]*/);
+/* get_nodal_price(k) for any dual set of the caller's history (admm.lambdas[k], admm.mues[k], admm.rhos[k]) */
+int dopf_nodal_price_from(dopf_handle *h, const double *lam /*[T]*/, const double *mu /*[L][T]*/, const double *rho /*[L][T]*/,
+                          double *out /*[N][T]*/);
 int dopf_get_total_costs(dopf_handle *h, double *out);
+/* per-unit report of the newest iterate (ResultGenerator / ResultStorage fields penalty_term, U, K;
+ * src/optimization/subproblems.jl:89-102, src/structures/results.jl:1-17): kind 0 = generator, 1 = storage, index in the
+ * caller's order; energy_balance/upper_flow/lower_flow are [T]; U, K are [L][T] and may be NULL. */
+int dopf_get_unit_penalty(dopf_handle *h, int32_t kind, int32_t index, double *energy_balance, double *upper_flow,
+                          double *lower_flow, double *U, double *K);
+/* result.penalty_term = sum of the units' penalty terms (src/structures/results.jl:73-76), each [T] */
+int dopf_get_penalty_totals(dopf_handle *h, double *energy_balance, double *upper_flow, double *lower_flow);
 
 /* ---- multi-GPU (one process per GPU; SURVEY.md 8(e) "agent block") ---------------------------------
  * Every rank creates its handle with the full network data and ITS block of the agents, then calls
