@@ -45,7 +45,7 @@ class DopfStatus(C.Structure):
 EXPORTS = ["dopf_version", "dopf_default_config", "dopf_create", "dopf_destroy", "dopf_step", "dopf_get_status",
            "dopf_get_iterate", "dopf_get_duals", "dopf_set_state", "dopf_get_nodal_price", "dopf_get_total_costs",
            "dopf_nodal_price_from", "dopf_get_unit_penalty", "dopf_get_penalty_totals",
-           "dopf_set_partition", "dopf_set_stream", "dopf_step_phase", "dopf_exchange_buffer", "dopf_last_error", "dopf_profile_iteration"]
+           "dopf_set_partition", "dopf_set_stream", "dopf_step_phase", "dopf_exchange_buffer", "dopf_last_error", "dopf_profile_iteration", "dopf_debug_counters"]
 
 
 def build(force=False, verbose=False):
@@ -92,6 +92,7 @@ def load():
     lib.dopf_nodal_price_from.argtypes = [C.c_void_p] + [C.c_void_p] * 4
     lib.dopf_get_unit_penalty.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 5
     lib.dopf_get_penalty_totals.argtypes = [C.c_void_p] + [C.c_void_p] * 3
+    lib.dopf_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32]
     lib.dopf_get_total_costs.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.dopf_profile_iteration.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]
     lib.dopf_set_partition.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]

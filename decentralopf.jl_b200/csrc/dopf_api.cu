@@ -245,7 +245,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     }
     AL(v.E, (size_t)S * T); AL(v.eta, (size_t)S * T); AL(v.cold_work, S); AL(v.wide_b, (size_t)T * 2 * L); AL(v.avgU, (size_t)Lp * ldt); AL(v.avgK, (size_t)Lp * ldt);
     AL(v.bplus, (size_t)Lp * ldt); AL(v.bminus, (size_t)Lp * ldt); AL(v.M, (size_t)Lp * ldt); AL(v.Wt, (size_t)Lp * ldt);
-    AL(v.g0, (size_t)Np * ldt); AL(v.s1, (size_t)Np * ldt); AL(v.rg, (size_t)Np * ldt);
+    AL(v.g0, (size_t)Np * ldt); AL(v.s1, (size_t)Np * ldt); AL(v.rg, (size_t)Np * ldt); AL(v.rg2, (size_t)Np * ldt);
     AL(v.dn, (size_t)Np * ldt); AL(v.dmax, ldt);
     for (int k = 0; k < 8; ++k) AL(v.nst[k], (size_t)Np * ldt);
     AL(v.flags, (size_t)ldt * Lp);
@@ -258,6 +258,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     AL(v.pair_row, v.pair_cap); AL(v.pair_node, v.pair_cap);
     AL(v.rowsumU, (size_t)2 * Lp * ldt); v.rowsumK = v.rowsumU + (size_t)Lp * ldt;   // contiguous: one exchange
     AL(v.ctrl, 1);
+    AL(v.counters, 32);
     AL(lp.tflag, (size_t)Lp * ldt);
 
     AL(h->d_scalar, 4);
@@ -597,6 +598,16 @@ int dopf_get_penalty_totals(dopf_handle *h, double *eb, double *upper, double *l
     CK(cudaMemcpyAsync(eb, h->d_pen, (size_t)v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(upper, h->d_pen + v.T, (size_t)v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(lower, h->d_pen + 2 * v.T, (size_t)v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DOPF_OK;
+}
+
+int dopf_debug_counters(dopf_handle *h, uint64_t *out, int32_t reset)
+{
+    if (!h || !out) return DOPF_E_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(out, h->lp.view.counters, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    if (reset) CK(cudaMemsetAsync(h->lp.view.counters, 0, 32 * sizeof(uint64_t), h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return DOPF_OK;
 }

@@ -87,6 +87,7 @@ struct View {
     double *bplus, *bminus, *M, *Wt;   // [Lp][ldt]
     double *g0, *s1;                   // [Np][ldt]
     double *rg;                        // [Np][ldt] 1/(prox + s1): generator step size
+    double *rg2;                       // [Np][ldt] 1/(prox + 2 s1) (storage steps with both variables free)
     unsigned long long *dn;            // [Np][ldt] max |delta| of the agents at (n,t) (bits)
     // node statistics of the moves delta_i of this rank's agents at (n,t), written by body_inject:
     //   nst[0] = min delta (<= 0), nst[1] = max delta (>= 0), nst[2] = largest negative delta (-inf if none),
@@ -107,6 +108,7 @@ struct View {
     int *fix_node_flag, *fix_node_list, *fix_node_slot;   // [Np] nodes with a storage on the work list (device path only)
     double *rowsumU, *rowsumK;         // [Lp][ldt] exact sum_i (b -+ p delta_i)_+ of tight rows
     int *pair_row, *pair_node; int pair_cap;   // (tight row, node) pairs whose agents must be summed one by one
+    unsigned long long *counters;   // [32] diagnostics (filled only by builds with -DDOPF_STATS)
     Ctrl *ctrl;
 };
 

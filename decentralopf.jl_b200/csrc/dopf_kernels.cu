@@ -270,6 +270,7 @@ __global__ void k_node_prep(View v, const double *Cpart, const double *C2part, i
     const double s1v = v.c.gamma + 2.0 * v.c.kappa * v.q[n] + b;
     v.s1[i] = s1v;
     v.rg[i] = 1.0 / (v.c.prox + s1v);     // generator step: delta = -(mc + g0) * rg
+    v.rg2[i] = 1.0 / (v.c.prox + 2.0 * s1v);
 }
 
 // epilogue of the flow product: line_utilization = ptdf * injection (results.jl:114)
@@ -370,10 +371,10 @@ __global__ void __launch_bounds__(128) k_sto_warm(View v)
 
 // warp-parallel active-set solve (dopf_sto_warp.cuh); storages it cannot verify are queued for k_sto_cold
 #ifndef DOPF_STO_MINB
-#define DOPF_STO_MINB 3
+#define DOPF_STO_MINB 4
 #endif
 template <int J>
-__global__ void __launch_bounds__(128, DOPF_STO_MINB) k_sto_warp(View v)
+__global__ void __launch_bounds__(128, (J <= 3 ? DOPF_STO_MINB : (J == 4 ? 3 : 2))) k_sto_warp(View v)
 {
     if (!DOPF_ACTIVE(v)) return;
     const int lane = threadIdx.x & 31;
@@ -614,6 +615,54 @@ __global__ void __launch_bounds__(256) k_verify(View v)
     }
 }
 
+// Root of the generator's optimality condition f(x) = c + a*x + corr(x) on [lo,hi] WITHOUT a hinge list: every
+// evaluation streams the wide row list of the timestep (whole warp).  Used when an agent's box holds more hinge
+// breakpoints than the shared-memory list of k_gen_fix (few agents on a large grid).  f is increasing and piecewise
+// linear: bracketed Newton steps with bisection as the safeguard; it ends as soon as the Newton step of the current
+// piece stays inside the piece (then it is the exact root), like root_monotone_pl.
+__device__ void stream_eval2(const View &v, int n, int t, double x, double &val, double &sL, double &sR, double &nL, double &nR)
+{
+    const int lane = threadIdx.x & 31;
+    const int cnt_in = v.wcnt[t];
+    const int *lst = v.wide + (size_t)t * 2 * v.L;
+    const double *lb = v.wide_b + (size_t)t * 2 * v.L;
+    const double *prow = v.ptdfT + (size_t)n * v.Lp;
+    val = 0.0; sL = 0.0; sR = 0.0; nL = -1e300; nR = 1e300;
+    const double tol = 1e-14 * (1.0 + fabs(x));
+    for (int j = lane; j < cnt_in; j += 32) {
+        const int e = lst[j];
+        Hinge h;
+        if (make_hinge(v.c, prow[e >> 1], lb[j], e & 1, h)) hinge_accum2(h, x, tol, val, sL, sR, nL, nR);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        val += __shfl_xor_sync(0xffffffffu, val, o); sL += __shfl_xor_sync(0xffffffffu, sL, o); sR += __shfl_xor_sync(0xffffffffu, sR, o);
+        nL = fmax(nL, __shfl_xor_sync(0xffffffffu, nL, o)); nR = fmin(nR, __shfl_xor_sync(0xffffffffu, nR, o));
+    }
+}
+__device__ double root_monotone_stream(const View &v, int n, int t, double c, double a, double lo, double hi)
+{
+    double val, sL, sR, nL, nR;
+    stream_eval2(v, n, t, lo, val, sL, sR, nL, nR);
+    if (c + a * lo + val >= 0.0) return lo;
+    stream_eval2(v, n, t, hi, val, sL, sR, nL, nR);
+    if (c + a * hi + val <= 0.0) return hi;
+    double xl = lo, xr = hi;                       // f(xl) < 0 < f(xr)
+    double x = -c / a;
+    if (!(x > xl && x < xr)) x = 0.5 * (xl + xr);
+    for (int it = 0; it < 200; ++it) {
+        stream_eval2(v, n, t, x, val, sL, sR, nL, nR);
+        const double f = c + a * x + val;
+        if (f == 0.0) return x;
+        double xn;
+        if (f < 0.0) { xl = x; xn = x - f / (a + sR); if (xn <= nR) return xn < hi ? xn : hi; }
+        else { xr = x; xn = x - f / (a + sL); if (xn >= nL) return xn > lo ? xn : lo; }
+        x = (xn > xl && xn < xr) ? xn : 0.5 * (xl + xr);
+        if (!(xr - xl > 1e-15 * (1.0 + fabs(xl)))) return x;
+    }
+    return x;
+}
+
 // exact re-solve of the generators on the work list: one warp per (agent, t)
 __global__ void __launch_bounds__(128) k_gen_fix(View v)
 {
@@ -656,10 +705,12 @@ __global__ void __launch_bounds__(128) k_gen_fix(View v)
                 __syncwarp();
                 int c1 = collect_hinges(v, n, t, alo, ahi, lists[wib], CAP);
                 __syncwarp();
-                if (c1 > CAP) { if (lane == 0) v.ctrl->error = DOPF_ERR_HINGE_CAP; c1 = CAP; }
+                double dstream = 0.0;
+                if (c1 > CAP)      // more breakpoints inside the agent's own box than the list holds: list-free solve
+                    dstream = root_monotone_stream(v, n, t, __shfl_sync(0xffffffffu, v.gen_mc[g], a) + v.g0[nt], v.c.prox + v.s1[nt], alo, ahi);
                 if (lane == a) {
                     HingeList hl; hl.h = lists[wib]; hl.n = c1; hl.sorted = false;
-                    const double d = root_monotone_pl(v.gen_mc[g] + v.g0[nt], v.c.prox + v.s1[nt], hl, lo, hi);
+                    const double d = c1 > CAP ? dstream : root_monotone_pl(v.gen_mc[g] + v.g0[nt], v.c.prox + v.s1[nt], hl, lo, hi);
                     double Pn = Pb + d;
                     Pn = Pn < 0.0 ? 0.0 : (Pn > pmax ? pmax : Pn);
                     sel(v.P, nxt)[(size_t)g * v.T + t] = Pn;
@@ -1051,7 +1102,7 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
         }
     }
     MAIN();
-    if (v.G > 0) LAUNCH(k_gen_fix<<<lp.num_sms * 2, 128, 0, cs>>>(v));
+    if (v.G > 0) LAUNCH(k_gen_fix<<<lp.num_sms * 8, 128, 0, cs>>>(v));
     JOIN();
     if (segment >= 0) LAUNCH(k_dmax<<<dim3(v.ldt / 32, 16), dim3(32, 32), 0, cs>>>(v));   // partitioned mode: maxima are exchanged
     XCHG(DOPF_X_DMAX);   // all ranks must build the same tight lists

@@ -57,6 +57,30 @@ DOPF_HD void hinge_accum(const Hinge h, double delta, double &val, double &slope
     }
 }
 
+// one hinge's share of: the correction value at delta, the slopes on both sides of delta and the nearest breakpoints
+// strictly beyond delta on both sides.  A breakpoint within `tol` of delta counts as reached: on each side the hinge is
+// in the state it has beyond the breakpoint.
+DOPF_HD void hinge_accum2(const Hinge h, double delta, double tol, double &val, double &sL, double &sR, double &nL, double &nR)
+{
+    const double bp = h.bp;
+    const double dir = h.sg > 0.0 ? 1.0 : -1.0, s = fabs(h.sg);
+    const bool anchored = dir * bp < 0.0;
+    const double w = delta - bp;
+    const bool at = fabs(w) <= tol;
+    if (!at) { if (bp > delta) { if (bp < nR) nR = bp; } else { if (bp > nL) nL = bp; } }
+    const bool pos = dir * w > 0.0;                         // side of the hinge delta is on (if not at it)
+    const bool actR = at ? dir > 0.0 : pos, actL = at ? dir < 0.0 : pos;
+    if (!anchored) {
+        if (actR) sR += s;
+        if (actL) sL += s;
+        if (!at && pos) val += s * w;
+    } else {
+        if (!actR) sR -= s;
+        if (!actL) sL -= s;
+        if (!at && !pos) val -= s * w;
+    }
+}
+
 // view of a hinge list (possibly empty)
 struct HingeList {
     const Hinge *h;
@@ -80,28 +104,13 @@ struct HingeList {
         val = 0.0; sL = 0.0; sR = 0.0; nL = -1e300; nR = 1e300;
         const double ad = fabs(delta), tol = 1e-14 * (1.0 + ad) + xtol;
         for (int i = 0; i < n; ++i) {
-            const double bp = h[i].bp, abp = fabs(bp);
+            const double abp = fabs(h[i].bp);
             if (sorted && abp > ad + tol) {
                 if (abp < nR) nR = abp;
                 if (-abp > nL) nL = -abp;
                 break;
             }
-            const double dir = h[i].sg > 0.0 ? 1.0 : -1.0, s = fabs(h[i].sg);
-            const bool anchored = dir * bp < 0.0;
-            const double w = delta - bp;
-            const bool at = fabs(w) <= tol;
-            if (!at) { if (bp > delta) { if (bp < nR) nR = bp; } else { if (bp > nL) nL = bp; } }
-            const bool pos = dir * w > 0.0;                         // side of the hinge delta is on (if not at it)
-            const bool actR = at ? dir > 0.0 : pos, actL = at ? dir < 0.0 : pos;
-            if (!anchored) {
-                if (actR) sR += s;
-                if (actL) sL += s;
-                if (!at && pos) val += s * w;
-            } else {
-                if (!actR) sR -= s;
-                if (!actL) sL -= s;
-                if (!at && !pos) val -= s * w;
-            }
+            hinge_accum2(h[i], delta, tol, val, sL, sR, nL, nR);
         }
     }
 };

@@ -88,6 +88,43 @@ __device__ __forceinline__ void seg_fwd2(double (&a)[J], double (&b)[J], const b
         if (open) { a[j] = opa(ca, a[j]); b[j] = opb(cb, b[j]); }
     }
 }
+// forward inclusive segmented scan of one array
+template <int J, class OpA>
+__device__ __forceinline__ void seg_fwd1(double (&a)[J], const bool (&head)[J], int lreach, OpA opa, double ida)
+{
+    const int lane = threadIdx.x & 31;
+    double ra = ida;
+#pragma unroll
+    for (int j = 0; j < J; ++j) { ra = head[j] ? a[j] : opa(ra, a[j]); a[j] = ra; }
+    double xa = ra;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double ya = __shfl_up_sync(FULL, xa, o); if (lreach >= o) xa = opa(ya, xa); }
+    double ca = __shfl_up_sync(FULL, xa, 1);
+    if (lane == 0) ca = ida;
+    bool open = true;
+#pragma unroll
+    for (int j = 0; j < J; ++j) { if (head[j]) open = false; if (open) a[j] = opa(ca, a[j]); }
+}
+// every element takes the value held by the tail of its run (one array of a 32-bit or 64-bit type)
+template <int J, class TB>
+__device__ __forceinline__ void seg_take_tail1(TB (&b)[J], const bool (&tail)[J], int lreach)
+{
+    const int lane = threadIdx.x & 31;
+    TB fb = TB();
+    {
+        TB cb = TB(); bool seen = false;
+#pragma unroll
+        for (int j = J - 1; j >= 0; --j) { if (tail[j]) { cb = b[j]; seen = true; } else if (seen) b[j] = cb; }
+        fb = cb;
+    }
+    TB xb = fb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const TB yb = __shfl_down_sync(FULL, xb, o); if (lreach >= o) xb = yb; }
+    const TB cb = __shfl_down_sync(FULL, xb, 1);
+    bool seen = false;
+#pragma unroll
+    for (int j = J - 1; j >= 0; --j) { if (tail[j]) seen = true; if (!seen && lane < 31) b[j] = cb; }
+}
 template <int J>
 __device__ __forceinline__ void seg_fwd_min_int(int (&a)[J], const bool (&head)[J], int lreach)
 {
@@ -162,14 +199,14 @@ __device__ __forceinline__ bool any_of(const bool (&p)[J])
 // ---- per-timestep clip table (independent of eta) ---------------------------------------------------------
 // Psi(nu) = nu - (g0 - eta) - s1*delta(nu) is piecewise linear with the four clip breakpoints bb[0..3] of
 // D(nu), C(nu); Psi(bb[i]) = eta - e[i] with the eta-thresholds e[i] = g0 + s1*dl[i] - bb[i] (non-increasing in
-// i, dl[i] = delta at bb[i]).  An evaluation therefore is: compare eta with e[0..3], interpolate nu on that
-// piece with the tabulated inverse slope, clip D and C.  Components (component-major in shared memory, comp c
-// of timestep t at tab[c*tstride + t], conflict-free):
-//   0-3 e | 4-7 bb | 8-10 isl (inverse slope of Psi on the inner pieces) | 11,12 dy for 1, 2 free variables
-//   13-16 dl | 17 g0 | 18 s1
-constexpr int TAB_E = 0, TAB_BB = 4, TAB_ISL = 8, TAB_DY = 11, TAB_DL = 13, TAB_G0 = 17, TAB_S1 = 18, TAB_COMPS = 19;
+// i, dl[i] = delta at bb[i]).  On a piece with nf free variables Psi has slope 1 + nf*s1/prox, so its inverse is
+// prox*r_nf with r_nf = 1/(prox + nf*s1), which k_node_prep provides per (node, t): no division here.  An
+// evaluation is: compare eta with e[0..3], interpolate nu on that piece, clip D and C.  Components
+// (component-major in shared memory, comp c of timestep t at tab[c*tstride + t], conflict-free):
+//   0-3 e | 4-7 bb | 8 r1 | 9 r2 | 10 number of free variables on the three inner pieces (2 bits each)
+constexpr int TAB_E = 0, TAB_BB = 4, TAB_R1 = 8, TAB_R2 = 9, TAB_NF = 10, TAB_COMPS = 11;
 
-__device__ __forceinline__ void clip_tab_build(const StoStep &st, const StoConst &k, double *tab, int tstride, int t)
+__device__ __forceinline__ void clip_tab_build(const StoStep &st, const StoConst &k, double r1, double r2, double *tab, int tstride, int t)
 {
     double b0 = k.prox * (st.Db - k.pmax) - k.mc, b1 = k.prox * st.Db - k.mc;
     double b2 = k.mc - k.prox * st.Cb, b3 = k.mc + k.prox * (k.pmax - st.Cb);
@@ -178,37 +215,43 @@ __device__ __forceinline__ void clip_tab_build(const StoStep &st, const StoConst
     if (b1 > b3) { x = b1; b1 = b3; b3 = x; }
     if (b1 > b2) { x = b1; b1 = b2; b2 = x; }
     const double bb[4] = { b0, b1, b2, b3 };
-    double e[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         double D, C; int nf;
         sto_dc_of_nu(st, k, bb[i], D, C, nf);
         const double dl = (D - st.Db) - (C - st.Cb);
-        e[i] = st.g0 + st.s1 * dl - bb[i];
-        tab[(TAB_E + i) * tstride + t] = e[i]; tab[(TAB_BB + i) * tstride + t] = bb[i]; tab[(TAB_DL + i) * tstride + t] = dl;
+        tab[(TAB_E + i) * tstride + t] = st.g0 + st.s1 * dl - bb[i]; tab[(TAB_BB + i) * tstride + t] = bb[i];
     }
+    int code = 0;
 #pragma unroll
-    for (int f = 0; f < 3; ++f)
-        tab[(TAB_ISL + f) * tstride + t] = (e[f] == e[f + 1]) ? 0.0 : (bb[f + 1] - bb[f]) / (e[f] - e[f + 1]);
-    tab[(TAB_DY + 0) * tstride + t] = -1.0 / (k.prox + st.s1);
-    tab[(TAB_DY + 1) * tstride + t] = -2.0 / (k.prox + 2.0 * st.s1);
-    tab[TAB_G0 * tstride + t] = st.g0; tab[TAB_S1 * tstride + t] = st.s1;
+    for (int f = 0; f < 3; ++f) {
+        double D, C; int nf;
+        sto_dc_of_nu(st, k, 0.5 * (bb[f] + bb[f + 1]), D, C, nf);
+        code |= nf << (2 * f);
+    }
+    tab[TAB_R1 * tstride + t] = r1; tab[TAB_R2 * tstride + t] = r2;
+    tab[TAB_NF * tstride + t] = (double)code;
 }
 // same result as sto_eval() for a hinge-free step
 __device__ __forceinline__ StoEval eval_tab(const StoStep &st, const StoConst &k, const double *tab, int tstride, int t, double eta)
 {
     const double e0 = tab[(TAB_E + 0) * tstride + t], e1 = tab[(TAB_E + 1) * tstride + t];
     const double e2 = tab[(TAB_E + 2) * tstride + t], e3 = tab[(TAB_E + 3) * tstride + t];
+    const double r1 = tab[TAB_R1 * tstride + t], r2 = tab[TAB_R2 * tstride + t];
     // anchor breakpoint a and piece: left of all (slope 1), right of all (slope 1), inner piece f = a
     const bool left = eta >= e0, right = !left && eta <= e3;
     const int a = left ? 0 : (right ? 3 : (eta >= e1 ? 0 : (eta >= e2 ? 1 : 2)));
     const double ae = a == 0 ? e0 : (a == 1 ? e1 : (a == 2 ? e2 : e3));
     const double ab = tab[(TAB_BB + a) * tstride + t];
-    const double as = (left || right) ? 1.0 : tab[(TAB_ISL + a) * tstride + t];
+    double as = 1.0;
+    if (!(left || right)) {
+        const int nfp = ((int)tab[TAB_NF * tstride + t] >> (2 * a)) & 3;
+        as = nfp == 0 ? 1.0 : k.prox * (nfp == 1 ? r1 : r2);
+    }
     const double nu = ab - (eta - ae) * as;
     StoEval r; int nf;
     sto_dc_of_nu(st, k, nu, r.D, r.C, nf);
-    r.dy = nf == 0 ? 0.0 : tab[(TAB_DY + nf - 1) * tstride + t];
+    r.dy = nf == 0 ? 0.0 : (nf == 1 ? -r1 : -2.0 * r2);
     return r;
 }
 // nearest eta-breakpoint strictly beyond eta (same as sto_next_break)
@@ -226,19 +269,19 @@ __device__ __forceinline__ void next_breaks_tab(const double *tab, int tstride, 
 __device__ __forceinline__ void flat_interval_tab(const StoStep &st, const double *tab, int tstride, int t, double eta, double D, double C, double &ilo, double &ihi)
 {
     ilo = ihi = eta;
-    const double g0 = tab[TAB_G0 * tstride + t], s1 = tab[TAB_S1 * tstride + t];
-    const double nu = g0 - eta + s1 * ((D - st.Db) - (C - st.Cb));
+    const double nu = st.g0 - eta + st.s1 * ((D - st.Db) - (C - st.Cb));
     const double tol = 1e-10 * (1.0 + fabs(nu));
-    double bb[4], dl[4], e[4];
+    double bb[4], e[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { bb[i] = tab[(TAB_BB + i) * tstride + t]; dl[i] = tab[(TAB_DL + i) * tstride + t]; e[i] = tab[(TAB_E + i) * tstride + t]; }
+    for (int i = 0; i < 4; ++i) { bb[i] = tab[(TAB_BB + i) * tstride + t]; e[i] = tab[(TAB_E + i) * tstride + t]; }
+    const int code = (int)tab[TAB_NF * tstride + t];
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         const bool linf = j == 0, rinf = j == 4;
         const double plo = linf ? 0.0 : bb[j - 1], phi = rinf ? 0.0 : bb[j];
         if (!linf && nu < plo - tol) continue;
         if (!rinf && nu > phi + tol) continue;
-        if (!linf && !rinf && (!(phi > plo) || dl[j - 1] != dl[j])) continue;   // a variable is free on this piece
+        if (!linf && !rinf && (!(phi > plo) || ((code >> (2 * (j - 1))) & 3) != 0)) continue;   // a variable is free on this piece
         const double eh = linf ? WBIG : e[j - 1];
         const double el = rinf ? -WBIG : e[j];
         ilo = el < ilo ? el : ilo; ihi = eh > ihi ? eh : ihi;
@@ -274,8 +317,8 @@ __device__ __forceinline__ void flat_range_hinge(const StoStep &st, const StoCon
 // run status bits broadcast from the tail
 enum { RS_CONV = 1, RS_BAD = 2, RS_FLAT = 4, RS_EMPTY = 8, RS_FREEBAD = 16, RS_ENDBAD = 32 };
 
-// shared memory per warp: the clip table (19 doubles per timestep)
-__host__ __device__ inline size_t sto_warp_smem_per_warp(int T) { return (size_t)19 * (size_t)((T + 1) | 1) * sizeof(double); }
+// shared memory per warp: the clip table (11 doubles per timestep)
+__host__ __device__ inline size_t sto_warp_smem_per_warp(int T) { return (size_t)TAB_COMPS * (size_t)((T + 1) | 1) * sizeof(double); }
 
 // returns true if the storage was solved and written; false => caller queues it for the exact sequential solver
 template <int J, bool HINGES>
@@ -292,7 +335,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
     HingeList hl[J];
     bool valid[J];
     int kind[J];          // anchor at the end of t: +1 level = emax, -1 level = 0, 0 none
-    double eta[J], hmin[J];
+    double eta[J], hmin[J], r1[J], r2[J];
     // blocked ownership (lane owns timesteps lane*J .. lane*J+J-1): the warp reads one contiguous range per array,
     // J strided passes of 8 bytes per lane that hit the same L1 lines
     __syncwarp();
@@ -304,6 +347,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
         const size_t o = (size_t)s * T + tt, on = (size_t)n * v.ldt + tt;
         st[j].Db = sel(v.D, cur)[o]; st[j].Cb = sel(v.C, cur)[o];
         st[j].g0 = v.g0[on]; st[j].s1 = v.s1[on];
+        r1[j] = v.rg[on]; r2[j] = v.rg2[on];          // 1/(prox + s1), 1/(prox + 2 s1) from k_node_prep
         eta[j] = v.eta[o];
         const double Ep = v.E[o];
         hl[j].h = HINGES ? hinges + (size_t)tt * v.hcap : nullptr;
@@ -316,11 +360,17 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < J; ++j)                    // clip tables (overwrite the staging area)
-        if (valid[j]) clip_tab_build(st[j], k, tab, tstride, lane * J + j);
+        if (valid[j]) clip_tab_build(st[j], k, r1[j], r2[j], tab, tstride, lane * J + j);
     __syncwarp();
 
     double D[J], C[J], pre[J];
     bool accepted = false;
+#ifdef DOPF_STATS
+    int st_rounds = 0, st_passes = 0;
+#define DOPF_STAT(i, n) do { if (lane == 0) atomicAdd(v.counters + (HINGES ? 16 : 0) + (i), (unsigned long long)(n)); } while (0)
+#else
+#define DOPF_STAT(i, n) do { } while (0)
+#endif
     const int as_cap = 24 + T / 2;                 // one new anchor per run and round: long horizons need more rounds from a cold start
     for (int as_it = 0; as_it < as_cap && !accepted; ++as_it) {
         // ---- run structure from the anchors (timesteps beyond T are isolated one-element runs) ------
@@ -367,6 +417,9 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
         bool capped = true;
         for (int it = 0; it < 24; ++it) {
             double dy[J];
+#ifdef DOPF_STATS
+            ++st_passes;
+#endif
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 if (valid[j]) {
@@ -437,7 +490,10 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
             }
             seg_take_tail<J, int>(eta, rs, tail, rf);
         }
-        if (capped) return false;                                             // Newton cap reached
+#ifdef DOPF_STATS
+        ++st_rounds;
+#endif
+        if (capped) { DOPF_STAT(5, 1); return false; }                        // Newton cap reached
         // final run state for every element: multiplier, status, "flat" (sum of derivatives at the tail)
 #pragma unroll
         for (int j = 0; j < J; ++j) if (valid[j] && tail[j] && !(totd[j] < -1e-300)) rs[j] |= RS_FLAT;
@@ -476,36 +532,46 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
                 hdn[j] = head[j] && prevk[j] >= 0;
             }
             const int rup = lane_reach_back<J>(hup), rdn = lane_reach_back<J>(hdn);
-            double d1[J], d2[J];
-#pragma unroll
-            for (int j = 0; j < J; ++j) { d1[j] = 0.0; d2[j] = 0.0; }
-            seg_fwd2<J>(Fhi, d1, hup, rup, OpMin(), OpAdd(), WBIG, 0.0);
-            seg_fwd2<J>(Flo, d2, hdn, rdn, OpMax(), OpAdd(), -WBIG, 0.0);
+            seg_fwd1<J>(Fhi, hup, rup, OpMin(), WBIG);
+            seg_fwd1<J>(Flo, hdn, rdn, OpMax(), -WBIG);
         }
-        // the new anchor of a run is its most violated timestep (the level path peaks where the bound finally
-        // binds; anchoring the first violated step instead needs one round per step of a long violated stretch)
+        // new anchors: the most violated timestep of every maximal stretch of consecutive violated timesteps of one
+        // kind inside a run (the level path peaks where the bound finally binds).  One anchor per run and round would
+        // need as many rounds as the run has separate peaks and troughs (a daily pattern over a multi-day horizon).
+        bool newanchor[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) newanchor[j] = false;
         {
             bool anyv[J];
 #pragma unroll
             for (int j = 0; j < J; ++j) anyv[j] = vio_up[j] || vio_dn[j];
             if (any_of<J>(anyv)) {
-                double m[J], z[J];
+                int vk[J], vp[J], vn[J];
 #pragma unroll
-                for (int j = 0; j < J; ++j) { m[j] = vmag[j]; z[j] = 0.0; }
-                seg_fwd2<J>(m, z, head, rb, OpMax(), OpAdd(), -1.0, 0.0);      // tails hold the largest violation of the run
-                int zi[J];
+                for (int j = 0; j < J; ++j) vk[j] = vio_up[j] ? 1 : (vio_dn[j] ? -1 : 0);
+                shift_from_prev<J, int>(vk, vp, 0);
+                shift_from_next<J, int>(vk, vn, 0);
+                bool shead[J], stail[J];
 #pragma unroll
-                for (int j = 0; j < J; ++j) zi[j] = 0;
-                seg_take_tail<J, int>(m, zi, tail, rf);
+                for (int j = 0; j < J; ++j) { shead[j] = head[j] || vk[j] != vp[j]; stail[j] = tail[j] || vk[j] != vn[j]; }
+                const int rbs = lane_reach_back<J>(shead), rfs = lane_reach_fwd<J>(stail);
+                double m[J];
 #pragma unroll
-                for (int j = 0; j < J; ++j) vmag[j] = (anyv[j] && vmag[j] >= m[j]) ? 1.0 : -1.0;
+                for (int j = 0; j < J; ++j) m[j] = vmag[j];
+                seg_fwd1<J>(m, shead, rbs, OpMax(), -1.0);               // stretch tails hold the largest violation
+                seg_take_tail1<J, double>(m, stail, rfs);
+                int cand[J];
+#pragma unroll
+                for (int j = 0; j < J; ++j) cand[j] = (anyv[j] && vmag[j] >= m[j]) ? lane * J + j : 0x7fffffff;
+                seg_fwd_min_int<J>(cand, shead, rbs);                   // first candidate of the stretch so far
+#pragma unroll
+                for (int j = 0; j < J; ++j) newanchor[j] = anyv[j] && vmag[j] >= m[j] && cand[j] == lane * J + j;
             }
         }
-        int tv[J], flag[J];
+        int flag[J];
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const int t = lane * J + j;
-            tv[j] = ((vio_up[j] || vio_dn[j]) && vmag[j] > 0.0) ? t : 0x7fffffff;
             flag[j] = 0;
             if (valid[j] && tail[j] && !(rs[j] & RS_BAD)) {
                 const double a = Flo[j], b = Fhi[j];
@@ -522,15 +588,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
             }
             if (valid[j] && tail[j] && (rs[j] & RS_BAD)) flag[j] |= RS_BAD;
         }
-        seg_fwd_min_int<J>(tv, head, rb);                           // tails hold the first violated timestep
-        {
-            double tvd[J];                                          // ... and tell their run (timestep as double, flags as int)
-#pragma unroll
-            for (int j = 0; j < J; ++j) tvd[j] = (double)tv[j];
-            seg_take_tail<J, int>(tvd, flag, tail, rf);
-#pragma unroll
-            for (int j = 0; j < J; ++j) tv[j] = (int)tvd[j];
-        }
+        seg_take_tail1<J, int>(flag, tail, rf);                     // the run's verdict, known to all its elements
 
 #ifdef DOPF_DEBUG_STO
         if (HINGES && (v.debug & 4) && s == ((v.debug >> 8) & 0xfff) && v.ctrl->iteration == (v.debug >> 20)) {
@@ -543,17 +601,16 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
         int wantdrop[J];                                            // head of a run that wants the previous anchor gone
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-            const int t = lane * J + j;
             anybad |= valid[j] && (flag[j] != 0 || vio_up[j] || vio_dn[j]);
             wantdrop[j] = (valid[j] && head[j] && ((flag[j] & (RS_EMPTY | RS_FREEBAD)) || ((flag[j] & RS_BAD) && freeend[j]))) ? 1 : 0;
-            if (valid[j] && tv[j] == t) { kind[j] = vio_up[j] ? 1 : -1; change = true; }       // (1) new anchor
+            if (valid[j] && newanchor[j]) { kind[j] = vio_up[j] ? 1 : -1; change = true; }       // (1) new anchors
         }
         int nextwant[J];
         shift_from_next<J, int>(wantdrop, nextwant, 0);
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const int t = lane * J + j;
-            if (!valid[j] || kind[j] == 0 || tv[j] == t) continue;
+            if (!valid[j] || kind[j] == 0 || newanchor[j]) continue;
             bool drop = nextwant[j] != 0;                                                       // (2) wrong sign at my anchor
             if (tail[j] && (flag[j] & RS_BAD)) drop = true;                                     //     my run cannot meet its target
             if (t == T - 1 && (flag[j] & RS_ENDBAD)) drop = true;                               //     wrong sign at the horizon end
@@ -562,13 +619,33 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
         anybad = __any_sync(FULL, anybad);
         change = __any_sync(FULL, change);
         if (!anybad) accepted = true;
-        else if (!change) return false;
+        else if (!change) { DOPF_STAT(6, 1); return false; }
         if (accepted) {
 #pragma unroll
             for (int j = 0; j < J; ++j) pre[j] += e0[j];            // levels
         }
     }
-    if (!accepted) return false;
+    if (!accepted) { DOPF_STAT(6, 1); return false; }
+#ifdef DOPF_STATS
+    {
+        int nruns = 0, nsingle = 0, nanch = 0, nfree = 0;
+        for (int j = 0; j < J; ++j) if (valid[j]) {
+            // run structure at acceptance: a singleton run is a step whose predecessor and itself are anchors
+            const int t = lane * J + j;
+            nanch += kind[j] != 0;
+            nfree += (D[j] > 0.0 && D[j] < k.pmax) || (C[j] > 0.0 && C[j] < k.pmax);
+            (void)t;
+        }
+        for (int o = 16; o > 0; o >>= 1) { nanch += __shfl_xor_sync(FULL, nanch, o); nfree += __shfl_xor_sync(FULL, nfree, o); }
+        DOPF_STAT(0, 1); DOPF_STAT(1, st_rounds); DOPF_STAT(2, st_passes); DOPF_STAT(3, nanch); DOPF_STAT(4, nfree);
+        if (nanch >= T - 1) DOPF_STAT(7, 1);            // (almost) every step anchored
+        if (nfree == 0) DOPF_STAT(8, 1);                // every step clipped
+        if (st_rounds == 1) DOPF_STAT(9, 1);
+        if (st_rounds == 1 && st_passes <= 2) DOPF_STAT(10, 1);
+        DOPF_STAT(11, st_rounds > 8 ? 1 : 0);
+        (void)nruns; (void)nsingle;
+    }
+#endif
 
     // ---- emit (blocked, same access pattern as the loads) --------------------------------------------------
 #pragma unroll

@@ -138,6 +138,11 @@ class DeviceADMM:
         self._check(self.lib.dopf_get_penalty_totals(self.h, _ptr(eb), _ptr(up), _ptr(lo)), "dopf_get_penalty_totals")
         return dict(energy_balance=eb, upper_flow=up, lower_flow=lo)
 
+    def debug_counters(self, reset=True):
+        out = (C.c_uint64 * 32)()
+        self._check(self.lib.dopf_debug_counters(self.h, out, int(reset)), "dopf_debug_counters")
+        return [int(x) for x in out]
+
     def total_costs(self):
         v = C.c_double()
         self._check(self.lib.dopf_get_total_costs(self.h, C.byref(v)), "dopf_get_total_costs")

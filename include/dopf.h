@@ -150,6 +150,9 @@ int dopf_step_phase(dopf_handle *h, int32_t phase);
  * the buffer to all-reduce after `phase` = which */
 int dopf_exchange_buffer(dopf_handle *h, int32_t which, void **device_ptr, int64_t *count);
 
+/* diagnostics: 32 device-side event counters (all zero unless the library was built with -DDOPF_STATS) */
+int dopf_debug_counters(dopf_handle *h, uint64_t *out /*[32]*/, int32_t reset);
+
 const char *dopf_last_error(dopf_handle *h);   /* handle may be NULL: error of the last failed dopf_create */
 const char *dopf_version(void);
 

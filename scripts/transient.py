@@ -12,6 +12,7 @@ prof_at = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 and sys.
 prob, cfg = bench.make_case(pkg, wl, 0)
 A = prob.G + prob.S
 cfg["flow_weight"] = wscale / A
+if len(sys.argv) > 5: cfg["gamma"] = float(sys.argv[5]) / A
 dev = DeviceADMM(prob, device=0, hinge_capacity=64, **cfg)
 g0 = s0 = q0 = 0
 rows = []
