@@ -44,15 +44,53 @@ METRIC = "agent_timestep_updates_per_s"
 UNIT = "agent*timestep/s"
 
 
-def make_case(pkg, workload, seed, agents=None):
+def make_case(pkg, workload, seed, agents=None, params="ref_ratio", params_agents=None):
+    """synthetic case of a workload; `agents` overrides (G, S) (bounded CPU samples, N x agents for weak scaling);
+    the ADMM parameters are derived from `params_agents` (default: the agents of the case itself)"""
     N, L, G, S, T = WORKLOADS[workload]
     if agents is not None:
         G, S = agents
     d = pkg.cases.synthetic_arrays(N=N, L=L, G=G, S=S, T=T, seed=seed)
-    A = G + S
-    # gamma and flow weight scaled with 1/A keep the reference's Jacobi update stable at scale
-    # (DESIGN.md section 6); prox weight stays the reference's literal.
-    return pkg.Problem.from_arrays(d), dict(gamma=0.3 / A, flow_weight=1.0 / A, prox_weight=1.0)
+    return pkg.Problem.from_arrays(d), params_for(params_agents or (G + S), params)
+
+
+def measure_dgemm_peak(torch, L, N, T, reps=8):
+    """fp64 GEMM throughput of cuBLAS (torch.matmul) on THIS box: the two products of the iteration in their exact
+    shapes and a square 4096^3 DGEMM; the best of the three is the denominator of the tensor-bound roofline
+    (there is no fp64 figure in MEASURED_PEAKS.json).  CUDA events, best of `reps` after a warm-up."""
+    out = {}
+    shapes = {"flow_LxN_NxT": (L, N, T), "ptdfT_NxL_LxT": (N, L, T), "square_4096": (4096, 4096, 4096)}
+    for name, (m, k, n) in shapes.items():
+        a = torch.randn(m, k, dtype=torch.float64, device="cuda"); b = torch.randn(k, n, dtype=torch.float64, device="cuda")
+        c = torch.empty(m, n, dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            torch.matmul(a, b, out=c)
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b, out=c); e1.record(); e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        out[name] = 2.0 * m * k * n / (best * 1e-3) / 1e12
+        del a, b, c
+    return out
+
+
+# ADMM parameters of the synthetic workloads.  The reference's literals (gamma 0.3, flow weight 10, three_node with 5
+# agents) do not carry over to 10^3..10^5 agents: every agent reacts to the whole imbalance / overload (Jacobi update),
+# so the loop gain grows with the number of agents A (SURVEY.md 7.4(5)).  Measured on B200 (scripts/param_scan.py,
+# profiles/r2_param_scan.md): (0.3/A, 10/A) and (0.1/A, 3.33/A) end in a bang-bang limit cycle (dual residuals constant
+# at 14 / 4.7, ~10 % of all generator timesteps need the hinge correction every iteration), (0.03/A, 1/A) is damped.
+# Default = the reference's RATIO flow_weight/gamma = 10/0.3 at the largest damped scale; prox weight is the literal.
+PARAMS = {
+    "ref_ratio": (0.03, 1.0),          # gamma*A, flow_weight*A : w/gamma = 33.3 (the reference's), damped  [default]
+    "ref_literal_over_A": (0.3, 10.0),  # the literals divided by A: w/gamma = 33.3, limit cycle
+    "round1": (0.3, 1.0),              # round-1 bench parameters: w/gamma = 3.3
+}
+
+
+def params_for(A, name="ref_ratio"):
+    gs, ws = PARAMS[name]
+    return dict(gamma=gs / A, flow_weight=ws / A, prox_weight=1.0)
 
 
 class ClockSampler:
@@ -107,13 +145,14 @@ def oracle_rate(pkg, workload, steps, warmup, budget_s=150.0):
     from oracle import oracle
     oracle.set_num_threads(len(os.sched_getaffinity(0)))      # all host cores, whatever OMP_NUM_THREADS the launcher exported
     g_s, s_s = SAMPLE_AGENTS[workload]
-    prob, cfg = make_case(pkg, workload, seed=0, agents=(max(g_s // 5, 8), max(s_s // 5, 2)))
+    full_agents = WORKLOADS[workload][2] + WORKLOADS[workload][3]       # the sample runs with the FULL case's gamma and flow weight
+    prob, cfg = make_case(pkg, workload, seed=0, agents=(max(g_s // 5, 8), max(s_s // 5, 2)), params_agents=full_agents)
     ora = oracle.OracleADMM(prob, cfg["gamma"], flow_weight=cfg["flow_weight"], prox_weight=cfg["prox_weight"])
     ora.iterate(0)
     t0 = time.perf_counter(); ora.iterate(0); probe = time.perf_counter() - t0
     scale = budget_s / max(steps + warmup, 1) / max(probe, 1e-6)      # affordable multiple of the probe size
     frac = min(1.0, max(0.2, scale / 5.0))
-    prob, cfg = make_case(pkg, workload, seed=0, agents=(max(int(g_s * frac), 8), max(int(s_s * frac), 2)))
+    prob, cfg = make_case(pkg, workload, seed=0, agents=(max(int(g_s * frac), 8), max(int(s_s * frac), 2)), params_agents=full_agents)
     ora = oracle.OracleADMM(prob, cfg["gamma"], flow_weight=cfg["flow_weight"], prox_weight=cfg["prox_weight"])
     for _ in range(warmup):
         ora.iterate(0)
@@ -231,12 +270,14 @@ def run_dopf(args):
         if name.startswith("k_gemm") and "true" in name: return 4.0 * L * N * T          # PTDF^T M and (PTDF.^2)^T W
         if name.startswith("k_gemm"): return 2.0 * L * N * T
         return None
+    dgemm = measure_dgemm_peak(torch, L, N, T) if rank == 0 else {}
+    fp64_peak = max(dgemm.values()) if dgemm else 37.0
     if dom is None:
         roof = None
     elif gemm_flops_of(dom):
         ach = gemm_flops_of(dom) / (kern[dom] * 1e-3) / 1e12
-        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": 37.0, "unit": "TFLOP/s", "frac": ach / 37.0, "traffic": None,
-                "peak_source": "nominal B200 fp64 (DMMA) 37 TFLOP/s - no fp64 figure in MEASURED_PEAKS.json"}
+        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None,
+                "peak_source": "cuBLAS DGEMM measured in this run (best of the two product shapes and a square 4096^3): %s" % json.dumps({k_: round(v_, 2) for k_, v_ in dgemm.items()})}
     else:
         b = alg_bytes_of(dom) or 40.0 * S * T
         ach = b / (kern[dom] * 1e-3) / 1e9

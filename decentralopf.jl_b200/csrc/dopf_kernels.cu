@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(128) k_sto_warm(View v)
 
 // warp-parallel active-set solve (dopf_sto_warp.cuh); storages it cannot verify are queued for k_sto_cold
 #ifndef DOPF_STO_MINB
-#define DOPF_STO_MINB 4
+#define DOPF_STO_MINB 3
 #endif
 template <int J>
 __global__ void __launch_bounds__(128, (J <= 3 ? DOPF_STO_MINB : (J == 4 ? 3 : 2))) k_sto_warp(View v)

@@ -199,12 +199,13 @@ __device__ __forceinline__ bool any_of(const bool (&p)[J])
 // ---- per-timestep clip table (independent of eta) ---------------------------------------------------------
 // Psi(nu) = nu - (g0 - eta) - s1*delta(nu) is piecewise linear with the four clip breakpoints bb[0..3] of
 // D(nu), C(nu); Psi(bb[i]) = eta - e[i] with the eta-thresholds e[i] = g0 + s1*dl[i] - bb[i] (non-increasing in
-// i, dl[i] = delta at bb[i]).  On a piece with nf free variables Psi has slope 1 + nf*s1/prox, so its inverse is
-// prox*r_nf with r_nf = 1/(prox + nf*s1), which k_node_prep provides per (node, t): no division here.  An
-// evaluation is: compare eta with e[0..3], interpolate nu on that piece, clip D and C.  Components
+// i, dl[i] = delta at bb[i]).  The thresholds cut the eta-axis into five pieces p = #{i : eta < e[i]}; on piece p
+// nu is affine in eta, nu = NU0[p] + NUS[p]*eta, and dy/deta = DY[p] is constant.  On a piece with nf free variables
+// Psi has slope 1 + nf*s1/prox, whose inverse is prox*r_nf with r_nf = 1/(prox + nf*s1) from k_node_prep: no division
+// here.  An evaluation is: four comparisons, three table reads by piece index, one fma, two clips.  Components
 // (component-major in shared memory, comp c of timestep t at tab[c*tstride + t], conflict-free):
-//   0-3 e | 4-7 bb | 8 r1 | 9 r2 | 10 number of free variables on the three inner pieces (2 bits each)
-constexpr int TAB_E = 0, TAB_BB = 4, TAB_R1 = 8, TAB_R2 = 9, TAB_NF = 10, TAB_COMPS = 11;
+//   0-3 e | 4-8 NU0 | 9-13 NUS | 14-18 DY
+constexpr int TAB_E = 0, TAB_NU0 = 4, TAB_NUS = 9, TAB_DY = 14, TAB_COMPS = 19;
 
 __device__ __forceinline__ void clip_tab_build(const StoStep &st, const StoConst &k, double r1, double r2, double *tab, int tstride, int t)
 {
@@ -215,43 +216,39 @@ __device__ __forceinline__ void clip_tab_build(const StoStep &st, const StoConst
     if (b1 > b3) { x = b1; b1 = b3; b3 = x; }
     if (b1 > b2) { x = b1; b1 = b2; b2 = x; }
     const double bb[4] = { b0, b1, b2, b3 };
+    double e[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         double D, C; int nf;
         sto_dc_of_nu(st, k, bb[i], D, C, nf);
-        const double dl = (D - st.Db) - (C - st.Cb);
-        tab[(TAB_E + i) * tstride + t] = st.g0 + st.s1 * dl - bb[i]; tab[(TAB_BB + i) * tstride + t] = bb[i];
+        e[i] = st.g0 + st.s1 * ((D - st.Db) - (C - st.Cb)) - bb[i];
+        tab[(TAB_E + i) * tstride + t] = e[i];
     }
-    int code = 0;
+    // outer pieces: both variables clipped, slope 1
+    tab[(TAB_NU0 + 0) * tstride + t] = bb[0] + e[0]; tab[(TAB_NUS + 0) * tstride + t] = -1.0; tab[(TAB_DY + 0) * tstride + t] = 0.0;
+    tab[(TAB_NU0 + 4) * tstride + t] = bb[3] + e[3]; tab[(TAB_NUS + 4) * tstride + t] = -1.0; tab[(TAB_DY + 4) * tstride + t] = 0.0;
 #pragma unroll
-    for (int f = 0; f < 3; ++f) {
+    for (int f = 0; f < 3; ++f) {     // inner piece between bb[f] and bb[f+1] = eta-piece p = f+1, anchored at breakpoint f
         double D, C; int nf;
         sto_dc_of_nu(st, k, 0.5 * (bb[f] + bb[f + 1]), D, C, nf);
-        code |= nf << (2 * f);
+        const double rn = nf == 1 ? r1 : r2;
+        const double as = nf == 0 ? 1.0 : k.prox * rn;
+        tab[(TAB_NU0 + f + 1) * tstride + t] = bb[f] + e[f] * as; tab[(TAB_NUS + f + 1) * tstride + t] = -as;
+        tab[(TAB_DY + f + 1) * tstride + t] = nf == 0 ? 0.0 : -(double)nf * rn;
     }
-    tab[TAB_R1 * tstride + t] = r1; tab[TAB_R2 * tstride + t] = r2;
-    tab[TAB_NF * tstride + t] = (double)code;
 }
 // same result as sto_eval() for a hinge-free step
 __device__ __forceinline__ StoEval eval_tab(const StoStep &st, const StoConst &k, const double *tab, int tstride, int t, double eta)
 {
     const double e0 = tab[(TAB_E + 0) * tstride + t], e1 = tab[(TAB_E + 1) * tstride + t];
     const double e2 = tab[(TAB_E + 2) * tstride + t], e3 = tab[(TAB_E + 3) * tstride + t];
-    const double r1 = tab[TAB_R1 * tstride + t], r2 = tab[TAB_R2 * tstride + t];
-    // anchor breakpoint a and piece: left of all (slope 1), right of all (slope 1), inner piece f = a
-    const bool left = eta >= e0, right = !left && eta <= e3;
-    const int a = left ? 0 : (right ? 3 : (eta >= e1 ? 0 : (eta >= e2 ? 1 : 2)));
-    const double ae = a == 0 ? e0 : (a == 1 ? e1 : (a == 2 ? e2 : e3));
-    const double ab = tab[(TAB_BB + a) * tstride + t];
-    double as = 1.0;
-    if (!(left || right)) {
-        const int nfp = ((int)tab[TAB_NF * tstride + t] >> (2 * a)) & 3;
-        as = nfp == 0 ? 1.0 : k.prox * (nfp == 1 ? r1 : r2);
-    }
-    const double nu = ab - (eta - ae) * as;
-    StoEval r; int nf;
-    sto_dc_of_nu(st, k, nu, r.D, r.C, nf);
-    r.dy = nf == 0 ? 0.0 : (nf == 1 ? -r1 : -2.0 * r2);
+    const int p = (eta < e0) + (eta < e1) + (eta < e2) + (eta < e3);
+    const double *q = tab + p * tstride + t;
+    const double nu = q[TAB_NU0 * tstride] + q[TAB_NUS * tstride] * eta;
+    StoEval r;
+    r.D = clip01(st.Db - (k.mc + nu) * k.iprox, k.pmax);
+    r.C = clip01(st.Cb - (k.mc - nu) * k.iprox, k.pmax);
+    r.dy = q[TAB_DY * tstride];
     return r;
 }
 // nearest eta-breakpoint strictly beyond eta (same as sto_next_break)
@@ -263,28 +260,6 @@ __device__ __forceinline__ void next_breaks_tab(const double *tab, int tstride, 
         const double e = tab[(TAB_E + i) * tstride + t];
         if (e > eta && e < up) up = e;
         if (e < eta && e > dn) dn = e;
-    }
-}
-// maximal eta-interval around eta on which y_t stays constant (same as sto_flat_interval)
-__device__ __forceinline__ void flat_interval_tab(const StoStep &st, const double *tab, int tstride, int t, double eta, double D, double C, double &ilo, double &ihi)
-{
-    ilo = ihi = eta;
-    const double nu = st.g0 - eta + st.s1 * ((D - st.Db) - (C - st.Cb));
-    const double tol = 1e-10 * (1.0 + fabs(nu));
-    double bb[4], e[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { bb[i] = tab[(TAB_BB + i) * tstride + t]; e[i] = tab[(TAB_E + i) * tstride + t]; }
-    const int code = (int)tab[TAB_NF * tstride + t];
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        const bool linf = j == 0, rinf = j == 4;
-        const double plo = linf ? 0.0 : bb[j - 1], phi = rinf ? 0.0 : bb[j];
-        if (!linf && nu < plo - tol) continue;
-        if (!rinf && nu > phi + tol) continue;
-        if (!linf && !rinf && (!(phi > plo) || ((code >> (2 * (j - 1))) & 3) != 0)) continue;   // a variable is free on this piece
-        const double eh = linf ? WBIG : e[j - 1];
-        const double el = rinf ? -WBIG : e[j];
-        ilo = el < ilo ? el : ilo; ihi = eh > ihi ? eh : ihi;
     }
 }
 
@@ -317,7 +292,7 @@ __device__ __forceinline__ void flat_range_hinge(const StoStep &st, const StoCon
 // run status bits broadcast from the tail
 enum { RS_CONV = 1, RS_BAD = 2, RS_FLAT = 4, RS_EMPTY = 8, RS_FREEBAD = 16, RS_ENDBAD = 32 };
 
-// shared memory per warp: the clip table (11 doubles per timestep)
+// shared memory per warp: the clip table (19 doubles per timestep)
 __host__ __device__ inline size_t sto_warp_smem_per_warp(int T) { return (size_t)TAB_COMPS * (size_t)((T + 1) | 1) * sizeof(double); }
 
 // returns true if the storage was solved and written; false => caller queues it for the exact sequential solver
@@ -514,7 +489,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
             if (valid[j]) {
                 if (!(rs[j] & RS_FLAT)) { Ilo[j] = eta[j]; Ihi[j] = eta[j]; }
                 else if (HINGES && hl[j].n != 0) flat_range_hinge(st[j], k, hl[j], hmin[j], eta[j], D[j], C[j], Ilo[j], Ihi[j]);
-                else flat_interval_tab(st[j], tab, tstride, lane * J + j, eta[j], D[j], C[j], Ilo[j], Ihi[j]);
+                else flat_range_hinge(st[j], k, hl[j], WBIG, eta[j], D[j], C[j], Ilo[j], Ihi[j]);
             }
         }
         seg_fwd2<J>(Ilo, Ihi, head, rb, OpMax(), OpMin(), -WBIG, WBIG);          // tails now hold the run interval

@@ -21,7 +21,10 @@ for at in ats:
     for base, lab in ((0, "predict"), (16, "fix")):
         n = max(c[base], 1)
         print("it %d %s: " % (at, lab) + ", ".join("%s %d" % (names[i], c[base + i]) for i in range(len(names))) + " | per storage: rounds %.2f passes %.2f anchors %.1f free %.1f" % (c[base + 1] / n, c[base + 2] / n, c[base + 3] / n, c[base + 4] / n))
-    it = dev.get_iterate(("D", "C", "E"))
+    it = dev.get_iterate(("D", "C", "E", "flow", "avgU", "avgK"))
+    g2w = gs / (2 * ws)
+    bp = prob.fmax[:, None] - it["flow"] + g2w * it["avgU"]; bm = prob.fmax[:, None] + it["flow"] + g2w * it["avgK"]
+    print("   anchored hinge rows (W != 0): %.2f%% of L*T; rows with any: per t %.1f of %d lines" % (100 * ((bp < 0) | (bm < 0)).mean(), ((bp < 0) | (bm < 0)).sum(0).mean(), prob.L))
     idle = (np.abs(it["D"]).max(1) + np.abs(it["C"]).max(1)) == 0
     act = (it["D"] > 0) | (it["C"] > 0)
     print("   idle storages %d of %d; active steps per non-idle storage %.1f of %d; steps at E=0: %.1f%%, at emax: %.1f%%" % (idle.sum(), prob.S, act[~idle].sum(1).mean() if (~idle).any() else 0, prob.T,
