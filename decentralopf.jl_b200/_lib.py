@@ -28,7 +28,8 @@ class DopfProblem(C.Structure):
 class DopfConfig(C.Structure):
     _fields_ = [("gamma", C.c_double), ("flow_weight", C.c_double), ("prox_weight", C.c_double),
                 ("slack_mask_tol", C.c_double), ("eps", C.c_double),
-                ("device", C.c_int32), ("hinge_capacity", C.c_int32), ("use_graph", C.c_int32), ("debug_flags", C.c_int32)]
+                ("device", C.c_int32), ("hinge_capacity", C.c_int32), ("use_graph", C.c_int32), ("debug_flags", C.c_int32),
+                ("n_scenarios", C.c_int32), ("gemm_ksplit", C.c_int32)]
 
 
 class DopfStatus(C.Structure):
@@ -45,7 +46,7 @@ class DopfStatus(C.Structure):
 EXPORTS = ["dopf_version", "dopf_default_config", "dopf_create", "dopf_destroy", "dopf_step", "dopf_get_status",
            "dopf_get_iterate", "dopf_get_duals", "dopf_set_state", "dopf_get_nodal_price", "dopf_get_total_costs",
            "dopf_nodal_price_from", "dopf_get_unit_penalty", "dopf_get_penalty_totals",
-           "dopf_set_partition", "dopf_set_stream", "dopf_step_phase", "dopf_exchange_buffer", "dopf_last_error", "dopf_profile_iteration", "dopf_debug_counters"]
+           "dopf_set_partition", "dopf_set_stream", "dopf_step_phase", "dopf_exchange_buffer", "dopf_last_error", "dopf_profile_iteration", "dopf_debug_counters", "dopf_get_scenario_status"]
 
 
 def build(force=False, verbose=False):
@@ -85,6 +86,7 @@ def load():
     lib.dopf_destroy.argtypes = [C.c_void_p]
     lib.dopf_step.argtypes = [C.c_void_p, C.c_int32, C.POINTER(DopfStatus)]
     lib.dopf_get_status.argtypes = [C.c_void_p, C.POINTER(DopfStatus)]
+    lib.dopf_get_scenario_status.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dopf_get_iterate.argtypes = [C.c_void_p] + [C.c_void_p] * 8
     lib.dopf_get_duals.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 3
     lib.dopf_set_state.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 8
@@ -93,7 +95,7 @@ def load():
     lib.dopf_get_unit_penalty.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 5
     lib.dopf_get_penalty_totals.argtypes = [C.c_void_p] + [C.c_void_p] * 3
     lib.dopf_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32]
-    lib.dopf_get_total_costs.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.dopf_get_total_costs.argtypes = [C.c_void_p, C.c_void_p]
     lib.dopf_profile_iteration.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]
     lib.dopf_set_partition.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
     lib.dopf_set_stream.argtypes = [C.c_void_p, C.c_void_p]

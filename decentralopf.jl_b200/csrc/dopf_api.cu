@@ -34,6 +34,8 @@ struct dopf_handle {
     Ctrl *h_ctrl = nullptr;          // pinned mirror of the device control block
     double *d_scalar = nullptr;
     double *d_nodal = nullptr;
+    double *d_stage = nullptr;             // scenario batches: [C][rows][T] staging of one network matrix
+    std::vector<int32_t> h_sc_i; std::vector<double> h_sc_d;
     double *d_pen = nullptr;               // lazily allocated: 3*T penalty values + U,K [L][T] of one unit
     std::vector<int> gen_perm, sto_perm;   // sorted position -> caller's index
     bool gen_identity = true, sto_identity = true;
@@ -131,6 +133,7 @@ void dopf_default_config(dopf_config *c)
 {
     c->gamma = 0.3; c->flow_weight = 10.0; c->prox_weight = 1.0; c->slack_mask_tol = 1e-2; c->eps = 1e-3;
     c->device = -1; c->hinge_capacity = 0; c->use_graph = 1; c->debug_flags = 0;
+    c->n_scenarios = 1; c->gemm_ksplit = 0;
 }
 
 const char *dopf_last_error(dopf_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -155,13 +158,17 @@ void dopf_destroy(dopf_handle *h)
 
 static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config *cfg)
 {
-    const int N = p->N, L = p->L, T = p->T, G = p->G, S = p->S;
-    if (N < 1 || L < 1 || T < 1 || G < 0 || S < 0 || G + S < 1) { h->err = "invalid dimensions"; return DOPF_E_ARG; }
+    // a batch of C scenarios becomes ONE problem with C*T columns and C*G + C*S agents on virtual nodes c*N + n
+    const int C = cfg->n_scenarios > 1 ? cfg->n_scenarios : 1;
+    const int N = p->N, L = p->L, T = p->T, Gs = p->G, Ss = p->S;
+    if (N < 1 || L < 1 || T < 1 || Gs < 0 || Ss < 0 || Gs + Ss < 1) { h->err = "invalid dimensions"; return DOPF_E_ARG; }
+    if ((long long)C * Gs >= (1ll << 31) || (long long)C * Ss >= (1ll << 31) || (long long)C * T >= (1ll << 30) || (long long)C * N >= (1ll << 31)) { h->err = "batch too large"; return DOPF_E_UNSUPPORTED; }
+    const int G = C * Gs, S = C * Ss, TC = C * T;
     if (!p->ptdf || !p->f_max || !p->demand || (G && (!p->gen_mc || !p->gen_pmax || !p->gen_node)) ||
         (S && (!p->sto_mc || !p->sto_pmax || !p->sto_emax || !p->sto_node))) { h->err = "null input array"; return DOPF_E_ARG; }
     if (!(cfg->gamma > 0.0) || !(cfg->flow_weight > 0.0) || !(cfg->prox_weight > 0.0)) { h->err = "gamma, flow_weight, prox_weight must be > 0"; return DOPF_E_ARG; }
-    for (int g = 0; g < G; ++g) if (p->gen_node[g] < 0 || p->gen_node[g] >= N) { h->err = "gen_node out of range"; return DOPF_E_ARG; }
-    for (int s = 0; s < S; ++s) if (p->sto_node[s] < 0 || p->sto_node[s] >= N) { h->err = "sto_node out of range"; return DOPF_E_ARG; }
+    for (int g = 0; g < Gs; ++g) if (p->gen_node[g] < 0 || p->gen_node[g] >= N) { h->err = "gen_node out of range"; return DOPF_E_ARG; }
+    for (int s = 0; s < Ss; ++s) if (p->sto_node[s] < 0 || p->sto_node[s] >= N) { h->err = "sto_node out of range"; return DOPF_E_ARG; }
     if ((long long)G * T >= (1ll << 31) || (long long)S * T >= (1ll << 31)) { h->err = "G*T or S*T exceeds 2^31"; return DOPF_E_UNSUPPORTED; }
     if (T / (T % 4 == 0 ? 4 : (T % 2 == 0 ? 2 : 1)) > 1024) { h->err = "horizon too long for this build (T/vec > 1024 timestep slots per block)"; return DOPF_E_UNSUPPORTED; }
 
@@ -185,8 +192,8 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
 
     LaunchPlan &lp = h->lp;
     View &v = lp.view;
-    v.N = N; v.L = L; v.T = T; v.G = G; v.S = S; v.A = G + S;
-    v.ldt = round_up(T, 32); v.Np = round_up(N, 64); v.Lp = round_up(L, 64);
+    v.N = N; v.L = L; v.T = T; v.G = G; v.S = S; v.A = Gs + Ss; v.NS = C; v.TC = TC;
+    v.ldt = round_up(TC, 32); v.Np = round_up(N, 64); v.Lp = round_up(L, 64);
     v.hcap = cfg->hinge_capacity > 0 ? cfg->hinge_capacity : 32;
     v.c = Coef::make(cfg->gamma, cfg->flow_weight, cfg->prox_weight, cfg->slack_mask_tol, cfg->eps);
     v.demand_on = 1;
@@ -195,24 +202,29 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     h->use_graph = cfg->use_graph != 0;
 
     // ---- agents sorted by node (stable), CSR offsets -------------------------------------------
+    // caller's agent index of the batch: c*Gs + g (scenario-major); virtual node of it: c*N + node[g]
+    auto gvn = [&](int a) { return (a / std::max(Gs, 1)) * N + p->gen_node[a % std::max(Gs, 1)]; };
+    auto svn = [&](int a) { return (a / std::max(Ss, 1)) * N + p->sto_node[a % std::max(Ss, 1)]; };
     h->gen_perm.resize(G); std::iota(h->gen_perm.begin(), h->gen_perm.end(), 0);
-    std::stable_sort(h->gen_perm.begin(), h->gen_perm.end(), [&](int a, int b) { return p->gen_node[a] < p->gen_node[b]; });
+    std::stable_sort(h->gen_perm.begin(), h->gen_perm.end(), [&](int a, int b) { return gvn(a) < gvn(b); });
     h->sto_perm.resize(S); std::iota(h->sto_perm.begin(), h->sto_perm.end(), 0);
-    std::stable_sort(h->sto_perm.begin(), h->sto_perm.end(), [&](int a, int b) { return p->sto_node[a] < p->sto_node[b]; });
+    std::stable_sort(h->sto_perm.begin(), h->sto_perm.end(), [&](int a, int b) { return svn(a) < svn(b); });
     h->gen_identity = true; for (int i = 0; i < G; ++i) if (h->gen_perm[i] != i) h->gen_identity = false;
     h->sto_identity = true; for (int i = 0; i < S; ++i) if (h->sto_perm[i] != i) h->sto_identity = false;
 
     std::vector<double> gmc(G), gpm(G), smc(S), spm(S), sem(S);
-    std::vector<int> gnode(G), snode(S), gptr(N + 1, 0), sptr(N + 1, 0);
-    for (int i = 0; i < G; ++i) { int o = h->gen_perm[i]; gmc[i] = p->gen_mc[o]; gpm[i] = p->gen_pmax[o]; gnode[i] = p->gen_node[o]; gptr[gnode[i] + 1]++; }
-    for (int i = 0; i < S; ++i) { int o = h->sto_perm[i]; smc[i] = p->sto_mc[o]; spm[i] = p->sto_pmax[o]; sem[i] = p->sto_emax[o]; snode[i] = p->sto_node[o]; sptr[snode[i] + 1]++; }
-    for (int n = 0; n < N; ++n) { gptr[n + 1] += gptr[n]; sptr[n + 1] += sptr[n]; }
+    const int NV = C * N;      // virtual nodes
+    std::vector<int> gnode(G), snode(S), gptr(NV + 1, 0), sptr(NV + 1, 0);
+    // per-scenario agent data: [C][Gs] / [C][Ss] when C > 1 (the node of an agent is shared by all scenarios)
+    for (int i = 0; i < G; ++i) { int o = h->gen_perm[i]; gmc[i] = p->gen_mc[o]; gpm[i] = p->gen_pmax[o]; gnode[i] = gvn(o); gptr[gnode[i] + 1]++; }
+    for (int i = 0; i < S; ++i) { int o = h->sto_perm[i]; smc[i] = p->sto_mc[o]; spm[i] = p->sto_pmax[o]; sem[i] = p->sto_emax[o]; snode[i] = svn(o); sptr[snode[i] + 1]++; }
+    for (int n = 0; n < NV; ++n) { gptr[n + 1] += gptr[n]; sptr[n + 1] += sptr[n]; }
 
     // ---- padded network data and derived statics -----------------------------------------------
     std::vector<double> ptdf((size_t)Lp * Np, 0.0), fmax(Lp, 0.0), demand((size_t)Np * ldt, 0.0);
-    std::vector<double> q(Np, 0.0), prow(Lp, 0.0), mwide(Lp, 0.0), nag(Np, 0.0), rbox(Np, 0.0);
-    for (int i = 0; i < G; ++i) { nag[gnode[i]] += 1.0; rbox[gnode[i]] = std::max(rbox[gnode[i]], gpm[i]); }
-    for (int i = 0; i < S; ++i) { nag[snode[i]] += 1.0; rbox[snode[i]] = std::max(rbox[snode[i]], 2.0 * spm[i]); }
+    std::vector<double> q(Np, 0.0), prow(Lp, 0.0), mwide(Lp, 0.0), nag((size_t)C * Np, 0.0), rbox(Np, 0.0);
+    for (int i = 0; i < G; ++i) { const int c = gnode[i] / N, n = gnode[i] % N; nag[(size_t)c * Np + n] += 1.0; rbox[n] = std::max(rbox[n], gpm[i]); }
+    for (int i = 0; i < S; ++i) { const int c = snode[i] / N, n = snode[i] % N; nag[(size_t)c * Np + n] += 1.0; rbox[n] = std::max(rbox[n], 2.0 * spm[i]); }
     for (int l = 0; l < L; ++l) {
         fmax[l] = p->f_max[l];
         for (int n = 0; n < N; ++n) {
@@ -223,7 +235,8 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
             mwide[l] = std::max(mwide[l], std::fabs(a) * rbox[n]);
         }
     }
-    for (int n = 0; n < N; ++n) for (int t = 0; t < T; ++t) demand[(size_t)n * ldt + t] = p->demand[(size_t)n * T + t];
+    for (int c = 0; c < C; ++c) for (int n = 0; n < N; ++n) for (int t = 0; t < T; ++t)
+        demand[(size_t)n * ldt + (size_t)c * T + t] = p->demand[((size_t)c * N + n) * T + t];      // [C][N][T] -> columns
 
     int rc;
 #define UP(dst, vec) if ((rc = upload(h, &dst, vec))) return rc
@@ -243,26 +256,31 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
         AL(v.lam[k], ldt); AL(v.mu[k], (size_t)Lp * ldt); AL(v.rho[k], (size_t)Lp * ldt);
         v.injloc[k] = v.inj[k];
     }
-    AL(v.E, (size_t)S * T); AL(v.eta, (size_t)S * T); AL(v.cold_work, S); AL(v.wide_b, (size_t)T * 2 * L); AL(v.avgU, (size_t)Lp * ldt); AL(v.avgK, (size_t)Lp * ldt);
+    AL(v.E, (size_t)S * T); AL(v.eta, (size_t)S * T); AL(v.cold_work, S); AL(v.wide_b, (size_t)TC * 2 * L); AL(v.avgU, (size_t)Lp * ldt); AL(v.avgK, (size_t)Lp * ldt);
     AL(v.bplus, (size_t)Lp * ldt); AL(v.bminus, (size_t)Lp * ldt); AL(v.M, (size_t)Lp * ldt); AL(v.Wt, (size_t)Lp * ldt);
     AL(v.g0, (size_t)Np * ldt); AL(v.s1, (size_t)Np * ldt); AL(v.rg, (size_t)Np * ldt); AL(v.rg2, (size_t)Np * ldt);
     AL(v.dn, (size_t)Np * ldt); AL(v.dmax, ldt);
     for (int k = 0; k < 8; ++k) AL(v.nst[k], (size_t)Np * ldt);
     AL(v.flags, (size_t)ldt * Lp);
-    AL(v.wide, (size_t)T * 2 * L); AL(v.wcnt, T); AL(v.tight, (size_t)T * 2 * L); AL(v.tight_b, (size_t)T * 2 * std::max(L, 1)); AL(v.tcnt, T);
+    AL(v.wide, (size_t)TC * 2 * L); AL(v.wcnt, TC); AL(v.tight, (size_t)TC * 2 * L); AL(v.tight_b, (size_t)TC * 2 * std::max(L, 1)); AL(v.tcnt, TC);
     v.gen_work_cap = (int)std::min<long long>((long long)G * T, 1ll << 30);
     AL(v.gen_work, (size_t)std::max(v.gen_work_cap, 1)); AL(v.gen_grp, (size_t)2 * std::max(v.gen_work_cap, 1)); AL(v.sto_work, S); AL(v.sto_flag, S);
-    AL(v.fix_node_flag, Np); AL(v.fix_node_list, Np); AL(v.fix_node_slot, Np);
-    if (N >= (1 << 20) || T >= (1 << 11)) { h->err = "N >= 2^20 or T >= 2^11 not supported by the pair queue encoding"; return DOPF_E_UNSUPPORTED; }
-    v.pair_cap = 1 << 20;
-    AL(v.pair_row, v.pair_cap); AL(v.pair_node, v.pair_cap);
+    AL(v.fix_node_flag, NV); AL(v.fix_node_list, NV); AL(v.fix_node_slot, NV);
+    AL(v.sc_iteration, C); AL(v.sc_converged, C); AL(v.sc_conv, 3 * C); AL(v.sc_res_bits, 3 * C); AL(v.sc_res, 3 * C);
+    {
+        std::vector<int> ones(C, 1);
+        CK(cudaMemcpyAsync(v.sc_iteration, ones.data(), sizeof(int) * C, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (C > 1) AL(h->d_stage, (size_t)std::max(N, L) * TC);
+    h->h_sc_i.resize((size_t)5 * C); h->h_sc_d.resize((size_t)3 * C);
     AL(v.rowsumU, (size_t)2 * Lp * ldt); v.rowsumK = v.rowsumU + (size_t)Lp * ldt;   // contiguous: one exchange
     AL(v.ctrl, 1);
     AL(v.counters, 32);
     AL(lp.tflag, (size_t)Lp * ldt);
 
-    AL(h->d_scalar, 4);
-    AL(h->d_nodal, (size_t)N * T);
+    AL(h->d_scalar, std::max(4, C));
+    AL(h->d_nodal, (size_t)C * N * T);
 
     // ---- launch plan -----------------------------------------------------------------------------
     lp.num_sms = prop.multiProcessorCount;
@@ -273,6 +291,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
         // split-K: the kernel runs in waves of num_sms blocks per resident slot, so pick the split with the
         // fewest waves per unit of work among those that give every SM at least two blocks
         const int ksmax = std::max(1, std::min(8, Kp / 16 / 8));
+        if (cfg->gemm_ksplit > 0) { ks = std::min(cfg->gemm_ksplit, ksmax); return; }      // fixed summation order (bitwise reproducibility across batch sizes)
         double best = 1e300; ks = 1;
         for (int k = 1; k <= ksmax; ++k) {
             const int blocks = tiles * k;
@@ -283,8 +302,8 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     // the transposed product is only needed at the nodes that carry agents of this handle (all of them on one GPU,
     // a contiguous node range per rank in the agent-partitioned mode): restrict it to the 64-row tiles of that range
     int nmin = N, nmax = -1;
-    for (int g = 0; g < G; ++g) { nmin = std::min(nmin, (int)p->gen_node[g]); nmax = std::max(nmax, (int)p->gen_node[g]); }
-    for (int s2 = 0; s2 < S; ++s2) { nmin = std::min(nmin, (int)p->sto_node[s2]); nmax = std::max(nmax, (int)p->sto_node[s2]); }
+    for (int g = 0; g < Gs; ++g) { nmin = std::min(nmin, (int)p->gen_node[g]); nmax = std::max(nmax, (int)p->gen_node[g]); }
+    for (int s2 = 0; s2 < Ss; ++s2) { nmin = std::min(nmin, (int)p->sto_node[s2]); nmax = std::max(nmax, (int)p->sto_node[s2]); }
     if (nmax < 0) { nmin = 0; nmax = 0; }
     lp.mt_base = (nmin / 64) * 64;
     lp.mt_rows = (nmax / 64 + 1) * 64 - lp.mt_base;
@@ -303,12 +322,13 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
         if (lp.sto_j > 0 && set_storage_smem_attr(T) != 0) { h->err = "cudaFuncSetAttribute(shared memory) failed"; return DOPF_E_CUDA; }
         // scratch: one slot per node with a storage on the work list (up to 512 MB) + one per solver block for the overflow
         const size_t slot_bytes = (size_t)T * v.hcap * sizeof(Hinge) + (size_t)T * sizeof(int);
-        lp.sto_fix_slots = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(N, 1), ((size_t)512 << 20) / slot_bytes));
+        lp.sto_fix_slots = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(NV, 1), ((size_t)512 << 20) / slot_bytes));
         const size_t warps = (size_t)lp.sto_fix_slots + (size_t)lp.sto_fix_blocks;
         AL(lp.hinge_scratch, S ? warps * T * v.hcap : 1);
         AL(lp.hcnt_scratch, S ? warps * T : 1);
     }
-    lp.slack_blocks_x = std::max(1, std::min(64, (8 * lp.num_sms + T - 1) / T));
+    lp.gen_flat = (cfg->debug_flags & 8) ? 1 : ((cfg->debug_flags & 16) ? 0 : (G < 24ll * NV ? 1 : 0));      // bits 3/4 force one variant (A/B timing)
+    lp.slack_blocks_x = std::max(1, std::min(64, (8 * lp.num_sms + TC - 1) / TC));
 
     // ---- state before iteration 1 (admm.jl:29-36; helpers/results.jl:14-73 "zeros") ----------
     Ctrl c0;
@@ -418,15 +438,30 @@ int dopf_get_status(dopf_handle *h, dopf_status *out)
 }
 
 // copy a padded device matrix [rows][ldt] to a dense host matrix [rows][T]
+// (scenario batches: host [C][rows][T] <-> device columns c*T + t, re-laid on the device through a staging buffer)
 static int d2h_matrix(dopf_handle *h, double *dst, const double *src, int rows, int T, int ld)
 {
     if (!dst) return 0;
+    const int C = h->lp.view.NS;
+    if (C > 1) {
+        launch_pack_cols(const_cast<double *>(src), h->d_stage, rows, C, T, ld, 0, h->stream);
+        CK(cudaMemcpyAsync(dst, h->d_stage, (size_t)C * rows * T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));      // the staging buffer is reused by the next matrix
+        return 0;
+    }
     CK(cudaMemcpy2DAsync(dst, (size_t)T * sizeof(double), src, (size_t)ld * sizeof(double), (size_t)T * sizeof(double), rows, cudaMemcpyDeviceToHost, h->stream));
     return 0;
 }
 static int h2d_matrix(dopf_handle *h, double *dst, const double *src, int rows, int T, int ld)
 {
     if (!src) return 0;
+    const int C = h->lp.view.NS;
+    if (C > 1) {
+        CK(cudaMemcpyAsync(h->d_stage, src, (size_t)C * rows * T * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        launch_pack_cols(dst, h->d_stage, rows, C, T, ld, 1, h->stream);
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
     CK(cudaMemcpy2DAsync(dst, (size_t)ld * sizeof(double), src, (size_t)T * sizeof(double), (size_t)T * sizeof(double), rows, cudaMemcpyHostToDevice, h->stream));
     return 0;
 }
@@ -478,7 +513,7 @@ int dopf_get_duals(dopf_handle *h, int32_t which, double *lam, double *mu, doubl
     const View &v = h->lp.view;
     const int k = which == 0 ? h->h_ctrl->cur : 1 - h->h_ctrl->cur;
     int rc;
-    if (lam) CK(cudaMemcpyAsync(lam, v.lam[k], (size_t)v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (lam) CK(cudaMemcpyAsync(lam, v.lam[k], (size_t)v.TC * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if ((rc = d2h_matrix(h, mu, v.mu[k], v.L, v.T, v.ldt))) return rc;
     if ((rc = d2h_matrix(h, rho, v.rho[k], v.L, v.T, v.ldt))) return rc;
     CK(cudaStreamSynchronize(h->stream));
@@ -508,7 +543,7 @@ int dopf_set_state(dopf_handle *h, int32_t iteration, const double *P, const dou
     if ((rc = h2d_matrix(h, v.avgU, avgU, v.L, v.T, v.ldt))) return rc;
     if ((rc = h2d_matrix(h, v.avgK, avgK, v.L, v.T, v.ldt))) return rc;
     const size_t lt = (size_t)v.Lp * v.ldt * sizeof(double);
-    if (lam) CK(cudaMemcpyAsync(v.lam[nxt], lam, (size_t)v.T * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (lam) CK(cudaMemcpyAsync(v.lam[nxt], lam, (size_t)v.TC * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     else CK(cudaMemcpyAsync(v.lam[nxt], v.lam[cur], (size_t)v.ldt * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     if (mu) { if ((rc = h2d_matrix(h, v.mu[nxt], mu, v.L, v.T, v.ldt))) return rc; }
     else CK(cudaMemcpyAsync(v.mu[nxt], v.mu[cur], lt, cudaMemcpyDeviceToDevice, h->stream));
@@ -517,6 +552,12 @@ int dopf_set_state(dopf_handle *h, int32_t iteration, const double *P, const dou
     Ctrl c = *h->h_ctrl;
     c.iteration = iteration; c.converged = c.conv_lambda = c.conv_mue = c.conv_rho = 0; c.error = 0;
     c.iters_done = 0;
+    {
+        std::vector<int> its(v.NS, iteration);
+        CK(cudaMemcpyAsync(v.sc_iteration, its.data(), sizeof(int) * v.NS, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemsetAsync(v.sc_converged, 0, sizeof(int) * v.NS, h->stream)); CK(cudaMemsetAsync(v.sc_conv, 0, sizeof(int) * 3 * v.NS, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
     *h->h_ctrl = c;
     CK(cudaMemcpyAsync(v.ctrl, h->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, h->stream));
     launch_rebuild_derived(h->lp, h->stream);
@@ -532,7 +573,7 @@ int dopf_get_nodal_price(dopf_handle *h, int32_t which, double *out)
     const View &v = h->lp.view;
     const int k = which == 0 ? h->h_ctrl->cur : 1 - h->h_ctrl->cur;
     launch_nodal_price(v, v.lam[k], v.mu[k], v.rho[k], h->d_nodal, h->stream);
-    CK(cudaMemcpyAsync(out, h->d_nodal, (size_t)v.N * v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(out, h->d_nodal, (size_t)v.NS * v.N * v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return DOPF_OK;
 }
@@ -544,11 +585,11 @@ int dopf_nodal_price_from(dopf_handle *h, const double *lam, const double *mu, c
     const View &v = h->lp.view;
     // staging in per-iteration scratch (M, Wt, first row of g0): all three are rewritten at the start of every iteration
     int rc;
-    CK(cudaMemcpyAsync(v.g0, lam, (size_t)v.T * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(v.g0, lam, (size_t)v.TC * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     if ((rc = h2d_matrix(h, v.M, mu, v.L, v.T, v.ldt))) return rc;
     if ((rc = h2d_matrix(h, v.Wt, rho, v.L, v.T, v.ldt))) return rc;
     launch_nodal_price(v, v.g0, v.M, v.Wt, h->d_nodal, h->stream);
-    CK(cudaMemcpyAsync(out, h->d_nodal, (size_t)v.N * v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(out, h->d_nodal, (size_t)v.NS * v.N * v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return DOPF_OK;
 }
@@ -564,21 +605,21 @@ int dopf_get_unit_penalty(dopf_handle *h, int32_t kind, int32_t index, double *e
 {
     if (!h || kind < 0 || kind > 1 || !eb || !upper || !lower) return DOPF_E_ARG;
     const View &v = h->lp.view;
-    if (index < 0 || index >= (kind == 0 ? v.G : v.S)) return DOPF_E_ARG;
+    if (index < 0 || index >= (kind == 0 ? v.G : v.S)) return DOPF_E_ARG;      // batches: index = c*G_per_scenario + g
     CK(cudaSetDevice(h->device));
     int rc = need_iteration_done(h, "dopf_get_unit_penalty");
     if (rc) return rc;
-    if (!h->d_pen) { if ((rc = dev_alloc(h, &h->d_pen, (size_t)3 * v.T + (size_t)2 * v.L * v.T))) return rc; }
+    if (!h->d_pen) { if ((rc = dev_alloc(h, &h->d_pen, (size_t)3 * v.TC + (size_t)2 * v.L * v.T))) return rc; }
     // caller's index -> position in the node-sorted device order
     const std::vector<int> &perm = kind == 0 ? h->gen_perm : h->sto_perm;
     int pos = index;
     if (!(kind == 0 ? h->gen_identity : h->sto_identity)) pos = (int)(std::find(perm.begin(), perm.end(), index) - perm.begin());
-    double *dU = h->d_pen + (size_t)3 * v.T, *dK = dU + (size_t)v.L * v.T;
-    launch_unit_penalty(v, kind, pos, h->d_pen, h->d_pen + v.T, h->d_pen + 2 * v.T, U ? dU : nullptr, K ? dK : nullptr, h->stream);
+    double *dU = h->d_pen + (size_t)3 * v.TC, *dK = dU + (size_t)v.L * v.T;
+    launch_unit_penalty(v, kind, pos, h->d_pen, h->d_pen + v.TC, h->d_pen + 2 * v.TC, U ? dU : nullptr, K ? dK : nullptr, h->stream);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(eb, h->d_pen, (size_t)v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(upper, h->d_pen + v.T, (size_t)v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(lower, h->d_pen + 2 * v.T, (size_t)v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(upper, h->d_pen + v.TC, (size_t)v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(lower, h->d_pen + 2 * v.TC, (size_t)v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (U) CK(cudaMemcpyAsync(U, dU, (size_t)v.L * v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (K) CK(cudaMemcpyAsync(K, dK, (size_t)v.L * v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -592,12 +633,25 @@ int dopf_get_penalty_totals(dopf_handle *h, double *eb, double *upper, double *l
     CK(cudaSetDevice(h->device));
     int rc = need_iteration_done(h, "dopf_get_penalty_totals");
     if (rc) return rc;
-    if (!h->d_pen) { if ((rc = dev_alloc(h, &h->d_pen, (size_t)3 * v.T + (size_t)2 * v.L * v.T))) return rc; }
-    launch_penalty_totals(v, h->d_pen, h->d_pen + v.T, h->d_pen + 2 * v.T, h->stream);
+    if (!h->d_pen) { if ((rc = dev_alloc(h, &h->d_pen, (size_t)3 * v.TC + (size_t)2 * v.L * v.T))) return rc; }
+    launch_penalty_totals(v, h->d_pen, h->d_pen + v.TC, h->d_pen + 2 * v.TC, h->stream);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(eb, h->d_pen, (size_t)v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(upper, h->d_pen + v.T, (size_t)v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(lower, h->d_pen + 2 * v.T, (size_t)v.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(eb, h->d_pen, (size_t)v.TC * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(upper, h->d_pen + v.TC, (size_t)v.TC * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(lower, h->d_pen + 2 * v.TC, (size_t)v.TC * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return DOPF_OK;
+}
+
+int dopf_get_scenario_status(dopf_handle *h, int32_t *iteration, int32_t *converged, double *residuals)
+{
+    if (!h) return DOPF_E_ARG;
+    CK(cudaSetDevice(h->device));
+    const View &v = h->lp.view;
+    const size_t C = (size_t)v.NS;
+    if (iteration) CK(cudaMemcpyAsync(iteration, v.sc_iteration, C * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (converged) CK(cudaMemcpyAsync(converged, v.sc_converged, C * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (residuals) CK(cudaMemcpyAsync(residuals, v.sc_res, 3 * C * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return DOPF_OK;
 }
@@ -617,7 +671,7 @@ int dopf_get_total_costs(dopf_handle *h, double *out)
     if (!h || !out) return DOPF_E_ARG;
     CK(cudaSetDevice(h->device));
     launch_total_costs(h->lp.view, h->d_scalar, h->stream);
-    CK(cudaMemcpyAsync(out, h->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(out, h->d_scalar, sizeof(double) * h->lp.view.NS, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return DOPF_OK;
 }
@@ -637,6 +691,7 @@ int dopf_set_partition(dopf_handle *h, int32_t rank, int32_t nranks, int32_t tot
 {
     if (!h || nranks < 1 || rank < 0 || rank >= nranks || total_agents < h->lp.view.A) return DOPF_E_ARG;
     if (h->h_ctrl->iters_done != 0) { h->err = "dopf_set_partition must precede the first iteration"; return DOPF_E_ARG; }
+    if (h->lp.view.NS > 1) { h->err = "scenario batches are sharded by scenario (independent handles), not by agents"; return DOPF_E_UNSUPPORTED; }
     CK(cudaSetDevice(h->device));
     h->rank = rank; h->nranks = nranks;
     View &v = h->lp.view;

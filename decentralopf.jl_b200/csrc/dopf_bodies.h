@@ -40,20 +40,25 @@ struct Ctrl {
     int conv_lambda, conv_mue, conv_rho;
     int error;          // DOPF_ERR_*; set => every later kernel is a no-op, state stays valid
     int iters_done;     // iterations executed since create
+    int finish_cnt;     // blocks of k_lambda_finish that are done (scenario batches: the last one flips the buffers)
     int gen_work_cnt, sto_work_cnt, cold_work_cnt, pair_cnt, gen_grp_cnt, fix_node_cnt;
     int stat_sto_cold;                   // storages solved by the cold funnel in the last iteration
     int stat_fix_seq;                    // cumulated correction-pass storages that needed the sequential solver
     int stat_gen_fix, stat_sto_fix;      // cumulated corrected agents (statistics)
     int stat_tight_rows, stat_wide_rows; // of the last iteration
+    int stat_tight_acc, stat_wide_acc;   // accumulators of the batched finish kernel
     unsigned long long res_bits[3];      // max |dual_{k+1}-dual_k| for lambda, mue, rho (bits)
     double res[3];
     double total_costs;
 };
 
 struct View {
-    // sizes
-    int N, L, T, G, S, A;
-    int ldt;          // leading dimension of every [node|line][t] matrix (T rounded up to 32)
+    // sizes.  A batch of C independent scenarios on one grid (BASELINE configs[3]) is laid out as extra COLUMNS of the
+    // network matrices: scenario c owns the columns [c*T, (c+1)*T) (TC = C*T columns in total, one PTDF shared), and as
+    // C*G generators / C*S storages living on "virtual nodes" vn = c*N + n.  C = 1 is the plain single problem.
+    int N, L, T, G, S, A;   // G, S: ALL agents of the batch; A: agents of ONE scenario (the divisor of the average slacks)
+    int NS, TC;             // scenarios C, total columns C*T
+    int ldt;          // leading dimension of every [node|line][column] matrix (TC rounded up to 32)
     int Np, Lp;       // padded row counts (multiples of 64) of the node / line matrices
     int hcap;         // hinge capacity per (agent, t) in the correction pass
     int gen_work_cap;
@@ -67,8 +72,8 @@ struct View {
     const double *prow;     // [Lp]  max_n |ptdf[l,n]|
     double *mwide;          // [Lp]  max_n |ptdf[l,n]| * box range of node n
     double *rbox;           // [Np]  largest possible |delta| of an agent at node n (max-reduced over ranks)
-    const double *nagents;  // [Np]  number of agents at node n
-    const double *gen_mc, *gen_pmax; const int *gen_node; const int *gen_ptr;   // sorted by node; ptr [N+1]
+    const double *nagents;  // [C][Np]  number of agents at node n (of scenario c)
+    const double *gen_mc, *gen_pmax; const int *gen_node; const int *gen_ptr;   // sorted by virtual node (gen_node = c*N + n); ptr [C*N+1]
     const double *sto_mc, *sto_pmax, *sto_emax; const int *sto_node; const int *sto_ptr;
     // iterate (double buffered: [cur] = previous, [1-cur] = being written)
     double *P[2];           // [G][T]
@@ -107,9 +112,19 @@ struct View {
     int *sto_work, *sto_flag;          // [S], [S]
     int *fix_node_flag, *fix_node_list, *fix_node_slot;   // [Np] nodes with a storage on the work list (device path only)
     double *rowsumU, *rowsumK;         // [Lp][ldt] exact sum_i (b -+ p delta_i)_+ of tight rows
-    int *pair_row, *pair_node; int pair_cap;   // (tight row, node) pairs whose agents must be summed one by one
     unsigned long long *counters;   // [32] diagnostics (filled only by builds with -DDOPF_STATS)
+    // per-scenario convergence state (convergence.jl:1-31 for every scenario of the batch separately); a converged
+    // scenario is frozen: its agents, duals and average slacks are carried through unchanged while the others go on
+    int *sc_iteration, *sc_converged, *sc_conv;       // [C], [C], [C][3]
+    unsigned long long *sc_res_bits;                   // [C][3]
+    double *sc_res;                                    // [C][3]
     Ctrl *ctrl;
+
+    DOPF_HD int scen_of_vn(int vn) const { return NS == 1 ? 0 : vn / N; }
+    DOPF_HD int scen_of_col(int col) const { return NS == 1 ? 0 : col / T; }
+    // index of (agent-local timestep t) of an agent on virtual node vn in a [Np][ldt] node matrix
+    DOPF_HD size_t nt_of(int vn, int t) const { const int c = scen_of_vn(vn); return (size_t)(vn - c * N) * ldt + (size_t)c * T + t; }
+    DOPF_HD int col_of(int vn, int t) const { return scen_of_vn(vn) * T + t; }
 };
 
 // ---- row preparation: everything that depends on (line, t) only -------------------------------
@@ -120,7 +135,7 @@ DOPF_HD void body_row_prep(const View &v, int l, int t)
     const int cur = v.ctrl->cur;
     const size_t i = (size_t)l * v.ldt + t;
     RowPrep r = row_prep(v.c, v.fmax[l], sel(v.flow, cur)[i], v.avgU[i], v.avgK[i], sel(v.mu, cur)[i], sel(v.rho, cur)[i]);
-    const bool real = (l < v.L) && (t < v.T);
+    const bool real = (l < v.L) && (t < v.TC);
     v.bplus[i] = r.bplus; v.bminus[i] = r.bminus;
     v.M[i] = real ? r.M : 0.0; v.Wt[i] = real ? r.Wt : 0.0;
     unsigned char f = 0;
@@ -135,18 +150,18 @@ DOPF_HD void body_row_prep(const View &v, int l, int t)
 // (subproblems.jl:63-83 reduced; exact whenever no slack hinge lies in (0, delta])
 DOPF_HD double body_gen_predict(const View &v, int g, int t, double Pprev, int n, double mc, double pmax)
 {
-    const size_t nt = (size_t)n * v.ldt + t;
+    const size_t nt = v.nt_of(n, t);
     double Pn = Pprev - (mc + v.g0[nt]) * v.rg[nt];
     Pn = Pn < 0.0 ? 0.0 : (Pn > pmax ? pmax : Pn);
     return Pn;
 }
 
-DOPF_HD void note_move(const View &v, int n, int t, double delta)
+DOPF_HD void note_move(const View &v, int vn, int t, double delta)      // agent on virtual node vn, agent-local timestep t
 {
     const double ad = fabs(delta);
     if (ad == 0.0) return;
     const unsigned long long b = nonneg_bits(ad);
-    unsigned long long *pn = v.dn + (size_t)n * v.ldt + t;
+    unsigned long long *pn = v.dn + v.nt_of(vn, t);
     if (b > *pn) DOPF_ATOMIC_MAX_U64(pn, b);
     // dmax[t] = max_n dn[n][t] is computed by a separate column reduction (k_dmax): updating it here
     // would serialise every moving agent of a timestep on one address
@@ -187,7 +202,7 @@ DOPF_HD void sto_setup(const View &v, int s, StoConst &k, GlobalSteps &sp)
     const int cur = v.ctrl->cur, n = v.sto_node[s];
     k.mc = v.sto_mc[s]; k.pmax = v.sto_pmax[s]; k.emax = v.sto_emax[s]; k.prox = v.c.prox; k.iprox = 1.0 / v.c.prox;
     sp.Db = sel(v.D, cur) + (size_t)s * v.T; sp.Cb = sel(v.C, cur) + (size_t)s * v.T;
-    sp.g0 = v.g0 + (size_t)n * v.ldt; sp.s1 = v.s1 + (size_t)n * v.ldt;
+    sp.g0 = v.g0 + v.nt_of(n, 0); sp.s1 = v.s1 + v.nt_of(n, 0);
     sp.hinges = nullptr; sp.hcnt = nullptr; sp.hcap = 0; sp.sorted = false;
 }
 
@@ -283,26 +298,28 @@ DOPF_HD bool verify_sto_moved(const View &v, int s, int t, double lo, double hi)
     const double d = (sel(v.D, nxt)[i] - sel(v.D, cur)[i]) - (sel(v.C, nxt)[i] - sel(v.C, cur)[i]);
     return d > hi || d < lo;
 }
-DOPF_HD void body_verify(const View &v, int n, int t)
+DOPF_HD void body_verify(const View &v, int n, int col)
 {
     double lo, hi;
-    if (!verify_bounds(v, n, t, lo, hi)) return;
-    for (int g = v.gen_ptr[n]; g < v.gen_ptr[n + 1]; ++g) if (verify_gen_moved(v, g, t, lo, hi)) verify_note_gen(v, g, t);
-    for (int s = v.sto_ptr[n]; s < v.sto_ptr[n + 1]; ++s) if (verify_sto_moved(v, s, t, lo, hi)) verify_note_sto(v, s);
+    if (!verify_bounds(v, n, col, lo, hi)) return;
+    const int c = v.scen_of_col(col), vn = c * v.N + n, t = col - c * v.T;
+    for (int g = v.gen_ptr[vn]; g < v.gen_ptr[vn + 1]; ++g) if (verify_gen_moved(v, g, t, lo, hi)) verify_note_gen(v, g, t);
+    for (int s = v.sto_ptr[vn]; s < v.sto_ptr[vn + 1]; ++s) if (verify_sto_moved(v, s, t, lo, hi)) verify_note_sto(v, s);
 }
 
 // ---- nodal injection of the new iterate (results.jl:64,88-106) --------------------------------
 // injection of (n,t) and the node statistics st[0..7] of the moves (see View::nst)
-DOPF_HD double inject_compute(const View &v, int n, int t, double (&st)[8])
+DOPF_HD double inject_compute(const View &v, int n, int col, double (&st)[8])
 {
     const int cur = v.ctrl->cur, nxt = 1 - cur;
     double a = 0.0;
     double lo = 0.0, hi = 0.0, inneg = -INFINITY, inpos = INFINITY, sneg = 0.0, spos = 0.0, cneg = 0.0, cpos = 0.0;
-    if (n < v.N && t < v.T) {
-        a = v.demand_on ? -v.demand[(size_t)n * v.ldt + t] : 0.0;
+    if (n < v.N && col < v.TC) {
+        const int c = v.scen_of_col(col), vn = c * v.N + n, t = col - c * v.T;
+        a = v.demand_on ? -v.demand[(size_t)n * v.ldt + col] : 0.0;
         const double *Pn = sel(v.P, nxt), *Pc = sel(v.P, cur);
-        const int g1 = v.gen_ptr[n + 1];
-        int g = v.gen_ptr[n];
+        const int g1 = v.gen_ptr[vn + 1];
+        int g = v.gen_ptr[vn];
 #define DOPF_NOTE_MOVE(d)                                                                                   \
         if ((d) < 0.0) { lo = (d) < lo ? (d) : lo; inneg = (d) > inneg ? (d) : inneg; sneg += (d); cneg += 1.0; } \
         else if ((d) > 0.0) { hi = (d) > hi ? (d) : hi; inpos = (d) < inpos ? (d) : inpos; spos += (d); cpos += 1.0; }
@@ -324,8 +341,8 @@ DOPF_HD double inject_compute(const View &v, int n, int t, double (&st)[8])
             DOPF_NOTE_MOVE(d)
         }
         const double *Dn = sel(v.D, nxt), *Dc = sel(v.D, cur), *Cn = sel(v.C, nxt), *Cc = sel(v.C, cur);
-        const int s1 = v.sto_ptr[n + 1];
-        int s = v.sto_ptr[n];
+        const int s1 = v.sto_ptr[vn + 1];
+        int s = v.sto_ptr[vn];
         for (; s + 4 <= s1; s += 4) {
             double dn_[4], dc_[4], cn_[4], cc_[4];
 #if defined(__CUDA_ARCH__)
@@ -365,8 +382,8 @@ DOPF_HD void body_inject(const View &v, int n, int t)
 // over the agents).  Resting agents (delta = 0) contribute (b)_+ each.
 DOPF_HD double slack_node_closed(const View &v, double b, double sp, int n, int t, bool &ok)
 {
-    const size_t i = (size_t)t * v.Np + n;
-    const double na = v.nagents[n];
+    const size_t i = (size_t)t * v.Np + n;                 // t = column
+    const double na = v.nagents[(size_t)v.scen_of_col(t) * v.Np + n];
     ok = true;
     if (na == 0.0) return 0.0;
     if (sp == 0.0) return na * pospart(b);
@@ -411,12 +428,13 @@ DOPF_HD double body_slack_row_node(const View &v, int l, int side, int n, int t)
     const double c = slack_node_closed(v, b, sp, n, t, ok);
     if (ok) return c;
     double a = 0.0;
-    for (int g = v.gen_ptr[n]; g < v.gen_ptr[n + 1]; ++g) {
-        const double d = sel(v.P, nxt)[(size_t)g * v.T + t] - sel(v.P, cur)[(size_t)g * v.T + t];
+    const int sc = v.scen_of_col(t), vn = sc * v.N + n, tl = t - sc * v.T;
+    for (int g = v.gen_ptr[vn]; g < v.gen_ptr[vn + 1]; ++g) {
+        const double d = sel(v.P, nxt)[(size_t)g * v.T + tl] - sel(v.P, cur)[(size_t)g * v.T + tl];
         a += pospart(b + sp * d);
     }
-    for (int s = v.sto_ptr[n]; s < v.sto_ptr[n + 1]; ++s) {
-        const size_t i = (size_t)s * v.T + t;
+    for (int s = v.sto_ptr[vn]; s < v.sto_ptr[vn + 1]; ++s) {
+        const size_t i = (size_t)s * v.T + tl;
         const double d = (sel(v.D, nxt)[i] - sel(v.D, cur)[i]) - (sel(v.C, nxt)[i] - sel(v.C, cur)[i]);
         a += pospart(b + sp * d);
     }
@@ -456,20 +474,35 @@ DOPF_HD double body_lambda(const View &v, int t)
     return fabs(ln - sel(v.lam, cur)[t]);
 }
 
-// ---- end of iteration (convergence.jl:1-31) ----------------------------------------------------
-DOPF_HD void body_finish(const View &v)
+// ---- end of iteration (convergence.jl:1-31), per scenario -----------------------------------------
+DOPF_HD void body_finish_scenario(const View &v, int c)
+{
+    if (v.sc_converged[c]) return;                     // frozen
+    double r[3];
+    for (int k = 0; k < 3; ++k) { r[k] = bits_nonneg(v.sc_res_bits[3 * c + k]); v.sc_res[3 * c + k] = r[k]; }
+    if (v.sc_iteration[c] != 1) {
+        for (int k = 0; k < 3; ++k) v.sc_conv[3 * c + k] = r[k] < v.c.eps;
+        v.sc_converged[c] = v.sc_conv[3 * c] && v.sc_conv[3 * c + 1] && v.sc_conv[3 * c + 2];
+    }
+    if (!v.sc_converged[c]) v.sc_iteration[c] += 1;
+}
+// global part: the control block mirrors scenario 0 (the whole problem when C = 1); `converged` = all scenarios
+DOPF_HD void body_finish_global(const View &v, int all)
 {
     Ctrl *c = v.ctrl;
-    for (int k = 0; k < 3; ++k) c->res[k] = bits_nonneg(c->res_bits[k]);
-    if (c->iteration != 1) {
-        c->conv_lambda = c->res[0] < v.c.eps;
-        c->conv_mue = c->res[1] < v.c.eps;
-        c->conv_rho = c->res[2] < v.c.eps;
-        c->converged = c->conv_lambda && c->conv_mue && c->conv_rho;
-    }
-    if (!c->converged) c->iteration += 1;
+    for (int k = 0; k < 3; ++k) c->res[k] = v.sc_res[k];
+    c->conv_lambda = v.sc_conv[0]; c->conv_mue = v.sc_conv[1]; c->conv_rho = v.sc_conv[2];
+    c->iteration = v.sc_iteration[0];
+    c->converged = all;
     c->cur = 1 - c->cur;
     c->iters_done += 1;
+    c->finish_cnt = 0;
+}
+DOPF_HD void body_finish(const View &v)                // single problem
+{
+    for (int k = 0; k < 3; ++k) v.sc_res_bits[k] = v.ctrl->res_bits[k];
+    body_finish_scenario(v, 0);
+    body_finish_global(v, v.sc_converged[0]);
 }
 
 }  // namespace dopf

@@ -118,6 +118,64 @@ __global__ void __launch_bounds__(256) k_compact(View v, int mode, int inline_dm
     }
 }
 
+// the same lists for grids with few lines (L <= 1024): one WARP per column, 8 columns per block - a block per column
+// would leave most of its warps without rows (scenario batches of small grids have tens of thousands of columns)
+__global__ void __launch_bounds__(256) k_compact_w(View v, int mode, int inline_dmax)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (t >= v.TC) return;
+    if (mode == 1 && inline_dmax) {
+        unsigned long long a = 0ull;
+        for (int n = lane; n < v.N; n += 32) { const unsigned long long b = v.dn[(size_t)n * v.ldt + t]; a = b > a ? b : a; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long y = __shfl_xor_sync(0xffffffffu, a, o); a = y > a ? y : a; }
+        if (lane == 0) v.dmax[t] = a;
+        __syncwarp();
+    }
+    const int n_in = mode == 0 ? v.L : v.wcnt[t];
+    const unsigned char *fl = v.flags + (size_t)t * v.Lp;
+    const int *in = v.wide + (size_t)t * 2 * v.L;
+    const double dm = mode == 1 ? bits_nonneg(__shfl_sync(0xffffffffu, v.dmax[t], 0)) : 0.0;
+    int *out = (mode == 0 ? v.wide : v.tight) + (size_t)t * 2 * v.L;
+    int cnt = 0;
+    if (mode == 0) {
+        for (int base = 0; base < n_in; base += 128) {
+            const int r0 = base + 4 * lane;
+            const unsigned w4 = r0 < n_in ? *reinterpret_cast<const unsigned *>(fl + r0) : 0u;
+            unsigned bits = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (r0 + k < n_in) bits |= ((w4 >> (8 * k)) & 3u) << (2 * k);
+            const int mine = __popc(bits);
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+            int pos = cnt + incl - mine;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if ((bits >> q) & 1u) {
+                    const int i = r0 + (q >> 1), side = q & 1;
+                    out[pos] = i * 2 + side;
+                    v.wide_b[(size_t)t * 2 * v.L + pos] = side ? v.bminus[(size_t)i * v.ldt + t] : v.bplus[(size_t)i * v.ldt + t];
+                    ++pos;
+                }
+            }
+            cnt += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    } else {
+        for (int base = 0; base < n_in; base += 32) {
+            const int i = base + lane;
+            bool p = false; int e = 0; double be = 0.0;
+            if (i < n_in) { e = in[i]; be = v.wide_b[(size_t)t * 2 * v.L + i]; p = fabs(be) <= v.prow[e >> 1] * dm; }
+            const unsigned m = __ballot_sync(0xffffffffu, p);
+            if (p) { const int pos = cnt + __popc(m & ((1u << lane) - 1)); out[pos] = e; v.tight_b[(size_t)t * 2 * v.L + pos] = be; }
+            cnt += __popc(m);
+        }
+    }
+    if (lane == 0) (mode == 0 ? v.wcnt : v.tcnt)[t] = cnt;
+}
+
 // ------------------------------------------------------------------------------------------------
 // fp64 tensor-pipe GEMMs (DMMA m8n8k4; tcgen05 has no f64 kind).  cp.async double buffering,
 // split-K partials reduced by the epilogue kernels below (deterministic order).
@@ -260,7 +318,8 @@ __global__ void k_node_prep(View v, const double *Cpart, const double *C2part, i
     }
     if (i < v.ldt) v.dmax[i] = 0ull;
     for (int k = i; k < v.S; k += gridDim.x * blockDim.x) v.sto_flag[k] = 0;
-    if (i < v.Np) v.fix_node_flag[i] = 0;
+    for (int k = i; k < v.NS * v.N; k += gridDim.x * blockDim.x) v.fix_node_flag[k] = 0;
+    for (int k = i; k < 3 * v.NS; k += gridDim.x * blockDim.x) v.sc_res_bits[k] = 0ull;
     if (i >= v.Np * v.ldt) return;
     v.dn[i] = 0ull;
     const int n = i / v.ldt, t = i % v.ldt, cur = v.ctrl->cur;
@@ -305,14 +364,20 @@ template <int VEC>
 __global__ void __launch_bounds__(256) k_gen_predict(View v)
 {
     if (!DOPF_ACTIVE(v)) return;
-    const int n = blockIdx.x;
-    const int ga = v.gen_ptr[n], gb = v.gen_ptr[n + 1];
+    const int n = blockIdx.x, sc = blockIdx.y, vn = sc * v.N + n;      // block = (node, scenario)
+    const int ga = v.gen_ptr[vn], gb = v.gen_ptr[vn + 1];
     if (ga == gb) return;
     const int cur = v.ctrl->cur, nxt = 1 - cur;
     const double *__restrict__ Pc = sel(v.P, cur);
     double *__restrict__ Pn = sel(v.P, nxt);
     const int t = threadIdx.x * VEC, rows = blockDim.y;
-    const size_t nt = (size_t)n * v.ldt + t;
+    if (v.sc_converged[sc]) {          // frozen scenario: the iterate is carried through unchanged
+        for (int g = ga + threadIdx.y; g < gb; g += rows)
+#pragma unroll
+            for (int w = 0; w < VEC; ++w) Pn[(size_t)g * v.T + t + w] = Pc[(size_t)g * v.T + t + w];
+        return;
+    }
+    const size_t nt = (size_t)n * v.ldt + (size_t)sc * v.T + t;
     double g0[VEC], rg[VEC], mx[VEC];
 #pragma unroll
     for (int w = 0; w < VEC; ++w) { g0[w] = v.g0[nt + w]; rg[w] = v.rg[nt + w]; mx[w] = 0.0; }
@@ -350,7 +415,50 @@ __global__ void __launch_bounds__(256) k_gen_predict(View v)
         }
     }
 #pragma unroll
-    for (int w = 0; w < VEC; ++w) note_move(v, n, t + w, mx[w]);
+    for (int w = 0; w < VEC; ++w) note_move(v, vn, t + w, mx[w]);
+}
+
+// Agent-major variant for grids with few generators per node (a node-major block would be mostly idle): one thread
+// per (generator, VEC consecutive timesteps), the node's g0 / step size are gathered (generators are node-sorted, so
+// neighbouring threads read the same lines), the largest move per (node, t) is published per element.
+template <int VEC>
+__global__ void __launch_bounds__(256) k_gen_flat(View v)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    const int per = v.T / VEC;
+    const long long units = (long long)v.G * per;
+    const int cur = v.ctrl->cur, nxt = 1 - cur;
+    const double *__restrict__ Pc = sel(v.P, cur);
+    double *__restrict__ Pn = sel(v.P, nxt);
+    for (long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x; u < units; u += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(u / per), t = (int)(u % per) * VEC;
+        const int vn = v.gen_node[g], sc = v.scen_of_vn(vn);
+        const size_t o = (size_t)g * v.T + t, nt = (size_t)(vn - sc * v.N) * v.ldt + (size_t)sc * v.T + t;
+        double pp[VEC], pn[VEC];
+        if (VEC == 4) {
+            const double2 a = *reinterpret_cast<const double2 *>(Pc + o), b = *reinterpret_cast<const double2 *>(Pc + o + 2);
+            pp[0] = a.x; pp[1 % VEC] = a.y; pp[2 % VEC] = b.x; pp[3 % VEC] = b.y;
+        } else if (VEC == 2) {
+            const double2 a = *reinterpret_cast<const double2 *>(Pc + o);
+            pp[0] = a.x; pp[1 % VEC] = a.y;
+        } else pp[0] = Pc[o];
+        if (v.sc_converged[sc]) {
+#pragma unroll
+            for (int w = 0; w < VEC; ++w) pn[w] = pp[w];              // frozen scenario
+        } else {
+            const double mc = __ldg(v.gen_mc + g), pm = __ldg(v.gen_pmax + g);
+#pragma unroll
+            for (int w = 0; w < VEC; ++w) {
+                pn[w] = gen_unit(pp[w], mc, pm, v.g0[nt + w], v.rg[nt + w]);
+                note_move(v, vn, t + w, pn[w] - pp[w]);
+            }
+        }
+        if (VEC == 4) {
+            *reinterpret_cast<double2 *>(Pn + o) = make_double2(pn[0], pn[1 % VEC]);
+            *reinterpret_cast<double2 *>(Pn + o + 2) = make_double2(pn[2 % VEC], pn[3 % VEC]);
+        } else if (VEC == 2) *reinterpret_cast<double2 *>(Pn + o) = make_double2(pn[0], pn[1 % VEC]);
+        else Pn[o] = pn[0];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -366,6 +474,11 @@ __global__ void __launch_bounds__(128) k_sto_warm(View v)
     if (!DOPF_ACTIVE(v)) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= v.S) return;
+    if (v.sc_converged[v.scen_of_vn(v.sto_node[s])]) {     // frozen scenario
+        const int cur = v.ctrl->cur;
+        for (int t = 0; t < v.T; ++t) { const size_t o = (size_t)s * v.T + t; sel(v.D, 1 - cur)[o] = sel(v.D, cur)[o]; sel(v.C, 1 - cur)[o] = sel(v.C, cur)[o]; }
+        return;
+    }
     body_sto_warm(v, s);
 }
 
@@ -382,6 +495,11 @@ __global__ void __launch_bounds__(128, (J <= 3 ? DOPF_STO_MINB : (J == 4 ? 3 : 2
     extern __shared__ __align__(16) double sto_smem[];
     double *tab = sto_smem + (size_t)(threadIdx.x >> 5) * (sto_warp_smem_per_warp(v.T) / sizeof(double));
     for (int s = gw; s < v.S; s += nw) {
+        if (v.sc_converged[v.scen_of_vn(v.sto_node[s])]) {     // frozen scenario: carry D, C through (E, eta stay)
+            const int cur = v.ctrl->cur;
+            for (int t = lane; t < v.T; t += 32) { const size_t o = (size_t)s * v.T + t; sel(v.D, 1 - cur)[o] = sel(v.D, cur)[o]; sel(v.C, 1 - cur)[o] = sel(v.C, cur)[o]; }
+            continue;
+        }
         const bool ok = (v.debug & 2) ? false : sto_warp_solve<J, false>(v, s, nullptr, nullptr, tab);
         if (!ok && lane == 0) v.cold_work[atomicAdd(&v.ctrl->cold_work_cnt, 1)] = s;
         __syncwarp();
@@ -484,7 +602,7 @@ __global__ void __launch_bounds__(128) k_sto_collect(View v, Hinge *hinge_scratc
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const long long tasks = (long long)min(v.ctrl->fix_node_cnt, slots) * v.T;
     for (long long k = gw; k < tasks; k += nw) {
-        const int slot = (int)(k / v.T), t = (int)(k % v.T), n = v.fix_node_list[slot];
+        const int slot = (int)(k / v.T), t = (int)(k % v.T), n = v.fix_node_list[slot];      // n: virtual node, t: agent-local
         double lo = 0.0, hi = 0.0;                // union of the flagged storages' boxes (both contain 0)
         for (int s = v.sto_ptr[n] + lane; s < v.sto_ptr[n + 1]; s += 32) {
             if (!v.sto_flag[s]) continue;
@@ -494,7 +612,8 @@ __global__ void __launch_bounds__(128) k_sto_collect(View v, Hinge *hinge_scratc
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
-        sto_collect_lists(v, n, t, lo, hi, hinge_scratch + ((size_t)slot * v.T + t) * v.hcap, hcnt_scratch + (size_t)slot * v.T + t);
+        const int sc = v.scen_of_vn(n);
+        sto_collect_lists(v, n - sc * v.N, sc * v.T + t, lo, hi, hinge_scratch + ((size_t)slot * v.T + t) * v.hcap, hcnt_scratch + (size_t)slot * v.T + t);
     }
 }
 
@@ -516,7 +635,8 @@ __global__ void __launch_bounds__(32) k_sto_fix(View v, Hinge *hinge_scratch, in
             for (int t = 0; t < v.T; ++t) {
                 double lo, hi;
                 sto_collect_box(v, s, t, lo, hi);
-                sto_collect_lists(v, n, t, lo, hi, mylist + (size_t)t * v.hcap, mycnt + t);
+                const int sc = v.scen_of_vn(n);
+                sto_collect_lists(v, n - sc * v.N, sc * v.T + t, lo, hi, mylist + (size_t)t * v.hcap, mycnt + t);
             }
             __syncwarp();
         }
@@ -571,10 +691,10 @@ __global__ void __launch_bounds__(256) k_verify(View v)
     __shared__ double qlo[256], qhi[256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = blockIdx.x * 32 + lane;
-    const int t = blockIdx.y * (blockDim.x >> 5) + warp;
+    const int t = blockIdx.y * (blockDim.x >> 5) + warp;          // column
     if (threadIdx.x == 0) qcnt = 0;
     __syncthreads();
-    if (n < v.N && t < v.T) {
+    if (n < v.N && t < v.TC) {
         double lo, hi;
         if (verify_bounds_dev(v, n, t, lo, hi)) {
             const int q = atomicAdd(&qcnt, 1);
@@ -584,7 +704,8 @@ __global__ void __launch_bounds__(256) k_verify(View v)
     __syncthreads();
     const int total = qcnt;
     for (int q = warp; q < total; q += (blockDim.x >> 5)) {
-        const int nn = qn[q] >> 3, tt = blockIdx.y * (blockDim.x >> 5) + (qn[q] & 7);
+        const int np = qn[q] >> 3, col = blockIdx.y * (blockDim.x >> 5) + (qn[q] & 7);
+        const int sc = v.scen_of_col(col), nn = sc * v.N + np, tt = col - sc * v.T;      // virtual node, agent-local timestep
         const double lo = qlo[q], hi = qhi[q];
         // the flagged generators of one (n,t) share their hinge candidates: they are appended as one group of
         // consecutive work entries (one atomic per group) so that k_gen_fix collects the hinges once per group
@@ -680,15 +801,16 @@ __global__ void __launch_bounds__(128) k_gen_fix(View v)
         const int base = v.gen_grp[2 * k], cnt_g = v.gen_grp[2 * k + 1];
         const bool mine = lane < cnt_g;
         const int e = v.gen_work[base + (mine ? lane : 0)];
-        const int g = e / v.T, t = e % v.T, n = v.gen_node[g];
+        const int g = e / v.T, t = e % v.T, vn = v.gen_node[g];
+        const int sc = v.scen_of_vn(vn), n = vn - sc * v.N, col = sc * v.T + t;            // physical node, column
         const double Pb = sel(v.P, cur)[(size_t)g * v.T + t], pmax = v.gen_pmax[g];
         const double lo = -Pb, hi = pmax - Pb;
         double ulo = mine ? lo : 0.0, uhi = mine ? hi : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { ulo = fmin(ulo, __shfl_xor_sync(0xffffffffu, ulo, o)); uhi = fmax(uhi, __shfl_xor_sync(0xffffffffu, uhi, o)); }
-        int cnt = collect_hinges(v, n, t, ulo, uhi, lists[wib], CAP);
+        int cnt = collect_hinges(v, n, col, ulo, uhi, lists[wib], CAP);
         __syncwarp();
-        const size_t nt = (size_t)n * v.ldt + t;
+        const size_t nt = (size_t)n * v.ldt + col;
         if (cnt <= CAP) {
             if (mine) {
                 HingeList hl; hl.h = lists[wib]; hl.n = cnt; hl.sorted = false;
@@ -696,25 +818,25 @@ __global__ void __launch_bounds__(128) k_gen_fix(View v)
                 double Pn = Pb + d;
                 Pn = Pn < 0.0 ? 0.0 : (Pn > pmax ? pmax : Pn);
                 sel(v.P, nxt)[(size_t)g * v.T + t] = Pn;
-                note_move(v, n, t, Pn - Pb);
+                note_move(v, vn, t, Pn - Pb);
             }
         } else {
             // the union box holds more candidates than the list: one agent at a time with its own box
             for (int a = 0; a < cnt_g; ++a) {
                 const double alo = __shfl_sync(0xffffffffu, lo, a), ahi = __shfl_sync(0xffffffffu, hi, a);
                 __syncwarp();
-                int c1 = collect_hinges(v, n, t, alo, ahi, lists[wib], CAP);
+                int c1 = collect_hinges(v, n, col, alo, ahi, lists[wib], CAP);
                 __syncwarp();
                 double dstream = 0.0;
                 if (c1 > CAP)      // more breakpoints inside the agent's own box than the list holds: list-free solve
-                    dstream = root_monotone_stream(v, n, t, __shfl_sync(0xffffffffu, v.gen_mc[g], a) + v.g0[nt], v.c.prox + v.s1[nt], alo, ahi);
+                    dstream = root_monotone_stream(v, n, col, __shfl_sync(0xffffffffu, v.gen_mc[g], a) + v.g0[nt], v.c.prox + v.s1[nt], alo, ahi);
                 if (lane == a) {
                     HingeList hl; hl.h = lists[wib]; hl.n = c1; hl.sorted = false;
                     const double d = c1 > CAP ? dstream : root_monotone_pl(v.gen_mc[g] + v.g0[nt], v.c.prox + v.s1[nt], hl, lo, hi);
                     double Pn = Pb + d;
                     Pn = Pn < 0.0 ? 0.0 : (Pn > pmax ? pmax : Pn);
                     sel(v.P, nxt)[(size_t)g * v.T + t] = Pn;
-                    note_move(v, n, t, Pn - Pb);
+                    note_move(v, vn, t, Pn - Pb);
                 }
             }
         }
@@ -784,68 +906,75 @@ __global__ void k_colsum(View v)   // block (32,32): 32 timesteps, 32 row groups
 // ------------------------------------------------------------------------------------------------
 // exact average-slack sums of the tight rows (results.jl:83-84,110-112):
 //   rowsum[l,t,side] = sum over all agents i of (b_lt -+ p_{l,n(i)} * delta_it)_+
-// one block per (t, row).  Threads classify the nodes with the signed move range [dlo,dhi] of (n,t):
-// nodes whose agents all keep the hinge on one side contribute in closed form (node sums), the mixed
-// nodes are queued in shared memory and summed by the warps with the lanes over the agents of the node.
+// one block per (t, row).  Threads classify the nodes with the node statistics of the moves at (n,t): nodes whose
+// agents all keep the hinge on one side contribute in closed form; the few mixed nodes (the hinge threshold falls
+// between two movers of one sign) are queued in shared memory, ordered by node, and their agents are summed one
+// warp per node.  Every partial sum is added in a fixed order, so the result does not depend on scheduling
+// (a batch of scenarios reproduces the single runs bit for bit).
+constexpr int SLACK_MIXED_CAP = 256;
 __global__ void __launch_bounds__(512) k_slack_rows(View v, unsigned char *tflag)
 {
     if (!DOPF_ACTIVE(v)) return;
     __shared__ double red[16];
-    const int t = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int mixed[SLACK_MIXED_CAP], msort[SLACK_MIXED_CAP], mcnt;
+    __shared__ double mval[SLACK_MIXED_CAP];
+    const int t = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;      // t: column
     const int cnt = v.tcnt[t];
     const int *lst = v.tight + (size_t)t * 2 * v.L;
+    const int cur = v.ctrl->cur, nxt = 1 - cur;
+    const int sc = v.scen_of_col(t), tl = t - sc * v.T;
     for (int j = blockIdx.x; j < cnt; j += gridDim.x) {
         const int l = lst[j] >> 1, side = lst[j] & 1;
         const double b = side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t];
+        if (threadIdx.x == 0) mcnt = 0;
+        __syncthreads();
         double a = 0.0;
         for (int n = threadIdx.x; n < v.N; n += blockDim.x) {
             const double p = v.ptdf[(size_t)l * v.Np + n];
             bool ok;
             const double c = slack_node_closed(v, b, side ? p : -p, n, t, ok);
             if (ok) { a += c; continue; }
-            // mixed node: its agents are summed one by one by k_slack_pairs (whole-GPU parallelism)
-            const int q = atomicAdd(&v.ctrl->pair_cnt, 1);
-            if (q < v.pair_cap) { v.pair_row[q] = lst[j]; v.pair_node[q] = n | (t << 20); }
-            else a += body_slack_row_node(v, l, side, n, t);      // queue full: serial path
+            const int q = atomicAdd(&mcnt, 1);
+            if (q < SLACK_MIXED_CAP) mixed[q] = n;
+            else a += body_slack_row_node(v, l, side, n, t);      // queue full: serial path (thread-local, still deterministic)
         }
         a = Group<32>::sum(a);
         if (lane == 0) red[warp] = a;
         __syncthreads();
+        const int nm = min(mcnt, SLACK_MIXED_CAP);
+        // order the mixed nodes by node index (the queue order depends on scheduling), then one warp per node
+        for (int i = threadIdx.x; i < nm; i += blockDim.x) {
+            int r = 0;
+            for (int k2 = 0; k2 < nm; ++k2) r += mixed[k2] < mixed[i];
+            msort[r] = mixed[i];
+        }
+        __syncthreads();
+        for (int i = warp; i < nm; i += (blockDim.x >> 5)) {
+            const int n = msort[i], vn = sc * v.N + n;
+            const double p = v.ptdf[(size_t)l * v.Np + n], sp = side ? p : -p;
+            double x = 0.0;
+            for (int g = v.gen_ptr[vn] + lane; g < v.gen_ptr[vn + 1]; g += 32) {
+                const size_t o = (size_t)g * v.T + tl;
+                x += pospart(b + sp * (sel(v.P, nxt)[o] - sel(v.P, cur)[o]));
+            }
+            for (int s2 = v.sto_ptr[vn] + lane; s2 < v.sto_ptr[vn + 1]; s2 += 32) {
+                const size_t o = (size_t)s2 * v.T + tl;
+                x += pospart(b + sp * ((sel(v.D, nxt)[o] - sel(v.D, cur)[o]) - (sel(v.C, nxt)[o] - sel(v.C, cur)[o])));
+            }
+            x = Group<32>::sum(x);
+            if (lane == 0) mval[i] = x;
+        }
+        __syncthreads();
         if (threadIdx.x == 0) {
             double sum = 0.0;
             for (int k2 = 0; k2 < (int)(blockDim.x >> 5); ++k2) sum += red[k2];
+            for (int k2 = 0; k2 < nm; ++k2) sum += mval[k2];
             const size_t i = (size_t)l * v.ldt + t;
             (side ? v.rowsumK : v.rowsumU)[i] = sum;
             atomicOr(reinterpret_cast<unsigned int *>(tflag) + (i >> 2), (unsigned)(1u << side) << (8 * (i & 3)));
+            atomicAdd(&v.ctrl->pair_cnt, nm);            // statistics only
         }
         __syncthreads();
-    }
-}
-
-// mixed (row, node) pairs: one warp per pair, lanes over the agents of the node
-__global__ void __launch_bounds__(256) k_slack_pairs(View v)
-{
-    if (!DOPF_ACTIVE(v)) return;
-    const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    const int total = min(v.ctrl->pair_cnt, v.pair_cap);
-    const int cur = v.ctrl->cur, nxt = 1 - cur;
-    for (int q = gw; q < total; q += nw) {
-        const int e = v.pair_row[q], l = e >> 1, side = e & 1;
-        const int n = v.pair_node[q] & 0xfffff, t = v.pair_node[q] >> 20;
-        const double b = side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t];
-        const double p = v.ptdf[(size_t)l * v.Np + n], sp = side ? p : -p;
-        double a = 0.0;
-        for (int g = v.gen_ptr[n] + lane; g < v.gen_ptr[n + 1]; g += 32) {
-            const size_t o = (size_t)g * v.T + t;
-            a += pospart(b + sp * (sel(v.P, nxt)[o] - sel(v.P, cur)[o]));
-        }
-        for (int s = v.sto_ptr[n] + lane; s < v.sto_ptr[n + 1]; s += 32) {
-            const size_t o = (size_t)s * v.T + t;
-            a += pospart(b + sp * ((sel(v.D, nxt)[o] - sel(v.D, cur)[o]) - (sel(v.C, nxt)[o] - sel(v.C, cur)[o])));
-        }
-        a = Group<32>::sum(a);
-        if (lane == 0) atomicAdd((side ? v.rowsumK : v.rowsumU) + (size_t)l * v.ldt + t, a);
     }
 }
 
@@ -863,11 +992,23 @@ __global__ void __launch_bounds__(256) k_dual(View v, const unsigned char *tflag
             for (int z = 0; z < ksplit; ++z) f += Cpart[(size_t)z * v.Lp * v.ldt + i];
             sel(v.flow, 1 - v.ctrl->cur)[i] = f;
         }
-        if (t < v.T) {
-            const int flag = tflag[i];
-            body_dual(v, l, t, flag, a, b);
+        if (t < v.TC) {
+            const int sc = v.scen_of_col(t);
+            if (v.sc_converged[sc]) {          // frozen scenario: duals carried through, average slacks untouched
+                const int cur = v.ctrl->cur;
+                sel(v.mu, 1 - cur)[i] = sel(v.mu, cur)[i]; sel(v.rho, 1 - cur)[i] = sel(v.rho, cur)[i];
+            } else {
+                const int flag = tflag[i];
+                body_dual(v, l, t, flag, a, b);
+                if (v.NS > 1) {                 // per-scenario residual maxima (a warp may span scenarios)
+                    if (a > 0.0) { const unsigned long long bits = nonneg_bits(a); if (bits > v.sc_res_bits[3 * sc + 1]) atomicMax(&v.sc_res_bits[3 * sc + 1], bits); }
+                    if (b > 0.0) { const unsigned long long bits = nonneg_bits(b); if (bits > v.sc_res_bits[3 * sc + 2]) atomicMax(&v.sc_res_bits[3 * sc + 2], bits); }
+                    a = 0.0; b = 0.0;
+                }
+            }
         }
     }
+    if (v.NS > 1) return;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
@@ -911,35 +1052,80 @@ __global__ void __launch_bounds__(256) k_lambda_finish(View v)
     }
 }
 
-// total_costs (results.jl:95-105) - on demand only
-__global__ void k_total_costs(View v, double *out)
+// the same for a batch of scenarios: one warp per scenario (lanes over its timesteps) updates lambda, takes the
+// residual maximum and evaluates the scenario's own stop rule; the last block to finish does the global part
+// (all-converged flag, buffer flip)
+__global__ void __launch_bounds__(128) k_lambda_finish_batch(View v)
 {
-    __shared__ double red[8];
-    const int newest = v.ctrl->cur;   // after k_finish the newest iterate sits in [cur]
-    double a = 0.0;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)v.G * v.T; i += (long long)gridDim.x * blockDim.x)
-        a += sel(v.P, newest)[i] * v.gen_mc[i / v.T];
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)v.S * v.T; i += (long long)gridDim.x * blockDim.x)
-        a += (sel(v.D, newest)[i] + sel(v.C, newest)[i]) * v.sto_mc[i / v.T];
-    a = Group<32>::sum(a);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    if (!DOPF_ACTIVE(v)) return;
+    __shared__ int last;
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c < v.NS) {
+        const int cur = v.ctrl->cur, nxt = 1 - cur;
+        int nt = 0, nw = 0;
+        if (v.sc_converged[c]) {
+            for (int t = lane; t < v.T; t += 32) sel(v.lam, nxt)[c * v.T + t] = sel(v.lam, cur)[c * v.T + t];
+        } else {
+            double r = 0.0;
+            for (int t = lane; t < v.T; t += 32) { r = fmax(r, body_lambda(v, c * v.T + t)); nt += v.tcnt[c * v.T + t]; nw += v.wcnt[c * v.T + t]; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o)); nt += __shfl_xor_sync(0xffffffffu, nt, o); nw += __shfl_xor_sync(0xffffffffu, nw, o); }
+            if (lane == 0) {
+                v.sc_res_bits[3 * c] = nonneg_bits(r);
+                body_finish_scenario(v, c);
+                atomicAdd(&v.ctrl->stat_tight_acc, nt); atomicAdd(&v.ctrl->stat_wide_acc, nw);
+            }
+        }
+    }
+    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) s += red[k];
-        atomicAdd(out, s);
+    if (threadIdx.x == 0) last = atomicAdd(&v.ctrl->finish_cnt, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        int all = 1;
+        for (int k = threadIdx.x; k < v.NS; k += blockDim.x) all &= *(volatile int *)&v.sc_converged[k];
+        all = __syncthreads_and(all);
+        if (threadIdx.x == 0) {
+            v.ctrl->stat_tight_rows = v.ctrl->stat_tight_acc; v.ctrl->stat_wide_rows = v.ctrl->stat_wide_acc;
+            v.ctrl->stat_tight_acc = 0; v.ctrl->stat_wide_acc = 0;
+            body_finish_global(v, all);
+        }
+    }
+}
+
+// total_costs (results.jl:95-105) per scenario - on demand only: one warp per agent
+__global__ void k_total_costs(View v, double *out /*[C]*/)
+{
+    const int newest = v.ctrl->cur;   // after k_finish the newest iterate sits in [cur]
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int a = gw; a < v.G + v.S; a += nw) {
+        double x = 0.0; int vn;
+        if (a < v.G) {
+            vn = v.gen_node[a];
+            for (int t = lane; t < v.T; t += 32) x += sel(v.P, newest)[(size_t)a * v.T + t];
+            x *= v.gen_mc[a];
+        } else {
+            const int s = a - v.G; vn = v.sto_node[s];
+            for (int t = lane; t < v.T; t += 32) x += sel(v.D, newest)[(size_t)s * v.T + t] + sel(v.C, newest)[(size_t)s * v.T + t];
+            x *= v.sto_mc[s];
+        }
+        x = Group<32>::sum(x);
+        if (lane == 0) atomicAdd(out + v.scen_of_vn(vn), x);
     }
 }
 
 // nodal price (network_elements.jl:16-25): lambda_t + sum_l (mu+rho)[l,t] ptdf[l,n]
 __global__ void k_nodal_price(View v, const double *lam, const double *mu, const double *rho, double *out /*[N][T]*/)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= v.N * v.T) return;
-    const int n = i / v.T, t = i % v.T;
-    double a = lam[t];
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;       // out is [C][N][T]
+    if (i >= (long long)v.NS * v.N * v.T) return;
+    const int t = (int)(i % v.T), n = (int)((i / v.T) % v.N), col = (int)(i / ((long long)v.T * v.N)) * v.T + t;
+    double a = lam[col];
     for (int l = 0; l < v.L; ++l)
-        a += (mu[(size_t)l * v.ldt + t] + rho[(size_t)l * v.ldt + t]) * v.ptdf[(size_t)l * v.Np + n];
+        a += (mu[(size_t)l * v.ldt + col] + rho[(size_t)l * v.ldt + col]) * v.ptdf[(size_t)l * v.Np + n];
     out[i] = a;
 }
 
@@ -953,14 +1139,15 @@ __global__ void __launch_bounds__(128) k_unit_penalty(View v, int kind, int idx,
 {
     __shared__ double ru[4], rl[4];
     const int t = blockIdx.x, newest = v.ctrl->cur, prev = 1 - newest;
-    const int n = kind == 0 ? v.gen_node[idx] : v.sto_node[idx];
+    const int vn = kind == 0 ? v.gen_node[idx] : v.sto_node[idx];
+    const int n = vn - v.scen_of_vn(vn) * v.N, col = v.col_of(vn, t);
     const size_t o = (size_t)idx * v.T + t;
     const double delta = kind == 0 ? sel(v.P, newest)[o] - sel(v.P, prev)[o]
                                    : (sel(v.D, newest)[o] - sel(v.D, prev)[o]) - (sel(v.C, newest)[o] - sel(v.C, prev)[o]);
     const double sc = v.c.w2 / v.c.kk;
     double au = 0.0, al = 0.0;
     for (int l = threadIdx.x; l < v.L; l += blockDim.x) {
-        const size_t i = (size_t)l * v.ldt + t;
+        const size_t i = (size_t)l * v.ldt + col;
         const double p = v.ptdf[(size_t)l * v.Np + n], pd = p * delta, F = sel(v.flow, prev)[i], f = v.fmax[l];
         const double u = sc * pospart(v.bplus[i] - pd), k = sc * pospart(v.bminus[i] + pd);
         if (U) U[(size_t)l * v.T + t] = u;
@@ -972,7 +1159,7 @@ __global__ void __launch_bounds__(128) k_unit_penalty(View v, int kind, int idx,
     if ((threadIdx.x & 31) == 0) { ru[threadIdx.x >> 5] = au; rl[threadIdx.x >> 5] = al; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const double s = sel(v.ssum, prev)[t] + delta;
+        const double s = sel(v.ssum, prev)[col] + delta;
         eb[t] = s * s; up[t] = ru[0] + ru[1] + ru[2] + ru[3]; lo[t] = rl[0] + rl[1] + rl[2] + rl[3];
     }
 }
@@ -981,23 +1168,25 @@ __global__ void __launch_bounds__(128) k_unit_penalty(View v, int kind, int idx,
 // (line, t) walks the nodes and their agents (on demand only: A*L*T terms)
 __global__ void __launch_bounds__(128) k_penalty_totals(View v, double *eb, double *up, double *lo)
 {
-    const int t = blockIdx.x * 32 + (threadIdx.x & 31), l = blockIdx.y * 4 + (threadIdx.x >> 5);
-    if (t >= v.T || l >= v.L) return;
+    const int t = blockIdx.x * 32 + (threadIdx.x & 31), l = blockIdx.y * 4 + (threadIdx.x >> 5);     // t: column, outputs [C][T]
+    if (t >= v.TC || l >= v.L) return;
+    const int scn = v.scen_of_col(t), tl = t - scn * v.T;
     const int newest = v.ctrl->cur, prev = 1 - newest;
     const size_t i = (size_t)l * v.ldt + t;
     const double sc = v.c.w2 / v.c.kk, F = sel(v.flow, prev)[i], f = v.fmax[l], bp = v.bplus[i], bm = v.bminus[i], S = sel(v.ssum, prev)[t];
     double au = 0.0, al = 0.0, ae = 0.0;
     for (int n = 0; n < v.N; ++n) {
         const double p = v.ptdf[(size_t)l * v.Np + n];
-        for (int g = v.gen_ptr[n]; g < v.gen_ptr[n + 1]; ++g) {
-            const size_t o = (size_t)g * v.T + t;
+        const int vn = scn * v.N + n;
+        for (int g = v.gen_ptr[vn]; g < v.gen_ptr[vn + 1]; ++g) {
+            const size_t o = (size_t)g * v.T + tl;
             const double d = sel(v.P, newest)[o] - sel(v.P, prev)[o], pd = p * d;
             const double a = F + pd + sc * pospart(bp - pd) - f, b = sc * pospart(bm + pd) - F - pd - f;
             au += a * a; al += b * b;
             if (l == 0) ae += (S + d) * (S + d);
         }
-        for (int s = v.sto_ptr[n]; s < v.sto_ptr[n + 1]; ++s) {
-            const size_t o = (size_t)s * v.T + t;
+        for (int s = v.sto_ptr[vn]; s < v.sto_ptr[vn + 1]; ++s) {
+            const size_t o = (size_t)s * v.T + tl;
             const double d = (sel(v.D, newest)[o] - sel(v.D, prev)[o]) - (sel(v.C, newest)[o] - sel(v.C, prev)[o]), pd = p * d;
             const double a = F + pd + sc * pospart(bp - pd) - f, b = sc * pospart(bm + pd) - F - pd - f;
             au += a * a; al += b * b;
@@ -1052,7 +1241,8 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
         ++launches;                                                                                \
     } while (0)
     LAUNCH(k_row_prep<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, cs>>>(v, lp.tflag));
-    LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 0, 0));
+    if (v.L <= 1024) LAUNCH(k_compact_w<<<cdiv(v.TC, 8), 256, 0, cs>>>(v, 0, 0));
+    else LAUNCH(k_compact<<<v.TC, 256, 0, cs>>>(v, 0, 0));
     {   // PTDF^T M and (PTDF.^2)^T W
         dim3 grid(lp.mt_rows / lp.bm_t, v.ldt / BN, lp.ksplit_t);
         if (lp.bm_t == 64) LAUNCH(k_gemm<64, true><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, lp.part, lp.part2, v.Np, v.Lp, lp.ksplit_t, lp.mt_base));
@@ -1077,15 +1267,22 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     if (v.G > 0) {
         // one block per node: x = timestep slots of `vec` timesteps, y = agent rows
         const int vec = v.T % 4 == 0 ? 4 : (v.T % 2 == 0 ? 2 : 1), per = v.T / vec;   // per <= 1024 checked at create
-        const dim3 blk(per, max(1, 256 / per)), grd(v.N);
-        if (vec == 4) LAUNCH(k_gen_predict<4><<<grd, blk, 0, cs>>>(v));
+        const dim3 blk(per, max(1, 256 / per)), grd(v.N, v.NS);
+        if (lp.gen_flat) {
+            const int fb = (int)min((long long)lp.num_sms * 16, ((long long)v.G * per + 255) / 256);
+            if (vec == 4) LAUNCH(k_gen_flat<4><<<fb, 256, 0, cs>>>(v));
+            else if (vec == 2) LAUNCH(k_gen_flat<2><<<fb, 256, 0, cs>>>(v));
+            else LAUNCH(k_gen_flat<1><<<fb, 256, 0, cs>>>(v));
+        }
+        else if (vec == 4) LAUNCH(k_gen_predict<4><<<grd, blk, 0, cs>>>(v));
         else if (vec == 2) LAUNCH(k_gen_predict<2><<<grd, blk, 0, cs>>>(v));
         else LAUNCH(k_gen_predict<1><<<grd, blk, 0, cs>>>(v));
     }
     JOIN();
-    LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 1, 1));   // with the column maxima of the moves computed in place
+    if (v.L <= 1024) LAUNCH(k_compact_w<<<cdiv(v.TC, 8), 256, 0, cs>>>(v, 1, 1));
+    else LAUNCH(k_compact<<<v.TC, 256, 0, cs>>>(v, 1, 1));   // with the column maxima of the moves computed in place
     {
-        dim3 grid(cdiv(v.N, 32), cdiv(v.T, 8));
+        dim3 grid(cdiv(v.N, 32), cdiv(v.TC, 8));
         LAUNCH(k_verify<<<grid, 256, 0, cs>>>(v));
     }
     FORK();
@@ -1106,11 +1303,11 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     JOIN();
     if (segment >= 0) LAUNCH(k_dmax<<<dim3(v.ldt / 32, 16), dim3(32, 32), 0, cs>>>(v));   // partitioned mode: maxima are exchanged
     XCHG(DOPF_X_DMAX);   // all ranks must build the same tight lists
-    LAUNCH(k_compact<<<v.T, 256, 0, cs>>>(v, 1, segment < 0));   // moves may have grown
+    if (v.L <= 1024) LAUNCH(k_compact_w<<<cdiv(v.TC, 8), 256, 0, cs>>>(v, 1, segment < 0));
+    else LAUNCH(k_compact<<<v.TC, 256, 0, cs>>>(v, 1, segment < 0));   // moves may have grown
     LAUNCH(k_inject<<<dim3(v.Np / 8, v.ldt / 32), 256, 0, cs>>>(v));
     XCHG(DOPF_X_INJ);    // nodal injection of all ranks' agents
-    LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.T), 512, 0, cs>>>(v, lp.tflag));   // needs the local injection statistics only
-    LAUNCH(k_slack_pairs<<<lp.num_sms * 2, 256, 0, cs>>>(v));
+    LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.TC), (v.N <= 256 ? 128 : 512), 0, cs>>>(v, lp.tflag));   // needs the local injection statistics only
     LAUNCH(k_colsum<<<v.ldt / 32, dim3(32, 32), 0, cs>>>(v));
     {   // flow = PTDF * inj
         dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);
@@ -1119,7 +1316,8 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     }
     XCHG(DOPF_X_ROWSUM); // exact slack sums over all ranks' agents
     LAUNCH(k_dual<<<cdiv((long long)v.L * v.ldt, 256), 256, 0, cs>>>(v, lp.tflag, lp.part, lp.ksplit_n));
-    LAUNCH(k_lambda_finish<<<1, 256, 0, cs>>>(v));
+    if (v.NS == 1) LAUNCH(k_lambda_finish<<<1, 256, 0, cs>>>(v));
+    else LAUNCH(k_lambda_finish_batch<<<cdiv(v.NS, 4), 128, 0, cs>>>(v));
 #undef LAUNCH
 #undef XCHG
 #undef FORK
@@ -1141,13 +1339,13 @@ void launch_profile_warm(const LaunchPlan &lp, cudaStream_t st)
 
 void launch_total_costs(const View &v, double *d_out, cudaStream_t st)
 {
-    cudaMemsetAsync(d_out, 0, sizeof(double), st);
+    cudaMemsetAsync(d_out, 0, sizeof(double) * v.NS, st);
     k_total_costs<<<296, 256, 0, st>>>(v, d_out);
 }
 
 void launch_nodal_price(const View &v, const double *lam, const double *mu, const double *rho, double *d_out, cudaStream_t st)
 {
-    k_nodal_price<<<cdiv((long long)v.N * v.T, 128), 128, 0, st>>>(v, lam, mu, rho, d_out);
+    k_nodal_price<<<cdiv((long long)v.NS * v.N * v.T, 128), 128, 0, st>>>(v, lam, mu, rho, d_out);
 }
 
 void launch_unit_penalty(const View &v, int kind, int idx, double *eb, double *up, double *lo, double *U, double *K, cudaStream_t st)
@@ -1157,8 +1355,22 @@ void launch_unit_penalty(const View &v, int kind, int idx, double *eb, double *u
 
 void launch_penalty_totals(const View &v, double *eb, double *up, double *lo, cudaStream_t st)
 {
-    cudaMemsetAsync(up, 0, sizeof(double) * v.T, st); cudaMemsetAsync(lo, 0, sizeof(double) * v.T, st);
-    k_penalty_totals<<<dim3(cdiv(v.T, 32), cdiv(v.L, 4)), 128, 0, st>>>(v, eb, up, lo);
+    cudaMemsetAsync(up, 0, sizeof(double) * v.TC, st); cudaMemsetAsync(lo, 0, sizeof(double) * v.TC, st);
+    k_penalty_totals<<<dim3(cdiv(v.TC, 32), cdiv(v.L, 4)), 128, 0, st>>>(v, eb, up, lo);
+}
+
+// scenario batches: host layout [C][rows][T] <-> device layout [rows][ld] (scenario c in the columns c*T .. c*T+T-1)
+__global__ void k_pack_cols(double *dev, double *host_layout, int rows, int C, int T, int ld, int to_device)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)C * rows * T) return;
+    const int t = (int)(i % T), r = (int)((i / T) % rows), c = (int)(i / ((long long)T * rows));
+    double *d = dev + (size_t)r * ld + (size_t)c * T + t;
+    if (to_device) *d = host_layout[i]; else host_layout[i] = *d;
+}
+void launch_pack_cols(double *dev, double *host_layout, int rows, int C, int T, int ld, int to_device, cudaStream_t st)
+{
+    k_pack_cols<<<cdiv((long long)C * rows * T, 256), 256, 0, st>>>(dev, host_layout, rows, C, T, ld, to_device);
 }
 
 // static wide-row bound mwide[l] = max_n |ptdf[l,n]| * rbox[n]; one warp per line (re-run after the

@@ -319,7 +319,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
         const int t = lane * J + j;
         valid[j] = t < T;
         const int tt = valid[j] ? t : T - 1;
-        const size_t o = (size_t)s * T + tt, on = (size_t)n * v.ldt + tt;
+        const size_t o = (size_t)s * T + tt, on = v.nt_of(n, tt);      // n: virtual node
         st[j].Db = sel(v.D, cur)[o]; st[j].Cb = sel(v.C, cur)[o];
         st[j].g0 = v.g0[on]; st[j].s1 = v.s1[on];
         r1[j] = v.rg[on]; r2[j] = v.rg2[on];          // 1/(prox + s1), 1/(prox + 2 s1) from k_node_prep

@@ -19,7 +19,7 @@ class DeviceADMM:
     """Owns a `dopf_handle`.  Arrays are numpy float64, row-major, timestep contiguous."""
 
     def __init__(self, prob: Problem, gamma=0.3, flow_weight=10.0, prox_weight=1.0, slack_mask_tol=1e-2, eps=1e-3,
-                 device=-1, hinge_capacity=0, use_graph=True, debug_flags=0):
+                 device=-1, hinge_capacity=0, use_graph=True, debug_flags=0, gemm_ksplit=0):
         self.lib = _lib.load()
         self.prob = prob
         p = prob
@@ -35,6 +35,8 @@ class DeviceADMM:
         cfg.slack_mask_tol, cfg.eps = float(slack_mask_tol), float(eps)
         cfg.device, cfg.hinge_capacity, cfg.use_graph = int(device), int(hinge_capacity), int(bool(use_graph))
         cfg.debug_flags = int(debug_flags)
+        cfg.n_scenarios, cfg.gemm_ksplit = int(getattr(prob, "n_scen", 1)), int(gemm_ksplit)
+        self.C = cfg.n_scenarios
         self.h = C.c_void_p()
         rc = self.lib.dopf_create(C.byref(cp), C.byref(cfg), C.byref(self.h))
         if rc != 0:
@@ -78,8 +80,10 @@ class DeviceADMM:
     # ---- state transfer --------------------------------------------------------------------
     def get_iterate(self, want=("P", "D", "C", "E", "injection", "flow", "avgU", "avgK"), out=None):
         p = self.prob
+        lead = (self.C,) if self.C > 1 else ()
         shapes = dict(P=(p.G, p.T), D=(p.S, p.T), C=(p.S, p.T), E=(p.S, p.T), injection=(p.N, p.T),
                       flow=(p.L, p.T), avgU=(p.L, p.T), avgK=(p.L, p.T))
+        shapes = {k: lead + v for k, v in shapes.items()}
         res = out if out is not None else {}
         for k in want:
             if k not in res:
@@ -90,7 +94,8 @@ class DeviceADMM:
 
     def get_duals(self, which=0):
         p = self.prob
-        lam = np.empty(p.T); mu = np.empty((p.L, p.T)); rho = np.empty((p.L, p.T))
+        lead = (self.C,) if self.C > 1 else ()
+        lam = np.empty(lead + (p.T,)); mu = np.empty(lead + (p.L, p.T)); rho = np.empty(lead + (p.L, p.T))
         self._check(self.lib.dopf_get_duals(self.h, int(which), _ptr(lam), _ptr(mu), _ptr(rho)), "dopf_get_duals")
         return lam, mu, rho
 
@@ -111,14 +116,20 @@ class DeviceADMM:
             out.append(((m.group(1) + (m.group(2) or "")) if m else names[i].decode()[:40], float(ms[i])))
         return out
 
+    def scenario_status(self):
+        """per scenario: iteration [C], converged [C], residuals of the last check [C,3]"""
+        it = np.zeros(self.C, dtype=np.int32); cv = np.zeros(self.C, dtype=np.int32); res = np.zeros((self.C, 3))
+        self._check(self.lib.dopf_get_scenario_status(self.h, _ptr(it), _ptr(cv), _ptr(res)), "dopf_get_scenario_status")
+        return it, cv, res
+
     def nodal_price(self, which=1):
-        out = np.empty((self.prob.N, self.prob.T))
+        out = np.empty(((self.C,) if self.C > 1 else ()) + (self.prob.N, self.prob.T))
         self._check(self.lib.dopf_get_nodal_price(self.h, int(which), _ptr(out)), "dopf_get_nodal_price")
         return out
 
     def nodal_price_of(self, lam, mu, rho):
         """get_nodal_price for an arbitrary dual set of the caller's history"""
-        out = np.empty((self.prob.N, self.prob.T))
+        out = np.empty(((self.C,) if self.C > 1 else ()) + (self.prob.N, self.prob.T))
         a = [np.ascontiguousarray(x, dtype=np.float64) for x in (lam, mu, rho)]
         self._check(self.lib.dopf_nodal_price_from(self.h, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(out)), "dopf_nodal_price_from")
         return out
@@ -134,7 +145,8 @@ class DeviceADMM:
 
     def penalty_totals(self):
         p = self.prob
-        eb, up, lo = np.empty(p.T), np.empty(p.T), np.empty(p.T)
+        shp = ((self.C,) if self.C > 1 else ()) + (p.T,)
+        eb, up, lo = np.empty(shp), np.empty(shp), np.empty(shp)
         self._check(self.lib.dopf_get_penalty_totals(self.h, _ptr(eb), _ptr(up), _ptr(lo)), "dopf_get_penalty_totals")
         return dict(energy_balance=eb, upper_flow=up, lower_flow=lo)
 
@@ -144,6 +156,7 @@ class DeviceADMM:
         return [int(x) for x in out]
 
     def total_costs(self):
-        v = C.c_double()
-        self._check(self.lib.dopf_get_total_costs(self.h, C.byref(v)), "dopf_get_total_costs")
-        return v.value
+        """result.total_costs (one value per scenario for a batch)"""
+        v = (C.c_double * self.C)()
+        self._check(self.lib.dopf_get_total_costs(self.h, v), "dopf_get_total_costs")
+        return v[0] if self.C == 1 else np.array(list(v))

@@ -23,15 +23,26 @@ class Problem:
     sto_pmax: np.ndarray
     sto_emax: np.ndarray
     sto_node: np.ndarray
+    n_scen: int = 1       # > 1: batch of scenarios on one grid; demand [C,N,T], gen_mc/gen_pmax [C,G], sto_mc/sto_pmax/sto_emax [C,S]
 
     @staticmethod
     def from_arrays(d):
         f = lambda k, shape: np.ascontiguousarray(np.asarray(d[k], dtype=np.float64).reshape(shape))
         i = lambda k, shape: np.ascontiguousarray(np.asarray(d[k], dtype=np.int32).reshape(shape))
         N, L, T, G, S = (int(d[k]) for k in "NLTGS")
-        return Problem(N, L, T, G, S, f("ptdf", (L, N)), f("fmax", (L,)), f("demand", (N, T)),
-                       f("gen_mc", (G,)), f("gen_pmax", (G,)), i("gen_node", (G,)),
-                       f("sto_mc", (S,)), f("sto_pmax", (S,)), f("sto_emax", (S,)), i("sto_node", (S,)))
+        C = int(d.get("n_scen", 1))
+        lead = (C,) if C > 1 else ()
+        return Problem(N, L, T, G, S, f("ptdf", (L, N)), f("fmax", (L,)), f("demand", lead + (N, T)),
+                       f("gen_mc", lead + (G,)), f("gen_pmax", lead + (G,)), i("gen_node", (G,)),
+                       f("sto_mc", lead + (S,)), f("sto_pmax", lead + (S,)), f("sto_emax", lead + (S,)), i("sto_node", (S,)), C)
+
+    def scenario(self, c):
+        """the single problem of scenario c of a batch"""
+        if self.n_scen == 1:
+            return self
+        return Problem(self.N, self.L, self.T, self.G, self.S, self.ptdf, self.fmax, np.ascontiguousarray(self.demand[c]),
+                       np.ascontiguousarray(self.gen_mc[c]), np.ascontiguousarray(self.gen_pmax[c]), self.gen_node,
+                       np.ascontiguousarray(self.sto_mc[c]), np.ascontiguousarray(self.sto_pmax[c]), np.ascontiguousarray(self.sto_emax[c]), self.sto_node, 1)
 
     @staticmethod
     def from_structs(nodes, generators, storages, lines):

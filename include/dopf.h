@@ -68,11 +68,22 @@ typedef struct dopf_config {
     int32_t hinge_capacity;  /* per (agent,t) hinge list capacity of the correction pass; 0 = default 32 */
     int32_t use_graph;       /* 1 = replay one captured CUDA graph per iteration           */
     int32_t debug_flags;     /* 0; diagnostics: bit0 storage correction pass by the sequential solver, bit1 storage predict pass too */
+    int32_t n_scenarios;     /* 1; > 1: a batch of independent scenarios on one grid (BASELINE configs[3]), see below */
+    int32_t gemm_ksplit;     /* 0 = chosen by the launch plan; > 0 fixes the split-K (summation order) of the PTDF products */
 } dopf_config;
 
 /* fills the reference's literals: gamma 0.3, flow_weight 10, prox 1, mask 1e-2, eps 1e-3 */
 void dopf_default_config(dopf_config *c);
 
+/* Scenario batches (dopf_config.n_scenarios = C > 1): C independent problems on the same grid (ptdf, f_max and the
+ * node of every agent are shared; N, L, T, G, S in dopf_problem are per scenario) run as ONE device problem with C*T
+ * columns - every kernel launch, both PTDF products included, covers all scenarios.  Arrays gain a leading scenario
+ * dimension: demand [C][N][T], gen_mc/gen_pmax [C][G], sto_mc/sto_pmax/sto_emax [C][S]; dopf_get_iterate returns
+ * P [C][G][T], D,C,E [C][S][T], injection [C][N][T], flow/avgU/avgK [C][L][T]; dopf_get_duals lam [C][T], mu/rho
+ * [C][L][T]; dopf_get_nodal_price [C][N][T]; dopf_get_total_costs [C].  Every scenario follows the reference's stop
+ * rule on its own (convergence.jl:1-31): a converged scenario is frozen while the others continue, exactly as if each
+ * had been run alone; dopf_step returns when all have converged.  dopf_status reports scenario 0 (iteration, flags,
+ * residuals) and converged = all; dopf_get_scenario_status gives every scenario. */
 typedef struct dopf_status {
     int32_t iteration;       /* admm.iteration (1-based; not advanced by the converging iteration) */
     int32_t converged;       /* admm.convergence.all                                        */
@@ -95,6 +106,8 @@ void dopf_destroy(dopf_handle *h);
 /* runs up to max_iters iterations, stops early when converged; synchronises before returning */
 int dopf_step(dopf_handle *h, int32_t max_iters, dopf_status *out);
 int dopf_get_status(dopf_handle *h, dopf_status *out);
+/* per scenario: admm.iteration [C], admm.convergence.all [C], residuals of the last check [C][3]; any pointer may be NULL */
+int dopf_get_scenario_status(dopf_handle *h, int32_t *iteration, int32_t *converged, double *residuals);
 
 /* newest iterate; any pointer may be NULL (skipped).  Agent order = the order given at create. */
 int dopf_get_iterate(dopf_handle *h, double *P /*[G][T]*/, double *D, double *C, double *E /*[S][T]*/,

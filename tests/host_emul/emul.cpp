@@ -96,6 +96,7 @@ double emul_gen_root(double c, double a, int n, const double *hbp, const double 
 #include <cmath>
 
 struct Emul {
+    std::vector<unsigned long long> scbits;
     View v;
     std::vector<std::vector<double>> d;   // owned double arrays
     std::vector<std::vector<int>> iv;
@@ -121,7 +122,7 @@ void *emul_create(int N, int L, int T, int G, int S, const double *ptdf, const d
     Emul *e = new Emul();
     View &v = e->v;
     memset(&v, 0, sizeof v);
-    v.N = N; v.L = L; v.T = T; v.G = G; v.S = S; v.A = G + S;
+    v.N = N; v.L = L; v.T = T; v.G = G; v.S = S; v.A = G + S; v.NS = 1; v.TC = T;
     v.ldt = rup(T, 32); v.Np = rup(N, 64); v.Lp = rup(L, 64); v.hcap = hcap; v.gen_work_cap = std::max(1, G * T);
     v.c = Coef::make(gamma, w, prox, mask_tol, eps);
     v.demand_on = 1;
@@ -167,6 +168,8 @@ void *emul_create(int N, int L, int T, int G, int S, const double *ptdf, const d
     v.gen_work = e->mki(v.gen_work_cap); v.sto_work = e->mki(S); v.sto_flag = e->mki(S);
     v.rowsumU = e->mk((size_t)Lp * ldt); v.rowsumK = e->mk((size_t)Lp * ldt);
     memset(&e->ctrl, 0, sizeof e->ctrl); e->ctrl.iteration = 1; v.ctrl = &e->ctrl;
+    v.sc_iteration = e->mki(1); v.sc_iteration[0] = 1; v.sc_converged = e->mki(1); v.sc_conv = e->mki(3);
+    e->scbits.assign(3, 0ull); v.sc_res_bits = e->scbits.data(); v.sc_res = e->mk(3);
     e->scratch.resize((size_t)T * hcap); e->hcnt.resize(T);
     // initial state: inj = -demand (cur buffer), flows
     const int cur = 0;

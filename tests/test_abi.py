@@ -30,7 +30,7 @@ def test_library_builds_and_exports_header_symbols(pkg):
 def test_struct_layouts_match_header(pkg):
     from dopf_b200 import _lib
     assert C.sizeof(_lib.DopfProblem) == 5 * 4 + 4 + 10 * 8            # 5 int32 + pad + 10 pointers
-    assert C.sizeof(_lib.DopfConfig) == 5 * 8 + 4 * 4
+    assert C.sizeof(_lib.DopfConfig) == 5 * 8 + 6 * 4
     assert C.sizeof(_lib.DopfStatus) == 6 * 4 + 3 * 8 + 6 * 4 + 8 + 8
     cfg = _lib.DopfConfig()
     _lib.load().dopf_default_config(C.byref(cfg))
