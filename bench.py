@@ -1,24 +1,29 @@
 #!/usr/bin/env python
 """bench.py - ADMM iteration throughput of libdopf on B200 (one "step" = one ADMM iteration).
 
-    python bench.py --gpus N --steps K --warmup W [--workload target|cfg3|cfg2] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload target|cfg3|cfg2|cfg4] [--impl reference]
 
 metric  : agent*timestep updates per second = (G+S)*T*iterations / time,
           whole-job aggregate over all ranks; `iters_per_s` is reported beside it.
-workload: "target" = the north_star's synthetic 100k-agent x 96-period case (80k generators +
-          20k storages on the 2000-node / 3000-line grid of BASELINE configs[2]); inputs resident in
-          HBM; working set (~0.5 GB) exceeds the 126 MB L2, so no explicit L2 flush is needed.  It is the case the
-          north_star's target sentence names ("a synthetic 100k-agent x 96-period case ... on 1 B200") and the largest
-          single-GPU case of the list; "cfg2" = BASELINE configs[1] (118 nodes, 1k generators + 200 storages, 24 periods),
-          "cfg3" = BASELINE configs[2] (2k nodes, 20k generators + 5k storages, 96 periods) - see profiles/ for their lines.
-N > 1   : weak scaling, one process per GPU.  --shard agents (default): ONE case with N x the agents of
-          the workload on the same grid, agents partitioned over the ranks, network/dual part replicated;
-          per iteration torch.distributed (NCCL) all-reduces the per-timestep move maxima, the nodal
-          injection and the exact slack row sums between the phases of libdopf.
-          --shard scenarios: every rank runs an independent scenario (BASELINE configs[3] style), no
-          data-path collective.  Time = max over ranks of the device time.
---impl reference : the CPU oracle (oracle/, OpenMP on all host cores) on a bounded sample of the
-          same workload; the Julia/JuMP/Gurobi reference itself cannot be installed here (no Julia).
+workload: "target" = the north_star's synthetic 100k-agent x 96-period case (80k generators + 20k storages on the
+          2000-node / 3000-line grid of BASELINE configs[2]); inputs resident in HBM; working set (~0.5 GB) exceeds the
+          126 MB L2, so no explicit L2 flush is needed.  It is the case the north_star's target sentence names and the
+          largest single-GPU case of the list.  "cfg2" = BASELINE configs[1] (118 nodes, 1k generators + 200 storages,
+          24 periods), "cfg3" = configs[2] (2k nodes, 20k + 5k, 96 periods), "cfg4" = configs[3] (128 independent
+          118-node / 24-period scenarios per GPU as ONE batched device problem; 1024 over 8 GPUs, no collective).
+timing  : W warm-up iterations from the reference's cold start (all-zero iterate and duals), then exactly K timed
+          iterations, CUDA events on the library's stream, max over ranks.  The timed window therefore lies in the
+          start-up transient of the ADMM run; `steady_state` repeats the measurement at iterations 151.. of the same run.
+params  : gamma = 0.03/A, flow_weight = 1/A (the reference's ratio 10/0.3, damped scale; see PARAMS); `alt_params` holds
+          the same window for the literals divided by A and for the round-1 parameters.
+N > 1   : one process per GPU.  --shard agents (default): ONE case with N x the agents of the workload on the same grid
+          (weak; --scaling strong: the workload's agents split over the ranks), agents partitioned over the ranks,
+          network/dual part replicated; per iteration torch.distributed (NCCL) all-reduces the per-timestep move maxima,
+          the nodal injection and the exact slack row sums between the phases of libdopf; the whole
+          iteration incl. the collectives is one CUDA graph.  --path partitioned runs N = 1 through the same code path.
+          cfg4 / --shard scenarios: every rank runs independent scenarios, no data-path collective.
+--impl reference : the CPU oracle (oracle/, OpenMP on all host cores) on a bounded sample of the same workload with
+          the full case's parameters; the Julia/JuMP/Gurobi reference itself cannot be installed here (no Julia).
 """
 import argparse
 import json
@@ -38,8 +43,10 @@ WORKLOADS = {
     "target": (2000, 3000, 80000, 20000, 96),
     "cfg3": (2000, 3000, 20000, 5000, 96),
     "cfg2": (118, 186, 1000, 200, 24),
+    "cfg4": (118, 186, 1000, 200, 24),      # BASELINE configs[3]: SCENARIOS_PER_GPU independent scenarios of the cfg2 shape per GPU (1024 over 8)
 }
-SAMPLE_AGENTS = {"target": (200, 50), "cfg3": (200, 50), "cfg2": (1000, 200)}   # CPU-side bounded sample
+SCENARIOS_PER_GPU = 128
+SAMPLE_AGENTS = {"target": (200, 50), "cfg3": (200, 50), "cfg2": (1000, 200), "cfg4": (1000, 200)}   # CPU-side bounded sample
 METRIC = "agent_timestep_updates_per_s"
 UNIT = "agent*timestep/s"
 
@@ -184,6 +191,23 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def build_problem(pkg, args, rank, world):
+    """(problem, ADMM parameters, per-rank agent*timestep units, description) of this rank"""
+    N, L, G, S, T = WORKLOADS[args.workload]
+    if args.workload == "cfg4":
+        C = SCENARIOS_PER_GPU
+        d = pkg.cases.synthetic_scenarios(N=N, L=L, G=G, S=S, T=T, n_scen=C, seed=rank)     # every rank its own 128 scenarios
+        return pkg.Problem.from_arrays(d), params_for(G + S, args.params), C * (G + S) * T, f"{world} x {C} independent scenarios, no collective"
+    partitioned = world > 1 and args.shard == "agents"
+    if partitioned or args.path == "partitioned":
+        mult = world if args.scaling == "weak" else 1
+        prob, cfg = make_case(pkg, args.workload, seed=0, agents=(mult * G, mult * S), params=args.params)   # same case on every rank
+        return prob, cfg, mult * (G + S) * T // world, (f"{world} GPUs, agents of ONE case partitioned ({mult * (G + S)} agents on one grid, {args.scaling} scaling), "
+                                                         "NCCL all-reduce of move maxima / nodal injection / slack sums per iteration, iteration + collectives in one CUDA graph")
+    prob, cfg = make_case(pkg, args.workload, seed=rank, params=args.params)
+    return prob, cfg, (G + S) * T, f"{world} independent case(s), one per GPU, no collective"
+
+
 def run_dopf(args):
     import torch
     import __graft_entry__ as g
@@ -197,17 +221,14 @@ def run_dopf(args):
     pkg = g.load_package()
     from dopf_b200.device import DeviceADMM
     N, L, G, S, T = WORKLOADS[args.workload]
-    A = G + S
-    partitioned = world > 1 and args.shard == "agents"
+    prob, cfg, units_per_rank, parallelism = build_problem(pkg, args, rank, world)
+    partitioned = args.workload != "cfg4" and ((world > 1 and args.shard == "agents") or args.path == "partitioned")
     if partitioned:
         from dopf_b200 import multi
-        prob, cfg = make_case(pkg, args.workload, seed=0, agents=(world * G, world * S))   # same case on every rank
-        part = multi.PartitionedADMM(prob, rank, world, local, hinge_capacity=64, **cfg)
+        part = multi.PartitionedADMM(prob, rank, world, local, hinge_capacity=64, graph=not args.no_graph, **cfg)
         dev = part.dev
-        A = world * (G + S) // world      # per-rank agents (value below multiplies by world)
     else:
         part = None
-        prob, cfg = make_case(pkg, args.workload, seed=rank)   # one independent scenario per rank
         dev = DeviceADMM(prob, device=local, hinge_capacity=64, **cfg)
 
     def barrier():
@@ -216,38 +237,41 @@ def run_dopf(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def timed(steps):
+        """device time of `steps` iterations on the stream the library runs on, max over ranks"""
+        barrier()
+        if part is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(part.stream)
+            st_ = part.step(steps, check_every=steps)
+            e1.record(part.stream)
+            part.stream.synchronize()
+            ms_ = e0.elapsed_time(e1)
+        else:
+            st_ = dev.step(steps)              # CUDA events on the library's stream around the graph replays
+            ms_ = st_.last_step_ms
+        barrier()
+        tm_ = torch.tensor([ms_], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tm_, op=dist.ReduceOp.MAX)
+        return float(tm_.item()), st_
+
     clocks = ClockSampler(local) if rank == 0 else None
     if clocks:
         clocks.start()
     (part or dev).step(args.warmup)
     if clocks:
         clocks.wait_for_samples()
-    barrier()
     t_begin = time.time()
-    if partitioned:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(part.stream):       # libdopf and the collectives run on this stream
-            e0.record(part.stream)
-        st = part.step(args.steps, check_every=args.steps)
-        with torch.cuda.stream(part.stream):
-            e1.record(part.stream)
-        part.stream.synchronize()
-        ms_total = e0.elapsed_time(e1)
-    else:
-        st = dev.step(args.steps)              # device time by CUDA events on the library's stream
-        ms_total = st.last_step_ms
-    barrier()
+    ms_total, st = timed(args.steps)
     clk = clocks.stop(t_begin, time.time()) if clocks else None
-    tmax = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_total = float(tmax.item())
-    value = world * A * T * args.steps / (ms_total * 1e-3)
-    steady = dict(gen_corrected_per_iter=None, sto_corrected_per_iter=None, sto_cold_last=st.sto_cold,
+    value = world * units_per_rank * args.steps / (ms_total * 1e-3)
+    window = dict(iterations=f"{args.warmup + 1}..{args.warmup + args.steps} from the reference's cold start (all-zero iterate and duals)",
+                  gen_corrected_total=st.gen_corrected, sto_corrected_total=st.sto_corrected, sto_cold_last=st.sto_cold,
                   tight_rows=st.tight_rows, wide_rows=st.wide_rows, residuals=[st.res_lambda, st.res_mue, st.res_rho])
 
-    # ---- per-kernel device times of one iteration (CUDA event pair per launch) -> roofline ----
-    prof = dev.profile_iteration() if not partitioned else []
+    # ---- per-kernel device times of the NEXT iteration (CUDA event pair per launch) -> roofline ----
+    prof = dev.profile_iteration() if part is None else []
     kern = {}
     for name, ms in prof:
         kern[name] = kern.get(name, 0.0) + ms
@@ -259,18 +283,20 @@ def run_dopf(args):
         pass
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    C = SCENARIOS_PER_GPU if args.workload == "cfg4" else 1
+    Gr, Sr = dev.prob.G * C, dev.prob.S * C       # agents on this rank
     # algorithmic bytes per launch
     def alg_bytes_of(name):
-        if name.startswith("k_gen_predict"): return 16.0 * G * T
-        if name.startswith("k_sto_warp") or name.startswith("k_sto_warm"): return 40.0 * S * T
-        if name.startswith("k_inject"): return 8.0 * (G + 2 * S) * T + 16.0 * N * T
+        if name.startswith("k_gen_predict") or name.startswith("k_gen_flat"): return 16.0 * Gr * T
+        if name.startswith("k_sto_warp") or name.startswith("k_sto_warm"): return 40.0 * Sr * T
+        if name.startswith("k_inject"): return 8.0 * (Gr + 2 * Sr) * T + 16.0 * N * T * C
         return None
 
     def gemm_flops_of(name):
-        if name.startswith("k_gemm") and "true" in name: return 4.0 * L * N * T          # PTDF^T M and (PTDF.^2)^T W
-        if name.startswith("k_gemm"): return 2.0 * L * N * T
+        if name.startswith("k_gemm") and "true" in name: return 4.0 * L * N * T * C      # PTDF^T M and (PTDF.^2)^T W
+        if name.startswith("k_gemm"): return 2.0 * L * N * T * C
         return None
-    dgemm = measure_dgemm_peak(torch, L, N, T) if rank == 0 else {}
+    dgemm = measure_dgemm_peak(torch, L, N, T * C) if rank == 0 and part is None else {}
     fp64_peak = max(dgemm.values()) if dgemm else 37.0
     if dom is None:
         roof = None
@@ -279,22 +305,39 @@ def run_dopf(args):
         roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None,
                 "peak_source": "cuBLAS DGEMM measured in this run (best of the two product shapes and a square 4096^3): %s" % json.dumps({k_: round(v_, 2) for k_, v_ in dgemm.items()})}
     else:
-        b = alg_bytes_of(dom) or 40.0 * S * T
+        b = alg_bytes_of(dom) or 40.0 * Sr * T
         ach = b / (kern[dom] * 1e-3) / 1e9
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": b}
     if roof is not None:
         # DRAM bytes (read + write) per launch of that kernel from the committed ncu --set full capture of this workload
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
             roof["traffic"] = tr.get(args.workload, {}).get(dom)
         except Exception:
             pass
         roof["kernel_ms"] = kern[dom]
         roof["kernel_share_of_iteration"] = kern[dom] / sum(kern.values())
-    gp = next((v for k_, v in kern.items() if k_.startswith("k_gen_predict")), None)
-    if gp and roof is not None:
-        roof["generator_stream"] = {"kernel_ms": gp, "achieved_GBps": 16.0 * G * T / (gp * 1e-3) / 1e9, "frac": 16.0 * G * T / (gp * 1e-3) / 1e9 / hbm}
+        roof["profiled_iteration"] = args.warmup + args.steps + 1
+        # whole iteration against the HBM roofline: SURVEY.md 8(d) bytes per iteration / the timed ms per step
+        b_iter = C * (16.0 * dev.prob.G * T + 40.0 * dev.prob.S * T + 32.0 * N * T + 80.0 * L * T) + 16.0 * L * N
+        roof["whole_iteration"] = {"algorithmic_bytes": b_iter, "achieved_GBps": b_iter / (ms_total / args.steps * 1e-3) / 1e9,
+                                   "frac_of_hbm_peak": b_iter / (ms_total / args.steps * 1e-3) / 1e9 / hbm}
+        gp = next((v for k_, v in kern.items() if k_.startswith("k_gen_predict") or k_.startswith("k_gen_flat")), None)
+        if gp:
+            roof["generator_stream"] = {"kernel_ms": gp, "achieved_GBps": 16.0 * Gr * T / (gp * 1e-3) / 1e9, "frac": 16.0 * Gr * T / (gp * 1e-3) / 1e9 / hbm}
+        roof["dgemm_peaks_TFLOPs"] = {k_: round(v_, 2) for k_, v_ in dgemm.items()}
+        roof["gemm_TFLOPs"] = {k_: round(gemm_flops_of(k_) / (v_ * 1e-3) / 1e12, 2) for k_, v_ in kern.items() if gemm_flops_of(k_)}
+
+    # ---- steady state: the same measurement after the transient (iterations 151.. of this run) ----
+    steady = None
+    if not args.quick:
+        done = args.warmup + args.steps + (1 if part is None else 0)
+        if done < 150:
+            (part or dev).step(150 - done)
+        ms_s, st_s = timed(args.steps)
+        steady = {"ms_per_step": ms_s / args.steps, "value": world * units_per_rank * args.steps / (ms_s * 1e-3), "iterations": f"151..{150 + args.steps}",
+                  "tight_rows": st_s.tight_rows, "residuals": [st_s.res_lambda, st_s.res_mue, st_s.res_rho]}
 
     # ---- end to end through the C ABI with host buffers (pinned): upload state, iterate, read back ----
     e2e_steps = max(1, min(args.steps, 10))
@@ -308,46 +351,66 @@ def run_dopf(args):
     hl[...] = lam; hm[...] = mu; hr[...] = rho
     h2d = sum(hb[k].nbytes for k in ("P", "D", "C", "avgU", "avgK")) + hl.nbytes + hm.nbytes + hr.nbytes
     d2h = sum(hb[k].nbytes for k in ("P", "D", "C", "E")) + hl.nbytes + hm.nbytes + hr.nbytes
-    import ctypes as C
+    import ctypes as C_
     iteration = dev.status.iteration
     barrier()
     t0 = time.perf_counter()
-    if partitioned:
+    if part is not None:
         h2d = 0
     for _ in range(e2e_steps):
-        if partitioned:
+        if part is not None:
             part.step(1)                       # state stays on the device; results are read back every step
         else:
             dev.set_state(iteration, P=hb["P"], D=hb["D"], C_=hb["C"], avgU=hb["avgU"], avgK=hb["avgK"], lam=hl, mu=hm, rho=hr)
             dev.step(1)
         dev.get_iterate(("P", "D", "C", "E"), out=hb)
-        dev.lib.dopf_get_duals(dev.h, 0, hl.ctypes.data_as(C.c_void_p), hm.ctypes.data_as(C.c_void_p), hr.ctypes.data_as(C.c_void_p))
+        dev.lib.dopf_get_duals(dev.h, 0, hl.ctypes.data_as(C_.c_void_p), hm.ctypes.data_as(C_.c_void_p), hr.ctypes.data_as(C_.c_void_p))
         iteration = dev.status.iteration
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     tm = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    e2e_value = world * A * T * e2e_steps / float(tm.item())
+    e2e_value = world * units_per_rank * e2e_steps / float(tm.item())
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling if partitioned else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": args.workload, "nodes": N, "lines": L, "generators": G, "storages": S, "timesteps": T,
-                           "gamma": cfg["gamma"], "flow_weight": cfg["flow_weight"], "prox_weight": cfg["prox_weight"],
-                           "parallelism": (f"{world} GPUs, agents partitioned ({world}x{G + S} agents on one grid), NCCL all-reduce of move maxima / nodal injection / slack sums per iteration"
-                                           if partitioned else f"{world} independent scenario(s), one per GPU, no collective"),
-                           "l2": "working set larger than L2 (no flush)"},
-                "iters_per_s": world * args.steps / (ms_total * 1e-3),
+                           "scenarios_per_gpu": C, "agents_per_gpu": Gr + Sr,
+                           "gamma": cfg["gamma"], "flow_weight": cfg["flow_weight"], "prox_weight": cfg["prox_weight"], "params": args.params,
+                           "params_note": "gamma = %g/A, flow_weight = %g/A (A agents per case): the reference's ratio flow_weight/gamma = 10/0.3 at the largest damped scale; "
+                                          "the literals divided by A end in a limit cycle (see alt_params and profiles/r2_param_scan.md)" % PARAMS[args.params],
+                           "parallelism": parallelism, "l2": "working set larger than L2 (no flush)"},
+                "iters_per_s": args.steps / (ms_total * 1e-3),
                 "gpu_launches": dev.status.launches_per_iteration * args.steps,
                 "clocks": clk, "roofline": roof,
                 "kernels_ms": {k: round(v, 4) for k, v in kern.items()},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "steps": e2e_steps, "what": ("partitioned run: iterate + dopf_get_iterate/duals(host) every step (no per-step upload)" if partitioned
+                        "steps": e2e_steps, "what": ("partitioned run: iterate + dopf_get_iterate/duals(host) every step (no per-step upload)" if part is not None
                                                      else "dopf_set_state(host) + dopf_step(1) + dopf_get_iterate/duals(host), pinned buffers")},
-                "steady_state": steady}
-        if world == 1:
+                "timed_window": window, "steady_state": steady}
+        if part is not None:
+            line["partitioned_graph"] = {"captured": part.graph is not None, "error": part.graph_error}
+        if world == 1 and not args.quick and part is None and args.workload != "cfg4":
+            # the same window (5 warm-up + 20 timed iterations from the cold start) with the other parameter sets
+            alts = []
+            for name in PARAMS:
+                if name == args.params:
+                    continue
+                ad = DeviceADMM(prob, device=local, hinge_capacity=64, **params_for(G + S, name))
+                try:
+                    ad.step(5); g0, s0 = ad.status.gen_corrected, ad.status.sto_corrected
+                    sa = ad.step(20)
+                    alts.append({"params": name, "gamma_x_A": PARAMS[name][0], "flow_weight_x_A": PARAMS[name][1], "ms_per_step": sa.last_step_ms / 20,
+                                 "gen_corrected_per_iter": (sa.gen_corrected - g0) / 20, "sto_corrected_per_iter": (sa.sto_corrected - s0) / 20,
+                                 "tight_rows": sa.tight_rows, "residuals": [sa.res_lambda, sa.res_mue, sa.res_rho]})
+                except Exception as e:
+                    alts.append({"params": name, "error": str(e)})
+                ad.close()
+            line["alt_params"] = alts
+        if world == 1 and part is None:
             # time to tolerance on the reference's own case (three_node, gamma 0.3, literal weights, eps 1e-3: stops at
             # iteration 476 like src/opf_admm_decentral.jl) - SURVEY.md 8(d) "time-to-tolerance"
             try:
@@ -358,7 +421,7 @@ def run_dopf(args):
                 tn.close()
             except Exception as e:      # additional information only
                 line["three_node_to_tolerance"] = {"error": str(e)}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.quick and args.workload != "cfg4":
             v, ms, cores, sample = oracle_rate(pkg, args.workload, 3, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_iteration_of_sample": ms}
         print(json.dumps(line))
@@ -376,6 +439,11 @@ def main():
     ap.add_argument("--workload", default="target", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shard", default="agents", choices=["agents", "scenarios"], help="N>1: partition the agents of one case (NCCL exchanges) or run independent scenarios")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="agent partition: N x the workload's agents (weak) or the workload's agents split over the ranks (strong)")
+    ap.add_argument("--path", default="auto", choices=["auto", "partitioned"], help="partitioned: also N=1 runs through the phase-wise multi-GPU code path (like-for-like scaling baseline)")
+    ap.add_argument("--params", default="ref_ratio", choices=sorted(PARAMS), help="ADMM parameter set (see PARAMS)")
+    ap.add_argument("--no-graph", action="store_true", help="partitioned path without the CUDA graph (eager launches from Python)")
+    ap.add_argument("--quick", action="store_true", help="skip the steady-state / alt-params / cpu-baseline legs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -46,6 +46,7 @@ struct dopf_handle {
     // multi-GPU (agent-block partition; exchanges are done by the caller between the phases)
     int rank = 0, nranks = 1;
     int host_cur = 0;          // host mirror of Ctrl::cur, advanced by phase 3
+    bool partitioned = false;  // dopf_set_partition was called: stepped phase by phase
     cudaStream_t own_stream = nullptr;
 };
 
@@ -266,6 +267,9 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     v.gen_work_cap = (int)std::min<long long>((long long)G * T, 1ll << 30);
     AL(v.gen_work, (size_t)std::max(v.gen_work_cap, 1)); AL(v.gen_grp, (size_t)2 * std::max(v.gen_work_cap, 1)); AL(v.sto_work, S); AL(v.sto_flag, S);
     AL(v.fix_node_flag, NV); AL(v.fix_node_list, NV); AL(v.fix_node_slot, NV);
+    v.pair_cap = 1 << 20;
+    AL(v.pair_row, v.pair_cap); AL(v.pair_node, v.pair_cap); AL(v.pair_col, v.pair_cap); AL(v.pair_val, v.pair_cap);
+    AL(v.pbase, (size_t)TC * 2 * L); AL(v.pcnt, (size_t)TC * 2 * L);
     AL(v.sc_iteration, C); AL(v.sc_converged, C); AL(v.sc_conv, 3 * C); AL(v.sc_res_bits, 3 * C); AL(v.sc_res, 3 * C);
     {
         std::vector<int> ones(C, 1);
@@ -404,7 +408,7 @@ int dopf_step(dopf_handle *h, int32_t max_iters, dopf_status *out)
 int dopf_profile_iteration(dopf_handle *h, int32_t cap, float *ms, const char **names, int32_t *count)
 {
     if (!h || !ms || !names || !count || cap < 1) return DOPF_E_ARG;
-    if (h->nranks > 1) { h->err = "dopf_profile_iteration: single-GPU handles only"; return DOPF_E_UNSUPPORTED; }
+    if (h->partitioned) { h->err = "dopf_profile_iteration: single-GPU handles only"; return DOPF_E_UNSUPPORTED; }
     CK(cudaSetDevice(h->device));
     std::vector<cudaEvent_t> ev(2 * (size_t)cap);
     for (auto &e : ev) CK(cudaEventCreate(&e));
@@ -524,7 +528,7 @@ int dopf_set_state(dopf_handle *h, int32_t iteration, const double *P, const dou
                    const double *avgU, const double *avgK, const double *lam, const double *mu, const double *rho)
 {
     if (!h || iteration < 1) return DOPF_E_ARG;
-    if (h->nranks > 1) {     // the derived network state would need the exchanges of the partitioned mode
+    if (h->partitioned) {     // the derived network state would need the exchanges of the partitioned mode
         h->err = "dopf_set_state is not supported after dopf_set_partition";
         return DOPF_E_UNSUPPORTED;
     }
@@ -597,7 +601,7 @@ int dopf_nodal_price_from(dopf_handle *h, const double *lam, const double *mu, c
 static int need_iteration_done(dopf_handle *h, const char *what)
 {
     if (h->h_ctrl->iters_done < 1) { h->err = std::string(what) + ": no iteration has run yet"; return DOPF_E_ARG; }
-    if (h->nranks > 1) { h->err = std::string(what) + ": single-GPU handles only"; return DOPF_E_UNSUPPORTED; }
+    if (h->partitioned) { h->err = std::string(what) + ": single-GPU handles only"; return DOPF_E_UNSUPPORTED; }
     return 0;
 }
 
@@ -697,22 +701,23 @@ int dopf_set_partition(dopf_handle *h, int32_t rank, int32_t nranks, int32_t tot
     View &v = h->lp.view;
     v.A = total_agents;
     v.demand_on = rank == 0 ? 1 : 0;
-    if (nranks > 1 && v.injloc[0] == v.inj[0]) {
-        for (int k = 0; k < 2; ++k) {
-            double *q = nullptr;
-            int r2 = dev_alloc(h, &q, (size_t)v.Np * v.ldt);
-            if (r2) return r2;
-            v.injloc[k] = q;
-        }
+    if (!h->partitioned) {
+        // the local injection of BOTH iterates goes to one fixed exchange buffer: every device pointer an enqueued phase
+        // uses is then independent of the ping-pong parity, so the caller may capture an iteration (phases + its own
+        // collectives) in a CUDA graph and replay it
+        double *q = nullptr;
+        int r2 = dev_alloc(h, &q, (size_t)v.Np * v.ldt);
+        if (r2) return r2;
+        v.injloc[0] = v.injloc[1] = q;
+        h->partitioned = true;
     }
-    h->use_graph = nranks == 1 && h->use_graph;
+    h->use_graph = false;
     // local part of the state before iteration 1: staged injection (-demand on rank 0) in the inactive
     // buffers; the caller all-reduces DOPF_XBUF_INJ and then runs dopf_step_phase(h, -1) to finish
     int rc = sync_ctrl(h);
     if (rc) return rc;
     h->host_cur = h->h_ctrl->cur;
     launch_rebuild_derived(h->lp, h->stream, 0);
-    if (nranks > 1) CK(cudaMemcpyAsync(v.inj[1 - h->host_cur], v.injloc[1 - h->host_cur], (size_t)v.Np * v.ldt * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaGetLastError());
     return DOPF_OK;
 }
@@ -723,18 +728,19 @@ int dopf_step_phase(dopf_handle *h, int32_t phase)
     CK(cudaSetDevice(h->device));
     View &v = h->lp.view;
     if (phase == -1) {   // second half of the initial state after the injection / box-range exchanges
+        if (!h->partitioned) { h->err = "dopf_step_phase: call dopf_set_partition first"; return DOPF_E_ARG; }
         launch_mwide(v, h->stream);
+        launch_copy_inj(v, v.injloc[0], h->stream);       // the all-reduced initial injection
         launch_rebuild_derived(h->lp, h->stream, 1);
         h->host_cur = 1 - h->host_cur;
-        if (h->nranks > 1) CK(cudaMemcpyAsync(v.injloc[1 - h->host_cur], v.injloc[h->host_cur], (size_t)v.Np * v.ldt * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         CK(cudaGetLastError());
         return DOPF_OK;
     }
+    if (!h->partitioned) { h->err = "dopf_step_phase: call dopf_set_partition first"; return DOPF_E_ARG; }
+    if (phase == DOPF_X_INJ + 1) launch_copy_inj(v, v.injloc[0], h->stream);   // the injection exchanged after the previous phase
     const int n = enqueue_iteration(h->lp, h->stream, phase);
     if (phase == 0) h->launches_per_iter = 0;
-    h->launches_per_iter += n;
-    if (phase == DOPF_X_INJ && h->nranks > 1)   // the exchange runs in place on the global injection
-        CK(cudaMemcpyAsync(v.inj[1 - h->host_cur], v.injloc[1 - h->host_cur], (size_t)v.Np * v.ldt * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    h->launches_per_iter += n + (phase == DOPF_X_INJ + 1 ? 1 : 0);
     if (phase == DOPF_N_SEGMENTS - 1) h->host_cur = 1 - h->host_cur;
     CK(cudaGetLastError());
     return DOPF_OK;
@@ -744,10 +750,10 @@ int dopf_exchange_buffer(dopf_handle *h, int32_t which, void **device_ptr, int64
 {
     if (!h || !device_ptr || !count) return DOPF_E_ARG;
     View &v = h->lp.view;
-    const int nxt = 1 - h->host_cur;
-    switch (which) {
+    if (!h->partitioned) { h->err = "dopf_exchange_buffer: call dopf_set_partition first"; return DOPF_E_ARG; }
+    switch (which) {      // all four are fixed device addresses for the lifetime of the handle
     case DOPF_XBUF_DMAX: *device_ptr = v.dmax; *count = v.ldt; break;
-    case DOPF_XBUF_INJ: *device_ptr = v.inj[nxt]; *count = (int64_t)v.Np * v.ldt; break;
+    case DOPF_XBUF_INJ: *device_ptr = v.injloc[0]; *count = (int64_t)v.Np * v.ldt; break;
     case DOPF_XBUF_ROWSUM: *device_ptr = v.rowsumU; *count = (int64_t)2 * v.Lp * v.ldt; break;
     case DOPF_XBUF_RBOX: *device_ptr = v.rbox; *count = v.Np; break;
     default: return DOPF_E_ARG;
@@ -762,7 +768,7 @@ namespace dopf {
 // one whole iteration (single-GPU handles); returns the number of kernel launches or < 0
 int enqueue_iteration_comm(dopf_handle *h, cudaStream_t st)
 {
-    if (h->nranks > 1) {
+    if (h->partitioned) {
         h->err = "partitioned handles are stepped with dopf_step_phase (the caller does the exchanges)";
         return DOPF_E_UNSUPPORTED;
     }

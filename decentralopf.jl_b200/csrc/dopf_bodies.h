@@ -112,6 +112,8 @@ struct View {
     int *sto_work, *sto_flag;          // [S], [S]
     int *fix_node_flag, *fix_node_list, *fix_node_slot;   // [Np] nodes with a storage on the work list (device path only)
     double *rowsumU, *rowsumK;         // [Lp][ldt] exact sum_i (b -+ p delta_i)_+ of tight rows
+    int *pair_row, *pair_node, *pair_col; double *pair_val; int pair_cap;   // queue of (tight row, node, column) whose agents are summed one by one
+    int *pbase, *pcnt;                 // [TC][2L] queue range of every tight-list entry
     unsigned long long *counters;   // [32] diagnostics (filled only by builds with -DDOPF_STATS)
     // per-scenario convergence state (convergence.jl:1-31 for every scenario of the batch separately); a converged
     // scenario is frozen: its agents, duals and average slacks are carried through unchanged while the others go on

@@ -906,23 +906,23 @@ __global__ void k_colsum(View v)   // block (32,32): 32 timesteps, 32 row groups
 // ------------------------------------------------------------------------------------------------
 // exact average-slack sums of the tight rows (results.jl:83-84,110-112):
 //   rowsum[l,t,side] = sum over all agents i of (b_lt -+ p_{l,n(i)} * delta_it)_+
-// one block per (t, row).  Threads classify the nodes with the node statistics of the moves at (n,t): nodes whose
-// agents all keep the hinge on one side contribute in closed form; the few mixed nodes (the hinge threshold falls
-// between two movers of one sign) are queued in shared memory, ordered by node, and their agents are summed one
-// warp per node.  Every partial sum is added in a fixed order, so the result does not depend on scheduling
-// (a batch of scenarios reproduces the single runs bit for bit).
-constexpr int SLACK_MIXED_CAP = 256;
+// k_slack_rows: one block per (t, row).  Threads classify the nodes with the node statistics of the moves at (n,t):
+//   nodes whose agents all keep the hinge on one side contribute in closed form; the few mixed nodes (the hinge
+//   threshold falls between two movers of one sign) are ordered by node and appended to a global pair queue as ONE
+//   contiguous range per row;
+// k_slack_pairs: one warp per queued (row, node) pair sums the agents of the node (whole-GPU parallelism);
+// k_slack_fold: every row adds the values of its range in order.
+// Every partial sum is added in a fixed order, so the result does not depend on scheduling (a batch of scenarios
+// reproduces the single runs bit for bit; only the position of a row's range in the queue varies).
+constexpr int SLACK_MIXED_CAP = 512;
 __global__ void __launch_bounds__(512) k_slack_rows(View v, unsigned char *tflag)
 {
     if (!DOPF_ACTIVE(v)) return;
     __shared__ double red[16];
-    __shared__ int mixed[SLACK_MIXED_CAP], msort[SLACK_MIXED_CAP], mcnt;
-    __shared__ double mval[SLACK_MIXED_CAP];
+    __shared__ int mixed[SLACK_MIXED_CAP], mcnt, mbase;
     const int t = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;      // t: column
     const int cnt = v.tcnt[t];
     const int *lst = v.tight + (size_t)t * 2 * v.L;
-    const int cur = v.ctrl->cur, nxt = 1 - cur;
-    const int sc = v.scen_of_col(t), tl = t - sc * v.T;
     for (int j = blockIdx.x; j < cnt; j += gridDim.x) {
         const int l = lst[j] >> 1, side = lst[j] & 1;
         const double b = side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t];
@@ -936,46 +936,88 @@ __global__ void __launch_bounds__(512) k_slack_rows(View v, unsigned char *tflag
             if (ok) { a += c; continue; }
             const int q = atomicAdd(&mcnt, 1);
             if (q < SLACK_MIXED_CAP) mixed[q] = n;
-            else a += body_slack_row_node(v, l, side, n, t);      // queue full: serial path (thread-local, still deterministic)
+            else a += body_slack_row_node(v, l, side, n, t);      // list full: serial path (thread-local, still deterministic)
         }
         a = Group<32>::sum(a);
         if (lane == 0) red[warp] = a;
         __syncthreads();
         const int nm = min(mcnt, SLACK_MIXED_CAP);
-        // order the mixed nodes by node index (the queue order depends on scheduling), then one warp per node
-        for (int i = threadIdx.x; i < nm; i += blockDim.x) {
+        if (threadIdx.x == 0) {
+            int base = nm ? atomicAdd(&v.ctrl->pair_cnt, nm) : 0;
+            if (base + nm > v.pair_cap) base = -1;                // queue full: this row sums its mixed nodes itself
+            mbase = base;
+        }
+        __syncthreads();
+        const int base = mbase;
+        double extra = 0.0;
+        for (int i = threadIdx.x; i < nm; i += blockDim.x) {      // rank by node index: the order inside the row's range is fixed
             int r = 0;
             for (int k2 = 0; k2 < nm; ++k2) r += mixed[k2] < mixed[i];
-            msort[r] = mixed[i];
+            if (base >= 0) { v.pair_row[base + r] = lst[j]; v.pair_node[base + r] = mixed[i]; v.pair_col[base + r] = t; }
         }
-        __syncthreads();
-        for (int i = warp; i < nm; i += (blockDim.x >> 5)) {
-            const int n = msort[i], vn = sc * v.N + n;
-            const double p = v.ptdf[(size_t)l * v.Np + n], sp = side ? p : -p;
-            double x = 0.0;
-            for (int g = v.gen_ptr[vn] + lane; g < v.gen_ptr[vn + 1]; g += 32) {
-                const size_t o = (size_t)g * v.T + tl;
-                x += pospart(b + sp * (sel(v.P, nxt)[o] - sel(v.P, cur)[o]));
+        if (base < 0 && threadIdx.x == 0) {
+            // (never seen in practice) deterministic serial fallback in node order
+            for (int r = 0; r < nm; ++r) {
+                int best = -1;
+                for (int k2 = 0; k2 < nm; ++k2) { int c2 = 0; for (int k3 = 0; k3 < nm; ++k3) c2 += mixed[k3] < mixed[k2]; if (c2 == r) best = mixed[k2]; }
+                extra += body_slack_row_node(v, l, side, best, t);
             }
-            for (int s2 = v.sto_ptr[vn] + lane; s2 < v.sto_ptr[vn + 1]; s2 += 32) {
-                const size_t o = (size_t)s2 * v.T + tl;
-                x += pospart(b + sp * ((sel(v.D, nxt)[o] - sel(v.D, cur)[o]) - (sel(v.C, nxt)[o] - sel(v.C, cur)[o])));
-            }
-            x = Group<32>::sum(x);
-            if (lane == 0) mval[i] = x;
         }
-        __syncthreads();
         if (threadIdx.x == 0) {
             double sum = 0.0;
             for (int k2 = 0; k2 < (int)(blockDim.x >> 5); ++k2) sum += red[k2];
-            for (int k2 = 0; k2 < nm; ++k2) sum += mval[k2];
+            sum += extra;
             const size_t i = (size_t)l * v.ldt + t;
             (side ? v.rowsumK : v.rowsumU)[i] = sum;
+            v.pbase[(size_t)t * 2 * v.L + j] = base; v.pcnt[(size_t)t * 2 * v.L + j] = base >= 0 ? nm : 0;
             atomicOr(reinterpret_cast<unsigned int *>(tflag) + (i >> 2), (unsigned)(1u << side) << (8 * (i & 3)));
-            atomicAdd(&v.ctrl->pair_cnt, nm);            // statistics only
         }
         __syncthreads();
     }
+}
+
+// mixed (row, node) pairs: one warp per pair, lanes over the agents of the node
+__global__ void __launch_bounds__(256) k_slack_pairs(View v)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int total = min(v.ctrl->pair_cnt, v.pair_cap);
+    const int cur = v.ctrl->cur, nxt = 1 - cur;
+    for (int q = gw; q < total; q += nw) {
+        const int e = v.pair_row[q], l = e >> 1, side = e & 1;
+        const int n = v.pair_node[q], t = v.pair_col[q];              // physical node, column
+        const int sc = v.scen_of_col(t), vn = sc * v.N + n, tl = t - sc * v.T;
+        const double b = side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t];
+        const double p = v.ptdf[(size_t)l * v.Np + n], sp = side ? p : -p;
+        double a = 0.0;
+        for (int g = v.gen_ptr[vn] + lane; g < v.gen_ptr[vn + 1]; g += 32) {
+            const size_t o = (size_t)g * v.T + tl;
+            a += pospart(b + sp * (sel(v.P, nxt)[o] - sel(v.P, cur)[o]));
+        }
+        for (int s = v.sto_ptr[vn] + lane; s < v.sto_ptr[vn + 1]; s += 32) {
+            const size_t o = (size_t)s * v.T + tl;
+            a += pospart(b + sp * ((sel(v.D, nxt)[o] - sel(v.D, cur)[o]) - (sel(v.C, nxt)[o] - sel(v.C, cur)[o])));
+        }
+        a = Group<32>::sum(a);
+        if (lane == 0) v.pair_val[q] = a;
+    }
+}
+
+// every tight row adds the pair values of its queue range, in order
+__global__ void __launch_bounds__(128) k_slack_fold(View v)
+{
+    if (!DOPF_ACTIVE(v)) return;
+    const int t = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= v.tcnt[t]) return;
+    const size_t k = (size_t)t * 2 * v.L + j;
+    const int n = v.pcnt[k];
+    if (n == 0) return;
+    const int e = v.tight[k], base = v.pbase[k];
+    double *dst = ((e & 1) ? v.rowsumK : v.rowsumU) + (size_t)(e >> 1) * v.ldt + t;
+    double sum = *dst;
+    for (int q = 0; q < n; ++q) sum += v.pair_val[base + q];
+    *dst = sum;
 }
 
 // dual update + residual maxima (update_duals.jl, convergence.jl:3-12)
@@ -1308,6 +1350,8 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     LAUNCH(k_inject<<<dim3(v.Np / 8, v.ldt / 32), 256, 0, cs>>>(v));
     XCHG(DOPF_X_INJ);    // nodal injection of all ranks' agents
     LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.TC), (v.N <= 256 ? 128 : 512), 0, cs>>>(v, lp.tflag));   // needs the local injection statistics only
+    LAUNCH(k_slack_pairs<<<lp.num_sms * 2, 256, 0, cs>>>(v));
+    LAUNCH(k_slack_fold<<<dim3(cdiv(2 * v.L, 128), v.TC), 128, 0, cs>>>(v));
     LAUNCH(k_colsum<<<v.ldt / 32, dim3(32, 32), 0, cs>>>(v));
     {   // flow = PTDF * inj
         dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);
@@ -1357,6 +1401,17 @@ void launch_penalty_totals(const View &v, double *eb, double *up, double *lo, cu
 {
     cudaMemsetAsync(up, 0, sizeof(double) * v.TC, st); cudaMemsetAsync(lo, 0, sizeof(double) * v.TC, st);
     k_penalty_totals<<<dim3(cdiv(v.TC, 32), cdiv(v.L, 4)), 128, 0, st>>>(v, eb, up, lo);
+}
+
+// partitioned mode: the all-reduced injection (fixed exchange buffer) becomes the injection of the new iterate
+__global__ void k_copy_inj(View v, const double *src)
+{
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < (size_t)v.Np * v.ldt) sel(v.inj, 1 - v.ctrl->cur)[i] = src[i];
+}
+void launch_copy_inj(const View &v, const double *src, cudaStream_t st)
+{
+    k_copy_inj<<<cdiv((long long)v.Np * v.ldt, 256), 256, 0, st>>>(v, src);
 }
 
 // scenario batches: host layout [C][rows][T] <-> device layout [rows][ld] (scenario c in the columns c*T .. c*T+T-1)

@@ -38,6 +38,7 @@ void launch_total_costs(const View &v, double *d_out, cudaStream_t st);
 void launch_profile_warm(const LaunchPlan &lp, cudaStream_t st);
 void launch_nodal_price(const View &v, const double *lam, const double *mu, const double *rho, double *d_out, cudaStream_t st);
 void launch_unit_penalty(const View &v, int kind, int idx, double *eb, double *up, double *lo, double *U, double *K, cudaStream_t st);
+void launch_copy_inj(const View &v, const double *src, cudaStream_t st);
 void launch_pack_cols(double *dev, double *host_layout, int rows, int C, int T, int ld, int to_device, cudaStream_t st);
 void launch_penalty_totals(const View &v, double *eb, double *up, double *lo, cudaStream_t st);
 // segment 0: local injection of the staged iterate; segment 1: column sums, flows, levels, buffer flip

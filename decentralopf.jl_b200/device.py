@@ -1,5 +1,6 @@
 """DeviceADMM: thin array-level host object over one libdopf handle (one GPU)."""
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -34,7 +35,7 @@ class DeviceADMM:
         cfg.gamma, cfg.flow_weight, cfg.prox_weight = float(gamma), float(flow_weight), float(prox_weight)
         cfg.slack_mask_tol, cfg.eps = float(slack_mask_tol), float(eps)
         cfg.device, cfg.hinge_capacity, cfg.use_graph = int(device), int(hinge_capacity), int(bool(use_graph))
-        cfg.debug_flags = int(debug_flags)
+        cfg.debug_flags = int(debug_flags) | int(os.environ.get("DOPF_DEBUG_FLAGS", "0"))
         cfg.n_scenarios, cfg.gemm_ksplit = int(getattr(prob, "n_scen", 1)), int(gemm_ksplit)
         self.C = cfg.n_scenarios
         self.h = C.c_void_p()

@@ -39,10 +39,12 @@ class _DevBuf:
 
 
 class PartitionedADMM:
-    """One rank of an agent-partitioned run.  libdopf runs the four phases of an iteration on a torch
-    CUDA stream; torch.distributed (NCCL) all-reduces the exchange buffers in place between them."""
+    """One rank of an agent-partitioned run.  libdopf runs the four phases of an iteration on a torch CUDA stream;
+    torch.distributed (NCCL) all-reduces the exchange buffers in place between them.  All exchange buffers are fixed
+    device addresses, so one whole iteration - the library's kernels AND the three collectives - is captured once in a
+    CUDA graph and replayed: no interpreter / launch overhead per iteration (`graph=False` keeps the eager path)."""
 
-    def __init__(self, prob: Problem, rank, world, device, dist=None, **cfg):
+    def __init__(self, prob: Problem, rank, world, device, dist=None, graph=True, **cfg):
         import torch
         import torch.distributed as tdist
         from .device import DeviceADMM
@@ -52,10 +54,12 @@ class PartitionedADMM:
         self.sub, self.gen_index, self.sto_index = shard_problem(prob, rank, world)
         self.dev = DeviceADMM(self.sub, device=device, use_graph=False, **cfg)
         self.stream = torch.cuda.Stream(device=device)
+        self.want_graph, self.graph, self.graph_error = bool(graph), None, None
         d = self.dev
         d._check(d.lib.dopf_set_stream(d.h, C.c_void_p(self.stream.cuda_stream)), "dopf_set_stream")
         with torch.cuda.stream(self.stream):
             d._check(d.lib.dopf_set_partition(d.h, rank, world, prob.G + prob.S), "dopf_set_partition")
+            self.bufs = {w: self._buffer(w) for w in (0, 1, 2, 3)}     # fixed addresses for the lifetime of the handle
             self._allreduce(1, self.dist.ReduceOp.SUM)     # initial injection (-demand from rank 0)
             self._allreduce(3, self.dist.ReduceOp.MAX)     # per-node box ranges -> identical candidate rows on all ranks
             d._check(d.lib.dopf_step_phase(d.h, -1), "dopf_step_phase")
@@ -68,19 +72,42 @@ class PartitionedADMM:
 
     def _allreduce(self, which, op):
         if self.world > 1:
-            self.dist.all_reduce(self._buffer(which), op=op)
+            self.dist.all_reduce(self.bufs[which], op=op)
+
+    def _enqueue_iteration(self):
+        d, lib, R = self.dev, self.dev.lib, self.dist.ReduceOp
+        d._check(lib.dopf_step_phase(d.h, 0), "phase 0"); self._allreduce(0, R.MAX)
+        d._check(lib.dopf_step_phase(d.h, 1), "phase 1"); self._allreduce(1, R.SUM)
+        d._check(lib.dopf_step_phase(d.h, 2), "phase 2"); self._allreduce(2, R.SUM)
+        d._check(lib.dopf_step_phase(d.h, 3), "phase 3")
+
+    def _capture(self):
+        """one iteration (kernels + collectives) -> CUDA graph; falls back to eager stepping if the capture fails"""
+        torch = self.torch
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.stream, capture_error_mode="thread_local"):
+                self._enqueue_iteration()
+            self.graph = g
+        except Exception as e:      # keep running eagerly, remember why
+            self.graph, self.graph_error, self.want_graph = None, repr(e), False
+            torch.cuda.synchronize()
 
     def step(self, iters=1, check_every=16):
         d, lib, R = self.dev, self.dev.lib, self.dist.ReduceOp
         done = 0
         with self.torch.cuda.stream(self.stream):
+            if self.want_graph and self.graph is None and iters > 1:
+                self._enqueue_iteration(); done += 1          # one eager iteration first (communicator warm-up)
+                self.stream.synchronize()
+                self._capture()
             while done < iters:
                 n = min(check_every, iters - done)
                 for _ in range(n):
-                    d._check(lib.dopf_step_phase(d.h, 0), "phase 0"); self._allreduce(0, R.MAX)
-                    d._check(lib.dopf_step_phase(d.h, 1), "phase 1"); self._allreduce(1, R.SUM)
-                    d._check(lib.dopf_step_phase(d.h, 2), "phase 2"); self._allreduce(2, R.SUM)
-                    d._check(lib.dopf_step_phase(d.h, 3), "phase 3")
+                    if self.graph is not None:
+                        self.graph.replay()
+                    else:
+                        self._enqueue_iteration()
                 done += n
                 rc = lib.dopf_get_status(d.h, C.byref(d.status))      # synchronises; < 0: device-side capacity error
                 if self.world > 1:       # a failing rank must stop ALL ranks (the others would all-reduce its stale buffers)
@@ -95,6 +122,7 @@ class PartitionedADMM:
         return d.status
 
     def close(self):
+        self.graph = None
         self.dev.close()
 
 
