@@ -196,7 +196,7 @@ def build_problem(pkg, args, rank, world):
     N, L, G, S, T = WORKLOADS[args.workload]
     if args.workload == "cfg4":
         C = SCENARIOS_PER_GPU
-        d = pkg.cases.synthetic_scenarios(N=N, L=L, G=G, S=S, T=T, n_scen=C, seed=rank)     # every rank its own 128 scenarios
+        d = pkg.cases.synthetic_scenarios(N=N, L=L, G=G, S=S, T=T, n_scen=C, seed=0, first_scenario=rank * C)     # one grid, every rank its own 128 scenarios
         return pkg.Problem.from_arrays(d), params_for(G + S, args.params), C * (G + S) * T, f"{world} x {C} independent scenarios, no collective"
     partitioned = world > 1 and args.shard == "agents"
     if partitioned or args.path == "partitioned":
@@ -424,10 +424,18 @@ def run_dopf(args):
         if world == 1 and not args.no_cpu_baseline and not args.quick and args.workload != "cfg4":
             v, ms, cores, sample = oracle_rate(pkg, args.workload, 3, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_iteration_of_sample": ms}
-        print(json.dumps(line))
-    dev.close()
+        print(json.dumps(line), flush=True)
+    # teardown order matters with a captured NCCL graph: drop the graph first, then the handle, then leave without the
+    # process-group destructor (destroying the communicator under a live graph blocks at interpreter exit)
+    if part is not None:
+        part.close()
+    else:
+        dev.close()
+    torch.cuda.synchronize()
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

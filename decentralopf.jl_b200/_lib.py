@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("DOPF_LIB", os.path.join(_HERE, "libdopf.so"))
-_SRCS = [os.path.join(_HERE, "csrc", f) for f in ("dopf_kernels.cu", "dopf_api.cu")]
+_SRCS = [os.path.join(_HERE, "csrc", f) for f in ("dopf_kernels.cu", "dopf_api.cu", "dopf_ptdf.cu")]
 _HDRS = [os.path.join(_HERE, "csrc", f) for f in ("dopf_math.h", "dopf_bodies.h", "dopf_kernels.h", "dopf_sto_warp.cuh")] + \
         [os.path.join(ROOT, "include", "dopf.h")]
 
@@ -46,7 +46,8 @@ class DopfStatus(C.Structure):
 EXPORTS = ["dopf_version", "dopf_default_config", "dopf_create", "dopf_destroy", "dopf_step", "dopf_get_status",
            "dopf_get_iterate", "dopf_get_duals", "dopf_set_state", "dopf_get_nodal_price", "dopf_get_total_costs",
            "dopf_nodal_price_from", "dopf_get_unit_penalty", "dopf_get_penalty_totals",
-           "dopf_set_partition", "dopf_set_stream", "dopf_step_phase", "dopf_exchange_buffer", "dopf_last_error", "dopf_profile_iteration", "dopf_debug_counters", "dopf_get_scenario_status"]
+           "dopf_set_partition", "dopf_set_stream", "dopf_step_phase", "dopf_exchange_buffer", "dopf_last_error", "dopf_profile_iteration", "dopf_debug_counters", "dopf_get_scenario_status",
+           "dopf_calculate_ptdf", "dopf_ptdf_last_error"]
 
 
 def build(force=False, verbose=False):
@@ -55,7 +56,7 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "--shared", "-cudart", "static", "-o", LIB_PATH] + _SRCS
+           "-Xcompiler", "-fPIC", "--shared", "-cudart", "static", "-o", LIB_PATH] + _SRCS + ["-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     if os.environ.get("DOPF_NVCC_FLAGS"):
@@ -96,6 +97,8 @@ def load():
     lib.dopf_get_penalty_totals.argtypes = [C.c_void_p] + [C.c_void_p] * 3
     lib.dopf_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32]
     lib.dopf_get_total_costs.argtypes = [C.c_void_p, C.c_void_p]
+    lib.dopf_calculate_ptdf.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    lib.dopf_ptdf_last_error.restype = C.c_char_p
     lib.dopf_profile_iteration.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]
     lib.dopf_set_partition.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
     lib.dopf_set_stream.argtypes = [C.c_void_p, C.c_void_p]

@@ -65,14 +65,15 @@ def synthetic_arrays(N, L, G, S, T, seed=0, ptdf_fn=None, congest_frac=0.05, gam
                 line_from=fr, line_to=to, susceptance=susc, slack=0, gamma=float(gamma))
 
 
-def synthetic_scenarios(N, L, G, S, T, n_scen, seed=0, **kw):
+def synthetic_scenarios(N, L, G, S, T, n_scen, seed=0, first_scenario=0, **kw):
     """Batch of `n_scen` independent scenarios on ONE synthetic grid (BASELINE configs[3]): grid, PTDF,
     line limits and the placement / capacities of the agents come from scenario `seed`; every scenario draws its own
-    demand (node base loads rescaled by U(0.7, 1.3) and a shifted diurnal phase) and its own generator costs."""
+    demand (node base loads rescaled by U(0.7, 1.3) and a shifted diurnal phase) and its own generator costs; the batch holds
+    the scenarios first_scenario .. first_scenario + n_scen - 1 of that sequence."""
     d = synthetic_arrays(N=N, L=L, G=G, S=S, T=T, seed=seed, **kw)
-    rng = np.random.default_rng(1000003 + seed)
     dem = np.empty((n_scen, N, T)); gmc = np.empty((n_scen, G))
     for c in range(n_scen):
+        rng = np.random.default_rng([1000003 + seed, first_scenario + c])      # scenario k is the same draw whichever rank holds it
         scale = rng.uniform(0.7, 1.3, size=N)[:, None]
         dem[c] = np.floor(np.roll(d["demand"], int(rng.integers(0, T)), axis=1) * scale)
         gmc[c] = rng.integers(1, 61, size=G)

@@ -171,7 +171,6 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     for (int g = 0; g < Gs; ++g) if (p->gen_node[g] < 0 || p->gen_node[g] >= N) { h->err = "gen_node out of range"; return DOPF_E_ARG; }
     for (int s = 0; s < Ss; ++s) if (p->sto_node[s] < 0 || p->sto_node[s] >= N) { h->err = "sto_node out of range"; return DOPF_E_ARG; }
     if ((long long)G * T >= (1ll << 31) || (long long)S * T >= (1ll << 31)) { h->err = "G*T or S*T exceeds 2^31"; return DOPF_E_UNSUPPORTED; }
-    if (T / (T % 4 == 0 ? 4 : (T % 2 == 0 ? 2 : 1)) > 1024) { h->err = "horizon too long for this build (T/vec > 1024 timestep slots per block)"; return DOPF_E_UNSUPPORTED; }
 
     int ndev = 0;
     cudaError_t e0 = cudaGetDeviceCount(&ndev);
@@ -317,6 +316,10 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     AL(lp.part2, (size_t)lp.ksplit_t * Np * ldt);
     {
         lp.sto_fix_blocks = std::max(1, std::min(lp.num_sms * 8, S));
+        {   // every solver block owns one overflow slot of hinge lists: bound them by 1 GB for long horizons
+            const size_t slot_b = (size_t)T * v.hcap * sizeof(Hinge) + (size_t)T * sizeof(int);
+            lp.sto_fix_blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)lp.sto_fix_blocks, ((size_t)1 << 30) / slot_b));
+        }
         {
             const int need = (T + 31) / 32;
             const int opts[6] = {1, 2, 3, 4, 6, 8};
@@ -332,6 +335,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
         AL(lp.hcnt_scratch, S ? warps * T : 1);
     }
     lp.gen_flat = (cfg->debug_flags & 8) ? 1 : ((cfg->debug_flags & 16) ? 0 : (G < 24ll * NV ? 1 : 0));      // bits 3/4 force one variant (A/B timing)
+    if (T / (T % 4 == 0 ? 4 : (T % 2 == 0 ? 2 : 1)) > 1024) lp.gen_flat = 1;      // the node-major kernel maps the horizon to at most 1024 threads
     lp.slack_blocks_x = std::max(1, std::min(64, (8 * lp.num_sms + TC - 1) / TC));
 
     // ---- state before iteration 1 (admm.jl:29-36; helpers/results.jl:14-73 "zeros") ----------

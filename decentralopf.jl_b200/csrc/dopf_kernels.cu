@@ -1004,20 +1004,23 @@ __global__ void __launch_bounds__(256) k_slack_pairs(View v)
     }
 }
 
-// every tight row adds the pair values of its queue range, in order
-__global__ void __launch_bounds__(128) k_slack_fold(View v)
+// every tight row adds the pair values of its queue range, in order (one warp per column, lanes over its tight rows)
+__global__ void __launch_bounds__(256) k_slack_fold(View v)
 {
     if (!DOPF_ACTIVE(v)) return;
-    const int t = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= v.tcnt[t]) return;
-    const size_t k = (size_t)t * 2 * v.L + j;
-    const int n = v.pcnt[k];
-    if (n == 0) return;
-    const int e = v.tight[k], base = v.pbase[k];
-    double *dst = ((e & 1) ? v.rowsumK : v.rowsumU) + (size_t)(e >> 1) * v.ldt + t;
-    double sum = *dst;
-    for (int q = 0; q < n; ++q) sum += v.pair_val[base + q];
-    *dst = sum;
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (t >= v.TC) return;
+    const int cnt = v.tcnt[t];
+    for (int j = lane; j < cnt; j += 32) {
+        const size_t k = (size_t)t * 2 * v.L + j;
+        const int n = v.pcnt[k];
+        if (n == 0) continue;
+        const int e = v.tight[k], base = v.pbase[k];
+        double *dst = ((e & 1) ? v.rowsumK : v.rowsumU) + (size_t)(e >> 1) * v.ldt + t;
+        double sum = *dst;
+        for (int q = 0; q < n; ++q) sum += v.pair_val[base + q];
+        *dst = sum;
+    }
 }
 
 // dual update + residual maxima (update_duals.jl, convergence.jl:3-12)
@@ -1351,7 +1354,7 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     XCHG(DOPF_X_INJ);    // nodal injection of all ranks' agents
     LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.TC), (v.N <= 256 ? 128 : 512), 0, cs>>>(v, lp.tflag));   // needs the local injection statistics only
     LAUNCH(k_slack_pairs<<<lp.num_sms * 2, 256, 0, cs>>>(v));
-    LAUNCH(k_slack_fold<<<dim3(cdiv(2 * v.L, 128), v.TC), 128, 0, cs>>>(v));
+    LAUNCH(k_slack_fold<<<cdiv(v.TC, 8), 256, 0, cs>>>(v));
     LAUNCH(k_colsum<<<v.ldt / 32, dim3(32, 32), 0, cs>>>(v));
     {   // flow = PTDF * inj
         dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);

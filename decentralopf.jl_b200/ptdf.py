@@ -23,6 +23,22 @@ def ptdf_from_arrays(N, line_from, line_to, susceptance, slack):
     return out
 
 
+def ptdf_device(N, line_from, line_to, susceptance, slack, device=-1):
+    """the same PTDF built on the GPU (dopf_calculate_ptdf: Cholesky + triangular solves of the slack-reduced susceptance
+    matrix); raises without a CUDA device"""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    fr = np.ascontiguousarray(line_from, dtype=np.int32); to = np.ascontiguousarray(line_to, dtype=np.int32)
+    b = np.ascontiguousarray(susceptance, dtype=np.float64)
+    out = np.empty((len(fr), N))
+    rc = lib.dopf_calculate_ptdf(N, len(fr), fr.ctypes.data_as(C.c_void_p), to.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
+                                 int(slack), int(device), out.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError(f"dopf_calculate_ptdf rc={rc}: {lib.dopf_ptdf_last_error().decode()}")
+    return out
+
+
 def calculate_ptdf(nodes, lines):
     """calculate_ptdf(nodes, lines) -> [L, N] float64 (ptdf.jl:1-41)."""
     idx = {id(n): i for i, n in enumerate(nodes)}

@@ -16,6 +16,7 @@
  *   dopf_set_state     <- (no reference counterpart) resume / inject a mid-trace state
  *   dopf_get_nodal_price <- get_nodal_price(iteration)                      src/helpers/network_elements.jl:16-25
  *   dopf_get_total_costs <- result.total_costs                              src/structures/results.jl:95-105
+ *   dopf_calculate_ptdf <- calculate_ptdf(nodes, lines)                     src/helpers/ptdf.jl:1-41
  *   dopf_get_unit_penalty <- unit_to_result[u].{penalty_term,U,K}           src/optimization/subproblems.jl:89-102
  *   dopf_get_penalty_totals <- result.penalty_term                          src/structures/results.jl:73-76
  *
@@ -165,6 +166,14 @@ int dopf_exchange_buffer(dopf_handle *h, int32_t which, void **device_ptr, int64
 
 /* diagnostics: 32 device-side event counters (all zero unless the library was built with -DDOPF_STATS) */
 int dopf_debug_counters(dopf_handle *h, uint64_t *out /*[32]*/, int32_t reset);
+
+/* calculate_ptdf(nodes, lines) on the GPU (src/helpers/ptdf.jl:1-41, called by ADMM(...) src/structures/admm.jl:44):
+ * line_from/line_to are 0-based node indices (incidence +1 / -1), slack = index of the first node with slack == true,
+ * out is [L][N] row-major with a zero slack column.  Cholesky + triangular solves of the slack-reduced susceptance matrix
+ * (cuSOLVER, loaded at run time) instead of the reference's dense inverse.  Error text: dopf_ptdf_last_error(). */
+int dopf_calculate_ptdf(int32_t N, int32_t L, const int32_t *line_from, const int32_t *line_to, const double *susceptance,
+                        int32_t slack, int32_t device, double *out);
+const char *dopf_ptdf_last_error(void);
 
 const char *dopf_last_error(dopf_handle *h);   /* handle may be NULL: error of the last failed dopf_create */
 const char *dopf_version(void);

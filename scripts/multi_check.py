@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node 2 scripts/multi_check.py : agent-partitioned run == single-GPU run."""
+"""torchrun --nproc-per-node N scripts/multi_check.py : agent-partitioned run (graph-captured) == single-GPU run."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,19 +10,24 @@ from dopf_b200 import multi
 local = int(os.environ.get("LOCAL_RANK", "0")); torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
-for (N, L, G, S, T, iters) in [(40, 60, 200, 40, 24, 30), (118, 186, 1000, 200, 24, 25), (2000, 3000, 20000, 5000, 96, 12)]:
+for (N, L, G, S, T, iters, graph) in [(40, 60, 200, 40, 24, 30, True), (118, 186, 1000, 200, 24, 25, True), (118, 186, 1000, 200, 24, 25, False), (2000, 3000, 20000, 5000, 96, 12, True)]:
     d = pkg.cases.synthetic_arrays(N=N, L=L, G=G, S=S, T=T, seed=1); prob = pkg.Problem.from_arrays(d); A = G + S
-    cfg = dict(gamma=0.3 / A, flow_weight=1.0 / A)
-    part = multi.PartitionedADMM(prob, rank, world, local, hinge_capacity=64, **cfg)
+    cfg = dict(gamma=0.03 / A, flow_weight=1.0 / A)
+    part = multi.PartitionedADMM(prob, rank, world, local, hinge_capacity=64, graph=graph, **cfg)
     dev, gi, si = part.dev, part.gen_index, part.sto_index
     torch.cuda.synchronize(); t0 = time.time(); st = part.step(iters); torch.cuda.synchronize(); dt = time.time() - t0
+    assert st.iterations_done == iters, (st.iterations_done, iters)
+    assert (part.graph is not None) == graph, part.graph_error
     it = dev.get_iterate(); lam, mu, rho = dev.get_duals(0)
     if rank == 0:
         ref = DeviceADMM(prob, device=local, hinge_capacity=64, **cfg); ref.step(iters)
         rit = ref.get_iterate(); rl, rm, rr = ref.get_duals(0)
         err = dict(P=np.abs(it["P"] - rit["P"][gi]).max(), D=np.abs(it["D"] - rit["D"][si]).max() if len(si) else 0.0, inj=np.abs(it["injection"] - rit["injection"]).max(),
                    flow=np.abs(it["flow"] - rit["flow"]).max(), avgU=np.abs(it["avgU"] - rit["avgU"]).max(), lam=np.abs(lam - rl).max(), mu=np.abs(mu - rm).max(), rho=np.abs(rho - rr).max())
-        print((N, L, G, S, T), f"world {world}: {dt / iters * 1e3:.3f} ms/iter (1 GPU: {ref.status.last_step_ms / iters:.3f}) max abs diff vs single GPU:", {k: float('%.2e' % v) for k, v in err.items()}, flush=True)
+        print((N, L, G, S, T), f"world {world} graph {graph}: {dt / iters * 1e3:.3f} ms/iter (1 GPU: {ref.status.last_step_ms / iters:.3f}) max abs diff vs single GPU:", {k: float('%.2e' % v) for k, v in err.items()}, flush=True)
         assert max(err.values()) < 1e-6 * max(1.0, np.abs(rit["flow"]).max())
+    part.close()
+    torch.cuda.synchronize()
     dist.barrier()
-dist.destroy_process_group()
+sys.stdout.flush()
+os._exit(0)       # a process group that carried a captured NCCL graph blocks in its destructor
