@@ -185,7 +185,10 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "nodes": N, "lines": L, "generators": G, "storages": S, "timesteps": T,
-                       "note": "reference arm = CPU oracle port on a bounded sample (Julia/JuMP/Gurobi not installable offline)"},
+                       "sampled": True, "same_config": False, "sample": sample,
+                       "note": "reference arm = CPU oracle port (exact per-agent solves, O(L) hinges per agent*timestep, dense QP per storage) on a bounded SAMPLE of the "
+                               "workload's agents with the full case's gamma / flow weight; the rate per agent*timestep is what is reported - "
+                               "Julia/JuMP/Gurobi are not installable offline"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

@@ -325,6 +325,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
             const int opts[6] = {1, 2, 3, 4, 6, 8};
             lp.sto_j = 0;
             for (int o : opts) if (o >= need) { lp.sto_j = o; break; }
+            if (cfg->debug_flags & 32) lp.sto_j = 0;      // diagnostics: force the sequential (thread per storage) solvers
         }
         if (lp.sto_j > 0 && set_storage_smem_attr(T) != 0) { h->err = "cudaFuncSetAttribute(shared memory) failed"; return DOPF_E_CUDA; }
         // scratch: one slot per node with a storage on the work list (up to 512 MB) + one per solver block for the overflow
