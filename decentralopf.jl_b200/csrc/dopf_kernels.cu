@@ -1296,7 +1296,9 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     }
     FORK();   // storages on the side stream ...
     if (v.S > 0) {
-        const int wblocks = min(cdiv(v.S, 4), lp.num_sms * 16);
+        // one storage per warp: the hardware block scheduler then balances the load - a straggler storage (many active-set
+        // rounds in the start-up transient) only holds its own block while the others stream through the remaining slots
+        const int wblocks = (lp.view.debug & 64) ? min(cdiv(v.S, 4), lp.num_sms * 16) : cdiv(v.S, 4);
         switch (lp.sto_j) {
         case 1: LAUNCH(k_sto_warp<1><<<wblocks, 128, 4 * sto_warp_smem_per_warp(v.T), cs>>>(v)); break;
         case 2: LAUNCH(k_sto_warp<2><<<wblocks, 128, 4 * sto_warp_smem_per_warp(v.T), cs>>>(v)); break;

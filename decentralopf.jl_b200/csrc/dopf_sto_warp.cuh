@@ -468,7 +468,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
 #ifdef DOPF_STATS
         ++st_rounds;
 #endif
-        if (capped) { DOPF_STAT(5, 1); return false; }                        // Newton cap reached
+        if (capped) { DOPF_STAT(5, 1); return false; }   // Newton cap reached
         // final run state for every element: multiplier, status, "flat" (sum of derivatives at the tail)
 #pragma unroll
         for (int j = 0; j < J; ++j) if (valid[j] && tail[j] && !(totd[j] < -1e-300)) rs[j] |= RS_FLAT;
@@ -618,6 +618,8 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
         if (st_rounds == 1) DOPF_STAT(9, 1);
         if (st_rounds == 1 && st_passes <= 2) DOPF_STAT(10, 1);
         DOPF_STAT(11, st_rounds > 8 ? 1 : 0);
+        if (lane == 0) atomicMax(v.counters + (HINGES ? 16 : 0) + 12, (unsigned long long)st_rounds);
+        if (lane == 0) atomicMax(v.counters + (HINGES ? 16 : 0) + 13, (unsigned long long)st_passes);
         (void)nruns; (void)nsingle;
     }
 #endif

@@ -10,7 +10,7 @@ wl = sys.argv[1]; gs = float(sys.argv[2]); ws = float(sys.argv[3]); ats = [int(x
 prob, cfg = bench.make_case(pkg, wl, 0)
 A = prob.G + prob.S
 dev = DeviceADMM(prob, device=0, hinge_capacity=64, gamma=gs / A, flow_weight=ws / A)
-names = ["storages", "rounds", "passes", "anchors", "free_steps", "newton_cap", "gave_up", "all_anchored", "all_clipped", "one_round", "one_round_le2_passes", "gt8_rounds"]
+names = ["storages", "rounds", "passes", "anchors", "free_steps", "newton_cap", "gave_up", "all_anchored", "all_clipped", "one_round", "one_round_le2_passes", "gt8_rounds", "max_rounds", "max_passes"]
 done = 0
 for at in ats:
     if at - 1 > done:
