@@ -705,15 +705,31 @@ int dopf_set_partition(dopf_handle *h, int32_t rank, int32_t nranks, int32_t tot
     h->rank = rank; h->nranks = nranks;
     View &v = h->lp.view;
     v.A = total_agents;
-    v.demand_on = rank == 0 ? 1 : 0;
+    // no rank carries the demand in its local injection: the all-reduced injection of the agents gets it subtracted
+    // (launch_copy_inj), and the flows are sum over the ranks of PTDF[:, own nodes] * (own injection) minus the constant
+    // PTDF * demand - so the flow product costs every rank 1/nranks of the single-GPU product
+    v.demand_on = 0;
     if (!h->partitioned) {
         // the local injection of BOTH iterates goes to one fixed exchange buffer: every device pointer an enqueued phase
         // uses is then independent of the ping-pong parity, so the caller may capture an iteration (phases + its own
         // collectives) in a CUDA graph and replay it
-        double *q = nullptr;
+        double *q = nullptr, *q3 = nullptr, *fd = nullptr;
         int r2 = dev_alloc(h, &q, (size_t)v.Np * v.ldt);
         if (r2) return r2;
         v.injloc[0] = v.injloc[1] = q;
+        // row sums and partial flows in ONE contiguous exchange buffer (one collective)
+        const size_t lt = (size_t)v.Lp * v.ldt;
+        if ((r2 = dev_alloc(h, &q3, 3 * lt))) return r2;
+        if ((r2 = dev_alloc(h, &fd, lt))) return r2;
+        v.rowsumU = q3; v.rowsumK = q3 + lt; v.xflow = q3 + 2 * lt;
+        LaunchPlan &lp = h->lp;
+        lp.bm_x = lp.bm_n;
+        const int tiles = (v.Lp / lp.bm_x) * (v.ldt / 32);
+        const int ksmax = std::max(1, std::min(8, lp.mt_rows / 16 / 8));
+        lp.ksplit_x = std::max(1, std::min(ksmax, (2 * lp.num_sms + tiles - 1) / tiles));
+        launch_flow_of_demand(lp, fd, h->stream);
+        CK(cudaGetLastError());
+        v.flowD = fd;
         h->partitioned = true;
     }
     h->use_graph = false;
@@ -759,7 +775,7 @@ int dopf_exchange_buffer(dopf_handle *h, int32_t which, void **device_ptr, int64
     switch (which) {      // all four are fixed device addresses for the lifetime of the handle
     case DOPF_XBUF_DMAX: *device_ptr = v.dmax; *count = v.ldt; break;
     case DOPF_XBUF_INJ: *device_ptr = v.injloc[0]; *count = (int64_t)v.Np * v.ldt; break;
-    case DOPF_XBUF_ROWSUM: *device_ptr = v.rowsumU; *count = (int64_t)2 * v.Lp * v.ldt; break;
+    case DOPF_XBUF_ROWSUM: *device_ptr = v.rowsumU; *count = (int64_t)3 * v.Lp * v.ldt; break;   // + the partial flows
     case DOPF_XBUF_RBOX: *device_ptr = v.rbox; *count = v.Np; break;
     default: return DOPF_E_ARG;
     }

@@ -42,6 +42,7 @@ struct Ctrl {
     int iters_done;     // iterations executed since create
     int finish_cnt;     // blocks of k_lambda_finish that are done (scenario batches: the last one flips the buffers)
     int gen_work_cnt, sto_work_cnt, cold_work_cnt, pair_cnt, gen_grp_cnt, fix_node_cnt;
+    int sto_next;       // work counter of the storage predict kernel (warps draw storages from it)
     int stat_sto_cold;                   // storages solved by the cold funnel in the last iteration
     int stat_fix_seq;                    // cumulated correction-pass storages that needed the sequential solver
     int stat_gen_fix, stat_sto_fix;      // cumulated corrected agents (statistics)
@@ -112,6 +113,10 @@ struct View {
     int *sto_work, *sto_flag;          // [S], [S]
     int *fix_node_flag, *fix_node_list, *fix_node_slot;   // [Np] nodes with a storage on the work list (device path only)
     double *rowsumU, *rowsumK;         // [Lp][ldt] exact sum_i (b -+ p delta_i)_+ of tight rows
+    // agent-partitioned mode: every rank multiplies PTDF with the injection of ITS agents over ITS node range only; the
+    // partial flows travel in the third slab of the row-sum exchange buffer and the demand part is a constant
+    double *xflow;                     // [Lp][ldt] partial flow PTDF[:, own nodes] * (injection of the own agents), summed over the ranks by the exchange
+    const double *flowD;               // [Lp][ldt] PTDF * demand (null on single-GPU handles: the demand is part of the injection)
     int *pair_row, *pair_node, *pair_col; double *pair_val; int pair_cap;   // queue of (tight row, node, column) whose agents are summed one by one
     int *pbase, *pcnt;                 // [TC][2L] queue range of every tight-list entry
     unsigned long long *counters;   // [32] diagnostics (filled only by builds with -DDOPF_STATS)

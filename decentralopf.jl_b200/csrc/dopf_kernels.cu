@@ -202,11 +202,13 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 template <int BM, bool TRANS>
 __global__ void __launch_bounds__(128) k_gemm(View v, const double *__restrict__ A, int lda, int ldb,
                                               double *__restrict__ Cpart, double *__restrict__ C2part,
-                                              int Mp, int Kp, int ksplit, int m_base)
+                                              int Mp, int Kp, int ksplit, int m_base,
+                                              const double *__restrict__ Bsrc = nullptr, int k_base = 0)
 {
     if (!DOPF_ACTIVE(v)) return;
-    // B operand: M (and W) for the transposed product, the new injection for the flow product
-    const double *__restrict__ B = TRANS ? v.M : sel(v.inj, 1 - v.ctrl->cur);
+    // B operand: M (and W) for the transposed product, the new injection for the flow product (Bsrc: another [K][ldt]
+    // matrix; k_base: first row of the K range [k_base, k_base + Kp) of A's columns / B's rows)
+    const double *__restrict__ B = Bsrc ? Bsrc : (TRANS ? v.M : sel(v.inj, 1 - v.ctrl->cur));
     const double *__restrict__ B2 = v.Wt;
     constexpr int MT = BM / 32;                       // m8 tiles per warp (4 warps along M)
     constexpr int AROW = TRANS ? (BM + 4) : (BK + 4); // padded smem row of the A tile
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(128) k_gemm(View v, const double *__restrict__
         for (int j = 0; j < 4; ++j) { acc[i][j][0] = acc[i][j][1] = 0.0; if (TRANS) { acc2[i][j][0] = acc2[i][j][1] = 0.0; } }
 
     auto load_tiles = [&](int buf, int ks) {
-        const int k0 = ks * BK;
+        const int k0 = k_base + ks * BK;
         if (TRANS) {   // A rows = k (lines), cols = m (nodes): BK x BM doubles
             constexpr int CH = BK * BM / 2;               // 16-byte chunks
             for (int c = tid; c < CH; c += 128) {
@@ -313,7 +315,7 @@ __global__ void k_node_prep(View v, const double *Cpart, const double *C2part, i
     // iteration prologue: reset the per-iteration counters, move maxima and work flags (nothing before this
     // kernel in the iteration touches them)
     if (i == 0) {
-        v.ctrl->gen_work_cnt = 0; v.ctrl->sto_work_cnt = 0; v.ctrl->cold_work_cnt = 0; v.ctrl->pair_cnt = 0; v.ctrl->gen_grp_cnt = 0; v.ctrl->fix_node_cnt = 0;
+        v.ctrl->gen_work_cnt = 0; v.ctrl->sto_work_cnt = 0; v.ctrl->cold_work_cnt = 0; v.ctrl->pair_cnt = 0; v.ctrl->gen_grp_cnt = 0; v.ctrl->fix_node_cnt = 0; v.ctrl->sto_next = 0;
         v.ctrl->res_bits[0] = v.ctrl->res_bits[1] = v.ctrl->res_bits[2] = 0ull;
     }
     if (i < v.ldt) v.dmax[i] = 0ull;
@@ -333,14 +335,14 @@ __global__ void k_node_prep(View v, const double *Cpart, const double *C2part, i
 }
 
 // epilogue of the flow product: line_utilization = ptdf * injection (results.jl:114)
-__global__ void k_flow_reduce(View v, const double *Cpart, int ksplit)
+__global__ void k_flow_reduce(View v, const double *Cpart, int ksplit, double *dst)
 {
     if (!DOPF_ACTIVE(v)) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= v.Lp * v.ldt) return;
     double a = 0.0;
     for (int z = 0; z < ksplit; ++z) a += Cpart[(size_t)z * v.Lp * v.ldt + i];
-    sel(v.flow, 1 - v.ctrl->cur)[i] = a;
+    (dst ? dst : sel(v.flow, 1 - v.ctrl->cur))[i] = a;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -483,24 +485,42 @@ __global__ void __launch_bounds__(128) k_sto_warm(View v)
 }
 
 // warp-parallel active-set solve (dopf_sto_warp.cuh); storages it cannot verify are queued for k_sto_cold
-#ifndef DOPF_STO_MINB
-#define DOPF_STO_MINB 3
+// DOPF_STO_WPB warps per block (measured on B200, target case: 1, 2, 4, 6, 8 and 12 warps per block run within 3 % of
+// each other - the kernel is bound by its own instruction stream, not by block granularity; profiles/r2_sto_variants.log)
+#ifndef DOPF_STO_WPB
+#define DOPF_STO_WPB 4
 #endif
+#ifndef DOPF_STO_MINB
+#define DOPF_STO_MINB (12 / DOPF_STO_WPB)
+#endif
+constexpr int sto_wpb(int J) { return J <= 3 ? DOPF_STO_WPB : 4; }
 template <int J>
-__global__ void __launch_bounds__(128, (J <= 3 ? DOPF_STO_MINB : (J == 4 ? 3 : 2))) k_sto_warp(View v)
+__global__ void __launch_bounds__(32 * sto_wpb(J), (J <= 3 ? DOPF_STO_MINB : (J == 4 ? 3 : 2))) k_sto_warp(View v)
 {
     if (!DOPF_ACTIVE(v)) return;
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     extern __shared__ __align__(16) double sto_smem[];
     double *tab = sto_smem + (size_t)(threadIdx.x >> 5) * (sto_warp_smem_per_warp(v.T) / sizeof(double));
+#ifndef DOPF_STO_STATIC
+    // warps draw storages from a device counter (reset by k_node_prep): a storage that needs many active-set rounds only
+    // holds its own warp, the others keep streaming
+    (void)gw; (void)nw;
+    for (;;) {
+        int s = 0;
+        if (lane == 0) s = atomicAdd(&v.ctrl->sto_next, 1);
+        s = __shfl_sync(0xffffffffu, s, 0);
+        if (s >= v.S) break;
+#else
     for (int s = gw; s < v.S; s += nw) {
+#endif
         if (v.sc_converged[v.scen_of_vn(v.sto_node[s])]) {     // frozen scenario: carry D, C through (E, eta stay)
             const int cur = v.ctrl->cur;
             for (int t = lane; t < v.T; t += 32) { const size_t o = (size_t)s * v.T + t; sel(v.D, 1 - cur)[o] = sel(v.D, cur)[o]; sel(v.C, 1 - cur)[o] = sel(v.C, cur)[o]; }
             continue;
         }
-        const bool ok = (v.debug & 2) ? false : sto_warp_solve<J, false>(v, s, nullptr, nullptr, tab);
+        const bool ok = (v.debug & 2) ? false : (v.T == 32 * J ? sto_warp_solve<J, false, true>(v, s, nullptr, nullptr, tab)
+                                                               : sto_warp_solve<J, false, false>(v, s, nullptr, nullptr, tab));
         if (!ok && lane == 0) v.cold_work[atomicAdd(&v.ctrl->cold_work_cnt, 1)] = s;
         __syncwarp();
     }
@@ -1035,6 +1055,7 @@ __global__ void __launch_bounds__(256) k_dual(View v, const unsigned char *tflag
         {   // epilogue of the flow product: line_utilization = ptdf * injection (results.jl:114), split-K partials in order
             double f = 0.0;
             for (int z = 0; z < ksplit; ++z) f += Cpart[(size_t)z * v.Lp * v.ldt + i];
+            if (v.flowD) f -= v.flowD[i];          // partitioned mode: the ranks' partial flows carry no demand
             sel(v.flow, 1 - v.ctrl->cur)[i] = f;
         }
         if (t < v.TC) {
@@ -1249,12 +1270,13 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 
 int set_storage_smem_attr(int T)
 {
-    const int bytes = (int)(4 * sto_warp_smem_per_warp(T));
-    if (bytes <= 48 * 1024) return 0;
     cudaError_t e = cudaSuccess;
-#define SETA(K) do { if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); } while (0)
-    SETA(k_sto_warp<1>); SETA(k_sto_warp<2>); SETA(k_sto_warp<3>); SETA(k_sto_warp<4>); SETA(k_sto_warp<6>); SETA(k_sto_warp<8>);
-    SETA(k_sto_fix<1>); SETA(k_sto_fix<2>); SETA(k_sto_fix<3>); SETA(k_sto_fix<4>); SETA(k_sto_fix<6>); SETA(k_sto_fix<8>);
+    // only the instantiation this horizon selects can be launched (32(J-1) < T <= 32J ... the plan picks the smallest fitting J)
+#define SETA(K, W) do { const int bytes = (int)((W) * sto_warp_smem_per_warp(T)); \
+        if (e == cudaSuccess && bytes > 48 * 1024 && bytes <= 227 * 1024) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); } while (0)
+    SETA(k_sto_warp<1>, sto_wpb(1)); SETA(k_sto_warp<2>, sto_wpb(2)); SETA(k_sto_warp<3>, sto_wpb(3));
+    SETA(k_sto_warp<4>, sto_wpb(4)); SETA(k_sto_warp<6>, sto_wpb(6)); SETA(k_sto_warp<8>, sto_wpb(8));
+    SETA(k_sto_fix<1>, 1); SETA(k_sto_fix<2>, 1); SETA(k_sto_fix<3>, 1); SETA(k_sto_fix<4>, 1); SETA(k_sto_fix<6>, 1); SETA(k_sto_fix<8>, 1);
 #undef SETA
     return (int)e;
 }
@@ -1298,14 +1320,18 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     if (v.S > 0) {
         // one storage per warp: the hardware block scheduler then balances the load - a straggler storage (many active-set
         // rounds in the start-up transient) only holds its own block while the others stream through the remaining slots
-        const int wblocks = (lp.view.debug & 64) ? min(cdiv(v.S, 4), lp.num_sms * 16) : cdiv(v.S, 4);
+        #ifndef DOPF_STO_STATIC
+        const int wpb = sto_wpb(lp.sto_j), wblocks = min(cdiv(v.S, wpb), lp.num_sms * (lp.sto_j <= 4 ? 12 : 8) / wpb);
+#else
+        const int wpb = sto_wpb(lp.sto_j), wblocks = (lp.view.debug & 64) ? min(cdiv(v.S, wpb), lp.num_sms * 16) : cdiv(v.S, wpb);
+#endif
         switch (lp.sto_j) {
-        case 1: LAUNCH(k_sto_warp<1><<<wblocks, 128, 4 * sto_warp_smem_per_warp(v.T), cs>>>(v)); break;
-        case 2: LAUNCH(k_sto_warp<2><<<wblocks, 128, 4 * sto_warp_smem_per_warp(v.T), cs>>>(v)); break;
-        case 3: LAUNCH(k_sto_warp<3><<<wblocks, 128, 4 * sto_warp_smem_per_warp(v.T), cs>>>(v)); break;
-        case 4: LAUNCH(k_sto_warp<4><<<wblocks, 128, 4 * sto_warp_smem_per_warp(v.T), cs>>>(v)); break;
-        case 6: LAUNCH(k_sto_warp<6><<<wblocks, 128, 4 * sto_warp_smem_per_warp(v.T), cs>>>(v)); break;
-        case 8: LAUNCH(k_sto_warp<8><<<wblocks, 128, 4 * sto_warp_smem_per_warp(v.T), cs>>>(v)); break;
+        case 1: LAUNCH(k_sto_warp<1><<<wblocks, 32 * wpb, wpb * sto_warp_smem_per_warp(v.T), cs>>>(v)); break;
+        case 2: LAUNCH(k_sto_warp<2><<<wblocks, 32 * wpb, wpb * sto_warp_smem_per_warp(v.T), cs>>>(v)); break;
+        case 3: LAUNCH(k_sto_warp<3><<<wblocks, 32 * wpb, wpb * sto_warp_smem_per_warp(v.T), cs>>>(v)); break;
+        case 4: LAUNCH(k_sto_warp<4><<<wblocks, 32 * wpb, wpb * sto_warp_smem_per_warp(v.T), cs>>>(v)); break;
+        case 6: LAUNCH(k_sto_warp<6><<<wblocks, 32 * wpb, wpb * sto_warp_smem_per_warp(v.T), cs>>>(v)); break;
+        case 8: LAUNCH(k_sto_warp<8><<<wblocks, 32 * wpb, wpb * sto_warp_smem_per_warp(v.T), cs>>>(v)); break;
         default: LAUNCH(k_sto_warm<<<cdiv(v.S, 128), 128, 0, cs>>>(v)); break;   // long horizons: sequential warm start
         }
         LAUNCH(k_sto_cold<<<min(cdiv(v.S, 64), lp.num_sms * 8), 64, 0, cs>>>(v));
@@ -1353,18 +1379,25 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     if (v.L <= 1024) LAUNCH(k_compact_w<<<cdiv(v.TC, 8), 256, 0, cs>>>(v, 1, segment < 0));
     else LAUNCH(k_compact<<<v.TC, 256, 0, cs>>>(v, 1, segment < 0));   // moves may have grown
     LAUNCH(k_inject<<<dim3(v.Np / 8, v.ldt / 32), 256, 0, cs>>>(v));
+    if (v.flowD) {   // partitioned mode: partial flow of the rank's own injection over its own node range (1/ranks of the product)
+        dim3 grid(v.Lp / lp.bm_x, v.ldt / BN, lp.ksplit_x);
+        double *dst = lp.ksplit_x == 1 ? v.xflow : lp.part;
+        if (lp.bm_x == 64) LAUNCH(k_gemm<64, false><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, dst, nullptr, v.Lp, lp.mt_rows, lp.ksplit_x, 0, v.injloc[0], lp.mt_base));
+        else LAUNCH(k_gemm<32, false><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, dst, nullptr, v.Lp, lp.mt_rows, lp.ksplit_x, 0, v.injloc[0], lp.mt_base));
+        if (lp.ksplit_x > 1) LAUNCH(k_flow_reduce<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, cs>>>(v, lp.part, lp.ksplit_x, v.xflow));
+    }
     XCHG(DOPF_X_INJ);    // nodal injection of all ranks' agents
     LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.TC), (v.N <= 256 ? 128 : 512), 0, cs>>>(v, lp.tflag));   // needs the local injection statistics only
     LAUNCH(k_slack_pairs<<<lp.num_sms * 2, 256, 0, cs>>>(v));
     LAUNCH(k_slack_fold<<<cdiv(v.TC, 8), 256, 0, cs>>>(v));
     LAUNCH(k_colsum<<<v.ldt / 32, dim3(32, 32), 0, cs>>>(v));
-    {   // flow = PTDF * inj
+    if (!v.flowD) {   // flow = PTDF * inj
         dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);
         if (lp.bm_n == 64) LAUNCH(k_gemm<64, false><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n, 0));
         else LAUNCH(k_gemm<32, false><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n, 0));
     }
-    XCHG(DOPF_X_ROWSUM); // exact slack sums over all ranks' agents
-    LAUNCH(k_dual<<<cdiv((long long)v.L * v.ldt, 256), 256, 0, cs>>>(v, lp.tflag, lp.part, lp.ksplit_n));
+    XCHG(DOPF_X_ROWSUM); // exact slack sums (and partial flows) over all ranks' agents
+    LAUNCH(k_dual<<<cdiv((long long)v.L * v.ldt, 256), 256, 0, cs>>>(v, lp.tflag, v.flowD ? v.xflow : lp.part, v.flowD ? 1 : lp.ksplit_n));
     if (v.NS == 1) LAUNCH(k_lambda_finish<<<1, 256, 0, cs>>>(v));
     else LAUNCH(k_lambda_finish_batch<<<cdiv(v.NS, 4), 128, 0, cs>>>(v));
 #undef LAUNCH
@@ -1412,7 +1445,7 @@ void launch_penalty_totals(const View &v, double *eb, double *up, double *lo, cu
 __global__ void k_copy_inj(View v, const double *src)
 {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i < (size_t)v.Np * v.ldt) sel(v.inj, 1 - v.ctrl->cur)[i] = src[i];
+    if (i < (size_t)v.Np * v.ldt) sel(v.inj, 1 - v.ctrl->cur)[i] = src[i] - v.demand[i];     // no rank carries the demand in its local injection
 }
 void launch_copy_inj(const View &v, const double *src, cudaStream_t st)
 {
@@ -1447,6 +1480,16 @@ __global__ void k_mwide(View v)
 }
 void launch_mwide(const View &v, cudaStream_t st) { k_mwide<<<cdiv((long long)v.L * 32, 128), 128, 0, st>>>(v); }
 
+// partitioned mode set-up: dst = PTDF * demand (the constant part of every flow)
+void launch_flow_of_demand(const LaunchPlan &lp, double *dst, cudaStream_t st)
+{
+    const View &v = lp.view;
+    dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);
+    if (lp.bm_n == 64) k_gemm<64, false><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n, 0, v.demand, 0);
+    else k_gemm<32, false><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n, 0, v.demand, 0);
+    k_flow_reduce<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, st>>>(v, lp.part, lp.ksplit_n, dst);
+}
+
 // levels of the staged iterate and buffer flip, used when a state is injected from the host
 __global__ void k_levels(View v)
 {
@@ -1473,7 +1516,7 @@ void launch_rebuild_derived(const LaunchPlan &lp, cudaStream_t st, int segment)
     dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);
     if (lp.bm_n == 64) k_gemm<64, false><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n, 0);
     else k_gemm<32, false><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n, 0);
-    k_flow_reduce<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, st>>>(v, lp.part, lp.ksplit_n);
+    k_flow_reduce<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, st>>>(v, lp.part, lp.ksplit_n, nullptr);
     if (v.S > 0) k_levels<<<cdiv(v.S, 128), 128, 0, st>>>(v);
     k_flip<<<1, 1, 0, st>>>(v);
 }

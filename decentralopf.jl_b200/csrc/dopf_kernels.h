@@ -12,6 +12,7 @@ struct LaunchPlan {
     int bm_t, ksplit_t;       // tile rows / split-K of the transposed product (PTDF^T M)
     int mt_base, mt_rows;     // node rows [mt_base, mt_base + mt_rows) the transposed product is computed for (multiples of 64)
     int bm_n, ksplit_n;       // ... of the flow product (PTDF * inj)
+    int bm_x, ksplit_x;       // ... of the partial flow product of the partitioned mode (K = the rank's node range)
     int sto_fix_blocks;       // grid of the storage correction pass (one 32-thread block = one affected storage)
     int sto_fix_slots;        // nodes whose hinge lists k_sto_collect gathers (one scratch slot each, shared by the node's storages)
     int gen_flat;             // 1: agent-major generator kernel (few generators per node)
@@ -38,7 +39,8 @@ void launch_total_costs(const View &v, double *d_out, cudaStream_t st);
 void launch_profile_warm(const LaunchPlan &lp, cudaStream_t st);
 void launch_nodal_price(const View &v, const double *lam, const double *mu, const double *rho, double *d_out, cudaStream_t st);
 void launch_unit_penalty(const View &v, int kind, int idx, double *eb, double *up, double *lo, double *U, double *K, cudaStream_t st);
-void launch_copy_inj(const View &v, const double *src, cudaStream_t st);
+void launch_copy_inj(const View &v, const double *src, cudaStream_t st);   // inj = src - demand
+void launch_flow_of_demand(const LaunchPlan &lp, double *dst, cudaStream_t st);
 void launch_pack_cols(double *dev, double *host_layout, int rows, int C, int T, int ld, int to_device, cudaStream_t st);
 void launch_penalty_totals(const View &v, double *eb, double *up, double *lo, cudaStream_t st);
 // segment 0: local injection of the staged iterate; segment 1: column sums, flows, levels, buffer flip

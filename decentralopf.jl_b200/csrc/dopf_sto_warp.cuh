@@ -25,6 +25,9 @@
 #define DOPF_STO_WARP_CUH
 
 #include "dopf_bodies.h"
+#ifdef DOPF_STATS
+#include <cstdio>
+#endif
 
 namespace dopf {
 
@@ -296,7 +299,8 @@ enum { RS_CONV = 1, RS_BAD = 2, RS_FLAT = 4, RS_EMPTY = 8, RS_FREEBAD = 16, RS_E
 __host__ __device__ inline size_t sto_warp_smem_per_warp(int T) { return (size_t)TAB_COMPS * (size_t)((T + 1) | 1) * sizeof(double); }
 
 // returns true if the storage was solved and written; false => caller queues it for the exact sequential solver
-template <int J, bool HINGES>
+// AV ("all valid"): the horizon fills the warp exactly (T = 32 J), the validity predicates fold away
+template <int J, bool HINGES, bool AV = false>
 __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const int *hcnt, double *tab)
 {
     const int lane = threadIdx.x & 31, T = v.T;
@@ -317,7 +321,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
 #pragma unroll
     for (int j = 0; j < J; ++j) {
         const int t = lane * J + j;
-        valid[j] = t < T;
+        valid[j] = AV || t < T;
         const int tt = valid[j] ? t : T - 1;
         const size_t o = (size_t)s * T + tt, on = v.nt_of(n, tt);      // n: virtual node
         st[j].Db = sel(v.D, cur)[o]; st[j].Cb = sel(v.C, cur)[o];
@@ -621,6 +625,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
         if (lane == 0) atomicMax(v.counters + (HINGES ? 16 : 0) + 12, (unsigned long long)st_rounds);
         if (lane == 0) atomicMax(v.counters + (HINGES ? 16 : 0) + 13, (unsigned long long)st_passes);
         (void)nruns; (void)nsingle;
+        if (st_rounds > 8 && lane == 0 && !HINGES) printf("STRAG it %d s %d rounds %d passes %d anch %d free %d pmax %g emax %g mc %g node %d\n", v.ctrl->iteration, s, st_rounds, st_passes, nanch, nfree, k.pmax, k.emax, k.mc, n);
     }
 #endif
 

@@ -145,11 +145,13 @@ int dopf_get_penalty_totals(dopf_handle *h, double *energy_balance, double *uppe
  * named device buffer IN PLACE over the ranks (torch.distributed / NCCL on the stream given to
  * dopf_set_stream, so no host synchronisation is needed):
  *     phase 0 -> all-reduce MAX  DOPF_XBUF_DMAX   (largest agent move per timestep)
- *     phase 1 -> all-reduce SUM  DOPF_XBUF_INJ    (nodal injection; rank 0 carries the demand)
- *     phase 2 -> all-reduce SUM  DOPF_XBUF_ROWSUM (exact slack row sums)
+ *     phase 1 -> all-reduce SUM  DOPF_XBUF_INJ    (nodal injection of the agents; the library subtracts the demand afterwards)
+ *     phase 2 -> all-reduce SUM  DOPF_XBUF_ROWSUM (exact slack row sums + partial line flows: every rank multiplies PTDF with
+ *                                                  the injection of its own agents over its own node range only, so both PTDF
+ *                                                  products cost each rank 1/nranks of the single-GPU work)
  *     phase 3    (dual update, convergence check, buffer flip)
  * Set-up: dopf_set_partition, all-reduce SUM DOPF_XBUF_INJ and MAX DOPF_XBUF_RBOX, dopf_step_phase(h, -1).
- * The network / dual part is replicated, so all ranks hold identical duals and convergence flags. */
+ * The elementwise network / dual part is replicated, so all ranks hold identical duals and convergence flags. */
 #define DOPF_XBUF_DMAX 0
 #define DOPF_XBUF_INJ 1
 #define DOPF_XBUF_ROWSUM 2
