@@ -197,6 +197,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     v.hcap = cfg->hinge_capacity > 0 ? cfg->hinge_capacity : 32;
     v.c = Coef::make(cfg->gamma, cfg->flow_weight, cfg->prox_weight, cfg->slack_mask_tol, cfg->eps);
     v.demand_on = 1;
+    v.rowsum_is_corr = 1;
     v.debug = cfg->debug_flags;
     const int ldt = v.ldt, Np = v.Np, Lp = v.Lp;
     h->use_graph = cfg->use_graph != 0;

@@ -5,6 +5,7 @@
 #ifndef DOPF_BODIES_H
 #define DOPF_BODIES_H
 
+#include <cstddef>
 #include "dopf_math.h"
 
 namespace dopf {
@@ -41,8 +42,10 @@ struct Ctrl {
     int error;          // DOPF_ERR_*; set => every later kernel is a no-op, state stays valid
     int iters_done;     // iterations executed since create
     int finish_cnt;     // blocks of k_lambda_finish that are done (scenario batches: the last one flips the buffers)
-    int gen_work_cnt, sto_work_cnt, cold_work_cnt, pair_cnt, gen_grp_cnt, fix_node_cnt;
     int sto_next;       // work counter of the storage predict kernel (warps draw storages from it)
+    // generator correction queue: entries (low word) and groups (high word) are advanced by ONE 64-bit atomic in k_verify
+    alignas(8) int gen_work_cnt; int gen_grp_cnt;
+    int sto_work_cnt, cold_work_cnt, pair_cnt, fix_node_cnt;
     int stat_sto_cold;                   // storages solved by the cold funnel in the last iteration
     int stat_fix_seq;                    // cumulated correction-pass storages that needed the sequential solver
     int stat_gen_fix, stat_sto_fix;      // cumulated corrected agents (statistics)
@@ -52,6 +55,8 @@ struct Ctrl {
     double res[3];
     double total_costs;
 };
+
+static_assert(offsetof(Ctrl, gen_work_cnt) % 8 == 0 && offsetof(Ctrl, gen_grp_cnt) == offsetof(Ctrl, gen_work_cnt) + 4, "packed queue counters");
 
 struct View {
     // sizes.  A batch of C independent scenarios on one grid (BASELINE configs[3]) is laid out as extra COLUMNS of the
@@ -112,7 +117,8 @@ struct View {
     int *gen_grp;                      // [gen_work_cap][2] groups of consecutive work entries of one (n,t): first entry, count
     int *sto_work, *sto_flag;          // [S], [S]
     int *fix_node_flag, *fix_node_list, *fix_node_slot;   // [Np] nodes with a storage on the work list (device path only)
-    double *rowsumU, *rowsumK;         // [Lp][ldt] exact sum_i (b -+ p delta_i)_+ of tight rows
+    double *rowsumU, *rowsumK;         // [Lp][ldt] tight rows: sum_i (b -+ p delta_i)_+ minus the closed form of an uncrossed row (rowsum_is_corr) or the whole sum
+    int rowsum_is_corr;
     // agent-partitioned mode: every rank multiplies PTDF with the injection of ITS agents over ITS node range only; the
     // partial flows travel in the third slab of the row-sum exchange buffer and the demand part is a constant
     double *xflow;                     // [Lp][ldt] partial flow PTDF[:, own nodes] * (injection of the own agents), summed over the ranks by the exchange
@@ -387,16 +393,15 @@ DOPF_HD void body_inject(const View &v, int n, int t)
 // closed form of sum_i (b + sp*delta_i)_+ over the agents of node n at time t from the node statistics;
 // ok = false if the hinge threshold falls strictly between two movers on one side (then the caller sums
 // over the agents).  Resting agents (delta = 0) contribute (b)_+ each.
-DOPF_HD double slack_node_closed(const View &v, double b, double sp, int n, int t, bool &ok)
+// (the common statistics are passed in: k_slack_rows loads them for several nodes at once before the first use)
+DOPF_HD double slack_node_closed_pre(const View &v, double b, double sp, int n, int t, double na, double lo, double hi, double s4, double s5, bool &ok)
 {
     const size_t i = (size_t)t * v.Np + n;                 // t = column
-    const double na = v.nagents[(size_t)v.scen_of_col(t) * v.Np + n];
     ok = true;
     if (na == 0.0) return 0.0;
     if (sp == 0.0) return na * pospart(b);
-    const double lo = v.nst[0][i], hi = v.nst[1][i];
     const double f0 = b + sp * lo, f1 = b + sp * hi;
-    const double sall = v.nst[4][i] + v.nst[5][i];
+    const double sall = s4 + s5;
     if (f0 >= 0.0 && f1 >= 0.0) return na * b + sp * sall;            // nobody is clipped
     if (f0 <= 0.0 && f1 <= 0.0 && b <= 0.0) return 0.0;               // everybody is clipped (resting agents: b <= 0)
     // movers that push the term down are the negative ones for sp > 0, the positive ones for sp < 0
@@ -421,6 +426,19 @@ DOPF_HD double slack_node_closed(const View &v, double b, double sp, int n, int 
     (void)s_dn;
     ok = false;
     return 0.0;
+}
+DOPF_HD double slack_node_closed(const View &v, double b, double sp, int n, int t, bool &ok)
+{
+    const size_t i = (size_t)t * v.Np + n;
+    return slack_node_closed_pre(v, b, sp, n, t, v.nagents[(size_t)v.scen_of_col(t) * v.Np + n], v.nst[0][i], v.nst[1][i], v.nst[4][i], v.nst[5][i], ok);
+}
+
+// contribution of node n to the closed form of an uncrossed row: every agent keeps the sign of b
+DOPF_HD double slack_node_lin(const View &v, double b, double sp, int n, int t)
+{
+    if (!(b > 0.0)) return 0.0;
+    const size_t i = (size_t)t * v.Np + n;
+    return v.nagents[(size_t)v.scen_of_col(t) * v.Np + n] * b + sp * (v.nst[4][i] + v.nst[5][i]);
 }
 
 // ---- exact slack sums of one tight row at one node (results.jl:83-84,110-112) ------------------
@@ -457,8 +475,11 @@ DOPF_HD void body_dual(const View &v, int l, int t, int is_tight, double &res_mu
     const double Fn = sel(v.flow, nxt)[i], dF = Fn - sel(v.flow, cur)[i];
     const double A = (double)v.A;
     const double bp = v.bplus[i], bm = v.bminus[i];
-    const double sU = (is_tight & 1) ? v.rowsumU[i] : (bp > 0.0 ? A * bp - dF : 0.0);
-    const double sK = (is_tight & 2) ? v.rowsumK[i] : (bm > 0.0 ? A * bm + dF : 0.0);
+    // closed form of a row nobody crosses; for a tight row the device kernels store the CORRECTION to it (the nodes whose
+    // agents can reach the hinge: exact minus closed form), the sequential emulation stores the whole exact sum
+    const double cU = bp > 0.0 ? A * bp - dF : 0.0, cK = bm > 0.0 ? A * bm + dF : 0.0;
+    const double sU = (is_tight & 1) ? (v.rowsum_is_corr ? cU + v.rowsumU[i] : v.rowsumU[i]) : cU;
+    const double sK = (is_tight & 2) ? (v.rowsum_is_corr ? cK + v.rowsumK[i] : v.rowsumK[i]) : cK;
     const double scale = v.c.w2 / (v.c.kk * A);
     const double aU = scale * sU, aK = scale * sK;
     const double f = v.fmax[l];

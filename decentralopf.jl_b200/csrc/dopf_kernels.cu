@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(256) k_compact(View v, int mode, int inline_dm
     if (!DOPF_ACTIVE(v)) return;
     __shared__ int wcount[8];
     __shared__ unsigned long long wmax[8];
+    __shared__ int unchanged;
     const int t = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (mode == 1 && inline_dmax) {
         // dmax[t] = column maximum of dn (largest move of any agent at t); the separate k_dmax is only needed when
@@ -46,9 +47,11 @@ __global__ void __launch_bounds__(256) k_compact(View v, int mode, int inline_dm
         __syncthreads();
         if (threadIdx.x == 0) {
             for (int k = 1; k < 8; ++k) a = wmax[k] > a ? wmax[k] : a;
+            unchanged = inline_dmax == 2 && a == v.dmax[t];
             v.dmax[t] = a;
         }
         __syncthreads();
+        if (unchanged) return;      // second pass of the iteration: the correction left this column's largest move as it was => same list
     }
     const int n_in = mode == 0 ? v.L : v.wcnt[t];
     // slice length per warp: a multiple of 128 rows in mode 0 (4 flag bytes per lane), of 32 entries in mode 1
@@ -131,8 +134,11 @@ __global__ void __launch_bounds__(256) k_compact_w(View v, int mode, int inline_
         for (int n = lane; n < v.N; n += 32) { const unsigned long long b = v.dn[(size_t)n * v.ldt + t]; a = b > a ? b : a; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { const unsigned long long y = __shfl_xor_sync(0xffffffffu, a, o); a = y > a ? y : a; }
+        const bool same = inline_dmax == 2 && a == v.dmax[t];
+        __syncwarp();
         if (lane == 0) v.dmax[t] = a;
         __syncwarp();
+        if (same) return;           // (see k_compact)
     }
     const int n_in = mode == 0 ? v.L : v.wcnt[t];
     const unsigned char *fl = v.flags + (size_t)t * v.Lp;
@@ -691,14 +697,17 @@ __device__ __forceinline__ bool verify_bounds_dev(const View &v, int n, int t, d
         else if (h.bp < 0.0) { if (h.bp > lo) lo = h.bp; }
         else { if (h.sg > 0.0) hi = 0.0; else lo = 0.0; }
     };
-    int j = 0;
-    for (; j + 2 <= cnt; j += 2) {
-        const int e0 = lst[j], e1 = lst[j + 1];
-        const double b0 = lb[j], b1 = lb[j + 1];
-        const double p0 = v.ptdf[(size_t)(e0 >> 1) * v.Np + n], p1 = v.ptdf[(size_t)(e1 >> 1) * v.Np + n];
-        one(e0, b0, p0); one(e1, b1, p1);
+    // eight rows in flight: the list entries (warp-uniform addresses) first, then the eight PTDF loads they address -
+    // two dependent memory latencies per eight rows (the kernel is latency bound)
+    for (int j = 0; j < cnt; j += 8) {
+        int e[8]; double b[8], p[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int jj = min(j + u, cnt - 1); e[u] = lst[jj]; b[u] = lb[jj]; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) p[u] = v.ptdf[(size_t)(e[u] >> 1) * v.Np + n];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (j + u < cnt) one(e[u], b[u], p[u]);
     }
-    if (j < cnt) { const int e0 = lst[j]; one(e0, lb[j], v.ptdf[(size_t)(e0 >> 1) * v.Np + n]); }
     return !(lo == -INFINITY && hi == INFINITY);
 }
 
@@ -736,11 +745,13 @@ __global__ void __launch_bounds__(256) k_verify(View v)
             if (m == 0u) continue;
             int base = 0;
             if (lane == 0) {
-                base = atomicAdd(&v.ctrl->gen_work_cnt, __popc(m));
-                if (base + __popc(m) <= v.gen_work_cap) {
-                    const int k = atomicAdd(&v.ctrl->gen_grp_cnt, 1);
-                    v.gen_grp[2 * k] = base; v.gen_grp[2 * k + 1] = __popc(m);
-                } else v.ctrl->error = DOPF_ERR_WORK_CAP;
+                // one round trip for both counters: low word += entries, high word += 1 group
+                const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(&v.ctrl->gen_work_cnt),
+                                                         (unsigned long long)__popc(m) | (1ull << 32));
+                base = (int)(unsigned)(old & 0xffffffffull);
+                const int k = (int)(old >> 32);                       // k <= base: every group has at least one entry
+                if (base + __popc(m) <= v.gen_work_cap) { v.gen_grp[2 * k] = base; v.gen_grp[2 * k + 1] = __popc(m); }
+                else v.ctrl->error = DOPF_ERR_WORK_CAP;
             }
             base = __shfl_sync(0xffffffffu, base, 0);
             if (hit && base + __popc(m) <= v.gen_work_cap) v.gen_work[base + __popc(m & ((1u << lane) - 1))] = g * v.T + tt;
@@ -925,7 +936,8 @@ __global__ void k_colsum(View v)   // block (32,32): 32 timesteps, 32 row groups
 
 // ------------------------------------------------------------------------------------------------
 // exact average-slack sums of the tight rows (results.jl:83-84,110-112):
-//   rowsum[l,t,side] = sum over all agents i of (b_lt -+ p_{l,n(i)} * delta_it)_+
+//   sum over all agents i of (b_lt -+ p_{l,n(i)} * delta_it)_+ = closed form of an uncrossed row (k_dual) + rowsum[l,t,side],
+//   the correction over the nodes whose agents can reach the hinge
 // k_slack_rows: one block per (t, row).  Threads classify the nodes with the node statistics of the moves at (n,t):
 //   nodes whose agents all keep the hinge on one side contribute in closed form; the few mixed nodes (the hinge
 //   threshold falls between two movers of one sign) are ordered by node and appended to a global pair queue as ONE
@@ -934,59 +946,78 @@ __global__ void k_colsum(View v)   // block (32,32): 32 timesteps, 32 row groups
 // k_slack_fold: every row adds the values of its range in order.
 // Every partial sum is added in a fixed order, so the result does not depend on scheduling (a batch of scenarios
 // reproduces the single runs bit for bit; only the position of a row's range in the queue varies).
-constexpr int SLACK_MIXED_CAP = 512;
+constexpr int SLACK_BM_WORDS = 512;       // mixed nodes of a row are marked in a shared-memory bitmap (nodes beyond 16384: summed in place)
 __global__ void __launch_bounds__(512) k_slack_rows(View v, unsigned char *tflag)
 {
     if (!DOPF_ACTIVE(v)) return;
     __shared__ double red[16];
-    __shared__ int mixed[SLACK_MIXED_CAP], mcnt, mbase;
+    __shared__ unsigned bm[SLACK_BM_WORDS];
+    __shared__ int bpre[SLACK_BM_WORDS], mtotal, mbase;
     const int t = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;      // t: column
     const int cnt = v.tcnt[t];
     const int *lst = v.tight + (size_t)t * 2 * v.L;
+    const int words = min(SLACK_BM_WORDS, (v.N + 31) >> 5);
     for (int j = blockIdx.x; j < cnt; j += gridDim.x) {
         const int l = lst[j] >> 1, side = lst[j] & 1;
         const double b = side ? v.bminus[(size_t)l * v.ldt + t] : v.bplus[(size_t)l * v.ldt + t];
-        if (threadIdx.x == 0) mcnt = 0;
+        for (int w = threadIdx.x; w < words; w += blockDim.x) bm[w] = 0u;
         __syncthreads();
         double a = 0.0;
+        // Only the nodes whose largest move reaches the hinge (|b| <= |p| * max move) are looked at: all the others
+        // contribute the closed form of an uncrossed row, which k_dual adds for the whole row from the flow change
+        // (A*b -+ dF).  The row sum stored here is the correction: exact minus closed form over the reachable nodes.
+        const size_t so = (size_t)t * v.Np;
         for (int n = threadIdx.x; n < v.N; n += blockDim.x) {
             const double p = v.ptdf[(size_t)l * v.Np + n];
+            const double dnm = fmax(-v.nst[0][so + n], v.nst[1][so + n]);      // largest |move| of an agent at (n,t)
+            if (fabs(b) > fabs(p) * dnm) continue;
+            const double sp = side ? p : -p;
             bool ok;
-            const double c = slack_node_closed(v, b, side ? p : -p, n, t, ok);
-            if (ok) { a += c; continue; }
-            const int q = atomicAdd(&mcnt, 1);
-            if (q < SLACK_MIXED_CAP) mixed[q] = n;
-            else a += body_slack_row_node(v, l, side, n, t);      // list full: serial path (thread-local, still deterministic)
+            const double c = slack_node_closed(v, b, sp, n, t, ok);
+            const double lin = slack_node_lin(v, b, sp, n, t);
+            if (ok) { a += c - lin; continue; }
+            a -= lin;                                             // the exact part of a mixed node follows from the pair queue
+            if ((n >> 5) < SLACK_BM_WORDS) atomicOr(&bm[n >> 5], 1u << (n & 31));
+            else a += body_slack_row_node(v, l, side, n, t);      // beyond the bitmap: summed in place (thread-local, still a fixed order)
         }
         a = Group<32>::sum(a);
         if (lane == 0) red[warp] = a;
         __syncthreads();
-        const int nm = min(mcnt, SLACK_MIXED_CAP);
-        if (threadIdx.x == 0) {
-            int base = nm ? atomicAdd(&v.ctrl->pair_cnt, nm) : 0;
-            if (base + nm > v.pair_cap) base = -1;                // queue full: this row sums its mixed nodes itself
-            mbase = base;
-        }
-        __syncthreads();
-        const int base = mbase;
-        double extra = 0.0;
-        for (int i = threadIdx.x; i < nm; i += blockDim.x) {      // rank by node index: the order inside the row's range is fixed
-            int r = 0;
-            for (int k2 = 0; k2 < nm; ++k2) r += mixed[k2] < mixed[i];
-            if (base >= 0) { v.pair_row[base + r] = lst[j]; v.pair_node[base + r] = mixed[i]; v.pair_col[base + r] = t; }
-        }
-        if (base < 0 && threadIdx.x == 0) {
-            // (never seen in practice) deterministic serial fallback in node order
-            for (int r = 0; r < nm; ++r) {
-                int best = -1;
-                for (int k2 = 0; k2 < nm; ++k2) { int c2 = 0; for (int k3 = 0; k3 < nm; ++k3) c2 += mixed[k3] < mixed[k2]; if (c2 == r) best = mixed[k2]; }
-                extra += body_slack_row_node(v, l, side, best, t);
+        if (warp == 0) {
+            // exclusive prefix of the bitmap's popcounts: the position of a mixed node in the row's queue range = its rank by
+            // node index, whatever order the threads found them in
+            const int per = (words + 31) >> 5, w0 = lane * per, w1 = min(words, w0 + per);
+            int sum = 0;
+            for (int w = w0; w < w1; ++w) sum += __popc(bm[w]);
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+            int run = incl - sum;
+            for (int w = w0; w < w1; ++w) { bpre[w] = run; run += __popc(bm[w]); }
+            if (lane == 31) {
+                const int nm = incl;
+                int base = nm ? atomicAdd(&v.ctrl->pair_cnt, nm) : 0;
+                if (base + nm > v.pair_cap) base = -1;            // queue full: this row sums its mixed nodes itself
+                mtotal = nm; mbase = base;
             }
         }
+        __syncthreads();
+        const int base = mbase, nm = mtotal;
+        if (base >= 0 && nm)
+            for (int w = threadIdx.x; w < words; w += blockDim.x) {
+                unsigned bits = bm[w];
+                int pos = base + bpre[w];
+                while (bits) {
+                    const int k = __ffs(bits) - 1; bits &= bits - 1;
+                    v.pair_row[pos] = lst[j]; v.pair_node[pos] = w * 32 + k; v.pair_col[pos] = t; ++pos;
+                }
+            }
         if (threadIdx.x == 0) {
             double sum = 0.0;
             for (int k2 = 0; k2 < (int)(blockDim.x >> 5); ++k2) sum += red[k2];
-            sum += extra;
+            if (base < 0)       // (never seen in practice) serial fallback in node order
+                for (int w = 0; w < words; ++w)
+                    for (unsigned bits = bm[w]; bits; bits &= bits - 1) sum += body_slack_row_node(v, l, side, w * 32 + __ffs(bits) - 1, t);
             const size_t i = (size_t)l * v.ldt + t;
             (side ? v.rowsumK : v.rowsumU)[i] = sum;
             v.pbase[(size_t)t * 2 * v.L + j] = base; v.pcnt[(size_t)t * 2 * v.L + j] = base >= 0 ? nm : 0;
@@ -1024,22 +1055,31 @@ __global__ void __launch_bounds__(256) k_slack_pairs(View v)
     }
 }
 
-// every tight row adds the pair values of its queue range, in order (one warp per column, lanes over its tight rows)
+// every tight row adds the pair values of its queue range in a fixed order: FOLD_X * 8 warps per column, each looks at 32
+// rows at a time (coalesced counts), and a row with pairs is summed by the whole warp (lane-strided partial sums, then
+// the fixed shuffle tree)
+constexpr int FOLD_X = 4;
 __global__ void __launch_bounds__(256) k_slack_fold(View v)
 {
     if (!DOPF_ACTIVE(v)) return;
-    const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (t >= v.TC) return;
+    const int t = blockIdx.y, lane = threadIdx.x & 31, wc = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int cnt = v.tcnt[t];
-    for (int j = lane; j < cnt; j += 32) {
-        const size_t k = (size_t)t * 2 * v.L + j;
-        const int n = v.pcnt[k];
-        if (n == 0) continue;
-        const int e = v.tight[k], base = v.pbase[k];
-        double *dst = ((e & 1) ? v.rowsumK : v.rowsumU) + (size_t)(e >> 1) * v.ldt + t;
-        double sum = *dst;
-        for (int q = 0; q < n; ++q) sum += v.pair_val[base + q];
-        *dst = sum;
+    for (int j0 = wc * 32; j0 < cnt; j0 += FOLD_X * 8 * 32) {
+        const size_t k = (size_t)t * 2 * v.L + j0 + lane;
+        const bool in = j0 + lane < cnt;
+        const int n_l = in ? v.pcnt[k] : 0, base_l = in ? v.pbase[k] : 0, e_l = in ? v.tight[k] : 0;
+        unsigned m = __ballot_sync(0xffffffffu, n_l > 0);
+        while (m) {
+            const int src = __ffs(m) - 1; m &= m - 1;
+            const int n = __shfl_sync(0xffffffffu, n_l, src), base = __shfl_sync(0xffffffffu, base_l, src), e = __shfl_sync(0xffffffffu, e_l, src);
+            double part = 0.0;
+            for (int q = lane; q < n; q += 32) part += v.pair_val[base + q];
+            part = Group<32>::sum(part);
+            if (lane == 0) {
+                double *dst = ((e & 1) ? v.rowsumK : v.rowsumU) + (size_t)(e >> 1) * v.ldt + t;
+                *dst += part;
+            }
+        }
     }
 }
 
@@ -1376,8 +1416,10 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     JOIN();
     if (segment >= 0) LAUNCH(k_dmax<<<dim3(v.ldt / 32, 16), dim3(32, 32), 0, cs>>>(v));   // partitioned mode: maxima are exchanged
     XCHG(DOPF_X_DMAX);   // all ranks must build the same tight lists
-    if (v.L <= 1024) LAUNCH(k_compact_w<<<cdiv(v.TC, 8), 256, 0, cs>>>(v, 1, segment < 0));
-    else LAUNCH(k_compact<<<v.TC, 256, 0, cs>>>(v, 1, segment < 0));   // moves may have grown
+    // moves may have grown: lists of the columns whose largest move changed are rebuilt (single-GPU mode: 2 = compare with
+    // the maximum the first pass used; partitioned mode: the maxima were just exchanged)
+    if (v.L <= 1024) LAUNCH(k_compact_w<<<cdiv(v.TC, 8), 256, 0, cs>>>(v, 1, segment < 0 ? 2 : 0));
+    else LAUNCH(k_compact<<<v.TC, 256, 0, cs>>>(v, 1, segment < 0 ? 2 : 0));
     LAUNCH(k_inject<<<dim3(v.Np / 8, v.ldt / 32), 256, 0, cs>>>(v));
     if (v.flowD) {   // partitioned mode: partial flow of the rank's own injection over its own node range (1/ranks of the product)
         dim3 grid(v.Lp / lp.bm_x, v.ldt / BN, lp.ksplit_x);
@@ -1389,7 +1431,7 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     XCHG(DOPF_X_INJ);    // nodal injection of all ranks' agents
     LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.TC), (v.N <= 256 ? 128 : 512), 0, cs>>>(v, lp.tflag));   // needs the local injection statistics only
     LAUNCH(k_slack_pairs<<<lp.num_sms * 2, 256, 0, cs>>>(v));
-    LAUNCH(k_slack_fold<<<cdiv(v.TC, 8), 256, 0, cs>>>(v));
+    LAUNCH(k_slack_fold<<<dim3(FOLD_X, v.TC), 256, 0, cs>>>(v));
     LAUNCH(k_colsum<<<v.ldt / 32, dim3(32, 32), 0, cs>>>(v));
     if (!v.flowD) {   // flow = PTDF * inj
         dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);

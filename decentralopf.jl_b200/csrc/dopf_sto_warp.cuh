@@ -304,6 +304,9 @@ template <int J, bool HINGES, bool AV = false>
 __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const int *hcnt, double *tab)
 {
     const int lane = threadIdx.x & 31, T = v.T;
+#ifdef DOPF_STATS
+    unsigned long long st_t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(st_t0));
+#endif
     const int tstride = (T + 1) | 1;
     const int cur = v.ctrl->cur, nxt = 1 - cur, n = v.sto_node[s];
     StoConst k;
@@ -625,7 +628,11 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
         if (lane == 0) atomicMax(v.counters + (HINGES ? 16 : 0) + 12, (unsigned long long)st_rounds);
         if (lane == 0) atomicMax(v.counters + (HINGES ? 16 : 0) + 13, (unsigned long long)st_passes);
         (void)nruns; (void)nsingle;
-        if (st_rounds > 8 && lane == 0 && !HINGES) printf("STRAG it %d s %d rounds %d passes %d anch %d free %d pmax %g emax %g mc %g node %d\n", v.ctrl->iteration, s, st_rounds, st_passes, nanch, nfree, k.pmax, k.emax, k.mc, n);
+        if (lane == 0 && !HINGES && (v.debug & 128) && (st_rounds > 8 || s >= v.S - 2 || s == v.S / 2)) {
+            unsigned long long st_t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(st_t1));
+            printf("STIME it %d s %d rounds %d t0 %llu t1 %llu dur_us %.1f\n", v.ctrl->iteration, s, st_rounds, st_t0, st_t1, (st_t1 - st_t0) * 1e-3);
+        }
+        if (st_rounds > 8 && lane == 0 && !HINGES && (v.debug & 256)) printf("STRAG it %d s %d rounds %d passes %d anch %d free %d pmax %g emax %g mc %g node %d\n", v.ctrl->iteration, s, st_rounds, st_passes, nanch, nfree, k.pmax, k.emax, k.mc, n);
     }
 #endif
 
