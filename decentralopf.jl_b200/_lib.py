@@ -47,7 +47,7 @@ EXPORTS = ["dopf_version", "dopf_default_config", "dopf_create", "dopf_destroy",
            "dopf_get_iterate", "dopf_get_duals", "dopf_set_state", "dopf_get_nodal_price", "dopf_get_total_costs",
            "dopf_nodal_price_from", "dopf_get_unit_penalty", "dopf_get_penalty_totals",
            "dopf_set_partition", "dopf_set_stream", "dopf_step_phase", "dopf_exchange_buffer", "dopf_last_error", "dopf_profile_iteration", "dopf_debug_counters", "dopf_get_scenario_status",
-           "dopf_calculate_ptdf", "dopf_ptdf_last_error"]
+           "dopf_calculate_ptdf", "dopf_ptdf_last_error", "dopf_comm_get_unique_id", "dopf_comm_init"]
 
 
 def build(force=False, verbose=False):
@@ -104,5 +104,7 @@ def load():
     lib.dopf_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.dopf_step_phase.argtypes = [C.c_void_p, C.c_int32]
     lib.dopf_exchange_buffer.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    lib.dopf_comm_get_unique_id.argtypes = [C.c_void_p]
+    lib.dopf_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
     _lib = lib
     return lib

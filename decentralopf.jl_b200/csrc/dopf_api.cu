@@ -2,6 +2,8 @@
 // state transfer, phase-wise stepping for the partitioned (multi-GPU) mode.  No CPU compute path exists in this library.
 #include "../../include/dopf.h"
 #include "dopf_kernels.h"
+#include <nccl.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -47,6 +49,10 @@ struct dopf_handle {
     int rank = 0, nranks = 1;
     int host_cur = 0;          // host mirror of Ctrl::cur, advanced by phase 3
     bool partitioned = false;  // dopf_set_partition was called: stepped phase by phase
+    // library-owned communicator (dopf_comm_init): dopf_step then runs the phases AND the all-reduces itself
+    ncclComm_t comm = nullptr;
+    bool cfg_use_graph = true;
+    int *d_flag = nullptr;     // [1] error agreement between the ranks
     cudaStream_t own_stream = nullptr;
 };
 
@@ -120,6 +126,41 @@ int check_device_error(dopf_handle *h)
     return DOPF_E_CAPACITY;
 }
 
+
+// ---- NCCL, loaded at run time (libdopf.so itself does not depend on libnccl) --------------------------------------------
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*get_unique_id)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*comm_init_rank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*all_reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*comm_destroy)(ncclComm_t) = nullptr;
+    const char *(*get_error_string)(ncclResult_t) = nullptr;
+    bool load(std::string &err)
+    {
+        if (lib) return true;
+        const char *names[] = {getenv("DOPF_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        void *l = nullptr;
+        for (const char *n : names) if (n && !l) l = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (!l) { err = std::string("libnccl.so.2 could not be loaded: ") + dlerror(); return false; }
+#define SYM(field, name) field = (decltype(field))dlsym(l, name); if (!field) { err = "libnccl: missing symbol " name; return false; }
+        SYM(get_unique_id, "ncclGetUniqueId"); SYM(comm_init_rank, "ncclCommInitRank"); SYM(all_reduce, "ncclAllReduce");
+        SYM(comm_destroy, "ncclCommDestroy"); SYM(get_error_string, "ncclGetErrorString");
+#undef SYM
+        lib = l;
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+#define NK(call)                                                                                   \
+    do {                                                                                           \
+        ncclResult_t r_ = (call);                                                                  \
+        if (r_ != ncclSuccess) {                                                                   \
+            h->err = std::string(#call " failed: ") + g_nccl.get_error_string(r_);                 \
+            return DOPF_E_COMM;                                                                    \
+        }                                                                                          \
+    } while (0)
+
 }  // namespace
 
 namespace dopf {
@@ -146,6 +187,7 @@ void dopf_destroy(dopf_handle *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->graph) cudaGraphDestroy(h->graph);
+    if (h->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(h->comm);     // after the graphs that captured its collectives
     if (h->lp.ev_fork) cudaEventDestroy(h->lp.ev_fork);
     if (h->lp.ev_join) cudaEventDestroy(h->lp.ev_join);
     if (h->lp.side_stream) cudaStreamDestroy(h->lp.side_stream);
@@ -201,6 +243,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
     v.debug = cfg->debug_flags;
     const int ldt = v.ldt, Np = v.Np, Lp = v.Lp;
     h->use_graph = cfg->use_graph != 0;
+    h->cfg_use_graph = h->use_graph;
 
     // ---- agents sorted by node (stable), CSR offsets -------------------------------------------
     // caller's agent index of the batch: c*Gs + g (scenario-major); virtual node of it: c*N + node[g]
@@ -381,13 +424,19 @@ int dopf_step(dopf_handle *h, int32_t max_iters, dopf_status *out)
 {
     if (!h) return DOPF_E_ARG;
     CK(cudaSetDevice(h->device));
-    int rc = build_graph(h);
-    if (rc) return rc;
+    int rc = 0;
     int remaining = max_iters;
     h->last_step_ms = 0.0;
     h->host_cur = h->h_ctrl->cur;
     while (remaining > 0 && !h->h_ctrl->converged && h->h_ctrl->error == 0) {
-        const int chunk = std::min(remaining, 64);
+        // library-owned communicator: the very first iteration runs eagerly (NCCL sets its channels up on first use, which
+        // must not happen inside a capture); the graph is captured afterwards
+        const bool warm = h->comm && h->use_graph && !h->graph_exec && h->h_ctrl->iters_done == 0;
+        if (!warm && (rc = build_graph(h))) {
+            if (!h->comm) return rc;
+            h->use_graph = false;                 // capture with collectives refused: keep going eagerly (all ranks see the same)
+        }
+        const int chunk = warm ? 1 : std::min(remaining, 64);
         CK(cudaEventRecord(h->ev0, h->stream));
         for (int i = 0; i < chunk; ++i) {
             if (h->graph_exec) CK(cudaGraphLaunch(h->graph_exec, h->stream));
@@ -405,6 +454,17 @@ int dopf_step(dopf_handle *h, int32_t max_iters, dopf_status *out)
         CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         h->last_step_ms += ms;
         remaining -= chunk;
+        if (h->comm) {
+            // a rank that hit a device-side capacity error has turned its kernels into no-ops: every rank must stop at the
+            // same chunk boundary (the others would go on all-reducing its stale buffers, and the collectives would no
+            // longer pair up)
+            int flag = h->h_ctrl->error != 0 ? 1 : 0;
+            CK(cudaMemcpyAsync(h->d_flag, &flag, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+            NK(g_nccl.all_reduce(h->d_flag, h->d_flag, 1, ncclInt32, ncclMax, h->comm, h->stream));
+            CK(cudaMemcpyAsync(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            if (flag && h->h_ctrl->error == 0) { h->err = "another rank reported a device-side capacity error"; return DOPF_E_CAPACITY; }
+        }
     }
     if ((rc = check_device_error(h))) return rc;
     if (out) fill_status(h, out);
@@ -744,6 +804,42 @@ int dopf_set_partition(dopf_handle *h, int32_t rank, int32_t nranks, int32_t tot
     return DOPF_OK;
 }
 
+int dopf_comm_get_unique_id(void *id_out)
+{
+    std::string err;
+    if (!id_out) return DOPF_E_ARG;
+    if (!g_nccl.load(err)) { g_create_error = err; return DOPF_E_COMM; }
+    ncclUniqueId id;
+    const ncclResult_t r = g_nccl.get_unique_id(&id);
+    if (r != ncclSuccess) { g_create_error = std::string("ncclGetUniqueId failed: ") + g_nccl.get_error_string(r); return DOPF_E_COMM; }
+    static_assert(sizeof(ncclUniqueId) == DOPF_COMM_ID_BYTES, "ncclUniqueId size");
+    memcpy(id_out, &id, sizeof id);
+    return DOPF_OK;
+}
+
+int dopf_comm_init(dopf_handle *h, const void *id_bytes, int32_t rank, int32_t nranks, int32_t total_agents)
+{
+    if (!h || !id_bytes) return DOPF_E_ARG;
+    if (h->comm) { h->err = "dopf_comm_init: the handle already has a communicator"; return DOPF_E_ARG; }
+    if (!g_nccl.load(h->err)) return DOPF_E_COMM;
+    int rc = dopf_set_partition(h, rank, nranks, total_agents);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof id);
+    NK(g_nccl.comm_init_rank(&h->comm, nranks, id, rank));
+    if ((rc = dev_alloc(h, &h->d_flag, 1))) return rc;
+    // set-up exchanges: initial injection of the agents, per-node box ranges (identical candidate rows on all ranks)
+    View &v = h->lp.view;
+    NK(g_nccl.all_reduce(v.injloc[0], v.injloc[0], (size_t)v.Np * v.ldt, ncclFloat64, ncclSum, h->comm, h->stream));
+    NK(g_nccl.all_reduce(v.rbox, v.rbox, (size_t)v.Np, ncclFloat64, ncclMax, h->comm, h->stream));
+    if ((rc = dopf_step_phase(h, -1))) return rc;
+    if ((rc = sync_ctrl(h))) return rc;
+    h->host_cur = h->h_ctrl->cur;
+    h->use_graph = h->cfg_use_graph;          // the whole iteration - kernels and collectives - is captured by dopf_step
+    return DOPF_OK;
+}
+
 int dopf_step_phase(dopf_handle *h, int32_t phase)
 {
     if (!h || phase < -1 || phase >= DOPF_N_SEGMENTS) return DOPF_E_ARG;
@@ -790,11 +886,24 @@ namespace dopf {
 // one whole iteration (single-GPU handles); returns the number of kernel launches or < 0
 int enqueue_iteration_comm(dopf_handle *h, cudaStream_t st)
 {
-    if (h->partitioned) {
-        h->err = "partitioned handles are stepped with dopf_step_phase (the caller does the exchanges)";
+    if (h->partitioned && !h->comm) {
+        h->err = "partitioned handles without a library communicator (dopf_comm_init) are stepped with dopf_step_phase (the caller does the exchanges)";
         return DOPF_E_UNSUPPORTED;
     }
-    return enqueue_iteration(h->lp, st);
+    if (!h->partitioned) return enqueue_iteration(h->lp, st);
+    // the four phases with the three exchanges in between, all on one stream (capturable: every buffer has a fixed address)
+    const View &v = h->lp.view;
+    int launches = 0;
+    for (int phase = 0; phase < DOPF_N_SEGMENTS; ++phase) {
+        if (phase == DOPF_X_INJ + 1) { launch_copy_inj(v, v.injloc[0], st); ++launches; }
+        launches += enqueue_iteration(h->lp, st, phase);
+        void *buf = nullptr; int64_t cnt = 0;
+        if (phase < DOPF_N_SEGMENTS - 1) {
+            dopf_exchange_buffer(h, phase, &buf, &cnt);
+            NK(g_nccl.all_reduce(buf, buf, (size_t)cnt, ncclFloat64, phase == DOPF_X_DMAX ? ncclMax : ncclSum, h->comm, st));
+        }
+    }
+    return launches;
 }
 
 }  // namespace dopf

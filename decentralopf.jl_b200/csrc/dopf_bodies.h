@@ -336,46 +336,37 @@ DOPF_HD double inject_compute(const View &v, int n, int col, double (&st)[8])
 #define DOPF_NOTE_MOVE(d)                                                                                   \
         if ((d) < 0.0) { lo = (d) < lo ? (d) : lo; inneg = (d) > inneg ? (d) : inneg; sneg += (d); cneg += 1.0; } \
         else if ((d) > 0.0) { hi = (d) > hi ? (d) : hi; inpos = (d) < inpos ? (d) : inpos; spos += (d); cpos += 1.0; }
-        for (; g + 8 <= g1; g += 8) {                 // 16 loads in flight before the dependent chain
+        // 16 loads in flight before the dependent chain; the last (partial) batch re-reads its final row instead of falling
+        // back to one load-wait per generator (the kernel is bound by load latency)
+        for (; g < g1; g += 8) {
             double pn[8], pc[8];
+            const int nv = g1 - g < 8 ? g1 - g : 8;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-            for (int u = 0; u < 8; ++u) { pn[u] = Pn[(size_t)(g + u) * v.T + t]; pc[u] = Pc[(size_t)(g + u) * v.T + t]; }
+            for (int u = 0; u < 8; ++u) { const size_t o = (size_t)(g + (u < nv ? u : nv - 1)) * v.T + t; pn[u] = Pn[o]; pc[u] = Pc[o]; }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-            for (int u = 0; u < 8; ++u) { const double d = pn[u] - pc[u]; a += pn[u]; DOPF_NOTE_MOVE(d) }
-        }
-        for (; g < g1; ++g) {
-            const size_t o = (size_t)g * v.T + t;
-            const double pn = Pn[o], d = pn - Pc[o];
-            a += pn;
-            DOPF_NOTE_MOVE(d)
+            for (int u = 0; u < 8; ++u) if (u < nv) { const double d = pn[u] - pc[u]; a += pn[u]; DOPF_NOTE_MOVE(d) }
         }
         const double *Dn = sel(v.D, nxt), *Dc = sel(v.D, cur), *Cn = sel(v.C, nxt), *Cc = sel(v.C, cur);
         const int s1 = v.sto_ptr[vn + 1];
         int s = v.sto_ptr[vn];
-        for (; s + 4 <= s1; s += 4) {
+        for (; s < s1; s += 4) {
             double dn_[4], dc_[4], cn_[4], cc_[4];
+            const int nv = s1 - s < 4 ? s1 - s : 4;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
             for (int u = 0; u < 4; ++u) {
-                const size_t o = (size_t)(s + u) * v.T + t;
+                const size_t o = (size_t)(s + (u < nv ? u : nv - 1)) * v.T + t;
                 dn_[u] = Dn[o]; dc_[u] = Dc[o]; cn_[u] = Cn[o]; cc_[u] = Cc[o];
             }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-            for (int u = 0; u < 4; ++u) { const double d = (dn_[u] - dc_[u]) - (cn_[u] - cc_[u]); a += dn_[u] - cn_[u]; DOPF_NOTE_MOVE(d) }
-        }
-        for (; s < s1; ++s) {
-            const size_t o = (size_t)s * v.T + t;
-            const double dn_ = Dn[o], cn_ = Cn[o];
-            const double d = (dn_ - Dc[o]) - (cn_ - Cc[o]);
-            a += dn_ - cn_;
-            DOPF_NOTE_MOVE(d)
+            for (int u = 0; u < 4; ++u) if (u < nv) { const double d = (dn_[u] - dc_[u]) - (cn_[u] - cc_[u]); a += dn_[u] - cn_[u]; DOPF_NOTE_MOVE(d) }
         }
 #undef DOPF_NOTE_MOVE
     }

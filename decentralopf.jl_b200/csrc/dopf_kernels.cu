@@ -882,7 +882,7 @@ __global__ void __launch_bounds__(128) k_gen_fix(View v)
 // block = 8 nodes x 32 timesteps: warp w sums the agents of node 8*blockIdx.x+w with the lanes along t (the
 // agent arrays are t-contiguous); the node statistics are stored timestep-major ([ldt][Np], read along the
 // nodes by k_slack_rows), so they go through a shared-memory transpose and leave as 64-byte runs.
-__global__ void __launch_bounds__(256) k_inject(View v)
+__global__ void __launch_bounds__(256, 4) k_inject(View v)
 {
     if (!DOPF_ACTIVE(v)) return;
     __shared__ double tile[8][32][9];

@@ -126,6 +126,41 @@ class PartitionedADMM:
         self.dev.close()
 
 
+class LibraryCommADMM:
+    """One rank of an agent-partitioned run with the collectives INSIDE libdopf (dopf_comm_init, SURVEY.md 8(b) "n_gpus"): the
+    host only hands the 128 opaque bytes of the NCCL id from rank 0 to the other ranks, then calls the ordinary dopf_step -
+    the call surface a Julia driver uses.  `exchange_id(bytes_or_None) -> bytes` is any broadcast from rank 0
+    (default: torch.distributed.broadcast_object_list on the default process group)."""
+
+    def __init__(self, prob: Problem, rank, world, device, exchange_id=None, **cfg):
+        from .device import DeviceADMM, DopfError
+        self.rank, self.world, self.full = rank, world, prob
+        self.sub, self.gen_index, self.sto_index = shard_problem(prob, rank, world)
+        self.dev = DeviceADMM(self.sub, device=device, **cfg)
+        d = self.dev
+        idb = C.create_string_buffer(128)
+        if rank == 0:
+            rc = d.lib.dopf_comm_get_unique_id(idb)
+            if rc != 0:
+                raise DopfError(f"dopf_comm_get_unique_id rc={rc}: {d.lib.dopf_last_error(None).decode()}")
+        if world > 1:
+            if exchange_id is None:
+                import torch.distributed as tdist
+
+                def exchange_id(b):
+                    box = [b]
+                    tdist.broadcast_object_list(box, src=0)
+                    return box[0]
+            idb.raw = exchange_id(idb.raw if rank == 0 else None)
+        d._check(d.lib.dopf_comm_init(d.h, idb, rank, world, prob.G + prob.S), "dopf_comm_init")
+
+    def step(self, iters=1):
+        return self.dev.step(iters)
+
+    def close(self):
+        self.dev.close()
+
+
 class LocalPartitionGroup:
     """`world` partition handles inside ONE process on ONE device, stepped in lockstep with the all-reduces done by
     plain torch ops on the exchange buffers.  It drives exactly the library code of the multi-GPU mode

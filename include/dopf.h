@@ -40,7 +40,7 @@ extern "C" {
 #define DOPF_E_ARG (-1)       /* invalid argument / dimension                         */
 #define DOPF_E_CUDA (-2)      /* CUDA runtime error (incl. "no device")               */
 #define DOPF_E_CAPACITY (-3)  /* a device work list / hinge list capacity was exceeded */
-#define DOPF_E_COMM (-4)      /* reserved (the collectives of the partitioned mode are the caller's) */
+#define DOPF_E_COMM (-4)      /* NCCL could not be loaded / a collective of dopf_comm_init or dopf_step failed */
 #define DOPF_E_UNSUPPORTED (-5)
 
 typedef struct dopf_handle dopf_handle;
@@ -165,6 +165,17 @@ int dopf_step_phase(dopf_handle *h, int32_t phase);
 /* device pointer and element count (float64, or the bit pattern of non-negative float64 for DMAX) of
  * the buffer to all-reduce after `phase` = which */
 int dopf_exchange_buffer(dopf_handle *h, int32_t which, void **device_ptr, int64_t *count);
+
+/* The same partition with the collectives INSIDE the library (SURVEY.md 8(b) "n_gpus"): the host - Julia included - only
+ * moves DOPF_COMM_ID_BYTES opaque bytes from rank 0 to the other ranks (any transport: MPI, a file, a socket).
+ *     rank 0:    dopf_comm_get_unique_id(id)               (ncclGetUniqueId; libnccl.so.2 is loaded at run time)
+ *     all ranks: dopf_create(... the rank's block of the agents ...); dopf_comm_init(h, id, rank, nranks, total_agents)
+ *     all ranks: dopf_step(h, n, &status)   - same call as on one GPU: the four phases and the three ncclAllReduce of every
+ *                                             iteration run on the library's stream, captured in ONE CUDA graph (use_graph).
+ * All ranks must call dopf_step with the same max_iters.  A device-side capacity error of any rank stops every rank. */
+#define DOPF_COMM_ID_BYTES 128
+int dopf_comm_get_unique_id(void *id_out /*[DOPF_COMM_ID_BYTES]*/);
+int dopf_comm_init(dopf_handle *h, const void *id /*[DOPF_COMM_ID_BYTES]*/, int32_t rank, int32_t nranks, int32_t total_agents);
 
 /* diagnostics: 32 device-side event counters (all zero unless the library was built with -DDOPF_STATS) */
 int dopf_debug_counters(dopf_handle *h, uint64_t *out /*[32]*/, int32_t reset);

@@ -65,6 +65,29 @@ def test_capacity_error_of_a_partition_surfaces(pkg):
     assert raised > 0
 
 
+def test_library_owned_communicator_single_rank(pkg):
+    """dopf_comm_init / dopf_step with the NCCL collectives issued by libdopf itself (one rank: every collective still runs,
+    the iteration - kernels and ncclAllReduce - is captured in the library's CUDA graph) == a plain single handle"""
+    from dopf_b200 import multi
+    from dopf_b200.device import DeviceADMM
+    N, L, G, S, T = 118, 186, 1000, 200, 24
+    d = pkg.cases.synthetic_arrays(N=N, L=L, G=G, S=S, T=T, seed=2)
+    prob = pkg.Problem.from_arrays(d); A = G + S
+    cfg = dict(gamma=0.3 / A, flow_weight=1.0 / A, hinge_capacity=64)
+    com = multi.LibraryCommADMM(prob, 0, 1, 0, **cfg)
+    ref = DeviceADMM(prob, device=0, **cfg)
+    st = com.step(1); st = com.step(29); ref.step(30)
+    assert st.iterations_done == 30 == ref.status.iterations_done
+    it = com.dev.get_iterate(); rit = ref.get_iterate()
+    gi, si = com.gen_index, com.sto_index
+    assert _rel(it["P"], rit["P"][gi]) < 1e-9 and _rel(it["D"], rit["D"][si]) < 1e-9 and _rel(it["E"], rit["E"][si]) < 1e-9
+    for k in ("injection", "flow", "avgU", "avgK"):
+        assert _rel(it[k], rit[k]) < 1e-9, k
+    for a, b in zip(com.dev.get_duals(0), ref.get_duals(0)):
+        assert _rel(a, b) < 1e-9
+    com.close(); ref.close()
+
+
 def test_two_gpu_nccl_run_equals_single_gpu():
     import torch
     if torch.cuda.device_count() < 2:
