@@ -226,7 +226,13 @@ def run_dopf(args):
     N, L, G, S, T = WORKLOADS[args.workload]
     prob, cfg, units_per_rank, parallelism = build_problem(pkg, args, rank, world)
     partitioned = args.workload != "cfg4" and ((world > 1 and args.shard == "agents") or args.path == "partitioned")
-    if partitioned:
+    libcomm = None
+    if partitioned and args.comm == "library":
+        # collectives inside libdopf (dopf_comm_init): the ordinary dopf_step drives the partitioned iteration
+        from dopf_b200 import multi
+        libcomm = multi.LibraryCommADMM(prob, rank, world, local, hinge_capacity=64, use_graph=not args.no_graph, **cfg)
+        part, dev = None, libcomm.dev
+    elif partitioned:
         from dopf_b200 import multi
         part = multi.PartitionedADMM(prob, rank, world, local, hinge_capacity=64, graph=not args.no_graph, **cfg)
         dev = part.dev
@@ -274,7 +280,7 @@ def run_dopf(args):
                   tight_rows=st.tight_rows, wide_rows=st.wide_rows, residuals=[st.res_lambda, st.res_mue, st.res_rho])
 
     # ---- per-kernel device times of the NEXT iteration (CUDA event pair per launch) -> roofline ----
-    prof = dev.profile_iteration() if part is None else []
+    prof = dev.profile_iteration() if part is None and libcomm is None else []
     kern = {}
     for name, ms in prof:
         kern[name] = kern.get(name, 0.0) + ms
@@ -299,7 +305,7 @@ def run_dopf(args):
         if name.startswith("k_gemm") and "true" in name: return 4.0 * L * N * T * C      # PTDF^T M and (PTDF.^2)^T W
         if name.startswith("k_gemm"): return 2.0 * L * N * T * C
         return None
-    dgemm = measure_dgemm_peak(torch, L, N, T * C) if rank == 0 and part is None else {}
+    dgemm = measure_dgemm_peak(torch, L, N, T * C) if rank == 0 and part is None and libcomm is None else {}
     fp64_peak = max(dgemm.values()) if dgemm else 37.0
     if dom is None:
         roof = None
@@ -335,7 +341,7 @@ def run_dopf(args):
     # ---- steady state: the same measurement after the transient (iterations 151.. of this run) ----
     steady = None
     if not args.quick:
-        done = args.warmup + args.steps + (1 if part is None else 0)
+        done = args.warmup + args.steps + (1 if part is None and libcomm is None else 0)
         if done < 150:
             (part or dev).step(150 - done)
         ms_s, st_s = timed(args.steps)
@@ -358,11 +364,11 @@ def run_dopf(args):
     iteration = dev.status.iteration
     barrier()
     t0 = time.perf_counter()
-    if part is not None:
+    if part is not None or libcomm is not None:
         h2d = 0
     for _ in range(e2e_steps):
-        if part is not None:
-            part.step(1)                       # state stays on the device; results are read back every step
+        if part is not None or libcomm is not None:
+            (part or dev).step(1)              # state stays on the device; results are read back every step
         else:
             dev.set_state(iteration, P=hb["P"], D=hb["D"], C_=hb["C"], avgU=hb["avgU"], avgK=hb["avgK"], lam=hl, mu=hm, rho=hr)
             dev.step(1)
@@ -391,12 +397,14 @@ def run_dopf(args):
                 "clocks": clk, "roofline": roof,
                 "kernels_ms": {k: round(v, 4) for k, v in kern.items()},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "steps": e2e_steps, "what": ("partitioned run: iterate + dopf_get_iterate/duals(host) every step (no per-step upload)" if part is not None
+                        "steps": e2e_steps, "what": ("partitioned run: iterate + dopf_get_iterate/duals(host) every step (no per-step upload)" if (part is not None or libcomm is not None)
                                                      else "dopf_set_state(host) + dopf_step(1) + dopf_get_iterate/duals(host), pinned buffers")},
                 "timed_window": window, "steady_state": steady}
         if part is not None:
             line["partitioned_graph"] = {"captured": part.graph is not None, "error": part.graph_error}
-        if world == 1 and not args.quick and part is None and args.workload != "cfg4":
+        if libcomm is not None:
+            line["collectives"] = "library-owned NCCL communicator (dopf_comm_init), iteration + ncclAllReduce captured in libdopf's CUDA graph"
+        if world == 1 and not args.quick and part is None and libcomm is None and args.workload != "cfg4":
             # the same window (5 warm-up + 20 timed iterations from the cold start) with the other parameter sets
             alts = []
             for name in PARAMS:
@@ -413,7 +421,7 @@ def run_dopf(args):
                     alts.append({"params": name, "error": str(e)})
                 ad.close()
             line["alt_params"] = alts
-        if world == 1 and part is None:
+        if world == 1 and part is None and libcomm is None:
             # time to tolerance on the reference's own case (three_node, gamma 0.3, literal weights, eps 1e-3: stops at
             # iteration 476 like src/opf_admm_decentral.jl) - SURVEY.md 8(d) "time-to-tolerance"
             try:
@@ -453,6 +461,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="agent partition: N x the workload's agents (weak) or the workload's agents split over the ranks (strong)")
     ap.add_argument("--path", default="auto", choices=["auto", "partitioned"], help="partitioned: also N=1 runs through the phase-wise multi-GPU code path (like-for-like scaling baseline)")
     ap.add_argument("--params", default="ref_ratio", choices=sorted(PARAMS), help="ADMM parameter set (see PARAMS)")
+    ap.add_argument("--comm", default="torch", choices=["torch", "library"], help="partitioned path: all-reduces by torch.distributed between dopf_step_phase calls, or by libdopf itself (dopf_comm_init + dopf_step)")
     ap.add_argument("--no-graph", action="store_true", help="partitioned path without the CUDA graph (eager launches from Python)")
     ap.add_argument("--quick", action="store_true", help="skip the steady-state / alt-params / cpu-baseline legs")
     args = ap.parse_args()
