@@ -296,6 +296,7 @@ static int create_impl(dopf_handle *h, const dopf_problem *p, const dopf_config 
 #define AL(ptr, count) if ((rc = dev_alloc(h, &ptr, (size_t)(count)))) return rc
     for (int k = 0; k < 2; ++k) {
         AL(v.P[k], (size_t)G * T); AL(v.D[k], (size_t)S * T); AL(v.C[k], (size_t)S * T);
+        if (k == 0) { AL(v.ssum_part, (size_t)COLSUM_R * ldt); AL(v.colsum_cnt, ldt / 32); }
         AL(v.inj[k], (size_t)Np * ldt); AL(v.ssum[k], ldt); AL(v.flow[k], (size_t)Lp * ldt);
         AL(v.lam[k], ldt); AL(v.mu[k], (size_t)Lp * ldt); AL(v.rho[k], (size_t)Lp * ldt);
         v.injloc[k] = v.inj[k];

@@ -90,6 +90,8 @@ struct View {
     double *injloc[2];      // [Np][ldt]  contribution of this rank's agents (== inj on one GPU)
     int demand_on;          // 1: this rank subtracts the demand (rank 0)
     double *ssum[2];        // [ldt]   sum_n inj
+    double *ssum_part;      // [COLSUM_R][ldt] partial column sums (fixed row groups, folded in order by the last block)
+    int *colsum_cnt;        // [ldt/32] arrival counters of k_colsum (self-resetting)
     double *flow[2];        // [Lp][ldt]
     double *avgU, *avgK;    // [Lp][ldt]
     double *lam[2];         // [ldt]

@@ -918,18 +918,37 @@ __global__ void k_dmax(View v)
     }
 }
 
-__global__ void k_colsum(View v)   // block (32,32): 32 timesteps, 32 row groups
+// grid (ldt/32, COLSUM_R), block (32,32): 32 columns x 32 rows in flight; block y sums its fixed group of node rows, the
+// last block of a column group to arrive adds the COLSUM_R partial sums in order (deterministic, and 8x the blocks of a
+// single pass - the kernel is latency bound)
+__global__ void k_colsum(View v)
 {
     if (!DOPF_ACTIVE(v)) return;
     __shared__ double part[32][33];
+    __shared__ int last;
     const int t = blockIdx.x * 32 + threadIdx.x, nxt = 1 - v.ctrl->cur;
+    const int rows = v.Np / COLSUM_R, n0 = blockIdx.y * rows;       // Np is a multiple of 64
     double a = 0.0;
-    for (int n = threadIdx.y; n < v.Np; n += 32) a += sel(v.inj, nxt)[(size_t)n * v.ldt + t];
+    for (int n = n0 + threadIdx.y; n < n0 + rows; n += 32) a += sel(v.inj, nxt)[(size_t)n * v.ldt + t];
     part[threadIdx.y][threadIdx.x] = a;
     __syncthreads();
     if (threadIdx.y == 0) {
         double s = 0.0;
         for (int k = 0; k < 32; ++k) s += part[k][threadIdx.x];
+        v.ssum_part[(size_t)blockIdx.y * v.ldt + t] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const int arrived = atomicAdd(&v.colsum_cnt[blockIdx.x], 1);
+        last = arrived == COLSUM_R - 1;
+        if (last) v.colsum_cnt[blockIdx.x] = 0;
+    }
+    __syncthreads();
+    if (last && threadIdx.y == 0) {
+        __threadfence();
+        double s = 0.0;
+        for (int r = 0; r < COLSUM_R; ++r) s += __ldcg(&v.ssum_part[(size_t)r * v.ldt + t]);
         sel(v.ssum, nxt)[t] = s;
     }
 }
@@ -1418,8 +1437,12 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
     XCHG(DOPF_X_DMAX);   // all ranks must build the same tight lists
     // moves may have grown: lists of the columns whose largest move changed are rebuilt (single-GPU mode: 2 = compare with
     // the maximum the first pass used; partitioned mode: the maxima were just exchanged)
+    // (the list rebuild is a small latency-bound kernel, the aggregation a bandwidth-bound one, and neither reads what the
+    // other writes: side by side)
+    FORK();
     if (v.L <= 1024) LAUNCH(k_compact_w<<<cdiv(v.TC, 8), 256, 0, cs>>>(v, 1, segment < 0 ? 2 : 0));
     else LAUNCH(k_compact<<<v.TC, 256, 0, cs>>>(v, 1, segment < 0 ? 2 : 0));
+    MAIN();
     LAUNCH(k_inject<<<dim3(v.Np / 8, v.ldt / 32), 256, 0, cs>>>(v));
     if (v.flowD) {   // partitioned mode: partial flow of the rank's own injection over its own node range (1/ranks of the product)
         dim3 grid(v.Lp / lp.bm_x, v.ldt / BN, lp.ksplit_x);
@@ -1428,11 +1451,12 @@ int enqueue_iteration(const LaunchPlan &lp, cudaStream_t st, int segment)
         else LAUNCH(k_gemm<32, false><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, dst, nullptr, v.Lp, lp.mt_rows, lp.ksplit_x, 0, v.injloc[0], lp.mt_base));
         if (lp.ksplit_x > 1) LAUNCH(k_flow_reduce<<<cdiv((long long)v.Lp * v.ldt, 256), 256, 0, cs>>>(v, lp.part, lp.ksplit_x, v.xflow));
     }
+    JOIN();
     XCHG(DOPF_X_INJ);    // nodal injection of all ranks' agents
     LAUNCH(k_slack_rows<<<dim3(lp.slack_blocks_x, v.TC), (v.N <= 256 ? 128 : 512), 0, cs>>>(v, lp.tflag));   // needs the local injection statistics only
     LAUNCH(k_slack_pairs<<<lp.num_sms * 2, 256, 0, cs>>>(v));
     LAUNCH(k_slack_fold<<<dim3(FOLD_X, v.TC), 256, 0, cs>>>(v));
-    LAUNCH(k_colsum<<<v.ldt / 32, dim3(32, 32), 0, cs>>>(v));
+    LAUNCH(k_colsum<<<dim3(v.ldt / 32, COLSUM_R), dim3(32, 32), 0, cs>>>(v));
     if (!v.flowD) {   // flow = PTDF * inj
         dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);
         if (lp.bm_n == 64) LAUNCH(k_gemm<64, false><<<grid, 128, 0, cs>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n, 0));
@@ -1554,7 +1578,7 @@ void launch_rebuild_derived(const LaunchPlan &lp, cudaStream_t st, int segment)
     const View &v = lp.view;
     if (segment <= 0) k_inject<<<dim3(v.Np / 8, v.ldt / 32), 256, 0, st>>>(v);
     if (segment == 0) return;
-    k_colsum<<<v.ldt / 32, dim3(32, 32), 0, st>>>(v);
+    k_colsum<<<dim3(v.ldt / 32, COLSUM_R), dim3(32, 32), 0, st>>>(v);
     dim3 grid(v.Lp / lp.bm_n, v.ldt / BN, lp.ksplit_n);
     if (lp.bm_n == 64) k_gemm<64, false><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n, 0);
     else k_gemm<32, false><<<grid, 128, 0, st>>>(v, v.ptdf, v.Np, v.ldt, lp.part, nullptr, v.Lp, v.Np, lp.ksplit_n, 0);

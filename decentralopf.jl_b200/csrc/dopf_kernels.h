@@ -6,6 +6,8 @@
 
 namespace dopf {
 
+constexpr int COLSUM_R = 8;     // row groups of the column sums of the injection (k_colsum)
+
 struct LaunchPlan {
     View view;
     int num_sms;
