@@ -262,3 +262,23 @@ function run_on_device!(admm::ADMM; max_iterations = 1_000_000)
     admm.convergence.all = s.converged != 0
     return admm
 end
+
+# ---- multi-GPU (one Julia process per GPU; SURVEY.md 8(e) agent block) --------------------------------------------------
+# The collectives live inside libdopf (dopf_comm_init: libnccl is loaded at run time, the iteration and its three
+# ncclAllReduce are captured in one CUDA graph), so the host side only has to move 128 opaque bytes from rank 0 to the other
+# ranks - with MPI.jl, a shared file, a socket - and build `admm` from ITS block of the node-sorted generators and storages
+# (include/dopf.h "multi-GPU").  After this call `run!(admm)`, `calculate_iteration!(admm)` and `run_on_device!(admm)` are the
+# same calls as on one GPU; the duals, flows and convergence flags are identical on all ranks.
+const DOPF_COMM_ID_BYTES = 128
+function dopf_comm_unique_id()
+    id = zeros(UInt8, DOPF_COMM_ID_BYTES)
+    rc = ccall((:dopf_comm_get_unique_id, libdopf), Cint, (Ptr{UInt8},), id)
+    rc == 0 || error("dopf_comm_get_unique_id failed (rc=$rc): " * unsafe_string(ccall((:dopf_last_error, libdopf), Cstring, (Ptr{Cvoid},), C_NULL)))
+    return id
+end
+function dopf_comm_init!(admm::ADMM, id::Vector{UInt8}, rank::Integer, nranks::Integer, total_agents::Integer)
+    length(id) == DOPF_COMM_ID_BYTES || error("the NCCL id has $DOPF_COMM_ID_BYTES bytes")
+    rc = ccall((:dopf_comm_init, libdopf), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint, Cint), admm.handle, id, rank, nranks, total_agents)
+    dopf_check(admm.handle, rc, "dopf_comm_init")
+    return admm
+end
