@@ -190,6 +190,71 @@ DOPF_HD void sto_dc_of_nu(const StoStep &st, const StoConst &k, double nu, doubl
     nfree = (du > 0.0 && du < k.pmax) + (cu > 0.0 && cu < k.pmax);
 }
 
+// ---- per-timestep clip table of the hinge-free storage step (independent of eta) ---------------------------------
+// Psi(nu) = nu - (g0 - eta) - s1*delta(nu) is piecewise linear with the four clip breakpoints bb[0..3] of D(nu), C(nu);
+// Psi(bb[i]) = eta - e[i] with the eta-thresholds e[i] = g0 + s1*dl[i] - bb[i] (non-increasing in i, dl[i] = delta at
+// bb[i]).  The thresholds cut the eta-axis into five pieces p = #{i : eta < e[i]}; on piece p nu is affine in eta,
+// nu = nu0[p] + nus[p]*eta, and dy/deta = dyv[p] is constant.  On a piece with nf free variables Psi has slope
+// 1 + nf*s1/prox, whose inverse is prox*r_nf with r_nf = 1/(prox + nf*s1) (r1, r2 passed in): no division here.
+//
+// Closed form: with u1 = pmax - D = clip((nu - c1)/prox, 0, pmax) and u2 = C = clip((nu - c2)/prox, 0, pmax) the move is
+// delta = K - (u1 + u2), K = pmax - Db + Cb, and u1 + u2 at the sorted breakpoints is 0, (bb1-bb0)/prox,
+// 2 pmax - (bb3-bb2)/prox, 2 pmax; the middle piece has two free variables if the two ramps overlap and none otherwise.
+DOPF_HD void sto_clip_table(const StoStep &st, const StoConst &k, double r1, double r2, double (&e)[4], double (&nu0)[5], double (&nus)[5], double (&dyv)[5])
+{
+    const double b0 = k.prox * (st.Db - k.pmax) - k.mc, b1 = k.prox * st.Db - k.mc;          // D leaves pmax / reaches 0
+    const double b2 = k.mc - k.prox * st.Cb, b3 = k.mc + k.prox * (k.pmax - st.Cb);          // C leaves 0 / reaches pmax
+    const double lo_hi = b0 > b2 ? b0 : b2, hi_lo = b1 < b3 ? b1 : b3;                        // later ramp start, earlier ramp end
+    double bb[4];
+    bb[0] = b0 < b2 ? b0 : b2; bb[3] = b1 > b3 ? b1 : b3;
+    bb[1] = lo_hi < hi_lo ? lo_hi : hi_lo; bb[2] = lo_hi < hi_lo ? hi_lo : lo_hi;
+    const bool overlap = lo_hi < hi_lo;
+    const double K = k.pmax - st.Db + st.Cb;
+    const double su[4] = { 0.0, (bb[1] - bb[0]) * k.iprox, 2.0 * k.pmax - (bb[3] - bb[2]) * k.iprox, 2.0 * k.pmax };
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 4; ++i) e[i] = st.g0 + st.s1 * (K - su[i]) - bb[i];
+    nu0[0] = bb[0] + e[0]; nus[0] = -1.0; dyv[0] = 0.0;           // outer pieces: both variables clipped, slope 1
+    nu0[4] = bb[3] + e[3]; nus[4] = -1.0; dyv[4] = 0.0;
+    const int nfp[3] = { bb[1] > bb[0] ? 1 : 0, overlap ? 2 : 0, bb[3] > bb[2] ? 1 : 0 };
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int f = 0; f < 3; ++f) {     // inner piece between bb[f] and bb[f+1] = eta-piece p = f+1, anchored at breakpoint f
+        const int nf = nfp[f];
+        const double rn = nf == 1 ? r1 : r2;
+        const double as = nf == 0 ? 1.0 : k.prox * rn;
+        nu0[f + 1] = bb[f] + e[f] * as; nus[f + 1] = -as; dyv[f + 1] = nf == 0 ? 0.0 : -(double)nf * rn;
+    }
+}
+// the same table from evaluations of D, C at the breakpoints and at the piece midpoints (the form the closed form is
+// checked against in tests/test_host_math.py)
+DOPF_HD void sto_clip_table_ref(const StoStep &st, const StoConst &k, double r1, double r2, double (&e)[4], double (&nu0)[5], double (&nus)[5], double (&dyv)[5])
+{
+    double b0 = k.prox * (st.Db - k.pmax) - k.mc, b1 = k.prox * st.Db - k.mc;
+    double b2 = k.mc - k.prox * st.Cb, b3 = k.mc + k.prox * (k.pmax - st.Cb);
+    double x;
+    if (b0 > b2) { x = b0; b0 = b2; b2 = x; }
+    if (b1 > b3) { x = b1; b1 = b3; b3 = x; }
+    if (b1 > b2) { x = b1; b1 = b2; b2 = x; }
+    const double bb[4] = { b0, b1, b2, b3 };
+    for (int i = 0; i < 4; ++i) {
+        double D, C; int nf;
+        sto_dc_of_nu(st, k, bb[i], D, C, nf);
+        e[i] = st.g0 + st.s1 * ((D - st.Db) - (C - st.Cb)) - bb[i];
+    }
+    nu0[0] = bb[0] + e[0]; nus[0] = -1.0; dyv[0] = 0.0;
+    nu0[4] = bb[3] + e[3]; nus[4] = -1.0; dyv[4] = 0.0;
+    for (int f = 0; f < 3; ++f) {
+        double D, C; int nf;
+        sto_dc_of_nu(st, k, 0.5 * (bb[f] + bb[f + 1]), D, C, nf);
+        const double rn = nf == 1 ? r1 : r2;
+        const double as = nf == 0 ? 1.0 : k.prox * rn;
+        nu0[f + 1] = bb[f] + e[f] * as; nus[f + 1] = -as; dyv[f + 1] = nf == 0 ? 0.0 : -(double)nf * rn;
+    }
+}
+
 DOPF_HD StoEval sto_eval(const StoStep &st, const StoConst &k, const HingeList &hl, double eta)
 {
     const double base = st.g0 - eta;

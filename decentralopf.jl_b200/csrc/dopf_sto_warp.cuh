@@ -212,32 +212,13 @@ constexpr int TAB_E = 0, TAB_NU0 = 4, TAB_NUS = 9, TAB_DY = 14, TAB_COMPS = 19;
 
 __device__ __forceinline__ void clip_tab_build(const StoStep &st, const StoConst &k, double r1, double r2, double *tab, int tstride, int t)
 {
-    double b0 = k.prox * (st.Db - k.pmax) - k.mc, b1 = k.prox * st.Db - k.mc;
-    double b2 = k.mc - k.prox * st.Cb, b3 = k.mc + k.prox * (k.pmax - st.Cb);
-    double x;
-    if (b0 > b2) { x = b0; b0 = b2; b2 = x; }
-    if (b1 > b3) { x = b1; b1 = b3; b3 = x; }
-    if (b1 > b2) { x = b1; b1 = b2; b2 = x; }
-    const double bb[4] = { b0, b1, b2, b3 };
-    double e[4];
+    double e[4], nu0[5], nus[5], dyv[5];
+    sto_clip_table(st, k, r1, r2, e, nu0, nus, dyv);          // closed form, dopf_math.h
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        double D, C; int nf;
-        sto_dc_of_nu(st, k, bb[i], D, C, nf);
-        e[i] = st.g0 + st.s1 * ((D - st.Db) - (C - st.Cb)) - bb[i];
-        tab[(TAB_E + i) * tstride + t] = e[i];
-    }
-    // outer pieces: both variables clipped, slope 1
-    tab[(TAB_NU0 + 0) * tstride + t] = bb[0] + e[0]; tab[(TAB_NUS + 0) * tstride + t] = -1.0; tab[(TAB_DY + 0) * tstride + t] = 0.0;
-    tab[(TAB_NU0 + 4) * tstride + t] = bb[3] + e[3]; tab[(TAB_NUS + 4) * tstride + t] = -1.0; tab[(TAB_DY + 4) * tstride + t] = 0.0;
+    for (int i = 0; i < 4; ++i) tab[(TAB_E + i) * tstride + t] = e[i];
 #pragma unroll
-    for (int f = 0; f < 3; ++f) {     // inner piece between bb[f] and bb[f+1] = eta-piece p = f+1, anchored at breakpoint f
-        double D, C; int nf;
-        sto_dc_of_nu(st, k, 0.5 * (bb[f] + bb[f + 1]), D, C, nf);
-        const double rn = nf == 1 ? r1 : r2;
-        const double as = nf == 0 ? 1.0 : k.prox * rn;
-        tab[(TAB_NU0 + f + 1) * tstride + t] = bb[f] + e[f] * as; tab[(TAB_NUS + f + 1) * tstride + t] = -as;
-        tab[(TAB_DY + f + 1) * tstride + t] = nf == 0 ? 0.0 : -(double)nf * rn;
+    for (int p = 0; p < 5; ++p) {
+        tab[(TAB_NU0 + p) * tstride + t] = nu0[p]; tab[(TAB_NUS + p) * tstride + t] = nus[p]; tab[(TAB_DY + p) * tstride + t] = dyv[p];
     }
 }
 // same result as sto_eval() for a hinge-free step

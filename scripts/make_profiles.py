@@ -34,7 +34,7 @@ with open(os.path.join(pr, f"{rnd}_kernel_shares.md"), "w") as f:
     for k, v in sorted(km.items(), key=lambda kv: -kv[1]):
         f.write(f"| {k} | {v:.4f} | {100 * v / ks:.1f} % |\n")
     f.write(f"\nsum of kernels {ks:.3f} ms (serial, each launch bracketed by events); graph replay with the fork/join of the independent groups "
-            f"(storages | generators, slack sums | flow product): {line['ms_per_step']:.3f} ms per iteration over the {line['steps']} timed iterations.\n\n")
+            f"(storages | generators in the predict and in the correction pass, list rebuild | aggregation): {line['ms_per_step']:.3f} ms per iteration over the {line['steps']} timed iterations.\n\n")
     f.write("## ncu launch list of the same bench command (`ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 python bench.py --steps 20 --warmup 5 --quick --no-cpu-baseline`)\n\n"
             "Cold-cache and serialised; covers the set-up, the 5 warm-up and the 20 timed iterations (the cold-start transient): compare SHARES.\n\n```\n")
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):

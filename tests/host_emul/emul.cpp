@@ -8,6 +8,26 @@ using namespace dopf;
 
 extern "C" {
 
+// clip table of one hinge-free storage step: which = 0 closed form (the device build), 1 evaluation-based reference;
+// out = e[4] | nu0[5] | nus[5] | dy[5]
+void emul_clip_table(double Db, double Cb, double g0, double s1, double mc, double pmax, double prox, int which, double *out)
+{
+    StoStep st; st.Db = Db; st.Cb = Cb; st.g0 = g0; st.s1 = s1;
+    StoConst k; k.mc = mc; k.pmax = pmax; k.emax = 0.0; k.prox = prox; k.iprox = 1.0 / prox;
+    double e[4], nu0[5], nus[5], dy[5];
+    const double r1 = 1.0 / (prox + s1), r2 = 1.0 / (prox + 2.0 * s1);
+    if (which == 0) sto_clip_table(st, k, r1, r2, e, nu0, nus, dy); else sto_clip_table_ref(st, k, r1, r2, e, nu0, nus, dy);
+    for (int i = 0; i < 4; ++i) out[i] = e[i];
+    for (int i = 0; i < 5; ++i) { out[4 + i] = nu0[i]; out[9 + i] = nus[i]; out[14 + i] = dy[i]; }
+}
+// D, C, dy of the step at eta through a table (same arithmetic as eval_tab in dopf_sto_warp.cuh)
+void emul_clip_eval(const double *tab, double Db, double Cb, double mc, double pmax, double prox, double eta, double *out)
+{
+    const int p = (eta < tab[0]) + (eta < tab[1]) + (eta < tab[2]) + (eta < tab[3]);
+    const double nu = tab[4 + p] + tab[9 + p] * eta;
+    out[0] = clip01(Db - (mc + nu) / prox, pmax); out[1] = clip01(Cb - (mc - nu) / prox, pmax); out[2] = tab[14 + p]; out[3] = nu;
+}
+
 // storage solve with optional per-t hinge lists (hbp/hsg [T][hcap], hcnt [T]; hcap may be 0)
 void emul_storage_solve(int T, double mc, double pmax, double emax, double prox,
                         const double *Db, const double *Cb, const double *g0, const double *s1,

@@ -194,3 +194,37 @@ def test_pipeline_emulation_equals_oracle_on_synthetic(pkg, emul, oracle_mod, di
         for a, b in ((o.P, e.P), (o.D, e.D), (o.C, e.C), (o.lam, e.lam), (o.mu, e.mu), (o.rho, e.rho), (o.avgU, e.avgU), (o.avgK, e.avgK)):
             assert np.abs(a - b).max() <= 1e-6 * max(1.0, np.abs(a).max())
     assert e.status[6] == 0 and e.status[2] > 0       # the correction pass was exercised
+
+
+def test_clip_table_closed_form_equals_evaluated_table(emul):
+    """The per-timestep clip table of the warp storage solver: the closed form (sto_clip_table, what the device builds) against
+    the table built from evaluations of D, C at the breakpoints and piece midpoints, and both against the defining equation
+    nu = g0 - eta + s1 * delta(nu) at random multipliers - including degenerate steps (pmax = 0, coinciding breakpoints)."""
+    import ctypes as C
+    lib = emul.lib()
+    dbl = C.c_double
+    lib.emul_clip_table.argtypes = [dbl] * 7 + [C.c_int, C.POINTER(dbl)]
+    lib.emul_clip_eval.argtypes = [C.POINTER(dbl)] + [dbl] * 6 + [C.POINTER(dbl)]
+    rng = np.random.default_rng(7)
+    worst_tab = worst_eq = 0.0
+    for trial in range(4000):
+        pmax = float(rng.choice([0.0, 1e-9, 5.0, 37.0, 50.0]))
+        mc = float(rng.choice([0.0, 1.0, 3.5])); prox = float(rng.choice([1.0, 0.25, 4.0]))
+        Db = float(rng.choice([0.0, pmax, rng.uniform(0, pmax)])); Cb = float(rng.choice([0.0, pmax, rng.uniform(0, pmax), Db]))
+        g0 = float(rng.normal(0, 30)); s1 = float(rng.choice([3e-7, 1e-3, 0.3, 2.0]))
+        a = np.zeros(19); b = np.zeros(19)
+        lib.emul_clip_table(Db, Cb, g0, s1, mc, pmax, prox, 0, a.ctypes.data_as(C.POINTER(dbl)))
+        lib.emul_clip_table(Db, Cb, g0, s1, mc, pmax, prox, 1, b.ctypes.data_as(C.POINTER(dbl)))
+        scale = 1.0 + abs(g0) + prox * pmax + mc
+        assert np.all(np.diff(a[:4]) <= 1e-12 * scale), (trial, a[:4])            # thresholds non-increasing
+        worst_tab = max(worst_tab, np.abs(a[:4] - b[:4]).max() / scale)
+        etas = np.concatenate([rng.normal(g0, 3 * scale, 6), a[:4], a[:4] + 1e-9 * scale, a[:4] - 1e-9 * scale])
+        for eta in etas:
+            oa = np.zeros(4); ob = np.zeros(4)
+            lib.emul_clip_eval(a.ctypes.data_as(C.POINTER(dbl)), Db, Cb, mc, pmax, prox, float(eta), oa.ctypes.data_as(C.POINTER(dbl)))
+            lib.emul_clip_eval(b.ctypes.data_as(C.POINTER(dbl)), Db, Cb, mc, pmax, prox, float(eta), ob.ctypes.data_as(C.POINTER(dbl)))
+            D, Cc, dy, nu = oa
+            # the defining equation of the hinge-free step
+            worst_eq = max(worst_eq, abs(nu - (g0 - eta + s1 * ((D - Db) - (Cc - Cb)))) / (scale + abs(eta)))
+            assert abs(D - ob[0]) <= 1e-10 * (1 + pmax) and abs(Cc - ob[1]) <= 1e-10 * (1 + pmax), (trial, eta, oa, ob)
+    assert worst_tab < 1e-13 and worst_eq < 1e-13, (worst_tab, worst_eq)
