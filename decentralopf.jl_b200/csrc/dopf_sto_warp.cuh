@@ -64,9 +64,13 @@ __device__ __forceinline__ int lane_reach_fwd(const bool (&tail)[J])
     return x >= 64 ? 0 : x - lane;                // 0 if this lane holds a tail (or none follows)
 }
 
+// largest reach of any lane: scan levels beyond it change nothing and are skipped (runs between level anchors are short -
+// about half of the timesteps of a storage are anchored in the steady state - so most rounds need 1-3 of the 5 levels)
+__device__ __forceinline__ int warp_max_reach(int r) { return (int)__reduce_max_sync(FULL, (unsigned)r); }
+
 // forward inclusive segmented scan of two arrays at once (segments start at head[j])
 template <int J, class OpA, class OpB>
-__device__ __forceinline__ void seg_fwd2(double (&a)[J], double (&b)[J], const bool (&head)[J], int lreach,
+__device__ __forceinline__ void seg_fwd2(double (&a)[J], double (&b)[J], const bool (&head)[J], int lreach, int mreach,
                                          OpA opa, OpB opb, double ida, double idb)
 {
     const int lane = threadIdx.x & 31;
@@ -79,6 +83,7 @@ __device__ __forceinline__ void seg_fwd2(double (&a)[J], double (&b)[J], const b
     double xa = ra, xb = rb;                      // aggregate of the segment that is open at the lane end
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
+        if (mreach < o) break;
         const double ya = __shfl_up_sync(FULL, xa, o), yb = __shfl_up_sync(FULL, xb, o);
         if (lreach >= o) { xa = opa(ya, xa); xb = opb(yb, xb); }
     }
@@ -93,7 +98,7 @@ __device__ __forceinline__ void seg_fwd2(double (&a)[J], double (&b)[J], const b
 }
 // forward inclusive segmented scan of one array
 template <int J, class OpA>
-__device__ __forceinline__ void seg_fwd1(double (&a)[J], const bool (&head)[J], int lreach, OpA opa, double ida)
+__device__ __forceinline__ void seg_fwd1(double (&a)[J], const bool (&head)[J], int lreach, int mreach, OpA opa, double ida)
 {
     const int lane = threadIdx.x & 31;
     double ra = ida;
@@ -101,7 +106,7 @@ __device__ __forceinline__ void seg_fwd1(double (&a)[J], const bool (&head)[J], 
     for (int j = 0; j < J; ++j) { ra = head[j] ? a[j] : opa(ra, a[j]); a[j] = ra; }
     double xa = ra;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const double ya = __shfl_up_sync(FULL, xa, o); if (lreach >= o) xa = opa(ya, xa); }
+    for (int o = 1; o < 32; o <<= 1) { if (mreach < o) break; const double ya = __shfl_up_sync(FULL, xa, o); if (lreach >= o) xa = opa(ya, xa); }
     double ca = __shfl_up_sync(FULL, xa, 1);
     if (lane == 0) ca = ida;
     bool open = true;
@@ -110,7 +115,7 @@ __device__ __forceinline__ void seg_fwd1(double (&a)[J], const bool (&head)[J], 
 }
 // every element takes the value held by the tail of its run (one array of a 32-bit or 64-bit type)
 template <int J, class TB>
-__device__ __forceinline__ void seg_take_tail1(TB (&b)[J], const bool (&tail)[J], int lreach)
+__device__ __forceinline__ void seg_take_tail1(TB (&b)[J], const bool (&tail)[J], int lreach, int mreach)
 {
     const int lane = threadIdx.x & 31;
     TB fb = TB();
@@ -122,14 +127,14 @@ __device__ __forceinline__ void seg_take_tail1(TB (&b)[J], const bool (&tail)[J]
     }
     TB xb = fb;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const TB yb = __shfl_down_sync(FULL, xb, o); if (lreach >= o) xb = yb; }
+    for (int o = 1; o < 32; o <<= 1) { if (mreach < o) break; const TB yb = __shfl_down_sync(FULL, xb, o); if (lreach >= o) xb = yb; }
     const TB cb = __shfl_down_sync(FULL, xb, 1);
     bool seen = false;
 #pragma unroll
     for (int j = J - 1; j >= 0; --j) { if (tail[j]) seen = true; if (!seen && lane < 31) b[j] = cb; }
 }
 template <int J>
-__device__ __forceinline__ void seg_fwd_min_int(int (&a)[J], const bool (&head)[J], int lreach)
+__device__ __forceinline__ void seg_fwd_min_int(int (&a)[J], const bool (&head)[J], int lreach, int mreach)
 {
     const int lane = threadIdx.x & 31;
     int r = 0x7fffffff;
@@ -137,7 +142,7 @@ __device__ __forceinline__ void seg_fwd_min_int(int (&a)[J], const bool (&head)[
     for (int j = 0; j < J; ++j) { r = head[j] ? a[j] : min(r, a[j]); a[j] = r; }
     int x = r;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, x, o); if (lreach >= o) x = min(y, x); }
+    for (int o = 1; o < 32; o <<= 1) { if (mreach < o) break; const int y = __shfl_up_sync(FULL, x, o); if (lreach >= o) x = min(y, x); }
     int c = __shfl_up_sync(FULL, x, 1);
     if (lane == 0) c = 0x7fffffff;
     bool open = true;
@@ -146,7 +151,7 @@ __device__ __forceinline__ void seg_fwd_min_int(int (&a)[J], const bool (&head)[
 }
 // every element takes the values held by the tail of its run
 template <int J, class TB>
-__device__ __forceinline__ void seg_take_tail(double (&a)[J], TB (&b)[J], const bool (&tail)[J], int lreach)
+__device__ __forceinline__ void seg_take_tail(double (&a)[J], TB (&b)[J], const bool (&tail)[J], int lreach, int mreach)
 {
     const int lane = threadIdx.x & 31;
     double fa = 0.0; TB fb = TB();               // values at the lane's FIRST tail (what lanes to the left need)
@@ -161,6 +166,7 @@ __device__ __forceinline__ void seg_take_tail(double (&a)[J], TB (&b)[J], const 
     double xa = fa; TB xb = fb;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
+        if (mreach < o) break;
         const double ya = __shfl_down_sync(FULL, xa, o); const TB yb = __shfl_down_sync(FULL, xb, o);
         if (lreach >= o) { xa = ya; xb = yb; }
     }
@@ -350,6 +356,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
             }
         }
         const int rb = lane_reach_back<J>(head), rf = lane_reach_fwd<J>(tail);
+        const int mrb = warp_max_reach(rb), mrf = warp_max_reach(rf);
         {
             // kind of the anchor that closed the previous run: heads read it at t-1 and spread it forward
             int kp[J];
@@ -357,10 +364,10 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
             int hk[J];
 #pragma unroll
             for (int j = 0; j < J; ++j) hk[j] = head[j] ? -kp[j] : 2;       // non-heads hold 2 => min = minus the head's value
-            seg_fwd_min_int<J>(hk, head, rb);
+            seg_fwd_min_int<J>(hk, head, rb, mrb);
 #pragma unroll
             for (int j = 0; j < J; ++j) { prevk[j] = -hk[j]; endk[j] = kind[j]; }
-            seg_take_tail<J, int>(eta, endk, tail, rf);                  // start multiplier and end kind of my run
+            seg_take_tail<J, int>(eta, endk, tail, rf, mrf);                  // start multiplier and end kind of my run
         }
         double e0[J], target[J];
         bool freeend[J];
@@ -399,7 +406,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
                     D[j] = e.D; C[j] = e.C; pre[j] = e.C - e.D; dy[j] = e.dy;
                 } else { D[j] = C[j] = pre[j] = dy[j] = 0.0; }
             }
-            seg_fwd2<J>(pre, dy, head, rb, OpAdd(), OpAdd(), 0.0, 0.0);
+            seg_fwd2<J>(pre, dy, head, rb, mrb, OpAdd(), OpAdd(), 0.0, 0.0);
             bool pending[J], needflat[J];
 #pragma unroll
             for (int j = 0; j < J; ++j) {
@@ -428,7 +435,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
                         } else next_breaks_tab(tab, tstride, lane * J + j, eta[j], bu[j], bd[j]);
                     }
                 }
-                seg_fwd2<J>(bu, bd, head, rb, OpMin(), OpMax(), WBIG, -WBIG);
+                seg_fwd2<J>(bu, bd, head, rb, mrb, OpMin(), OpMax(), WBIG, -WBIG);
             }
 #pragma unroll
             for (int j = 0; j < J; ++j) {
@@ -451,7 +458,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
                 }
                 eta[j] = en;
             }
-            seg_take_tail<J, int>(eta, rs, tail, rf);
+            seg_take_tail<J, int>(eta, rs, tail, rf, mrf);
         }
 #ifdef DOPF_STATS
         ++st_rounds;
@@ -460,7 +467,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
         // final run state for every element: multiplier, status, "flat" (sum of derivatives at the tail)
 #pragma unroll
         for (int j = 0; j < J; ++j) if (valid[j] && tail[j] && !(totd[j] < -1e-300)) rs[j] |= RS_FLAT;
-        seg_take_tail<J, int>(eta, rs, tail, rf);
+        seg_take_tail<J, int>(eta, rs, tail, rf, mrf);
 
         // ---- KKT check ------------------------------------------------------------------------------
         bool vio_up[J], vio_dn[J];
@@ -480,7 +487,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
                 else flat_range_hinge(st[j], k, hl[j], WBIG, eta[j], D[j], C[j], Ilo[j], Ihi[j]);
             }
         }
-        seg_fwd2<J>(Ilo, Ihi, head, rb, OpMax(), OpMin(), -WBIG, WBIG);          // tails now hold the run interval
+        seg_fwd2<J>(Ilo, Ihi, head, rb, mrb, OpMax(), OpMin(), -WBIG, WBIG);          // tails now hold the run interval
         // sign chain over the runs: after an upper anchor eta may not rise, after a lower anchor it may not
         // drop.  Only tails carry run values, the other elements are neutral; the chains restart at the
         // head of a run whose previous anchor has the other kind.
@@ -495,8 +502,8 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
                 hdn[j] = head[j] && prevk[j] >= 0;
             }
             const int rup = lane_reach_back<J>(hup), rdn = lane_reach_back<J>(hdn);
-            seg_fwd1<J>(Fhi, hup, rup, OpMin(), WBIG);
-            seg_fwd1<J>(Flo, hdn, rdn, OpMax(), -WBIG);
+            seg_fwd1<J>(Fhi, hup, rup, warp_max_reach(rup), OpMin(), WBIG);
+            seg_fwd1<J>(Flo, hdn, rdn, warp_max_reach(rdn), OpMax(), -WBIG);
         }
         // new anchors: the most violated timestep of every maximal stretch of consecutive violated timesteps of one
         // kind inside a run (the level path peaks where the bound finally binds).  One anchor per run and round would
@@ -518,15 +525,16 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
 #pragma unroll
                 for (int j = 0; j < J; ++j) { shead[j] = head[j] || vk[j] != vp[j]; stail[j] = tail[j] || vk[j] != vn[j]; }
                 const int rbs = lane_reach_back<J>(shead), rfs = lane_reach_fwd<J>(stail);
+                const int mrbs = warp_max_reach(rbs), mrfs = warp_max_reach(rfs);
                 double m[J];
 #pragma unroll
                 for (int j = 0; j < J; ++j) m[j] = vmag[j];
-                seg_fwd1<J>(m, shead, rbs, OpMax(), -1.0);               // stretch tails hold the largest violation
-                seg_take_tail1<J, double>(m, stail, rfs);
+                seg_fwd1<J>(m, shead, rbs, mrbs, OpMax(), -1.0);               // stretch tails hold the largest violation
+                seg_take_tail1<J, double>(m, stail, rfs, mrfs);
                 int cand[J];
 #pragma unroll
                 for (int j = 0; j < J; ++j) cand[j] = (anyv[j] && vmag[j] >= m[j]) ? lane * J + j : 0x7fffffff;
-                seg_fwd_min_int<J>(cand, shead, rbs);                   // first candidate of the stretch so far
+                seg_fwd_min_int<J>(cand, shead, rbs, mrbs);                   // first candidate of the stretch so far
 #pragma unroll
                 for (int j = 0; j < J; ++j) newanchor[j] = anyv[j] && vmag[j] >= m[j] && cand[j] == lane * J + j;
             }
@@ -551,7 +559,7 @@ __device__ bool sto_warp_solve(const View &v, int s, const Hinge *hinges, const 
             }
             if (valid[j] && tail[j] && (rs[j] & RS_BAD)) flag[j] |= RS_BAD;
         }
-        seg_take_tail1<J, int>(flag, tail, rf);                     // the run's verdict, known to all its elements
+        seg_take_tail1<J, int>(flag, tail, rf, mrf);                     // the run's verdict, known to all its elements
 
 #ifdef DOPF_DEBUG_STO
         if (HINGES && (v.debug & 4) && s == ((v.debug >> 8) & 0xfff) && v.ctrl->iteration == (v.debug >> 20)) {
