@@ -38,7 +38,8 @@ struct OpAdd { __device__ double operator()(double a, double b) const { return a
 struct OpMin { __device__ double operator()(double a, double b) const { return a < b ? a : b; } };
 struct OpMax { __device__ double operator()(double a, double b) const { return a > b ? a : b; } };
 
-// lane-level reach for a set of segment heads: how many lanes back a lane may combine
+// lane-level reach for a set of segment heads: how many lanes back a lane may combine (one ballot: the nearest lane at or
+// below mine that holds a head)
 template <int J>
 __device__ __forceinline__ int lane_reach_back(const bool (&head)[J])
 {
@@ -46,10 +47,8 @@ __device__ __forceinline__ int lane_reach_back(const bool (&head)[J])
     bool any = false;
 #pragma unroll
     for (int j = 0; j < J; ++j) any |= head[j];
-    int x = any ? lane : -1;                      // lane 0 always holds a head (t = 0)
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int xo = __shfl_up_sync(FULL, x, o); if (lane >= o) x = max(x, xo); }
-    return lane - x;                              // 0 if this lane holds a head
+    const unsigned m = __ballot_sync(FULL, any) & (0xffffffffu >> (31 - lane));      // lanes <= mine with a head
+    return m ? lane - (31 - __clz(m)) : lane + 1;                                      // 0 if this lane holds a head
 }
 template <int J>
 __device__ __forceinline__ int lane_reach_fwd(const bool (&tail)[J])
@@ -58,10 +57,8 @@ __device__ __forceinline__ int lane_reach_fwd(const bool (&tail)[J])
     bool any = false;
 #pragma unroll
     for (int j = 0; j < J; ++j) any |= tail[j];
-    int x = any ? lane : 64;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int xo = __shfl_down_sync(FULL, x, o); if (lane + o < 32) x = min(x, xo); }
-    return x >= 64 ? 0 : x - lane;                // 0 if this lane holds a tail (or none follows)
+    const unsigned m = __ballot_sync(FULL, any) & (0xffffffffu << lane);              // lanes >= mine with a tail
+    return m ? (__ffs(m) - 1) - lane : 0;                                              // 0 if this lane holds a tail (or none follows)
 }
 
 // largest reach of any lane: scan levels beyond it change nothing and are skipped (runs between level anchors are short -
