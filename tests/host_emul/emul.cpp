@@ -125,6 +125,10 @@ struct Emul {
     Ctrl ctrl;
     std::vector<Hinge> scratch;
     std::vector<int> hcnt;
+    // partitioned mode (mirror of dopf_set_partition / dopf_step_phase): exchange buffers and constants
+    std::vector<double> rbox, dmaxd;
+    double *injx = nullptr, *xrow = nullptr, *flowD = nullptr;
+    bool partitioned = false;
     double *mk(size_t n) { d.emplace_back(n ? n : 1, 0.0); return d.back().data(); }
     int *mki(size_t n) { iv.emplace_back(n ? n : 1, 0); return iv.back().data(); }
 };
@@ -160,6 +164,7 @@ void *emul_create(int N, int L, int T, int G, int S, const double *ptdf, const d
     }
     for (int n = 0; n < N; ++n) for (int t = 0; t < T; ++t) dm[(size_t)n * ldt + t] = demand[(size_t)n * T + t];
     v.ptdf = P; v.fmax = f; v.demand = dm; v.q = q; v.prow = prow; v.mwide = mw; v.nagents = na; v.rbox = nullptr;
+    e->rbox = rbox;
     double *a;
     int *ip;
     a = e->mk(G); std::copy(gmc, gmc + G, a); v.gen_mc = a;
@@ -204,10 +209,10 @@ void emul_destroy(void *h) { delete (Emul *)h; }
 void emul_warm_fail(int *out) { for (int i = 0; i < 8; ++i) { out[i] = g_warm_fail[i]; g_warm_fail[i] = 0; } }
 #endif
 
-static void compact(Emul *e, int mode)
+static void compact(Emul *e, int mode, bool keep_dmax = false)
 {
     View &v = e->v;
-    if (mode == 1)
+    if (mode == 1 && !keep_dmax)
         for (int t = 0; t < v.ldt; ++t) { unsigned long long m = 0; for (int n = 0; n < v.N; ++n) m = std::max(m, v.dn[(size_t)n * v.ldt + t]); v.dmax[t] = m; }
     for (int t = 0; t < v.T; ++t) {
         int cnt = 0;
@@ -263,6 +268,28 @@ static void storage_pass(Emul *e, bool fix)
     }
 }
 
+static void gen_fix_pass(Emul *e)
+{
+    View &v = e->v;
+    const int cur = v.ctrl->cur, nxt = 1 - cur, ldt = v.ldt, Np = v.Np, T = v.T;
+    for (int w = 0; w < v.ctrl->gen_work_cnt; ++w) {
+        const int g = v.gen_work[w] / T, t = v.gen_work[w] % T, n = v.gen_node[g];
+        const double Pb = v.P[cur][(size_t)g * T + t], pmax = v.gen_pmax[g], lo = -Pb, hi = pmax - Pb;
+        std::vector<Hinge> lst;
+        for (int j = 0; j < v.wcnt[t]; ++j) {
+            int en = v.wide[(size_t)t * 2 * v.L + j]; int l = en >> 1, side = en & 1; Hinge hh;
+            if (make_hinge(v.c, v.ptdf[(size_t)l * Np + n], side ? v.bminus[(size_t)l * ldt + t] : v.bplus[(size_t)l * ldt + t], side, hh) && hh.bp > lo && hh.bp < hi) lst.push_back(hh);
+        }
+        HingeList hl; hl.h = lst.data(); hl.n = (int)lst.size(); hl.sorted = false;
+        const size_t nt = (size_t)n * ldt + t;
+        double dd = root_monotone_pl(v.gen_mc[g] + v.g0[nt], v.c.prox + v.s1[nt], hl, lo, hi);
+        double Pn = Pb + dd; Pn = Pn < 0 ? 0 : (Pn > pmax ? pmax : Pn);
+        v.P[nxt][(size_t)g * T + t] = Pn;
+        note_move(v, n, t, Pn - Pb);
+        v.ctrl->stat_gen_fix++;
+    }
+}
+
 void emul_iterate(void *h)
 {
     Emul *e = (Emul *)h;
@@ -291,22 +318,7 @@ void emul_iterate(void *h)
     storage_pass(e, false);
     compact(e, 1);
     for (int n = 0; n < v.N; ++n) for (int t = 0; t < T; ++t) body_verify(v, n, t);
-    for (int w = 0; w < v.ctrl->gen_work_cnt; ++w) {
-        const int g = v.gen_work[w] / T, t = v.gen_work[w] % T, n = v.gen_node[g];
-        const double Pb = v.P[cur][(size_t)g * T + t], pmax = v.gen_pmax[g], lo = -Pb, hi = pmax - Pb;
-        std::vector<Hinge> lst;
-        for (int j = 0; j < v.wcnt[t]; ++j) {
-            int en = v.wide[(size_t)t * 2 * v.L + j]; int l = en >> 1, side = en & 1; Hinge hh;
-            if (make_hinge(v.c, v.ptdf[(size_t)l * Np + n], side ? v.bminus[(size_t)l * ldt + t] : v.bplus[(size_t)l * ldt + t], side, hh) && hh.bp > lo && hh.bp < hi) lst.push_back(hh);
-        }
-        HingeList hl; hl.h = lst.data(); hl.n = (int)lst.size(); hl.sorted = false;
-        const size_t nt = (size_t)n * ldt + t;
-        double dd = root_monotone_pl(v.gen_mc[g] + v.g0[nt], v.c.prox + v.s1[nt], hl, lo, hi);
-        double Pn = Pb + dd; Pn = Pn < 0 ? 0 : (Pn > pmax ? pmax : Pn);
-        v.P[nxt][(size_t)g * T + t] = Pn;
-        note_move(v, n, t, Pn - Pb);
-        v.ctrl->stat_gen_fix++;
-    }
+    gen_fix_pass(e);
     storage_pass(e, true);
     compact(e, 1);
     for (int n = 0; n < Np; ++n) for (int t = 0; t < ldt; ++t) body_inject(v, n, t);
@@ -326,6 +338,102 @@ void emul_iterate(void *h)
     int tr = 0, wr = 0; for (int t = 0; t < T; ++t) { tr += v.tcnt[t]; wr += v.wcnt[t]; }
     v.ctrl->stat_tight_rows = tr; v.ctrl->stat_wide_rows = wr;
     body_finish(v);
+}
+
+// ---- partitioned mode: the four phases of dopf_step_phase with the three exchange buffers of dopf_exchange_buffer -----
+// (same per-element bodies as the device kernels; the row sums are stored as corrections like k_slack_rows does)
+void emul_partition_init(void *h, int total_agents)
+{
+    Emul *e = (Emul *)h; View &v = e->v;
+    const int ldt = v.ldt, Np = v.Np, Lp = v.Lp;
+    v.A = total_agents; v.demand_on = 0; v.rowsum_is_corr = 1; e->partitioned = true;
+    e->injx = e->mk((size_t)Np * ldt); v.injloc[0] = v.injloc[1] = e->injx;
+    e->xrow = e->mk((size_t)3 * Lp * ldt); v.rowsumU = e->xrow; v.rowsumK = e->xrow + (size_t)Lp * ldt; v.xflow = e->xrow + (size_t)2 * Lp * ldt;
+    e->flowD = e->mk((size_t)Lp * ldt); v.flowD = e->flowD;
+    for (int l = 0; l < Lp; ++l) for (int t = 0; t < ldt; ++t) { double s = 0; for (int n = 0; n < Np; ++n) s += v.ptdf[(size_t)l * Np + n] * v.demand[(size_t)n * ldt + t]; e->flowD[(size_t)l * ldt + t] = s; }
+    e->dmaxd.assign(ldt, 0.0);
+}
+// which: 0 move maxima [ldt] (MAX), 1 local injection [Np*ldt] (SUM), 2 row-sum corrections + partial flows [3*Lp*ldt] (SUM),
+// 3 per-node box ranges [Np] (MAX, set-up)
+double *emul_exchange_buffer(void *h, int which, long long *count)
+{
+    Emul *e = (Emul *)h; View &v = e->v;
+    switch (which) {
+    case 0: *count = v.ldt; return e->dmaxd.data();
+    case 1: *count = (long long)v.Np * v.ldt; return e->injx;
+    case 2: *count = (long long)3 * v.Lp * v.ldt; return e->xrow;
+    default: *count = v.Np; return e->rbox.data();
+    }
+}
+void emul_partition_finish_setup(void *h)      // after the box ranges were max-reduced: identical candidate rows on all ranks
+{
+    Emul *e = (Emul *)h; View &v = e->v;
+    for (int l = 0; l < v.L; ++l) { double m = 0; for (int n = 0; n < v.N; ++n) m = std::max(m, std::fabs(v.ptdf[(size_t)l * v.Np + n]) * e->rbox[n]); v.mwide[l] = m; }
+}
+void emul_phase(void *h, int phase)
+{
+    Emul *e = (Emul *)h; View &v = e->v;
+    if (v.ctrl->converged || v.ctrl->error) return;
+    const int cur = v.ctrl->cur, nxt = 1 - cur, ldt = v.ldt, Np = v.Np, Lp = v.Lp, T = v.T;
+    if (phase == 0) {
+        v.ctrl->gen_work_cnt = v.ctrl->sto_work_cnt = 0;
+        v.ctrl->res_bits[0] = v.ctrl->res_bits[1] = v.ctrl->res_bits[2] = 0;
+        std::fill(e->dn.begin(), e->dn.end(), 0ull); std::fill(e->dmax.begin(), e->dmax.end(), 0ull);
+        for (int s = 0; s < v.S; ++s) v.sto_flag[s] = 0;
+        for (int l = 0; l < Lp; ++l) for (int t = 0; t < ldt; ++t) body_row_prep(v, l, t);
+        std::fill(e->xrow, e->xrow + (size_t)3 * Lp * ldt, 0.0);                 // k_row_prep zeroes the exchange slabs
+        compact(e, 0);
+        for (int n = 0; n < Np; ++n) for (int t = 0; t < ldt; ++t) {
+            double a = 0, b = 0;
+            for (int l = 0; l < Lp; ++l) { double p = v.ptdf[(size_t)l * Np + n]; a += p * v.M[(size_t)l * ldt + t]; b += p * p * v.Wt[(size_t)l * ldt + t]; }
+            v.g0[(size_t)n * ldt + t] = v.lam[cur][t] + v.c.gamma * v.ssum[cur][t] + a;
+            v.s1[(size_t)n * ldt + t] = v.c.gamma + 2.0 * v.c.kappa * v.q[n] + b;
+            v.rg[(size_t)n * ldt + t] = 1.0 / (v.c.prox + v.s1[(size_t)n * ldt + t]);
+        }
+        for (int g = 0; g < v.G; ++g) for (int t = 0; t < T; ++t) {
+            const double pp = v.P[cur][(size_t)g * T + t];
+            const double pn = body_gen_predict(v, g, t, pp, v.gen_node[g], v.gen_mc[g], v.gen_pmax[g]);
+            v.P[nxt][(size_t)g * T + t] = pn;
+            note_move(v, v.gen_node[g], t, pn - pp);
+        }
+        storage_pass(e, false);
+        compact(e, 1);                                   // local maxima: enough for the rank's own agents
+        for (int n = 0; n < v.N; ++n) for (int t = 0; t < T; ++t) body_verify(v, n, t);
+        gen_fix_pass(e);
+        storage_pass(e, true);
+        for (int t = 0; t < ldt; ++t) { unsigned long long m = 0; for (int n = 0; n < v.N; ++n) m = std::max(m, v.dn[(size_t)n * ldt + t]); e->dmaxd[t] = bits_nonneg(m); }
+    } else if (phase == 1) {
+        for (int t = 0; t < ldt; ++t) v.dmax[t] = nonneg_bits(e->dmaxd[t]);      // exchanged maxima -> identical tight lists
+        compact(e, 1, true);
+        for (int n = 0; n < Np; ++n) for (int t = 0; t < ldt; ++t) body_inject(v, n, t);     // agents only (demand_on = 0)
+        for (int l = 0; l < Lp; ++l) for (int t = 0; t < ldt; ++t) { double s = 0; for (int n = 0; n < Np; ++n) s += v.ptdf[(size_t)l * Np + n] * e->injx[(size_t)n * ldt + t]; v.xflow[(size_t)l * ldt + t] = s; }
+    } else if (phase == 2) {
+        for (size_t i = 0; i < (size_t)Np * ldt; ++i) v.inj[nxt][i] = e->injx[i] - v.demand[i];                 // launch_copy_inj
+        for (int t = 0; t < ldt; ++t) { double s = 0; for (int n = 0; n < Np; ++n) s += v.inj[nxt][(size_t)n * ldt + t]; v.ssum[nxt][t] = s; }
+        std::fill(e->tflag.begin(), e->tflag.end(), 0);
+        for (int t = 0; t < T; ++t) for (int j = 0; j < v.tcnt[t]; ++j) {
+            const int en = v.tight[(size_t)t * 2 * v.L + j], l = en >> 1, side = en & 1;
+            const double b = side ? v.bminus[(size_t)l * ldt + t] : v.bplus[(size_t)l * ldt + t];
+            double a = 0;
+            for (int n = 0; n < v.N; ++n) {              // k_slack_rows: only the nodes whose largest move reaches the hinge
+                const double p = v.ptdf[(size_t)l * Np + n], sp = side ? p : -p;
+                const double dnm = std::max(-v.nst[0][(size_t)t * Np + n], v.nst[1][(size_t)t * Np + n]);
+                if (std::fabs(b) > std::fabs(p) * dnm) continue;
+                a += body_slack_row_node(v, l, side, n, t) - slack_node_lin(v, b, sp, n, t);
+            }
+            (side ? v.rowsumK : v.rowsumU)[(size_t)l * ldt + t] = a;
+            e->tflag[(size_t)l * ldt + t] |= (1 << side);
+        }
+    } else {
+        for (int l = 0; l < Lp; ++l) for (int t = 0; t < ldt; ++t) v.flow[nxt][(size_t)l * ldt + t] = v.xflow[(size_t)l * ldt + t] - e->flowD[(size_t)l * ldt + t];   // k_dual epilogue
+        double rm = 0, rr = 0, rl = 0;
+        for (int l = 0; l < v.L; ++l) for (int t = 0; t < T; ++t) { double a, b; body_dual(v, l, t, e->tflag[(size_t)l * ldt + t], a, b); rm = std::max(rm, a); rr = std::max(rr, b); }
+        for (int t = 0; t < T; ++t) rl = std::max(rl, body_lambda(v, t));
+        v.ctrl->res_bits[0] = nonneg_bits(rl); v.ctrl->res_bits[1] = nonneg_bits(rm); v.ctrl->res_bits[2] = nonneg_bits(rr);
+        int tr = 0, wr = 0; for (int t = 0; t < T; ++t) { tr += v.tcnt[t]; wr += v.wcnt[t]; }
+        v.ctrl->stat_tight_rows = tr; v.ctrl->stat_wide_rows = wr;
+        body_finish(v);
+    }
 }
 
 // newest iterate; matrices dense [rows][T]

@@ -29,6 +29,11 @@ def lib():
         _lib = C.CDLL(_SO)
         _lib.emul_create.restype = C.c_void_p
         _lib.emul_gen_root.restype = C.c_double
+        _lib.emul_exchange_buffer.restype = _dp
+        _lib.emul_exchange_buffer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]
+        _lib.emul_partition_init.argtypes = [C.c_void_p, C.c_int]
+        _lib.emul_partition_finish_setup.argtypes = [C.c_void_p]
+        _lib.emul_phase.argtypes = [C.c_void_p, C.c_int]
     return _lib
 
 
@@ -52,6 +57,26 @@ class EmulADMM:
 
     def iterate(self):
         lib().emul_iterate(self.h)
+        lib().emul_get(self.h, _d(self.P), _d(self.D), _d(self.C), _d(self.E), _d(self.inj), _d(self.flow), _d(self.avgU), _d(self.avgK),
+                       _d(self.lam), _d(self.mu), _d(self.rho), self.status.ctypes.data_as(_ip))
+
+    # ---- partitioned mode: mirror of dopf_set_partition / dopf_step_phase / dopf_exchange_buffer ----
+    def partition_init(self, total_agents):
+        lib().emul_partition_init(self.h, int(total_agents))
+
+    def exchange_buffer(self, which):
+        """numpy view (no copy) of exchange buffer 0 move maxima / 1 local injection / 2 row sums + partial flows / 3 box ranges"""
+        n = C.c_longlong()
+        ptr = lib().emul_exchange_buffer(self.h, which, C.byref(n))
+        return np.ctypeslib.as_array(ptr, shape=(n.value,))
+
+    def partition_finish_setup(self):
+        lib().emul_partition_finish_setup(self.h)
+
+    def phase(self, k):
+        lib().emul_phase(self.h, k)
+
+    def fetch(self):
         lib().emul_get(self.h, _d(self.P), _d(self.D), _d(self.C), _d(self.E), _d(self.inj), _d(self.flow), _d(self.avgU), _d(self.avgK),
                        _d(self.lam), _d(self.mu), _d(self.rho), self.status.ctypes.data_as(_ip))
 
