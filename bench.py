@@ -173,6 +173,32 @@ def oracle_rate(pkg, workload, steps, warmup, budget_s=150.0):
     return A * prob.T * steps / dt, dt / steps * 1e3, oracle.num_threads(), sample
 
 
+def reduced_cpu_rate(pkg, workload, params="ref_ratio"):
+    """agent*timestep updates/s of a SEQUENTIAL CPU run of the same reduced algebra on the WHOLE workload: the library's
+    per-element device code (csrc/dopf_math.h, dopf_bodies.h) compiled for the host and run as plain loops (tests/host_emul:
+    test infrastructure that mirrors enqueue_iteration; dense products as triple loops, one thread).  One warm-up iteration
+    from the cold start, then one timed iteration.  Not the reference and not the oracle - a second, stated CPU baseline on
+    the same config beside `cpu_baseline`."""
+    from tests.host_emul import emul
+    from dopf_b200 import multi
+    prob, cfg = make_case(pkg, workload, 0, params=params)
+    sub, _, _ = multi.shard_problem(prob, 0, 1)             # node-sorted agents
+    e = emul.EmulADMM(sub, gamma=cfg["gamma"], flow_weight=cfg["flow_weight"], prox_weight=cfg["prox_weight"], hcap=64)
+    t0 = time.perf_counter(); e.iterate(); first = time.perf_counter() - t0
+    which, dt = "iteration 1 from the cold start", first
+    if first < 30.0:
+        t0 = time.perf_counter(); e.iterate(); dt = time.perf_counter() - t0
+        which = "iteration 2 from the cold start (after one warm-up iteration)"
+    if int(e.status[6]) != 0:
+        raise RuntimeError("host emulation reported a capacity error")
+    A = prob.G + prob.S
+    return {"value": A * prob.T / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"the whole '{workload}' case ({prob.G} generators + {prob.S} storages, N={prob.N}, L={prob.L}, T={prob.T}), {which}; "
+                      "the library's per-element device code compiled for the host, sequential (tests/host_emul)",
+            "ms_per_iteration": dt * 1e3, "same_config": True,
+            "gen_corrected": int(e.status[2]), "sto_corrected": int(e.status[3]), "tight_rows": int(e.status[4])}
+
+
 def run_reference(args):
     import __graft_entry__ as g
     rank = int(os.environ.get("RANK", "0"))
@@ -435,6 +461,10 @@ def run_dopf(args):
         if world == 1 and not args.no_cpu_baseline and not args.quick and args.workload != "cfg4":
             v, ms, cores, sample = oracle_rate(pkg, args.workload, 3, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_iteration_of_sample": ms}
+            try:        # additional information: the same reduced algebra, sequential, on the whole case
+                line["cpu_reduced_algebra_baseline"] = reduced_cpu_rate(pkg, args.workload, args.params)
+            except Exception as e:
+                line["cpu_reduced_algebra_baseline"] = {"error": str(e)[:300]}
         print(json.dumps(line), flush=True)
     # teardown order matters with a captured NCCL graph: drop the graph first, then the handle, then leave without the
     # process-group destructor (destroying the communicator under a live graph blocks at interpreter exit)
