@@ -88,7 +88,7 @@ struct View {
     double *eta;            // [S][T] level-multiplier path of the last storage solve (warm start)
     double *inj[2];         // [Np][ldt]  nodal injection (all ranks' agents)
     double *injloc[2];      // [Np][ldt]  contribution of this rank's agents (== inj on one GPU)
-    int demand_on;          // 1: this rank subtracts the demand (rank 0)
+    int demand_on;          // 1: the local injection carries -demand (single-GPU handles); 0 in the partitioned mode (subtracted after the exchange)
     double *ssum[2];        // [ldt]   sum_n inj
     double *ssum_part;      // [COLSUM_R][ldt] partial column sums (fixed row groups, folded in order by the last block)
     int *colsum_cnt;        // [ldt/32] arrival counters of k_colsum (self-resetting)

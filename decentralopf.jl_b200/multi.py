@@ -60,7 +60,7 @@ class PartitionedADMM:
         with torch.cuda.stream(self.stream):
             d._check(d.lib.dopf_set_partition(d.h, rank, world, prob.G + prob.S), "dopf_set_partition")
             self.bufs = {w: self._buffer(w) for w in (0, 1, 2, 3)}     # fixed addresses for the lifetime of the handle
-            self._allreduce(1, self.dist.ReduceOp.SUM)     # initial injection (-demand from rank 0)
+            self._allreduce(1, self.dist.ReduceOp.SUM)     # initial injection of the agents (the library subtracts the demand)
             self._allreduce(3, self.dist.ReduceOp.MAX)     # per-node box ranges -> identical candidate rows on all ranks
             d._check(d.lib.dopf_step_phase(d.h, -1), "dopf_step_phase")
         self.stream.synchronize()
