@@ -73,3 +73,21 @@ def test_product_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".h", ".jl")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.lower() or f == "__init__.py" and "oracle" not in src, (dirpath, f)
+
+
+def test_julia_shim_matches_the_abi(pkg):
+    """The Julia side cannot be executed here (no Julia in the image), so at least keep it consistent statically: the three C
+    structs of dopf_imports.jl have the fields of the ctypes mirrors (same names, order and C types), and every symbol the
+    shim `ccall`s is exported by libdopf.so."""
+    import ctypes as C
+    import re
+    from dopf_b200 import _lib
+    src = open(os.path.join(os.path.dirname(_lib.__file__), "julia", "dopf_imports.jl")).read()
+    ctype = {"Cint": C.c_int32, "Cdouble": C.c_double, "Ptr{Cdouble}": _lib._dp, "Ptr{Cint}": _lib._ip}
+    for name, mirror in (("DopfProblem", _lib.DopfProblem), ("DopfConfig", _lib.DopfConfig), ("DopfStatus", _lib.DopfStatus)):
+        body = re.search(r"struct %s\n(.*?)\nend" % name, src, re.S).group(1)
+        fields = re.findall(r"(\w+)::([\w{}]+)", body)
+        assert [(f, ctype[t]) for f, t in fields] == list(mirror._fields_), name
+    called = set(re.findall(r"ccall\(\(:(\w+), libdopf\)", src))
+    assert called and called <= set(_lib.EXPORTS), called - set(_lib.EXPORTS)
+    assert {"dopf_create", "dopf_step", "dopf_get_iterate", "dopf_get_duals", "dopf_comm_init", "dopf_comm_get_unique_id"} <= called
