@@ -91,3 +91,9 @@ def test_julia_shim_matches_the_abi(pkg):
     called = set(re.findall(r"ccall\(\(:(\w+), libdopf\)", src))
     assert called and called <= set(_lib.EXPORTS), called - set(_lib.EXPORTS)
     assert {"dopf_create", "dopf_step", "dopf_get_iterate", "dopf_get_duals", "dopf_comm_init", "dopf_comm_get_unique_id"} <= called
+    # every ccall passes as many arguments as the ctypes binding (which mirrors the header) declares
+    lib = _lib.load()
+    for m in re.finditer(r"ccall\(\(:(\w+), libdopf\), (\w+), \(([^)]*)\)", src):
+        fn, _, args = m.groups()
+        n = len([a for a in args.split(",") if a.strip()])
+        assert getattr(lib, fn).argtypes is not None and n == len(getattr(lib, fn).argtypes), (fn, n)
